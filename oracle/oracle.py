@@ -1,0 +1,266 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/_build/liblyra_oracle.so (plain-C restatement of the reference hot path,
+see oracle/lyra_oracle.h).  Imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / ``--impl reference`` legs — never by lyra_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liblyra_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    """Compile the C restatement (gcc, a few seconds). Building the checker is not using it."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        sigs = {
+            "lo_net_create": (vp, [C.c_char_p]), "lo_net_free": (None, [vp]), "lo_net_reset": (ci, [vp]),
+            "lo_net_invoke": (ci, [vp, vp, ci, vp, ci]), "lo_net_num_tensors": (ci, [vp]),
+            "lo_net_tensor_info": (ci, [vp, ci, vp, vp, vp, vp]), "lo_net_read_tensor": (ci, [vp, ci, vp, ci]),
+            "lo_net_num_vars": (ci, [vp]), "lo_net_var_name": (C.c_char_p, [vp, ci]),
+            "lo_net_var_count": (ci, [vp, ci]), "lo_net_read_var": (ci, [vp, ci, vp, ci]),
+            "lo_quantize_multiplier": (None, [C.c_double, vp, vp]), "lo_mbqm": (C.c_int32, [C.c_int32, C.c_int32, ci]),
+            "lo_rvq_create": (vp, [C.c_char_p]), "lo_rvq_free": (None, [vp]), "lo_rvq_num_stages": (ci, [vp]),
+            "lo_rvq_bits_per_stage": (ci, [vp]), "lo_rvq_codebook": (vp, [vp, ci]),
+            "lo_rvq_encode": (ci, [vp, vp, ci, vp]), "lo_rvq_decode": (ci, [vp, vp, vp]),
+            "lo_rvq_quantize_bits": (ci, [vp, vp, ci, vp]), "lo_rvq_decode_bits": (ci, [vp, C.c_char_p, ci, vp]),
+            "lo_packet_size": (ci, [ci, ci]), "lo_packet_pack": (ci, [C.c_char_p, ci, ci, vp]),
+            "lo_packet_unpack": (ci, [vp, ci, ci, ci, vp]),
+            "lo_int16_to_unit": (cf, [C.c_int16]), "lo_unit_to_int16": (C.c_int16, [cf]),
+            "lo_log_spectral_distance": (cf, [vp, vp, ci]),
+            "lo_logmel_create": (vp, [ci, ci, ci, ci]), "lo_logmel_free": (None, [vp]),
+            "lo_logmel_extract": (ci, [vp, vp, ci, vp]),
+            "lo_codec_create": (vp, [C.c_char_p]), "lo_codec_free": (None, [vp]), "lo_codec_reset": (ci, [vp]),
+            "lo_codec_encode": (ci, [vp, vp, ci, vp, vp, vp]), "lo_codec_decode": (ci, [vp, vp, ci, vp, vp, vp]),
+            "lo_codec_encoder_net": (vp, [vp]), "lo_codec_decoder_net": (vp, [vp]),
+            "lo_cpu_bench": (C.c_double, [C.c_char_p, ci, ci, ci, ci, C.c_uint32, vp, vp]),
+        }
+        for name, (res, args) in sigs.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_NP = {0: np.float32, 2: np.int32, 9: np.int8, 4: np.int64, 6: np.bool_, 3: np.uint8}
+
+
+class Net:
+    """One stream of soundstream_encoder.tflite or lyragan.tflite."""
+
+    def __init__(self, path=None, handle=None, owner=None):
+        self._own = handle is None
+        self._owner = owner
+        self.h = lib().lo_net_create(path.encode()) if handle is None else handle
+        if not self.h:
+            raise RuntimeError("oracle: cannot load %s" % path)
+
+    def __del__(self):
+        if getattr(self, "_own", False) and self.h:
+            lib().lo_net_free(self.h)
+            self.h = None
+
+    def reset(self):
+        assert lib().lo_net_reset(self.h) == 0
+
+    def invoke(self, x, n_out):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.empty(n_out, dtype=np.float32)
+        rc = lib().lo_net_invoke(self.h, _p(x), x.size, _p(y), n_out)
+        if rc != 0:
+            raise RuntimeError("oracle invoke failed rc=%d" % rc)
+        return y
+
+    def tensor(self, idx):
+        t, c, s, z = C.c_int(), C.c_int(), C.c_float(), C.c_int()
+        assert lib().lo_net_tensor_info(self.h, idx, C.byref(t), C.byref(c), C.byref(s), C.byref(z)) == 0
+        a = np.empty(c.value, dtype=_NP[t.value])
+        assert lib().lo_net_read_tensor(self.h, idx, _p(a), a.nbytes) == a.nbytes
+        return a
+
+    def tensor_quant(self, idx):
+        t, c, s, z = C.c_int(), C.c_int(), C.c_float(), C.c_int()
+        assert lib().lo_net_tensor_info(self.h, idx, C.byref(t), C.byref(c), C.byref(s), C.byref(z)) == 0
+        return s.value, z.value
+
+    def variables(self):
+        out = {}
+        for v in range(lib().lo_net_num_vars(self.h)):
+            n = lib().lo_net_var_count(self.h, v)
+            a = np.empty(n, dtype=np.float32)
+            assert lib().lo_net_read_var(self.h, v, _p(a), n) == n
+            out[lib().lo_net_var_name(self.h, v).decode()] = a
+        return out
+
+
+class Rvq:
+    def __init__(self, path):
+        self.h = lib().lo_rvq_create(path.encode())
+        if not self.h:
+            raise RuntimeError("oracle: cannot load %s" % path)
+        self.num_stages = lib().lo_rvq_num_stages(self.h)
+        self.bits_per_stage = lib().lo_rvq_bits_per_stage(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lo_rvq_free(self.h)
+            self.h = None
+
+    def codebooks(self):
+        out = np.empty((self.num_stages, 16, 64), dtype=np.float32)
+        for s in range(self.num_stages):
+            ptr = lib().lo_rvq_codebook(self.h, s)
+            out[s] = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(16, 64))
+        return out
+
+    def encode(self, features, num_quantizers):
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        idx = np.empty(self.num_stages, dtype=np.int32)
+        assert lib().lo_rvq_encode(self.h, _p(f), num_quantizers, _p(idx)) == 0
+        return idx
+
+    def decode(self, indices):
+        i = np.ascontiguousarray(indices, dtype=np.int32)
+        assert i.size == self.num_stages
+        out = np.empty(64, dtype=np.float32)
+        assert lib().lo_rvq_decode(self.h, _p(i), _p(out)) == 0
+        return out
+
+    def quantize(self, features, num_bits):
+        """ResidualVectorQuantizer::Quantize -> '0'/'1' string or None."""
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        buf = C.create_string_buffer(256)
+        rc = lib().lo_rvq_quantize_bits(self.h, _p(f), num_bits, buf)
+        return buf.value.decode() if rc == 0 else None
+
+    def decode_to_lossy_features(self, bits):
+        out = np.empty(64, dtype=np.float32)
+        rc = lib().lo_rvq_decode_bits(self.h, bits.encode(), len(bits), _p(out))
+        return out if rc == 0 else None
+
+
+def packet_size(num_header_bits, num_quantized_bits):
+    return lib().lo_packet_size(num_header_bits, num_quantized_bits)
+
+
+def packet_pack(bits, num_header_bits=0, num_quantized_bits=None):
+    nq = len(bits) if num_quantized_bits is None else num_quantized_bits
+    buf = np.zeros(32, dtype=np.uint8)
+    n = lib().lo_packet_pack(bits.encode(), num_header_bits, nq, _p(buf))
+    return None if n < 0 else bytes(buf[:n])
+
+
+def packet_unpack(data, num_header_bits, num_quantized_bits):
+    a = np.frombuffer(bytes(data), dtype=np.uint8).copy()
+    out = C.create_string_buffer(256)
+    n = lib().lo_packet_unpack(_p(a), a.size, num_header_bits, num_quantized_bits, out)
+    return None if n < 0 else out.value.decode()
+
+
+def int16_to_unit(v):
+    return lib().lo_int16_to_unit(int(v))
+
+
+def unit_to_int16(v):
+    return lib().lo_unit_to_int16(float(v))
+
+
+def log_spectral_distance(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    return lib().lo_log_spectral_distance(_p(a), _p(b), a.size)
+
+
+class LogMel:
+    def __init__(self, sample_rate_hz, hop, window, num_mel_bins):
+        self.h = lib().lo_logmel_create(sample_rate_hz, hop, window, num_mel_bins)
+        self.nmel = num_mel_bins
+        if not self.h:
+            raise ValueError("oracle logmel: bad parameters")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lo_logmel_free(self.h)
+            self.h = None
+
+    def extract(self, audio):
+        a = np.ascontiguousarray(audio, dtype=np.int16)
+        out = np.empty(self.nmel, dtype=np.float32)
+        rc = lib().lo_logmel_extract(self.h, _p(a), a.size, _p(out))
+        return out if rc == 0 else None
+
+
+class Codec:
+    """One 16 kHz stream: LyraEncoder::Encode / LyraDecoder::SetEncodedPacket+DecodeSamples(320)."""
+
+    def __init__(self, model_dir):
+        self.h = lib().lo_codec_create(model_dir.encode())
+        if not self.h:
+            raise RuntimeError("oracle: cannot load models from %s" % model_dir)
+        self.encoder_net = Net(handle=lib().lo_codec_encoder_net(self.h), owner=self)
+        self.decoder_net = Net(handle=lib().lo_codec_decoder_net(self.h), owner=self)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lo_codec_free(self.h)
+            self.h = None
+
+    def reset(self):
+        assert lib().lo_codec_reset(self.h) == 0
+
+    def encode(self, pcm, num_bits):
+        """-> (packet bytes, features f32[64], indices i32[46])"""
+        a = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert a.size == 320
+        pkt = np.zeros(24, dtype=np.uint8)
+        feat = np.empty(64, dtype=np.float32)
+        idx = np.empty(46, dtype=np.int32)
+        n = lib().lo_codec_encode(self.h, _p(a), num_bits, _p(pkt), _p(feat), _p(idx))
+        if n < 0:
+            return None
+        return bytes(pkt[:n]), feat, idx
+
+    def decode(self, packet, num_bits):
+        """packet=None -> concealment with zero features. -> (pcm i16[320], lossy features, unit float[320])"""
+        pcm = np.empty(320, dtype=np.int16)
+        lossy = np.empty(64, dtype=np.float32)
+        unit = np.empty(320, dtype=np.float32)
+        if packet is None:
+            rc = lib().lo_codec_decode(self.h, None, num_bits, _p(pcm), _p(lossy), _p(unit))
+        else:
+            a = np.frombuffer(bytes(packet), dtype=np.uint8).copy()
+            rc = lib().lo_codec_decode(self.h, _p(a), num_bits, _p(pcm), _p(lossy), _p(unit))
+        return None if rc != 0 else (pcm, lossy, unit)
+
+
+def cpu_bench(model_dir, streams, frames, num_bits, threads, seed=0x4C595241):
+    """-> dict(wall_s, frames, frames_per_s, stage_us[4], checksum)"""
+    st = (C.c_double * 4)()
+    cs = C.c_uint64()
+    wall = lib().lo_cpu_bench(model_dir.encode(), streams, frames, num_bits, threads, seed, st, C.byref(cs))
+    if wall < 0:
+        raise RuntimeError("oracle cpu bench failed")
+    return dict(wall_s=wall, frames=streams * frames, frames_per_s=streams * frames / wall,
+                stage_us=list(st), checksum=cs.value)
