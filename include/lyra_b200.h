@@ -1,0 +1,109 @@
+/*
+ * lyra_b200 — C ABI of the B200-native Lyra v1.3.2 hot path.
+ *
+ * This is the seam that replaces `TfLiteModelWrapper` (reference: lyra/tflite_model_wrapper.h:32-67)
+ * underneath the three plugin classes bound in lyra/lyra_components.cc:42-55.  Plain pointers and
+ * sizes only; the caller owns every buffer; one context per GPU; calls on one context must be
+ * serialised by the caller.  Stream ids are integers in [0, max_streams): each id owns the
+ * per-stream convolution state that a SoundStreamEncoder / LyraGanModel object owns in the
+ * reference (TFLite resource variables, zero-initialised).
+ *
+ * Return value: 0 on success, a negative LYRA_B200_E* code otherwise.  A failing call maps onto the
+ * reference's `std::nullopt` / `false` / `nullptr` conventions; it never aborts.
+ * There is NO CPU fallback: without a CUDA device lyra_b200_create fails with LYRA_B200_ENODEV.
+ */
+#ifndef LYRA_B200_H_
+#define LYRA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LYRA_B200_OK 0
+#define LYRA_B200_EINVAL (-1) /* bad argument: sample/feature count, bit count, stream id, duplicate id */
+#define LYRA_B200_ENODEV (-2) /* no CUDA device or a CUDA runtime failure */
+#define LYRA_B200_EMODEL (-3) /* model files missing, wrong version or unexpected graph structure */
+
+#define LYRA_B200_HOP 320          /* samples per 20 ms hop at 16 kHz (lyra/lyra_config.h:70-73) */
+#define LYRA_B200_NUM_FEATURES 64  /* lyra/lyra_config.cc:36 */
+#define LYRA_B200_MAX_BITS 184     /* lyra/residual_vector_quantizer.h:50 */
+#define LYRA_B200_MAX_STAGES 46
+
+typedef struct lyra_b200_ctx lyra_b200_ctx;
+
+/* Replaces {SoundStreamEncoder,ResidualVectorQuantizer,LyraGanModel}::Create
+ * (lyra/soundstream_encoder.cc:36-46, lyra/residual_vector_quantizer.cc:36-67, lyra/lyra_gan_model.cc:36-46)
+ * and the asset/version gate of AreParamsSupported (lyra/lyra_config.h:119-168): loads the three
+ * .tflite files + lyra_config.binarypb from `model_dir`, uploads weights, allocates the state of
+ * `max_streams` streams on CUDA device `device`.  *out is NULL on failure. */
+int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b200_ctx** out);
+void lyra_b200_destroy(lyra_b200_ctx* ctx);
+/* Human-readable reason of the last failure on this context (or of the last failed create when ctx is NULL). */
+const char* lyra_b200_last_error(const lyra_b200_ctx* ctx);
+int lyra_b200_max_streams(const lyra_b200_ctx* ctx);
+int lyra_b200_tile_streams(const lyra_b200_ctx* ctx);
+
+/* Replaces TfLiteModelWrapper::ResetVariableTensors (lyra/tflite_model_wrapper.cc:111-113) per stream:
+ * encoder, decoder and log-mel state of the listed streams go back to the initial (zero) state.
+ * stream_ids == NULL resets streams 0..n-1. */
+int lyra_b200_reset(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n);
+
+/* ---- fused codec calls: host buffers in, host buffers out ------------------------------------------ */
+
+/* LyraEncoder::Encode at 16 kHz without DTX (lyra/lyra_encoder.cc:113-156) for n streams:
+ * pcm[n][320] -> packets[n][ceil(num_bits/8)].  num_bits in {64,120,184} or any multiple of 4 <= 184.
+ * stream_ids == NULL means streams 0..n-1. */
+int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const int16_t* pcm, int num_bits,
+                     uint8_t* packets);
+
+/* LyraDecoder::SetEncodedPacket + DecodeSamples(320) in the no-fade paths (lyra/lyra_decoder.cc:172-226,
+ * 317-326): packets[n][ceil(num_bits/8)] -> pcm[n][320].  received[i] == 0 marks a lost packet: the
+ * generative model is then fed 64 zero features (ZeroFeatureEstimator).  received == NULL: all received. */
+int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const uint8_t* packets,
+                     const uint8_t* received, int num_bits, int16_t* pcm);
+
+/* ---- the plugin surface, call by call --------------------------------------------------------------- */
+
+/* FeatureExtractorInterface::Extract as implemented by SoundStreamEncoder
+ * (lyra/feature_extractor_interface.h:32-39, lyra/soundstream_encoder.cc:53-64): pcm[n][320] -> features[n][64]. */
+int lyra_b200_extract_features(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const int16_t* pcm, float* features);
+
+/* VectorQuantizerInterface::Quantize + PacketInterface::PackQuantized
+ * (lyra/vector_quantizer_interface.h:28-41, lyra/residual_vector_quantizer.cc:77-110, lyra/packet.h:56-60):
+ * features[n][64] -> packets[n][ceil(num_bits/8)] and, if indices != NULL, indices[n][46] (-1 for unused
+ * stages, the graph's output_0).  Stateless.  LYRA_B200_EINVAL for num_bits > 184 or num_bits % 4 != 0. */
+int lyra_b200_quantize(lyra_b200_ctx* ctx, int n, const float* features, int num_bits, uint8_t* packets, int32_t* indices);
+
+/* PacketInterface::UnpackPacket + VectorQuantizerInterface::DecodeToLossyFeatures
+ * (lyra/packet.h:62-71, lyra/residual_vector_quantizer.cc:112-168): packets -> features[n][64].  Stateless. */
+int lyra_b200_dequantize(lyra_b200_ctx* ctx, int n, const uint8_t* packets, int num_bits, float* features);
+
+/* GenerativeModel::RunConditioning + RunModel(320) as implemented by LyraGanModel
+ * (lyra/generative_model_interface.h:62-101, lyra/lyra_gan_model.cc:53-64): features[n][64] -> pcm[n][320]. */
+int lyra_b200_generate(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const float* features, int16_t* pcm);
+
+/* LogMelSpectrogramExtractorImpl::Extract for (16 kHz, hop 320, window 640)
+ * (lyra/log_mel_spectrogram_extractor_impl.cc:96-126): pcm[n][320] -> out[n][num_mel_bins];
+ * num_mel_bins is 160 (NoiseEstimator's extractor, lyra/lyra_config.cc:37) or 64 (integration test).
+ * `bank` (0 or 1) selects which of the two independent per-stream extractor states is advanced
+ * (the reference creates one extractor object per use). */
+int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* stream_ids, int n, const int16_t* pcm,
+                     int num_mel_bins, float* out);
+
+/* ---- device-resident variants (pointers are CUDA device pointers; asynchronous on the context's
+ *      stream; streams 0..n-1).  Used by bench.py for the HBM-resident `value` measurement and by
+ *      callers that keep audio on the GPU. ---------------------------------------------------------- */
+int lyra_b200_set_stream(lyra_b200_ctx* ctx, void* cuda_stream); /* NULL restores the context's own stream */
+int lyra_b200_encode_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets);
+int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received,
+                            int num_bits, int16_t* d_pcm);
+int lyra_b200_synchronize(lyra_b200_ctx* ctx);
+/* number of CUDA kernels this context has launched so far */
+uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LYRA_B200_H_ */

@@ -1,0 +1,205 @@
+"""ctypes binding of the C ABI in include/lyra_b200.h.
+
+``load()`` binds the nvcc-built product library ``lyra_b200/liblyra_b200.so`` and nothing else; it
+raises if the library is missing (run ``python -c 'import __graft_entry__ as g; g.build()'``).  There
+is no CPU fallback.  (``CApi(path)`` exists so the CPU test tier can bind the test-only emulated
+build of the same sources; the package itself never does.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_SO = os.path.join(_HERE, "liblyra_b200.so")
+MODEL_DIR = os.path.join(_HERE, "model_coeffs")
+
+OK, EINVAL, ENODEV, EMODEL = 0, -1, -2, -3
+HOP = 320
+NUM_FEATURES = 64
+MAX_STAGES = 46
+
+
+class LyraB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("lyra_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CApi:
+    def __init__(self, so_path):
+        if not os.path.exists(so_path):
+            raise FileNotFoundError(
+                "%s not found: the CUDA extension is not built (python -c 'import __graft_entry__ as g; g.build()')" % so_path)
+        L = C.CDLL(so_path)
+        vp, ci = C.c_void_p, C.c_int
+        sig = {
+            "lyra_b200_create": (ci, [C.c_char_p, ci, ci, C.POINTER(vp)]),
+            "lyra_b200_destroy": (None, [vp]),
+            "lyra_b200_last_error": (C.c_char_p, [vp]),
+            "lyra_b200_max_streams": (ci, [vp]),
+            "lyra_b200_tile_streams": (ci, [vp]),
+            "lyra_b200_reset": (ci, [vp, vp, ci]),
+            "lyra_b200_encode": (ci, [vp, vp, ci, vp, ci, vp]),
+            "lyra_b200_decode": (ci, [vp, vp, ci, vp, vp, ci, vp]),
+            "lyra_b200_extract_features": (ci, [vp, vp, ci, vp, vp]),
+            "lyra_b200_quantize": (ci, [vp, ci, vp, ci, vp, vp]),
+            "lyra_b200_dequantize": (ci, [vp, ci, vp, ci, vp]),
+            "lyra_b200_generate": (ci, [vp, vp, ci, vp, vp]),
+            "lyra_b200_logmel": (ci, [vp, ci, vp, ci, vp, ci, vp]),
+            "lyra_b200_set_stream": (ci, [vp, vp]),
+            "lyra_b200_encode_device": (ci, [vp, ci, vp, ci, vp]),
+            "lyra_b200_decode_device": (ci, [vp, ci, vp, vp, ci, vp]),
+            "lyra_b200_synchronize": (ci, [vp]),
+            "lyra_b200_launch_count": (C.c_uint64, [vp]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)   # AttributeError here = the library does not export the declared ABI
+            fn.restype = res
+            fn.argtypes = args
+        self.lib = L
+        self.path = so_path
+
+    EXPORTS = ["lyra_b200_create", "lyra_b200_destroy", "lyra_b200_last_error", "lyra_b200_max_streams",
+               "lyra_b200_tile_streams", "lyra_b200_reset", "lyra_b200_encode", "lyra_b200_decode",
+               "lyra_b200_extract_features", "lyra_b200_quantize", "lyra_b200_dequantize", "lyra_b200_generate",
+               "lyra_b200_logmel", "lyra_b200_set_stream", "lyra_b200_encode_device", "lyra_b200_decode_device",
+               "lyra_b200_synchronize", "lyra_b200_launch_count"]
+
+
+_product = None
+
+
+def load():
+    """Bind the product library (nvcc build). Fails loudly if it is missing."""
+    global _product
+    if _product is None:
+        _product = CApi(PRODUCT_SO)
+    return _product
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _ids(stream_ids, n):
+    if stream_ids is None:
+        return None
+    a = np.ascontiguousarray(stream_ids, dtype=np.int32)
+    if a.size != n:
+        raise ValueError("stream_ids must have one id per row")
+    return a
+
+
+def packet_bytes(num_bits):
+    return (num_bits + 7) // 8
+
+
+class Context:
+    """One GPU context: weights + the streaming state of ``max_streams`` independent 16 kHz streams."""
+
+    def __init__(self, max_streams, model_dir=MODEL_DIR, device=0, capi=None):
+        self.api = capi or load()
+        h = C.c_void_p()
+        rc = self.api.lib.lyra_b200_create(str(model_dir).encode(), int(device), int(max_streams), C.byref(h))
+        if rc != OK:
+            raise LyraB200Error(rc, (self.api.lib.lyra_b200_last_error(None) or b"").decode())
+        self.h = h
+        self.max_streams = max_streams
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.api.lib.lyra_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc != OK:
+            raise LyraB200Error(rc, (self.api.lib.lyra_b200_last_error(self.h) or b"").decode())
+
+    @property
+    def launch_count(self):
+        return int(self.api.lib.lyra_b200_launch_count(self.h))
+
+    @property
+    def tile_streams(self):
+        return int(self.api.lib.lyra_b200_tile_streams(self.h))
+
+    def reset(self, stream_ids=None, n=None):
+        if stream_ids is None:
+            n = self.max_streams if n is None else n
+            self._check(self.api.lib.lyra_b200_reset(self.h, None, n))
+        else:
+            a = np.ascontiguousarray(stream_ids, dtype=np.int32)
+            self._check(self.api.lib.lyra_b200_reset(self.h, _ptr(a), a.size))
+
+    def encode(self, pcm, num_bits, stream_ids=None):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, HOP)
+        n = pcm.shape[0]
+        ids = _ids(stream_ids, n)
+        out = np.empty((n, packet_bytes(num_bits)), dtype=np.uint8)
+        self._check(self.api.lib.lyra_b200_encode(self.h, _ptr(ids), n, _ptr(pcm), num_bits, _ptr(out)))
+        return out
+
+    def decode(self, packets, num_bits, stream_ids=None, received=None):
+        packets = np.ascontiguousarray(packets, dtype=np.uint8).reshape(-1, packet_bytes(num_bits))
+        n = packets.shape[0]
+        ids = _ids(stream_ids, n)
+        rec = None if received is None else np.ascontiguousarray(received, dtype=np.uint8)
+        out = np.empty((n, HOP), dtype=np.int16)
+        self._check(self.api.lib.lyra_b200_decode(self.h, _ptr(ids), n, _ptr(packets), _ptr(rec), num_bits, _ptr(out)))
+        return out
+
+    def extract_features(self, pcm, stream_ids=None):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, HOP)
+        n = pcm.shape[0]
+        ids = _ids(stream_ids, n)
+        out = np.empty((n, NUM_FEATURES), dtype=np.float32)
+        self._check(self.api.lib.lyra_b200_extract_features(self.h, _ptr(ids), n, _ptr(pcm), _ptr(out)))
+        return out
+
+    def quantize(self, features, num_bits, want_indices=False):
+        f = np.ascontiguousarray(features, dtype=np.float32).reshape(-1, NUM_FEATURES)
+        n = f.shape[0]
+        out = np.empty((n, packet_bytes(num_bits)), dtype=np.uint8)
+        idx = np.empty((n, MAX_STAGES), dtype=np.int32) if want_indices else None
+        self._check(self.api.lib.lyra_b200_quantize(self.h, n, _ptr(f), num_bits, _ptr(out), _ptr(idx)))
+        return (out, idx) if want_indices else out
+
+    def dequantize(self, packets, num_bits):
+        p = np.ascontiguousarray(packets, dtype=np.uint8).reshape(-1, packet_bytes(num_bits))
+        out = np.empty((p.shape[0], NUM_FEATURES), dtype=np.float32)
+        self._check(self.api.lib.lyra_b200_dequantize(self.h, p.shape[0], _ptr(p), num_bits, _ptr(out)))
+        return out
+
+    def generate(self, features, stream_ids=None):
+        f = np.ascontiguousarray(features, dtype=np.float32).reshape(-1, NUM_FEATURES)
+        n = f.shape[0]
+        ids = _ids(stream_ids, n)
+        out = np.empty((n, HOP), dtype=np.int16)
+        self._check(self.api.lib.lyra_b200_generate(self.h, _ptr(ids), n, _ptr(f), _ptr(out)))
+        return out
+
+    def logmel(self, pcm, num_mel_bins=160, bank=0, stream_ids=None):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, HOP)
+        n = pcm.shape[0]
+        ids = _ids(stream_ids, n)
+        out = np.empty((n, num_mel_bins), dtype=np.float32)
+        self._check(self.api.lib.lyra_b200_logmel(self.h, bank, _ptr(ids), n, _ptr(pcm), num_mel_bins, _ptr(out)))
+        return out
+
+    # ---- device-resident variants (raw CUDA device pointers as ints, e.g. torch.Tensor.data_ptr()) ----
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.api.lib.lyra_b200_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def encode_device(self, n, d_pcm, num_bits, d_packets):
+        self._check(self.api.lib.lyra_b200_encode_device(self.h, n, C.c_void_p(d_pcm), num_bits, C.c_void_p(d_packets)))
+
+    def decode_device(self, n, d_packets, d_received, num_bits, d_pcm):
+        self._check(self.api.lib.lyra_b200_decode_device(self.h, n, C.c_void_p(d_packets), C.c_void_p(d_received or 0),
+                                                         num_bits, C.c_void_p(d_pcm)))
+
+    def synchronize(self):
+        self._check(self.api.lib.lyra_b200_synchronize(self.h))

@@ -1,0 +1,420 @@
+// Context + launch logic + the C ABI of include/lyra_b200.h.
+// Compiled by nvcc for sm_100a (product) and, for the CPU test tier only, by g++ with -DLYRA_EMU.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lyra_b200.h"
+#include "aux_kernels.cuh"
+#include "model_spec.h"
+#include "net_kernels.cuh"
+
+using namespace lyra_b200;
+
+namespace {
+
+constexpr int kS = 16;   // streams per tile
+std::string g_create_error;
+
+#define CU(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+      return LYRA_B200_ENODEV;                                                          \
+    }                                                                                   \
+  } while (0)
+
+}  // namespace
+
+struct lyra_b200_ctx {
+  ModelSpec spec;
+  int device = 0, max_streams = 0, ntiles = 0, padded = 0;
+  uint8_t* d_blob = nullptr;
+  // streaming state, one block per kernel
+  uint32_t* d_state[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t* d_init[4] = {nullptr, nullptr, nullptr, nullptr};
+  int* d_n18[4] = {nullptr, nullptr, nullptr, nullptr};
+  int units[4] = {EncStateA::kUnits, EncStateB::kUnits, DecStateC::kUnits, DecStateD::kUnits};
+  float* d_mid_enc = nullptr;
+  float* d_mid_dec = nullptr;
+  int16_t* d_logmel_prev[2] = {nullptr, nullptr};
+  // device staging for the host-buffer API
+  int16_t* d_pcm = nullptr;
+  uint8_t* d_packets = nullptr;
+  uint8_t* d_received = nullptr;
+  float* d_features = nullptr;
+  float* d_melout = nullptr;
+  int* d_indices = nullptr;
+  int* d_ids = nullptr;
+  // tile map
+  int* d_tile_list = nullptr;
+  int* d_slot_of = nullptr;
+  std::vector<int> h_tile_list, h_slot_of;
+  int map_dense_n = -1;     // >= 0: the device map currently describes streams 0..n-1
+  int active_tiles = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int PacketBytes(int num_bits) { return (num_bits + 7) / 8; }
+
+bool BitsOk(lyra_b200_ctx* ctx, int num_bits) {
+  // lyra/residual_vector_quantizer.cc:79-89,116-126
+  if (num_bits <= 0 || num_bits > LYRA_B200_MAX_BITS) { ctx->err = "the number of bits cannot exceed 184"; return false; }
+  if (num_bits % ctx->spec.bits_per_stage != 0) { ctx->err = "the number of bits has to be divisible by the bits per quantizer (4)"; return false; }
+  return true;
+}
+
+// Build / upload the (tile list, slot-of-stream) map for this call.
+int PrepareMap(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
+  if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
+  if (ids == nullptr && ctx->map_dense_n == n) return LYRA_B200_OK;
+  std::fill(ctx->h_slot_of.begin(), ctx->h_slot_of.end(), -1);
+  ctx->h_tile_list.clear();
+  std::vector<char> tile_used((size_t)ctx->ntiles, 0);
+  for (int k = 0; k < n; ++k) {
+    const int id = ids ? ids[k] : k;
+    if (id < 0 || id >= ctx->max_streams) { ctx->err = "stream id out of range"; ctx->map_dense_n = -1; return LYRA_B200_EINVAL; }
+    if (ctx->h_slot_of[(size_t)id] != -1) { ctx->err = "duplicate stream id in one call"; ctx->map_dense_n = -1; return LYRA_B200_EINVAL; }
+    ctx->h_slot_of[(size_t)id] = k;
+    if (!tile_used[(size_t)(id / kS)]) { tile_used[(size_t)(id / kS)] = 1; ctx->h_tile_list.push_back(id / kS); }
+  }
+  ctx->active_tiles = (int)ctx->h_tile_list.size();
+  CU(cudaMemcpyAsync(ctx->d_slot_of, ctx->h_slot_of.data(), sizeof(int) * (size_t)ctx->padded, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_tile_list, ctx->h_tile_list.data(), sizeof(int) * (size_t)ctx->active_tiles, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));   // the host vectors are reused by the next call
+  ctx->map_dense_n = ids ? -1 : n;
+  return LYRA_B200_OK;
+}
+
+int LaunchEncoderNets(lyra_b200_ctx* ctx, const int16_t* d_pcm, float* d_features) {
+  const TileIo io{ctx->d_tile_list, ctx->d_slot_of};
+  LYRA_LAUNCH(EncoderKernelA<kS>, dim3((unsigned)ctx->active_tiles), dim3(EncA<kS>::NT), (size_t)EncA<kS>::kSmemBytes, ctx->stream,
+              ctx->d_blob, ctx->spec.enc, io, d_pcm, reinterpret_cast<float*>(ctx->d_state[0]), ctx->d_n18[0], ctx->d_mid_enc);
+  LYRA_LAUNCH(EncoderKernelB<kS>, dim3((unsigned)ctx->active_tiles), dim3(EncB<kS>::NT), (size_t)EncB<kS>::kSmemBytes, ctx->stream,
+              ctx->d_blob, ctx->spec.enc, io, ctx->d_mid_enc, reinterpret_cast<float*>(ctx->d_state[1]), ctx->d_n18[1], d_features);
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  return LYRA_B200_OK;
+}
+
+int LaunchQuantize(lyra_b200_ctx* ctx, const float* d_features, int n, int num_bits, uint8_t* d_packets, int* d_indices) {
+  const int nq = num_bits / ctx->spec.bits_per_stage;
+  const int blocks = (n + kRvqSlotsPerBlock - 1) / kRvqSlotsPerBlock;
+  LYRA_LAUNCH(RvqEncodeKernel, dim3((unsigned)blocks), dim3(kRvqThreads), (size_t)(kRvqSlotsPerBlock * (64 * 4 + 48 * 4)), ctx->stream,
+              ctx->d_blob, ctx->spec.rvq, d_features, n, nq, d_packets, PacketBytes(num_bits), d_indices);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  return LYRA_B200_OK;
+}
+
+int LaunchDequantize(lyra_b200_ctx* ctx, const uint8_t* d_packets, const uint8_t* d_received, int n, int num_bits, float* d_features) {
+  const int nq = num_bits / ctx->spec.bits_per_stage;
+  const int blocks = (n * 64 + 255) / 256;
+  LYRA_LAUNCH(RvqDecodeKernel, dim3((unsigned)blocks), dim3(256), (size_t)0, ctx->stream,
+              ctx->d_blob, ctx->spec.rvq, d_packets, PacketBytes(num_bits), d_received, n, nq, d_features);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  return LYRA_B200_OK;
+}
+
+int LaunchDecoderNets(lyra_b200_ctx* ctx, const float* d_features, int16_t* d_pcm) {
+  const TileIo io{ctx->d_tile_list, ctx->d_slot_of};
+  LYRA_LAUNCH(DecoderKernelC<kS>, dim3((unsigned)ctx->active_tiles), dim3(DecC<kS>::NT), (size_t)DecC<kS>::kSmemBytes, ctx->stream,
+              ctx->d_blob, ctx->spec.dec, io, d_features, reinterpret_cast<float*>(ctx->d_state[2]), ctx->d_n18[2], ctx->d_mid_dec);
+  LYRA_LAUNCH(DecoderKernelD<kS>, dim3((unsigned)ctx->active_tiles), dim3(DecD<kS>::NT), (size_t)DecD<kS>::kSmemBytes, ctx->stream,
+              ctx->d_blob, ctx->spec.dec, io, ctx->d_mid_dec, reinterpret_cast<float*>(ctx->d_state[3]), ctx->d_n18[3], d_pcm);
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  return LYRA_B200_OK;
+}
+
+// initial value of every 4-byte state unit (all zero; int8 rings hold packed zero points)
+std::vector<uint32_t> InitImage(const ModelSpec& s, int which) {
+  auto pack = [](int zp) { const uint32_t b = (uint32_t)(zp & 0xff); return b | (b << 8) | (b << 16) | (b << 24); };
+  std::vector<uint32_t> v;
+  if (which == 0) {
+    v.assign(EncStateA::kUnits, 0u);
+  } else if (which == 1) {
+    v.assign(EncStateB::kUnits, 0u);
+    for (int i = EncStateB::kRingQ0; i < EncStateB::kRingQ1; ++i) v[(size_t)i] = pack(s.enc.zp_state[0]);
+    for (int i = EncStateB::kRingQ1; i < EncStateB::kDown2; ++i) v[(size_t)i] = pack(s.enc.zp_state[1]);
+    for (int i = EncStateB::kDown2; i < EncStateB::kBott; ++i) v[(size_t)i] = pack(s.enc.zp_state[2]);
+    for (int i = EncStateB::kBott; i < EncStateB::kUnits; ++i) v[(size_t)i] = pack(s.enc.zp_state[3]);
+  } else if (which == 2) {
+    v.assign(DecStateC::kUnits, 0u);
+    for (int i = DecStateC::kRingM; i < DecStateC::kRingQ0; ++i) v[(size_t)i] = pack(s.dec.zp_state[0]);
+    for (int i = DecStateC::kRingQ0; i < DecStateC::kRingQ1; ++i) v[(size_t)i] = pack(s.dec.zp_state[1]);
+    for (int i = DecStateC::kRingQ1; i < DecStateC::kUnits; ++i) v[(size_t)i] = pack(s.dec.zp_state[2]);
+  } else {
+    v.assign(DecStateD::kUnits, 0u);
+  }
+  return v;
+}
+
+int ResetImpl(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
+  if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
+  const int* d_ids = nullptr;
+  if (ids) {
+    for (int k = 0; k < n; ++k)
+      if (ids[k] < 0 || ids[k] >= ctx->max_streams) { ctx->err = "stream id out of range"; return LYRA_B200_EINVAL; }
+    CU(cudaMemcpyAsync(ctx->d_ids, ids, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    d_ids = ctx->d_ids;
+  }
+  for (int w = 0; w < 4; ++w) {
+    LYRA_LAUNCH(ResetStateKernel, dim3((unsigned)n), dim3(256), (size_t)0, ctx->stream,
+                ctx->d_state[w], ctx->d_init[w], ctx->units[w], kS, d_ids, n, ctx->d_n18[w]);
+    ctx->launches += 1;
+  }
+  CU(cudaGetLastError());
+  // log-mel carried samples
+  for (int b = 0; b < 2; ++b) {
+    if (!ids) {
+      CU(cudaMemsetAsync(ctx->d_logmel_prev[b], 0, sizeof(int16_t) * 320 * (size_t)n, ctx->stream));
+    } else {
+      for (int k = 0; k < n; ++k)
+        CU(cudaMemsetAsync(ctx->d_logmel_prev[b] + (size_t)ids[k] * 320, 0, sizeof(int16_t) * 320, ctx->stream));
+    }
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+template <typename T>
+cudaError_t DevAlloc(T** p, size_t count) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, sizeof(T) * (count ? count : 1));
+  return e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b200_ctx** out) {
+  if (out) *out = nullptr;
+  if (!out || !model_dir || max_streams <= 0) { g_create_error = "bad argument"; return LYRA_B200_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    g_create_error = "no CUDA device available (lyra_b200 has no CPU fallback)";
+    return LYRA_B200_ENODEV;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "CUDA device index out of range"; return LYRA_B200_ENODEV; }
+  lyra_b200_ctx* ctx = new lyra_b200_ctx();
+  try {
+    ctx->spec = BuildModelSpec(model_dir);
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    delete ctx;
+    return LYRA_B200_EMODEL;
+  }
+  ctx->device = device;
+  ctx->max_streams = max_streams;
+  ctx->ntiles = (max_streams + kS - 1) / kS;
+  ctx->padded = ctx->ntiles * kS;
+  ctx->h_slot_of.assign((size_t)ctx->padded, -1);
+  const size_t P = (size_t)ctx->padded;
+  bool ok = cudaSetDevice(device) == cudaSuccess;
+  ok = ok && cudaStreamCreate(&ctx->own_stream) == cudaSuccess;
+  ctx->stream = ctx->own_stream;
+  ok = ok && DevAlloc(&ctx->d_blob, ctx->spec.blob.size()) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->d_blob, ctx->spec.blob.data(), ctx->spec.blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+  for (int w = 0; w < 4 && ok; ++w) {
+    const std::vector<uint32_t> img = InitImage(ctx->spec, w);
+    ok = ok && DevAlloc(&ctx->d_state[w], (size_t)ctx->units[w] * P) == cudaSuccess;
+    ok = ok && DevAlloc(&ctx->d_init[w], img.size()) == cudaSuccess;
+    ok = ok && cudaMemcpy(ctx->d_init[w], img.data(), img.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && DevAlloc(&ctx->d_n18[w], P) == cudaSuccess;
+  }
+  ok = ok && DevAlloc(&ctx->d_mid_enc, (size_t)ctx->ntiles * 128 * 4 * kS) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_mid_dec, (size_t)ctx->ntiles * 128 * 4 * kS) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_logmel_prev[0], P * 320) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_logmel_prev[1], P * 320) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_pcm, P * 320) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_packets, P * 24) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_received, P) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_features, P * 64) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_melout, P * 160) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_indices, P * 46) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_ids, P) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_tile_list, (size_t)ctx->ntiles) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_slot_of, P) == cudaSuccess;
+  if (ok) {
+    ok = LYRA_SET_MAX_SMEM(EncoderKernelA<kS>, EncA<kS>::kSmemBytes) == 0 && LYRA_SET_MAX_SMEM(EncoderKernelB<kS>, EncB<kS>::kSmemBytes) == 0 &&
+         LYRA_SET_MAX_SMEM(DecoderKernelC<kS>, DecC<kS>::kSmemBytes) == 0 && LYRA_SET_MAX_SMEM(DecoderKernelD<kS>, DecD<kS>::kSmemBytes) == 0;
+  }
+  if (!ok) {
+    g_create_error = std::string("CUDA allocation / setup failed: ") + cudaGetErrorString(cudaGetLastError());
+    lyra_b200_destroy(ctx);
+    return LYRA_B200_ENODEV;
+  }
+  if (ResetImpl(ctx, nullptr, max_streams) != LYRA_B200_OK) {
+    g_create_error = ctx->err;
+    lyra_b200_destroy(ctx);
+    return LYRA_B200_ENODEV;
+  }
+  *out = ctx;
+  return LYRA_B200_OK;
+}
+
+void lyra_b200_destroy(lyra_b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaFree(ctx->d_blob);
+  for (int w = 0; w < 4; ++w) { cudaFree(ctx->d_state[w]); cudaFree(ctx->d_init[w]); cudaFree(ctx->d_n18[w]); }
+  cudaFree(ctx->d_mid_enc); cudaFree(ctx->d_mid_dec);
+  cudaFree(ctx->d_logmel_prev[0]); cudaFree(ctx->d_logmel_prev[1]);
+  cudaFree(ctx->d_pcm); cudaFree(ctx->d_packets); cudaFree(ctx->d_received); cudaFree(ctx->d_features);
+  cudaFree(ctx->d_melout); cudaFree(ctx->d_indices); cudaFree(ctx->d_ids); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_slot_of);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* lyra_b200_last_error(const lyra_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int lyra_b200_max_streams(const lyra_b200_ctx* ctx) { return ctx ? ctx->max_streams : 0; }
+int lyra_b200_tile_streams(const lyra_b200_ctx* ctx) { return ctx ? kS : 0; }
+uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lyra_b200_reset(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n) {
+  if (!ctx) return LYRA_B200_EINVAL;
+  return ResetImpl(ctx, stream_ids, n);
+}
+
+int lyra_b200_set_stream(lyra_b200_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return LYRA_B200_EINVAL;
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_synchronize(lyra_b200_ctx* ctx) {
+  if (!ctx) return LYRA_B200_EINVAL;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_encode_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets) {
+  if (!ctx || !d_pcm || !d_packets) return LYRA_B200_EINVAL;
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, nullptr, n);
+  if (rc) return rc;
+  if ((rc = LaunchEncoderNets(ctx, d_pcm, ctx->d_features))) return rc;
+  return LaunchQuantize(ctx, ctx->d_features, n, num_bits, d_packets, nullptr);
+}
+
+int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits,
+                            int16_t* d_pcm) {
+  if (!ctx || !d_packets || !d_pcm) return LYRA_B200_EINVAL;
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, nullptr, n);
+  if (rc) return rc;
+  if ((rc = LaunchDequantize(ctx, d_packets, d_received, n, num_bits, ctx->d_features))) return rc;
+  return LaunchDecoderNets(ctx, ctx->d_features, d_pcm);
+}
+
+int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, int num_bits, uint8_t* packets) {
+  if (!ctx || !pcm || !packets) return LYRA_B200_EINVAL;
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, ids, n);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = LaunchEncoderNets(ctx, ctx->d_pcm, ctx->d_features))) return rc;
+  if ((rc = LaunchQuantize(ctx, ctx->d_features, n, num_bits, ctx->d_packets, nullptr))) return rc;
+  CU(cudaMemcpyAsync(packets, ctx->d_packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_t* packets, const uint8_t* received,
+                     int num_bits, int16_t* pcm) {
+  if (!ctx || !packets || !pcm) return LYRA_B200_EINVAL;
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, ids, n);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->d_packets, packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if (received) CU(cudaMemcpyAsync(ctx->d_received, received, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = LaunchDequantize(ctx, ctx->d_packets, received ? ctx->d_received : nullptr, n, num_bits, ctx->d_features))) return rc;
+  if ((rc = LaunchDecoderNets(ctx, ctx->d_features, ctx->d_pcm))) return rc;
+  CU(cudaMemcpyAsync(pcm, ctx->d_pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_extract_features(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, float* features) {
+  if (!ctx || !pcm || !features) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, ids, n);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = LaunchEncoderNets(ctx, ctx->d_pcm, ctx->d_features))) return rc;
+  CU(cudaMemcpyAsync(features, ctx->d_features, sizeof(float) * 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_quantize(lyra_b200_ctx* ctx, int n, const float* features, int num_bits, uint8_t* packets, int32_t* indices) {
+  if (!ctx || !features || !packets) return LYRA_B200_EINVAL;
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  if (n <= 0 || n > ctx->max_streams) { ctx->err = "count out of range"; return LYRA_B200_EINVAL; }
+  CU(cudaMemcpyAsync(ctx->d_features, features, sizeof(float) * 64 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = LaunchQuantize(ctx, ctx->d_features, n, num_bits, ctx->d_packets, indices ? ctx->d_indices : nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(packets, ctx->d_packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (indices) CU(cudaMemcpyAsync(indices, ctx->d_indices, sizeof(int) * 46 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_dequantize(lyra_b200_ctx* ctx, int n, const uint8_t* packets, int num_bits, float* features) {
+  if (!ctx || !features || !packets) return LYRA_B200_EINVAL;
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  if (n <= 0 || n > ctx->max_streams) { ctx->err = "count out of range"; return LYRA_B200_EINVAL; }
+  CU(cudaMemcpyAsync(ctx->d_packets, packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = LaunchDequantize(ctx, ctx->d_packets, nullptr, n, num_bits, ctx->d_features);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(features, ctx->d_features, sizeof(float) * 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_generate(lyra_b200_ctx* ctx, const int32_t* ids, int n, const float* features, int16_t* pcm) {
+  if (!ctx || !features || !pcm) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, ids, n);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->d_features, features, sizeof(float) * 64 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = LaunchDecoderNets(ctx, ctx->d_features, ctx->d_pcm))) return rc;
+  CU(cudaMemcpyAsync(pcm, ctx->d_pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* ids, int n, const int16_t* pcm, int num_mel_bins, float* out) {
+  if (!ctx || !pcm || !out) return LYRA_B200_EINVAL;
+  if (bank < 0 || bank > 1) { ctx->err = "log-mel bank must be 0 or 1"; return LYRA_B200_EINVAL; }
+  if (num_mel_bins != 160 && num_mel_bins != 64) { ctx->err = "log-mel supports 160 or 64 mel bins"; return LYRA_B200_EINVAL; }
+  if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
+  const int* d_ids = nullptr;
+  if (ids) {
+    std::vector<char> seen((size_t)ctx->max_streams, 0);
+    for (int k = 0; k < n; ++k) {
+      if (ids[k] < 0 || ids[k] >= ctx->max_streams || seen[(size_t)ids[k]]) { ctx->err = "bad or duplicate stream id"; return LYRA_B200_EINVAL; }
+      seen[(size_t)ids[k]] = 1;
+    }
+    CU(cudaMemcpyAsync(ctx->d_ids, ids, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    d_ids = ctx->d_ids;
+  }
+  const LogMelParams& P = num_mel_bins == 160 ? ctx->spec.logmel160 : ctx->spec.logmel64;
+  CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t smem = sizeof(double) * (size_t)(2 * P.fft + P.fft / 2 + 1);
+  LYRA_LAUNCH(LogMelKernel, dim3((unsigned)n), dim3(256), smem, ctx->stream,
+              ctx->d_blob, P, d_ids, n, ctx->d_pcm, ctx->d_logmel_prev[bank], ctx->d_melout);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, ctx->d_melout, sizeof(float) * (size_t)num_mel_bins * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+}  // extern "C"

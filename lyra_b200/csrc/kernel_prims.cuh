@@ -1,0 +1,301 @@
+// Device primitives shared by the four conv-net kernels.
+//
+// Data layout (one thread block = one tile of S streams):
+//   fp32 activations in shared memory:  act[c * ld + row * S + s]     (channel-major, stream-minor)
+//   int8 activations in shared memory:  word[(c/4) * ld + row * S + s] (4 consecutive channels / word)
+// so every convolution tap is a row offset, every thread owns TM consecutive streams of one output
+// row and TN consecutive output channels, and both operands of the inner product are 16-byte
+// shared-memory loads.  Weights stream from L2 through a cp.async double buffer.
+//
+// Bit-exactness contract (matches oracle/net_interp.c): each fp32 output is ONE fmaf chain over
+// (tap ascending, cin ascending) starting from +0, bias added afterwards with a separate rounding;
+// all other fp32 ops use the non-contracting __f*_rn intrinsics.
+#pragma once
+
+#include "device_compat.h"
+#include "net_params.h"
+
+namespace lyra_b200 {
+
+template <typename T>
+__device__ __forceinline__ const T* BlobPtr(const uint8_t* blob, uint32_t off) {
+  return reinterpret_cast<const T*>(blob + off);
+}
+
+__device__ __forceinline__ float LeakyRelu(float v) { return v > 0.0f ? v : __fmul_rn(v, 0.3f); }
+
+// TFLite reference AffineQuantize: round-half-away(v / scale) + zp, clamped to int8
+__device__ __forceinline__ int QuantizeF32(float v, float scale, int zp) {
+  int q = (int)roundf(__fdiv_rn(v, scale)) + zp;
+  q = q < -128 ? -128 : (q > 127 ? 127 : q);
+  return q;
+}
+__device__ __forceinline__ float DequantizeI8(int q, float scale, int zp) { return __fmul_rn(scale, (float)(q - zp)); }
+
+// gemmlowp MultiplyByQuantizedMultiplier (SaturatingRoundingDoublingHighMul + RoundingDivideByPOT)
+__device__ __forceinline__ int Mbqm(int x, int qm, int shift) {
+  const int left = shift > 0 ? shift : 0, right = shift > 0 ? 0 : -shift;
+  const long long ab = (long long)(x * (1 << left)) * (long long)qm;
+  const long long t = ab + (ab >= 0 ? (1ll << 30) : (1ll - (1ll << 30)));
+  const int hi = (int)(t >= 0 ? (t >> 31) : -((-t) >> 31));     // truncating division by 2^31
+  const int mask = (int)((1ll << right) - 1);
+  const int rem = hi & mask;
+  const int thr = (mask >> 1) + (hi < 0 ? 1 : 0);
+  return (hi >> right) + (rem > thr ? 1 : 0);
+}
+__device__ __forceinline__ int ClampI8(int v) { return v < -128 ? -128 : (v > 127 ? 127 : v); }
+__device__ __forceinline__ int RequantI8(int acc, int bias, int mult, int shift, int out_zp) {
+  return ClampI8(Mbqm(acc + bias, mult, shift) + out_zp);
+}
+__device__ __forceinline__ uint32_t PackI8x4(int a, int b, int c, int d) {
+  return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+__device__ __forceinline__ int UnpackI8(uint32_t w, int i) { return (int)(int8_t)((w >> (8 * i)) & 0xff); }
+
+// ------------------------------------------------------------------------------------------------
+// Weight chunk copy: `n16` 16-byte packets, contiguous in global memory, by all NT threads.
+template <int NT>
+__device__ __forceinline__ void StageChunk(void* smem_dst, const void* gsrc, int n16) {
+  for (int i = (int)threadIdx.x; i < n16; i += NT)
+    lyra_cp_async16(reinterpret_cast<char*>(smem_dst) + 16 * i, reinterpret_cast<const char*>(gsrc) + 16 * i);
+  lyra_cp_async_commit();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 tap-GEMM.   out[t][s][n] = sum_{tap < ntaps} sum_{ci < CinG} A[g*CinG + ci][rowA0 + t*row_stride + tap][s] * W[tap*CinG + ci][n]
+//   A: shared memory [channels][ldA]; if CIN1 the K loop runs over taps only (CinG == 1, single channel).
+//   W: global [ntaps*CinG][N];  wbuf: shared 2 * KC * N floats.
+//   Thread tile TM (streams) x TN (channels); tiles beyond NT are handled in extra passes.
+//   epi(t, s0, n0, acc) is called once per tile after the K loop (and after a block barrier when
+//   `sync_before_epi`, so epilogues may overwrite the A operand in place).
+template <int S, int NT, int TM, int TN, int KC, bool CIN1, typename Epi>
+__device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
+                                           int groups, int T_out, int N, const float* __restrict__ Wg, float* wbuf,
+                                           bool sync_before_epi, Epi epi) {
+  static_assert(S % TM == 0 && TM % 4 == 0 && TN % 2 == 0, "tile shape");
+  constexpr int MGS = S / TM;
+  const int MG = T_out * MGS, NG = N / TN, ntiles = MG * NG;
+  const int Ktot = ntaps * CinG, nchunks = Ktot / KC;
+  const int chunk16 = KC * N / 4;
+  const int CoutG = N / groups;
+  for (int pass0 = 0; pass0 < ntiles; pass0 += NT) {
+    const int tile = pass0 + (int)threadIdx.x;
+    const bool active = tile < ntiles;
+    const int mg = active ? tile % MG : 0, ng = active ? tile / MG : 0;
+    const int t_out = mg / MGS, s0 = (mg % MGS) * TM, n0 = ng * TN;
+    const int g = n0 / CoutG;
+    const float* Abase = A + (size_t)(g * CinG) * ldA + (rowA0 + t_out * row_stride) * S + s0;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+    StageChunk<NT>(wbuf, Wg, chunk16);
+    for (int c = 0; c < nchunks; ++c) {
+      float* wcur = wbuf + (c & 1) * (KC * N);
+      if (c + 1 < nchunks) {
+        StageChunk<NT>(wbuf + ((c + 1) & 1) * (KC * N), Wg + (size_t)(c + 1) * KC * N, chunk16);
+        lyra_cp_async_wait<1>();
+      } else {
+        lyra_cp_async_wait<0>();
+      }
+      __syncthreads();
+      if (active) {
+        const int kk0 = c * KC;
+        const float* Ap;
+        int astep;
+        if (CIN1) { Ap = Abase + kk0 * S; astep = S; }
+        else { const int tap = kk0 / CinG, ci0 = kk0 - tap * CinG; Ap = Abase + (size_t)ci0 * ldA + tap * S; astep = ldA; }
+        const float* wp = wcur + n0;
+#pragma unroll 4
+        for (int kk = 0; kk < KC; ++kk) {
+          float a[TM], w[TN];
+#pragma unroll
+          for (int i = 0; i < TM; i += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(Ap + i);
+            a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+          }
+          if (TN % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) {
+              const float4 v = *reinterpret_cast<const float4*>(wp + j);
+              w[j] = v.x; w[j + 1] = v.y; w[j + 2] = v.z; w[j + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < TN; j += 2) {
+              const float2 v = *reinterpret_cast<const float2*>(wp + j);
+              w[j] = v.x; w[j + 1] = v.y;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = __fmaf_rn(a[i], w[j], acc[i][j]);
+          Ap += astep;
+          wp += N;
+        }
+      }
+      __syncthreads();
+    }
+    (void)sync_before_epi;   // the loop above always ends with a block barrier
+    if (active) epi(t_out, s0, n0, acc);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// int8 tap-GEMM with dp4a.  A words [CinTotal/4][ldA], W words [ntaps*CinG/4][N]; KC4 word-rows per chunk.
+template <int S, int NT, int TM, int TN, int KC4, typename Epi>
+__device__ __forceinline__ void GemmI8Tap(const uint32_t* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
+                                          int groups, int T_out, int N, const uint32_t* __restrict__ Wg, uint32_t* wbuf,
+                                          Epi epi) {
+  static_assert(S % TM == 0 && TM % 4 == 0 && TN % 4 == 0, "tile shape");
+  constexpr int MGS = S / TM;
+  const int CinG4 = CinG / 4;
+  const int MG = T_out * MGS, NG = N / TN, ntiles = MG * NG;
+  const int Ktot4 = ntaps * CinG4, nchunks = Ktot4 / KC4;
+  const int chunk16 = KC4 * N / 4;
+  const int CoutG = N / groups;
+  for (int pass0 = 0; pass0 < ntiles; pass0 += NT) {
+    const int tile = pass0 + (int)threadIdx.x;
+    const bool active = tile < ntiles;
+    const int mg = active ? tile % MG : 0, ng = active ? tile / MG : 0;
+    const int t_out = mg / MGS, s0 = (mg % MGS) * TM, n0 = ng * TN;
+    const int g = n0 / CoutG;
+    const uint32_t* Abase = A + (size_t)(g * CinG4) * ldA + (rowA0 + t_out * row_stride) * S + s0;
+    int acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0;
+
+    StageChunk<NT>(wbuf, Wg, chunk16);
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t* wcur = wbuf + (c & 1) * (KC4 * N);
+      if (c + 1 < nchunks) {
+        StageChunk<NT>(wbuf + ((c + 1) & 1) * (KC4 * N), Wg + (size_t)(c + 1) * KC4 * N, chunk16);
+        lyra_cp_async_wait<1>();
+      } else {
+        lyra_cp_async_wait<0>();
+      }
+      __syncthreads();
+      if (active) {
+        const int kk0 = c * KC4;
+        const int tap = kk0 / CinG4, ci0 = kk0 - tap * CinG4;
+        const uint32_t* Ap = Abase + (size_t)ci0 * ldA + tap * S;
+        const uint32_t* wp = wcur + n0;
+#pragma unroll 4
+        for (int kk = 0; kk < KC4; ++kk) {
+          uint32_t a[TM], w[TN];
+#pragma unroll
+          for (int i = 0; i < TM; i += 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(Ap + i);
+            a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+          }
+#pragma unroll
+          for (int j = 0; j < TN; j += 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(wp + j);
+            w[j] = v.x; w[j + 1] = v.y; w[j + 2] = v.z; w[j + 3] = v.w;
+          }
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = __dp4a((int)a[i], (int)w[j], acc[i][j]);
+          Ap += ldA;
+          wp += N;
+        }
+      }
+      __syncthreads();
+    }
+    if (active) epi(t_out, s0, n0, acc);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ring addressing.  A dilated depthwise conv (k = 3, dilation d) needs a(i - 2d), a(i - d), a(i) for
+// absolute row i; the last R = 2d rows of every stream live in a global ring [C][R][S] (slot = i mod R).
+// frame counters are kept modulo 18 (every R divides 18), so base = (n18 * T) mod R.
+__device__ __forceinline__ int RingSlot(int base, int t, int R) {
+  int v = (base + t) % R;
+  return v < 0 ? v + R : v;
+}
+
+// fp32 depthwise conv over LeakyReLU(u).  u: shared [C][ldu] with the T new rows starting at row0u.
+// dout: shared [C][ldd] rows 0..T-1.  ring: global tile block [C][R][S].  n18: shared per-stream counters.
+template <int S, int NT>
+__device__ __forceinline__ void DwF32Ring(const float* u, int ldu, int row0u, float* dout, int ldd, int C, int T, int dil,
+                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                          float* __restrict__ ring, const int* n18, const int* active) {
+  const int R = 2 * dil;
+  const int total = C * T * S;
+  for (int idx = (int)threadIdx.x; idx < total; idx += NT) {
+    const int s = idx % S, t = (idx / S) % T, c = idx / (S * T);
+    const int base = (n18[s] * T) % R;
+    const float* uc = u + (size_t)c * ldu + row0u * S + s;
+    const float x2 = LeakyRelu(uc[t * S]);
+    const float x1 = t - dil >= 0 ? LeakyRelu(uc[(t - dil) * S]) : ring[((size_t)c * R + RingSlot(base, t - dil, R)) * S + s];
+    const float x0 = t - 2 * dil >= 0 ? LeakyRelu(uc[(t - 2 * dil) * S]) : ring[((size_t)c * R + RingSlot(base, t - 2 * dil, R)) * S + s];
+    float acc = __fmaf_rn(x0, w[c], 0.0f);
+    acc = __fmaf_rn(x1, w[C + c], acc);
+    acc = __fmaf_rn(x2, w[2 * C + c], acc);
+    dout[(size_t)c * ldd + t * S + s] = __fadd_rn(acc, bias[c]);
+  }
+  __syncthreads();
+  // the last min(T, R) rows become the ring's newest entries
+  const int tfirst = T > R ? T - R : 0;
+  const int nrows = T - tfirst;
+  const int wtotal = C * nrows * S;
+  for (int idx = (int)threadIdx.x; idx < wtotal; idx += NT) {
+    const int s = idx % S, t = tfirst + (idx / S) % nrows, c = idx / (S * nrows);
+    if (!active[s]) continue;
+    const int base = (n18[s] * T) % R;
+    ring[((size_t)c * R + RingSlot(base, t, R)) * S + s] = LeakyRelu(u[(size_t)c * ldu + (row0u + t) * S + s]);
+  }
+  __syncthreads();
+}
+
+// int8 depthwise conv on packed activations.  aq: shared words [C/4][lda], new rows at row0a.
+// dq: shared words [C/4][ldd] rows 0..T-1.  ring: global words [C/4][R][S].
+template <int S, int NT>
+__device__ __forceinline__ void DwI8Ring(const uint32_t* aq, int lda, int row0a, uint32_t* dq, int ldd, int C, int T, int dil,
+                                         const uint8_t* blob, const DwI8& p, uint32_t* __restrict__ ring, const int* n18,
+                                         const int* active) {
+  const int R = 2 * dil, C4 = C / 4;
+  const int* w = BlobPtr<int>(blob, p.w);
+  const int* bias = BlobPtr<int>(blob, p.bias);
+  const int* mult = BlobPtr<int>(blob, p.mult);
+  const int* shift = BlobPtr<int>(blob, p.shift);
+  const int total = C4 * T * S;
+  for (int idx = (int)threadIdx.x; idx < total; idx += NT) {
+    const int s = idx % S, t = (idx / S) % T, c4 = idx / (S * T);
+    const int base = (n18[s] * T) % R;
+    const uint32_t* ac = aq + (size_t)c4 * lda + row0a * S + s;
+    const uint32_t x2 = ac[t * S];
+    const uint32_t x1 = t - dil >= 0 ? ac[(t - dil) * S] : ring[((size_t)c4 * R + RingSlot(base, t - dil, R)) * S + s];
+    const uint32_t x0 = t - 2 * dil >= 0 ? ac[(t - 2 * dil) * S] : ring[((size_t)c4 * R + RingSlot(base, t - 2 * dil, R)) * S + s];
+    int o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int c = c4 * 4 + b;
+      const int acc = UnpackI8(x0, b) * w[c] + UnpackI8(x1, b) * w[C + c] + UnpackI8(x2, b) * w[2 * C + c];
+      o[b] = RequantI8(acc, bias[c], mult[c], shift[c], p.out_zp);
+    }
+    dq[(size_t)c4 * ldd + t * S + s] = PackI8x4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+  const int tfirst = T > R ? T - R : 0;
+  const int nrows = T - tfirst;
+  const int wtotal = C4 * nrows * S;
+  for (int idx = (int)threadIdx.x; idx < wtotal; idx += NT) {
+    const int s = idx % S, t = tfirst + (idx / S) % nrows, c4 = idx / (S * nrows);
+    if (!active[s]) continue;
+    const int base = (n18[s] * T) % R;
+    ring[((size_t)c4 * R + RingSlot(base, t, R)) * S + s] = aq[(size_t)c4 * lda + (row0a + t) * S + s];
+  }
+  __syncthreads();
+}
+
+}  // namespace lyra_b200

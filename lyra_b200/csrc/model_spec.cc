@@ -1,0 +1,580 @@
+// See model_spec.h.
+#include "model_spec.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+
+#include "tflite_model.h"
+
+namespace lyra_b200 {
+
+// ---------------------------------------------------------------- fixed point ----
+
+void QuantizeMultiplier(double real_multiplier, int32_t* qm, int* shift) {
+  if (real_multiplier == 0.0) { *qm = 0; *shift = 0; return; }
+  const double q = std::frexp(real_multiplier, shift);
+  int64_t q_fixed = (int64_t)std::round(q * (double)(1ll << 31));
+  if (q_fixed == (1ll << 31)) { q_fixed /= 2; ++*shift; }
+  if (*shift < -31) { *shift = 0; q_fixed = 0; }
+  *qm = (int32_t)q_fixed;
+}
+
+int32_t MultiplyByQuantizedMultiplier(int32_t x, int32_t qm, int shift) {
+  const int left = shift > 0 ? shift : 0, right = shift > 0 ? 0 : -shift;
+  const int32_t xs = x * (1 << left);
+  // saturating rounding doubling high multiply
+  int32_t hi;
+  if (xs == qm && xs == INT32_MIN) {
+    hi = INT32_MAX;
+  } else {
+    const int64_t ab = (int64_t)xs * (int64_t)qm;
+    const int32_t nudge = ab >= 0 ? (1 << 30) : (1 - (1 << 30));
+    hi = (int32_t)((ab + nudge) / (1ll << 31));
+  }
+  // rounding divide by power of two
+  const int32_t mask = (int32_t)((1ll << right) - 1);
+  const int32_t rem = hi & mask;
+  const int32_t thr = (mask >> 1) + (hi < 0 ? 1 : 0);
+  return (hi >> right) + (rem > thr ? 1 : 0);
+}
+
+namespace {
+
+#define SPEC_CHECK(cond, msg) do { if (!(cond)) throw std::runtime_error(std::string("model_spec: ") + msg); } while (0)
+
+int ClampI8(int v) { return v < -128 ? -128 : (v > 127 ? 127 : v); }
+
+template <typename T>
+uint32_t Append(std::vector<uint8_t>* blob, const std::vector<T>& v) {
+  while (blob->size() % 16) blob->push_back(0);
+  const size_t off = blob->size();
+  const size_t nb = v.size() * sizeof(T);
+  blob->resize(off + nb);
+  if (nb) std::memcpy(blob->data() + off, v.data(), nb);
+  SPEC_CHECK(off < 0xffffffffull, "blob too large");
+  return (uint32_t)off;
+}
+
+struct Net {
+  const TflModel& m;
+  const TflSubgraph& g;
+  std::vector<int> convs;   // CONV_2D / DEPTHWISE_CONV_2D / TRANSPOSE_CONV ops in graph order
+  std::vector<uint8_t>* blob;
+
+  Net(const TflModel& model, int sg, std::vector<uint8_t>* b) : m(model), g(model.subgraphs()[sg]), blob(b) {
+    for (size_t i = 0; i < g.ops.size(); ++i) {
+      const int c = g.ops[i].code;
+      if (c == kConv2D || c == kDepthwiseConv2D || c == kTransposeConv) convs.push_back((int)i);
+    }
+  }
+  const TflOp& op(int i) const { return g.ops[i]; }
+  const TflTensor& T(int i) const { return g.tensors[i]; }
+  const TflOp& conv(int i) const { return g.ops[convs.at(i)]; }
+
+  // tensor roles of a conv-like op
+  int in_tensor(const TflOp& o) const { return o.code == kTransposeConv ? o.inputs[2] : o.inputs[0]; }
+  int w_tensor(const TflOp& o) const { return o.inputs[1]; }
+  int b_tensor(const TflOp& o) const { return o.code == kTransposeConv ? o.inputs[3] : o.inputs[2]; }
+
+  int next(int tensor, int code) const { return g.sole_consumer(tensor, code); }
+  int out0(int opi) const { return g.ops[opi].outputs[0]; }
+
+  void expect_conv(const TflOp& o, int code, DType wt, int cout, int k, int cing, int stride, int dil = 1) const {
+    const TflTensor& w = T(w_tensor(o));
+    SPEC_CHECK(o.code == code, "unexpected op kind in conv sequence");
+    SPEC_CHECK(w.type == wt, "unexpected weight type");
+    SPEC_CHECK(w.shape.size() == 4 && w.shape[2] == 1, "unexpected filter rank");
+    if (code == kDepthwiseConv2D) {
+      SPEC_CHECK(w.shape[0] == 1 && w.shape[1] == k && w.shape[3] == cout, "unexpected depthwise filter shape");
+      SPEC_CHECK(m.OptI32(o, 2, 1) == 1 && m.OptI32(o, 6, 1) == dil && m.OptI32(o, 3, 1) == 1, "unexpected depthwise options");
+      SPEC_CHECK(m.OptI8(o, 0, 0) == 1 && m.OptI8(o, 4, 0) == 0, "depthwise padding/activation");
+    } else {
+      SPEC_CHECK(w.shape[0] == cout && w.shape[1] == k && w.shape[3] == cing, "unexpected filter shape");
+      SPEC_CHECK(m.OptI32(o, 2, 1) == stride, "unexpected stride");
+      SPEC_CHECK(m.OptI8(o, 0, 0) == 1, "padding must be VALID");
+      if (code == kConv2D) SPEC_CHECK(m.OptI32(o, 5, 1) == 1 && m.OptI8(o, 3, 0) == 0, "conv dilation/activation");
+    }
+  }
+
+  // ---- packers -------------------------------------------------------------------------------
+  GemmF32 PackConvF32(const TflOp& o) const {
+    const TflTensor& w = T(w_tensor(o));
+    const TflTensor& b = T(b_tensor(o));
+    const int Cout = w.shape[0], K = w.shape[1], CinG = w.shape[3];
+    std::vector<float> wt((size_t)K * CinG * Cout);
+    const float* src = w.as<float>();
+    for (int co = 0; co < Cout; ++co)
+      for (int k = 0; k < K; ++k)
+        for (int ci = 0; ci < CinG; ++ci)
+          wt[((size_t)k * CinG + ci) * Cout + co] = src[((size_t)co * K + k) * CinG + ci];
+    SPEC_CHECK((int)b.count() == Cout && b.data, "conv bias");
+    std::vector<float> bias(b.as<float>(), b.as<float>() + Cout);
+    return GemmF32{Append(blob, wt), Append(blob, bias)};
+  }
+
+  // transposed conv as a J-tap GEMM over (r, co) outputs: W'[(j,ci)][(r,co)] = W[co][r + s*(J-1-j)][ci]
+  GemmF32 PackTconvF32(const TflOp& o, int stride) const {
+    const TflTensor& w = T(w_tensor(o));
+    const TflTensor& b = T(b_tensor(o));
+    const int Cout = w.shape[0], K = w.shape[1], Cin = w.shape[3];
+    SPEC_CHECK(K % stride == 0, "transposed conv: K must be a multiple of the stride");
+    const int J = K / stride, N = stride * Cout;
+    std::vector<float> wt((size_t)J * Cin * N);
+    const float* src = w.as<float>();
+    for (int j = 0; j < J; ++j)
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int r = 0; r < stride; ++r)
+          for (int co = 0; co < Cout; ++co)
+            wt[((size_t)j * Cin + ci) * N + (size_t)r * Cout + co] = src[((size_t)co * K + (r + stride * (J - 1 - j))) * Cin + ci];
+    std::vector<float> bias(b.as<float>(), b.as<float>() + Cout);
+    return GemmF32{Append(blob, wt), Append(blob, bias)};
+  }
+
+  void RequantArrays(const TflTensor& x, const TflTensor& w, const TflTensor& y, int n, int repeat,
+                     std::vector<int32_t>* mult, std::vector<int32_t>* shift) const {
+    // kernel_util.cc PopulateConvolutionQuantizationParams: per-channel effective scale in double
+    for (int r = 0; r < repeat; ++r)
+      for (int c = 0; c < n; ++c) {
+        const float fs = w.scale[w.scale.size() > 1 ? (size_t)c : 0];
+        const double eff = (double)x.scale0() * (double)fs / (double)y.scale0();
+        int32_t qm; int sh;
+        QuantizeMultiplier(eff, &qm, &sh);
+        mult->push_back(qm);
+        shift->push_back(sh);
+      }
+  }
+
+  GemmI8 PackConvI8(const TflOp& o) const {
+    const TflTensor& w = T(w_tensor(o));
+    const TflTensor& b = T(b_tensor(o));
+    const TflTensor& x = T(in_tensor(o));
+    const TflTensor& y = T(o.outputs[0]);
+    const int Cout = w.shape[0], K = w.shape[1], CinG = w.shape[3];
+    SPEC_CHECK(CinG % 4 == 0, "int8 conv: CinG must be a multiple of 4");
+    const int K4 = K * CinG / 4;
+    std::vector<uint32_t> wt((size_t)K4 * Cout, 0u);
+    std::vector<int32_t> bias(Cout), mult, shift;
+    const int8_t* src = w.as<int8_t>();
+    const int32_t* bsrc = b.as<int32_t>();
+    const int in_zp = x.zp0();
+    for (int co = 0; co < Cout; ++co) {
+      int64_t wsum = 0;
+      for (int k = 0; k < K; ++k)
+        for (int ci = 0; ci < CinG; ++ci) {
+          const int8_t v = src[((size_t)co * K + k) * CinG + ci];
+          wsum += v;
+          const size_t kk = (size_t)k * CinG + ci;
+          wt[(kk / 4) * Cout + co] |= (uint32_t)(uint8_t)v << (8 * (kk % 4));
+        }
+      bias[co] = (int32_t)(bsrc[co] - (int64_t)in_zp * wsum);
+    }
+    RequantArrays(x, w, y, Cout, 1, &mult, &shift);
+    return GemmI8{Append(blob, wt), Append(blob, bias), Append(blob, mult), Append(blob, shift), y.zp0(), in_zp};
+  }
+
+  GemmI8 PackTconvI8(const TflOp& o, int stride) const {
+    const TflTensor& w = T(w_tensor(o));
+    const TflTensor& b = T(b_tensor(o));
+    const TflTensor& x = T(in_tensor(o));
+    const TflTensor& y = T(o.outputs[0]);
+    const int Cout = w.shape[0], K = w.shape[1], Cin = w.shape[3];
+    SPEC_CHECK(K % stride == 0 && Cin % 4 == 0, "int8 transposed conv geometry");
+    const int J = K / stride, N = stride * Cout, K4 = J * Cin / 4;
+    std::vector<uint32_t> wt((size_t)K4 * N, 0u);
+    std::vector<int32_t> bias(N), mult, shift;
+    const int8_t* src = w.as<int8_t>();
+    const int32_t* bsrc = b.as<int32_t>();
+    const int in_zp = x.zp0();
+    for (int r = 0; r < stride; ++r)
+      for (int co = 0; co < Cout; ++co) {
+        int64_t wsum = 0;
+        for (int j = 0; j < J; ++j)
+          for (int ci = 0; ci < Cin; ++ci) {
+            const int8_t v = src[((size_t)co * K + (r + stride * (J - 1 - j))) * Cin + ci];
+            wsum += v;
+            const size_t kk = (size_t)j * Cin + ci;
+            wt[(kk / 4) * N + (size_t)r * Cout + co] |= (uint32_t)(uint8_t)v << (8 * (kk % 4));
+          }
+        // rows outside the input are padded with the zero point, so the fold uses all J taps
+        bias[(size_t)r * Cout + co] = (int32_t)(bsrc[co] - (int64_t)in_zp * wsum);
+      }
+    RequantArrays(x, w, y, Cout, stride, &mult, &shift);
+    return GemmI8{Append(blob, wt), Append(blob, bias), Append(blob, mult), Append(blob, shift), y.zp0(), in_zp};
+  }
+
+  DwF32 PackDwF32(const TflOp& o) const {
+    const TflTensor& w = T(w_tensor(o));
+    const TflTensor& b = T(b_tensor(o));
+    std::vector<float> wt(w.as<float>(), w.as<float>() + w.count());
+    std::vector<float> bias(b.as<float>(), b.as<float>() + b.count());
+    return DwF32{Append(blob, wt), Append(blob, bias)};
+  }
+
+  DwI8 PackDwI8(const TflOp& o) const {
+    const TflTensor& w = T(w_tensor(o));
+    const TflTensor& b = T(b_tensor(o));
+    const TflTensor& x = T(in_tensor(o));
+    const TflTensor& y = T(o.outputs[0]);
+    const int K = w.shape[1], C = w.shape[3];
+    std::vector<int32_t> wt((size_t)K * C), bias(C), mult, shift;
+    const int in_zp = x.zp0();
+    for (int c = 0; c < C; ++c) {
+      int64_t wsum = 0;
+      for (int k = 0; k < K; ++k) { wt[(size_t)k * C + c] = w.as<int8_t>()[(size_t)k * C + c]; wsum += wt[(size_t)k * C + c]; }
+      bias[c] = (int32_t)(b.as<int32_t>()[c] - (int64_t)in_zp * wsum);
+    }
+    RequantArrays(x, w, y, C, 1, &mult, &shift);
+    return DwI8{Append(blob, wt), Append(blob, bias), Append(blob, mult), Append(blob, shift), y.zp0(), in_zp};
+  }
+
+  QuantP QP(int tensor) const { return QuantP{T(tensor).scale0(), T(tensor).zp0()}; }
+
+  // int8 LEAKY_RELU as a 256-entry table (kernels/activations.cc LeakyReluPrepare + QuantizeLeakyRelu)
+  LReluQ PackLRelu(int opi) const {
+    const TflOp& o = g.ops[opi];
+    SPEC_CHECK(o.code == kLeakyRelu, "expected LEAKY_RELU");
+    const TflTensor& x = T(o.inputs[0]);
+    const TflTensor& y = T(o.outputs[0]);
+    SPEC_CHECK(x.type == DType::I8 && y.type == DType::I8, "expected int8 LEAKY_RELU");
+    const float alpha = m.OptF32(o, 0, 0.0f);
+    const double alpha_mult = (double)(x.scale0() * alpha / y.scale0());   // float expression, widened
+    const double ident_mult = (double)(x.scale0() / y.scale0());
+    int32_t ma, mi; int sa, si;
+    QuantizeMultiplier(alpha_mult, &ma, &sa);
+    QuantizeMultiplier(ident_mult, &mi, &si);
+    std::vector<int8_t> lut(256);
+    for (int q = -128; q < 128; ++q) {
+      const int32_t v = q - x.zp0();
+      const int32_t u = y.zp0() + (v >= 0 ? MultiplyByQuantizedMultiplier(v, mi, si) : MultiplyByQuantizedMultiplier(v, ma, sa));
+      lut[(size_t)(q + 128)] = (int8_t)ClampI8(u);
+    }
+    return LReluQ{Append(blob, lut)};
+  }
+
+  // int8 ADD: per-input scaled terms as tables, final rescale on device (kernels/add.cc + integer_ops/add.h)
+  AddQ PackAdd(int opi) const {
+    const TflOp& o = g.ops[opi];
+    SPEC_CHECK(o.code == kAdd && m.OptI8(o, 0, 0) == 0, "expected ADD without activation");
+    const TflTensor& a = T(o.inputs[0]);
+    const TflTensor& b = T(o.inputs[1]);
+    const TflTensor& y = T(o.outputs[0]);
+    SPEC_CHECK(a.type == DType::I8 && b.type == DType::I8, "expected int8 ADD");
+    const int left_shift = 20;
+    const float maxs = a.scale0() > b.scale0() ? a.scale0() : b.scale0();
+    const double twice_max = (double)(2 * maxs);
+    const double r1 = (double)a.scale0() / twice_max, r2 = (double)b.scale0() / twice_max;
+    const double ro = twice_max / (double)((float)(1 << left_shift) * y.scale0());
+    int32_t m1, m2, m3; int s1, s2, s3;
+    QuantizeMultiplier(r1, &m1, &s1);
+    QuantizeMultiplier(r2, &m2, &s2);
+    QuantizeMultiplier(ro, &m3, &s3);
+    std::vector<int32_t> l1(256), l2(256);
+    for (int q = -128; q < 128; ++q) {
+      l1[(size_t)(q + 128)] = MultiplyByQuantizedMultiplier((q - a.zp0()) * (1 << left_shift), m1, s1);
+      l2[(size_t)(q + 128)] = MultiplyByQuantizedMultiplier((q - b.zp0()) * (1 << left_shift), m2, s2);
+    }
+    return AddQ{Append(blob, l1), Append(blob, l2), m3, s3, y.zp0()};
+  }
+
+  ResF32 PackResF32(int first_conv, int C, int dil, int groups2) const {
+    expect_conv(conv(first_conv), kDepthwiseConv2D, DType::F32, C, 3, C, 1, dil);
+    expect_conv(conv(first_conv + 1), kConv2D, DType::F32, C, 1, C, 1);
+    expect_conv(conv(first_conv + 2), kConv2D, DType::F32, C, 1, C / groups2, 1);
+    return ResF32{PackDwF32(conv(first_conv)), PackConvF32(conv(first_conv + 1)), PackConvF32(conv(first_conv + 2))};
+  }
+
+  ResI8 PackResI8(int first_conv, int C, int dil) const {
+    expect_conv(conv(first_conv), kDepthwiseConv2D, DType::I8, C, 3, C, 1, dil);
+    expect_conv(conv(first_conv + 1), kConv2D, DType::I8, C, 1, C, 1);
+    expect_conv(conv(first_conv + 2), kConv2D, DType::I8, C, 1, C / 4, 1);
+    ResI8 r;
+    r.dw = PackDwI8(conv(first_conv));
+    r.pw1 = PackConvI8(conv(first_conv + 1));
+    const int lr1 = next(conv(first_conv + 1).outputs[0], kLeakyRelu);
+    r.lr1 = PackLRelu(lr1);
+    SPEC_CHECK(in_tensor(conv(first_conv + 2)) == out0(lr1), "res-unit wiring (pw2 input)");
+    r.pw2 = PackConvI8(conv(first_conv + 2));
+    const int add = next(conv(first_conv + 2).outputs[0], kAdd);
+    SPEC_CHECK(g.ops[add].inputs[0] == conv(first_conv + 2).outputs[0], "res-unit ADD operand order");
+    r.add = PackAdd(add);
+    r.lr2 = PackLRelu(next(out0(add), kLeakyRelu));
+    return r;
+  }
+};
+
+EncoderParams BuildEncoder(const TflModel& m, std::vector<uint8_t>* blob) {
+  int sg = m.SignatureSubgraph("serving_default");
+  if (sg < 0) sg = 0;
+  Net n(m, sg, blob);
+  SPEC_CHECK(n.convs.size() == 32, "encoder: expected 32 convolution ops");
+  EncoderParams p;
+  std::memset(&p, 0, sizeof(p));
+  n.expect_conv(n.conv(0), kConv2D, DType::F32, 64, 64, 1, 16);
+  p.first = n.PackConvF32(n.conv(0));
+  const int dil[3] = {1, 3, 9};
+  for (int i = 0; i < 3; ++i) p.r0[i] = n.PackResF32(1 + 3 * i, 64, dil[i], 1);
+  n.expect_conv(n.conv(10), kConv2D, DType::F32, 128, 10, 64, 5);
+  p.down0 = n.PackConvF32(n.conv(10));
+  for (int i = 0; i < 3; ++i) p.r1[i] = n.PackResF32(11 + 3 * i, 128, dil[i], 2);
+  n.expect_conv(n.conv(20), kConv2D, DType::F32, 256, 4, 64, 2);
+  p.down1 = n.PackConvF32(n.conv(20));
+  // encoder_2/resnet_0: f32 dw + f32 1x1, then int8
+  n.expect_conv(n.conv(21), kDepthwiseConv2D, DType::F32, 256, 3, 256, 1, 1);
+  n.expect_conv(n.conv(22), kConv2D, DType::F32, 256, 1, 256, 1);
+  n.expect_conv(n.conv(23), kConv2D, DType::I8, 256, 1, 64, 1);
+  p.m_dw = n.PackDwF32(n.conv(21));
+  p.m_pw1 = n.PackConvF32(n.conv(22));
+  const int q1 = n.next(n.conv(22).outputs[0], kQuantize);
+  p.m_q1 = n.QP(n.out0(q1));
+  const int lr1 = n.next(n.out0(q1), kLeakyRelu);
+  p.m_lr1 = n.PackLRelu(lr1);
+  SPEC_CHECK(n.in_tensor(n.conv(23)) == n.out0(lr1), "encoder mixed unit wiring");
+  p.m_pw2 = n.PackConvI8(n.conv(23));
+  const int dq = n.next(n.conv(23).outputs[0], kDequantize);
+  p.m_dq = n.QP(n.conv(23).outputs[0]);
+  const int addf = n.next(n.out0(dq), kAdd);
+  SPEC_CHECK(n.g.ops[addf].inputs[1] == n.conv(20).outputs[0], "encoder mixed unit residual");
+  const int q2 = n.next(n.out0(addf), kQuantize);
+  p.m_q2 = n.QP(n.out0(q2));
+  // the quantised sum feeds both the next unit's ADD and a LEAKY_RELU
+  p.m_lr2 = n.PackLRelu(n.next(n.out0(q2), kLeakyRelu));
+  p.q[0] = n.PackResI8(24, 256, 3);
+  p.q[1] = n.PackResI8(27, 256, 9);
+  n.expect_conv(n.conv(30), kConv2D, DType::I8, 512, 4, 64, 2);
+  p.down2 = n.PackConvI8(n.conv(30));
+  p.down2_lr = n.PackLRelu(n.next(n.conv(30).outputs[0], kLeakyRelu));
+  n.expect_conv(n.conv(31), kConv2D, DType::I8, 64, 3, 128, 1);
+  p.bott = n.PackConvI8(n.conv(31));
+  p.out_dq = n.QP(n.conv(31).outputs[0]);
+  SPEC_CHECK(n.T(n.g.outputs[0]).count() == 64, "encoder output size");
+  p.zp_state[0] = p.q[0].dw.in_zp;
+  p.zp_state[1] = p.q[1].dw.in_zp;
+  p.zp_state[2] = p.down2.in_zp;
+  p.zp_state[3] = p.bott.in_zp;
+  return p;
+}
+
+DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
+  int sg = m.SignatureSubgraph("serving_default");
+  if (sg < 0) sg = 0;
+  Net n(m, sg, blob);
+  SPEC_CHECK(n.convs.size() == 36, "decoder: expected 36 convolution ops");
+  DecoderParams p;
+  std::memset(&p, 0, sizeof(p));
+  n.expect_conv(n.conv(0), kConv2D, DType::F32, 512, 3, 16, 1);
+  p.bott = n.PackConvF32(n.conv(0));
+  {
+    const int lr = n.next(n.conv(0).outputs[0], kLeakyRelu);
+    const int q = n.next(n.out0(lr), kQuantize);
+    p.bott_q = n.QP(n.out0(q));
+  }
+  // a bank of `G` TRANSPOSE_CONVs (convs first..first+G-1) fused into one grouped tap-GEMM
+  auto pack_up = [&](int first, int G) {
+    UpI8 up;
+    std::memset(&up, 0, sizeof(up));
+    const int stride = 2, K = 4, Cin = 128, Cout = 64, J = K / stride;
+    const int NG = stride * Cout, N = G * NG, K4 = J * Cin / 4;
+    std::vector<uint32_t> wt((size_t)K4 * N, 0u);
+    std::vector<int32_t> bias((size_t)N), mult((size_t)N), shift((size_t)N);
+    int in_zp = 0;
+    for (int gi = 0; gi < G; ++gi) {
+      const TflOp& o = n.conv(first + gi);
+      n.expect_conv(o, kTransposeConv, DType::I8, Cout, K, Cin, stride);
+      const TflTensor& w = n.T(n.w_tensor(o));
+      const TflTensor& b = n.T(n.b_tensor(o));
+      const TflTensor& x = n.T(n.in_tensor(o));
+      const TflTensor& y = n.T(o.outputs[0]);
+      if (gi == 0) in_zp = x.zp0();
+      SPEC_CHECK(x.zp0() == in_zp, "transposed conv bank: inputs must share quantisation");
+      const int8_t* src = w.as<int8_t>();
+      for (int r = 0; r < stride; ++r)
+        for (int co = 0; co < Cout; ++co) {
+          const size_t col = (size_t)gi * NG + (size_t)r * Cout + co;
+          int64_t wsum = 0;
+          for (int j = 0; j < J; ++j)
+            for (int ci = 0; ci < Cin; ++ci) {
+              const int8_t v = src[((size_t)co * K + (r + stride * (J - 1 - j))) * Cin + ci];
+              wsum += v;
+              const size_t kk = (size_t)j * Cin + ci;
+              wt[(kk / 4) * N + col] |= (uint32_t)(uint8_t)v << (8 * (kk % 4));
+            }
+          // rows outside the input are padded with the zero point, so the fold uses all J taps
+          bias[col] = (int32_t)(b.as<int32_t>()[co] - (int64_t)in_zp * wsum);
+          const double eff = (double)x.scale0() * (double)w.scale[w.scale.size() > 1 ? (size_t)co : 0] / (double)y.scale0();
+          int32_t qm; int sh;
+          QuantizeMultiplier(eff, &qm, &sh);
+          mult[col] = qm;
+          shift[col] = sh;
+        }
+      const int dq = n.next(o.outputs[0], kDequantize);
+      up.dq[gi] = n.QP(o.outputs[0]);
+      up.out_zp[gi] = y.zp0();
+      const int add = n.next(n.out0(dq), kAdd);
+      // the tail slice of the sum has the f32 bias subtracted before it becomes the next overlap state
+      int sub = -1;
+      for (int c : n.g.consumers(n.out0(add)))
+        if (n.g.ops[c].code == kStridedSlice)
+          for (int c2 : n.g.consumers(n.out0(c)))
+            if (n.g.ops[c2].code == kSub) sub = c2;
+      SPEC_CHECK(sub >= 0, "transposed conv: overlap SUB not found");
+      const TflTensor& bf = n.T(n.g.ops[sub].inputs[1]);
+      SPEC_CHECK(bf.data && bf.count() == 64 && bf.type == DType::F32, "transposed conv: f32 bias constant");
+      up.bias_f32[gi] = Append(blob, std::vector<float>(bf.as<float>(), bf.as<float>() + 64));
+    }
+    up.g = GemmI8{Append(blob, wt), Append(blob, bias), Append(blob, mult), Append(blob, shift), 0, in_zp};
+    return up;
+  };
+  p.up0 = pack_up(1, 4);
+  // mixed unit quant_decoder_0/resnet_0
+  n.expect_conv(n.conv(5), kDepthwiseConv2D, DType::I8, 256, 3, 256, 1, 1);
+  n.expect_conv(n.conv(6), kConv2D, DType::I8, 256, 1, 256, 1);
+  n.expect_conv(n.conv(7), kConv2D, DType::I8, 256, 1, 64, 1);
+  p.up0_q = n.QP(n.in_tensor(n.conv(5)));
+  p.m_dw = n.PackDwI8(n.conv(5));
+  p.m_pw1 = n.PackConvI8(n.conv(6));
+  p.m_lr1 = n.PackLRelu(n.next(n.conv(6).outputs[0], kLeakyRelu));
+  p.m_pw2 = n.PackConvI8(n.conv(7));
+  {
+    const int dq = n.next(n.conv(7).outputs[0], kDequantize);
+    p.m_dq = n.QP(n.conv(7).outputs[0]);
+    const int addf = n.next(n.out0(dq), kAdd);
+    const int q2 = n.next(n.out0(addf), kQuantize);
+    p.m_q2 = n.QP(n.out0(q2));
+    p.m_lr2 = n.PackLRelu(n.next(n.out0(q2), kLeakyRelu));
+  }
+  p.q[0] = n.PackResI8(8, 256, 3);
+  p.q[1] = n.PackResI8(11, 256, 9);
+  p.up1 = pack_up(14, 2);
+  const int dil[3] = {1, 3, 9};
+  for (int i = 0; i < 3; ++i) p.r1[i] = n.PackResF32(16 + 3 * i, 128, dil[i], 2);
+  n.expect_conv(n.conv(25), kTransposeConv, DType::F32, 64, 10, 128, 5);
+  p.up2 = n.PackTconvF32(n.conv(25), 5);
+  for (int i = 0; i < 3; ++i) p.r2[i] = n.PackResF32(26 + 3 * i, 64, dil[i], 1);
+  n.expect_conv(n.conv(35), kTransposeConv, DType::F32, 1, 64, 64, 16);
+  p.last = n.PackTconvF32(n.conv(35), 16);
+  p.zp_state[0] = p.m_dw.in_zp;
+  p.zp_state[1] = p.q[0].dw.in_zp;
+  p.zp_state[2] = p.q[1].dw.in_zp;
+  return p;
+}
+
+RvqParams BuildRvq(const TflModel& m, std::vector<uint8_t>* blob, int* bits_per_stage) {
+  const int se = m.SignatureSubgraph("encode"), sd = m.SignatureSubgraph("decode");
+  SPEC_CHECK(se >= 0 && sd >= 0, "quantizer: missing encode/decode signatures");
+  const TflSubgraph& ge = m.subgraphs()[se];
+  std::vector<const float*> stage_cb;
+  for (const TflOp& o : ge.ops)
+    if (o.code == kSquaredDifference) {
+      const TflTensor& cb = ge.tensors[o.inputs[1]];
+      SPEC_CHECK(cb.data && cb.count() == 16 * 64 && cb.type == DType::F32, "quantizer: codebook shape");
+      stage_cb.push_back(cb.as<float>());
+    }
+  SPEC_CHECK(stage_cb.size() == 46, "quantizer: expected 46 stages");
+  *bits_per_stage = 0;
+  for (int o : ge.outputs)
+    if (ge.tensors[o].data && ge.tensors[o].count() == 1) *bits_per_stage = ge.tensors[o].as<int32_t>()[0];
+  SPEC_CHECK(*bits_per_stage == 4, "quantizer: expected 4 bits per stage");
+  // the decode signature must use the same codebook for the same index slot
+  const TflSubgraph& gd = m.subgraphs()[sd];
+  int checked = 0;
+  for (const TflOp& o : gd.ops)
+    if (o.code == kGather) {
+      const int sl = gd.producer(o.inputs[1]);
+      SPEC_CHECK(sl >= 0 && gd.ops[sl].code == kStridedSlice, "quantizer: decode GATHER index is not a slice");
+      const TflTensor& bg = gd.tensors[gd.ops[sl].inputs[1]];
+      SPEC_CHECK(bg.data, "quantizer: decode slice begin");
+      const int stage = bg.as<int32_t>()[0];
+      SPEC_CHECK(stage >= 0 && stage < 46, "quantizer: decode stage index");
+      const TflTensor& cb = gd.tensors[o.inputs[0]];
+      SPEC_CHECK(cb.data && cb.count() == 16 * 64 && std::memcmp(cb.data, stage_cb[(size_t)stage], 16 * 64 * 4) == 0,
+                 "quantizer: decode codebook differs from encode codebook");
+      ++checked;
+    }
+  SPEC_CHECK(checked == 46, "quantizer: expected 46 decode GATHER ops");
+  std::vector<float> cbs((size_t)46 * 16 * 64), cbt((size_t)46 * 64 * 16);
+  for (int s = 0; s < 46; ++s)
+    for (int c = 0; c < 16; ++c)
+      for (int j = 0; j < 64; ++j) {
+        cbs[((size_t)s * 16 + c) * 64 + j] = stage_cb[(size_t)s][c * 64 + j];
+        cbt[((size_t)s * 64 + j) * 16 + c] = stage_cb[(size_t)s][c * 64 + j];
+      }
+  RvqParams p;
+  p.codebooks_t = Append(blob, cbt);
+  p.codebooks = Append(blob, cbs);
+  p.num_stages = 46;
+  return p;
+}
+
+}  // namespace
+
+// Spectrogram + mel filterbank tables (window, FFT twiddles, triangular weights), the constants
+// LogMelSpectrogramExtractorImpl::Create builds through audio_dsp
+// (lyra/log_mel_spectrogram_extractor_impl.cc:53-94; limits 0 .. 0.495*fs at :39-40).
+LogMelParams BuildLogMelParams(std::vector<uint8_t>* blob, int sample_rate_hz, int hop, int window, int num_mel) {
+  SPEC_CHECK(window >= hop && hop > 0 && num_mel > 0, "log-mel: window must be >= hop");
+  LogMelParams p;
+  std::memset(&p, 0, sizeof(p));
+  int fft = 1;
+  while (fft < window) fft <<= 1;
+  const int bins = fft / 2 + 1;
+  std::vector<double> win((size_t)window), tw((size_t)fft), weights((size_t)bins, 0.0);
+  std::vector<int32_t> band((size_t)bins, -2);
+  for (int i = 0; i < window; ++i) win[(size_t)i] = 0.5 - 0.5 * std::cos(2.0 * M_PI * i / (double)window);
+  for (int k = 0; k < fft / 2; ++k) {
+    const double ang = -2.0 * M_PI * (double)k / (double)fft;
+    tw[(size_t)2 * k] = std::cos(ang);
+    tw[(size_t)2 * k + 1] = std::sin(ang);
+  }
+  auto mel = [](double f) { return 1127.0 * std::log1p(f / 700.0); };
+  const double lower = 0.0, upper = 0.495 * sample_rate_hz;
+  const double mel_low = mel(lower), mel_hi = mel(upper);
+  const double spacing = (mel_hi - mel_low) / (double)(num_mel + 1);
+  std::vector<double> center((size_t)num_mel + 1);
+  for (int i = 0; i <= num_mel; ++i) center[(size_t)i] = mel_low + spacing * (i + 1);
+  const double hz_per_sbin = 0.5 * sample_rate_hz / (double)(bins - 1);
+  p.start_index = (int)(1.5 + lower / hz_per_sbin);
+  p.end_index = (int)(upper / hz_per_sbin);
+  int channel = 0;
+  for (int i = 0; i < bins; ++i) {
+    const double melf = mel(i * hz_per_sbin);
+    if (i < p.start_index || i > p.end_index) continue;
+    while (channel < num_mel && center[(size_t)channel] < melf) ++channel;
+    band[(size_t)i] = channel - 1;
+    const int ch = channel - 1;
+    if (ch >= 0) weights[(size_t)i] = (center[(size_t)ch + 1] - melf) / (center[(size_t)ch + 1] - center[(size_t)ch]);
+    else weights[(size_t)i] = (center[0] - melf) / (center[0] - mel_low);
+  }
+  p.window = Append(blob, win);
+  p.twiddle = Append(blob, tw);
+  p.weights = Append(blob, weights);
+  p.band = Append(blob, band);
+  p.num_mel = num_mel; p.fft = fft; p.window_len = window; p.hop = hop;
+  return p;
+}
+
+ModelSpec BuildModelSpec(const std::string& model_dir) {
+  ModelSpec s;
+  {
+    // lyra_config.binarypb: field 1 (identifier) varint == 3  (lyra/lyra_config.h:145-166)
+    std::ifstream f(model_dir + "/lyra_config.binarypb", std::ios::binary);
+    SPEC_CHECK((bool)f, "cannot open lyra_config.binarypb in " + model_dir);
+    char b[2] = {0, 0};
+    f.read(b, 2);
+    SPEC_CHECK(f.gcount() == 2 && b[0] == 0x08 && b[1] == 0x03, "lyra_config.binarypb identifier is not 3 (weights/code version mismatch)");
+  }
+  const TflModel enc = TflModel::Load(model_dir + "/soundstream_encoder.tflite");
+  const TflModel dec = TflModel::Load(model_dir + "/lyragan.tflite");
+  const TflModel rvq = TflModel::Load(model_dir + "/quantizer.tflite");
+  s.enc = BuildEncoder(enc, &s.blob);
+  s.dec = BuildDecoder(dec, &s.blob);
+  s.rvq = BuildRvq(rvq, &s.blob, &s.bits_per_stage);
+  s.logmel160 = BuildLogMelParams(&s.blob, 16000, 320, 640, 160);
+  s.logmel64 = BuildLogMelParams(&s.blob, 16000, 320, 640, 64);
+  while (s.blob.size() % 256) s.blob.push_back(0);
+  return s;
+}
+
+}  // namespace lyra_b200

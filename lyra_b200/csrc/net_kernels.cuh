@@ -1,0 +1,750 @@
+// The conv-net kernels of the per-frame hot path, one thread block per tile of S streams.
+//
+//   EncoderKernelA  first_layer .. encoder_0/simpleconv          (T = 20 rows, 64 ch)   -> mid [128][4][S]
+//   EncoderKernelB  encoder_1 .. quant_bottleneck_1               (T = 4/2/1)            -> features f32[64]
+//   DecoderKernelC  bottleneck_2 .. decoder_1                      (T = 1/2/4)            -> mid [128][4][S]
+//   DecoderKernelD  decoder_2/simple .. last_layer                 (T = 20 rows, 64 ch)   -> int16 PCM
+//
+// Together A+B replace SoundStreamEncoder::Extract's Interpreter::Invoke (lyra/soundstream_encoder.cc:53-64)
+// and C+D replace LyraGanModel::RunConditioning/RunModel (lyra/lyra_gan_model.cc:53-64) for S streams at once.
+// Streaming state (TFLite resource variables in the reference) lives in HBM, tile-blocked
+// [tile][unit][S]; dilated depthwise convs keep a ring of their last 2*dilation input rows.
+#pragma once
+
+#include "kernel_prims.cuh"
+
+namespace lyra_b200 {
+
+// ---- per-tile state layouts, in 4-byte units (each unit is S lanes wide) ----
+struct EncStateA {
+  static constexpr int kFirst = 0;                               // [48]
+  static constexpr int kRing0 = 48, kRing1 = kRing0 + 64 * 2, kRing2 = kRing1 + 64 * 6;   // [64][2|6|18]
+  static constexpr int kDown0 = kRing2 + 64 * 18;                // [64][5]
+  static constexpr int kUnits = kDown0 + 64 * 5;                 // 2032
+};
+struct EncStateB {
+  static constexpr int kRing0 = 0, kRing1 = 128 * 2, kRing2 = kRing1 + 128 * 6;           // f32 [128][2|6|18]
+  static constexpr int kDown1 = kRing2 + 128 * 18;               // f32 [128][2]
+  static constexpr int kRingM = kDown1 + 128 * 2;                // f32 [256][2]
+  static constexpr int kRingQ0 = kRingM + 256 * 2;               // words [64][6]
+  static constexpr int kRingQ1 = kRingQ0 + 64 * 6;               // words [64][18]
+  static constexpr int kDown2 = kRingQ1 + 64 * 18;               // words [64][2]
+  static constexpr int kBott = kDown2 + 64 * 2;                  // words [128][2]
+  static constexpr int kUnits = kBott + 128 * 2;                 // 6016
+};
+struct DecStateC {
+  static constexpr int kBott = 0;                                // f32 [64][2]
+  static constexpr int kUp0 = 128;                               // f32 [256][2]
+  static constexpr int kUp1 = kUp0 + 512;                        // f32 [128][2]
+  static constexpr int kRing0 = kUp1 + 256, kRing1 = kRing0 + 128 * 2, kRing2 = kRing1 + 128 * 6;  // f32 [128][2|6|18]
+  static constexpr int kRingM = kRing2 + 128 * 18;               // words [64][2]
+  static constexpr int kRingQ0 = kRingM + 64 * 2;                // words [64][6]
+  static constexpr int kRingQ1 = kRingQ0 + 64 * 6;               // words [64][18]
+  static constexpr int kUnits = kRingQ1 + 64 * 18;               // 5888
+};
+struct DecStateD {
+  static constexpr int kUp2 = 0;                                 // f32 [64][5]
+  static constexpr int kRing0 = 320, kRing1 = kRing0 + 64 * 2, kRing2 = kRing1 + 64 * 6;  // f32 [64][2|6|18]
+  static constexpr int kLast = kRing2 + 64 * 18;                 // f32 [48]
+  static constexpr int kUnits = kLast + 48;                      // 2032
+};
+
+struct TileIo {
+  const int* tile_list;        // tiles to process, one per block
+  const int* slot_of_stream;   // [max_streams] position of the stream in this call's I/O arrays, -1 = not in this call
+};
+
+template <int S>
+__device__ __forceinline__ void LoadTileMeta(const TileIo& io, const int* n18_global, int* slot, int* active, int* n18, int& tile) {
+  tile = io.tile_list[blockIdx.x];
+  if ((int)threadIdx.x < S) {
+    const int stream = tile * S + (int)threadIdx.x;
+    const int sl = io.slot_of_stream[stream];
+    slot[threadIdx.x] = sl;
+    active[threadIdx.x] = sl >= 0;
+    n18[threadIdx.x] = n18_global[stream];
+  }
+  __syncthreads();
+}
+
+// One fp32 residual unit:  d = dw(lrelu(u)); h = lrelu(pw1(d)); u' = pw2(h) + u.
+// u lives at row offset row0u of a [C][ldu] buffer; d is a [C][T*S] scratch.  When `last`, lrelu(u') is stored.
+template <int S, int NT, int TM, int TN1, int TN2>
+__device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p, float* u, int ldu, int row0u, float* d,
+                                           int C, int T, int dil, int groups2, float* ring, const int* n18,
+                                           const int* active, float* wbuf, bool last) {
+  const int ldd = T * S;
+  DwF32Ring<S, NT>(u, ldu, row0u, d, ldd, C, T, dil, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18, active);
+  {
+    const float* b1 = BlobPtr<float>(blob, p.pw1.bias);
+    GemmF32Tap<S, NT, TM, TN1, 16, false>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float>(blob, p.pw1.w), wbuf, true,
+      [&](int t, int s0, int n0, float (&acc)[TM][TN1]) {
+#pragma unroll
+        for (int j = 0; j < TN1; ++j) {
+          const float b = b1[n0 + j];
+          float* o = d + (size_t)(n0 + j) * ldd + t * S + s0;
+#pragma unroll
+          for (int i = 0; i < TM; ++i) o[i] = LeakyRelu(__fadd_rn(acc[i][j], b));
+        }
+      });
+  }
+  {
+    const float* b2 = BlobPtr<float>(blob, p.pw2.bias);
+    GemmF32Tap<S, NT, TM, TN2, 16, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float>(blob, p.pw2.w), wbuf, false,
+      [&](int t, int s0, int n0, float (&acc)[TM][TN2]) {
+#pragma unroll
+        for (int j = 0; j < TN2; ++j) {
+          const float b = b2[n0 + j];
+          float* o = u + (size_t)(n0 + j) * ldu + (row0u + t) * S + s0;
+#pragma unroll
+          for (int i = 0; i < TM; ++i) {
+            const float v = __fadd_rn(__fadd_rn(acc[i][j], b), o[i]);
+            o[i] = last ? LeakyRelu(v) : v;
+          }
+        }
+      });
+  }
+}
+
+// One int8 residual unit on packed activations (quant_encoder_2/resnet_{1,2}, quant_decoder_0/resnet_{1,2}).
+//   aq: LeakyReLU'd input (row offset row0a of [64][lda]); resq: the pre-activation residual; both updated in place.
+template <int S, int NT>
+__device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, uint32_t* aq, int lda, int row0a,
+                                          uint32_t* resq, uint32_t* dq8, uint32_t* hq, int dil, uint32_t* ring,
+                                          const int* n18, const int* active, uint32_t* wbuf) {
+  constexpr int T = 2, C = 256, LD = T * S;
+  DwI8Ring<S, NT>(aq, lda, row0a, dq8, LD, C, T, dil, blob, p.dw, ring, n18, active);
+  {
+    const int* bias = BlobPtr<int>(blob, p.pw1.bias);
+    const int* mult = BlobPtr<int>(blob, p.pw1.mult);
+    const int* shift = BlobPtr<int>(blob, p.pw1.shift);
+    const int8_t* lut = BlobPtr<int8_t>(blob, p.lr1.lut);
+    const int out_zp = p.pw1.out_zp;
+    GemmI8Tap<S, NT, 8, 4, 8>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint32_t>(blob, p.pw1.w), wbuf,
+      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int q[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
+          hq[(size_t)(n0 / 4) * LD + t * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
+        }
+      });
+  }
+  {
+    const int* bias = BlobPtr<int>(blob, p.pw2.bias);
+    const int* mult = BlobPtr<int>(blob, p.pw2.mult);
+    const int* shift = BlobPtr<int>(blob, p.pw2.shift);
+    const int* l1 = BlobPtr<int>(blob, p.add.lut1);
+    const int* l2 = BlobPtr<int>(blob, p.add.lut2);
+    const int8_t* lut = BlobPtr<int8_t>(blob, p.lr2.lut);
+    const int out_zp = p.pw2.out_zp, m3 = p.add.m3, s3 = p.add.s3, add_zp = p.add.out_zp;
+    GemmI8Tap<S, NT, 8, 4, 8>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint32_t>(blob, p.pw2.w), wbuf,
+      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const size_t ro = (size_t)(n0 / 4) * LD + t * S + s0 + i;
+          const uint32_t rw = resq[ro];
+          int r[4], a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int q = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
+            r[j] = ClampI8(Mbqm(l1[q + 128] + l2[UnpackI8(rw, j) + 128], m3, s3) + add_zp);
+            a[j] = lut[r[j] + 128];
+          }
+          resq[ro] = PackI8x4(r[0], r[1], r[2], r[3]);
+          aq[(size_t)(n0 / 4) * lda + (row0a + t) * S + s0 + i] = PackI8x4(a[0], a[1], a[2], a[3]);
+        }
+      });
+  }
+}
+
+// ================================================================================================
+//                                        ENCODER  A
+// ================================================================================================
+template <int S>
+struct EncA {
+  static constexpr int NT = 320;
+  static constexpr int LDU = 25 * S, LDD = 20 * S;
+  static constexpr int kSmemU = 0;
+  static constexpr int kSmemD = kSmemU + 64 * LDU * 4;
+  static constexpr int kSmemW = kSmemD + 64 * LDD * 4;
+  static constexpr int kSmemI = kSmemW + 2 * 16 * 128 * 4;
+  static constexpr int kSmemBytes = kSmemI + 3 * S * 4;
+  static_assert(368 * S <= 64 * LDD, "first-layer input must fit in the d buffer");
+};
+
+template <int S>
+__global__ void __launch_bounds__(320, 1)
+EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, const int16_t* __restrict__ pcm,
+               float* __restrict__ state, int* __restrict__ n18g, float* __restrict__ mid) {
+  using L = EncA<S>;
+  constexpr int NT = L::NT;
+  unsigned char* smem = LYRA_DYN_SMEM();
+  float* u = reinterpret_cast<float*>(smem + L::kSmemU);
+  float* d = reinterpret_cast<float*>(smem + L::kSmemD);
+  float* wbuf = reinterpret_cast<float*>(smem + L::kSmemW);
+  int* slot = reinterpret_cast<int*>(smem + L::kSmemI);
+  int* active = slot + S;
+  int* n18 = active + S;
+  int tile;
+  LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
+  float* st = state + (size_t)tile * EncStateA::kUnits * S;
+  const int tid = (int)threadIdx.x;
+
+  // ---- input window X[368][S] (aliases d): 48 carried samples + 320 new ones as unit floats (dsp_utils.h:104-108)
+  float* X = d;
+  for (int i = tid; i < 48 * S; i += NT) X[i] = st[EncStateA::kFirst * S + i];
+  for (int i = tid; i < 320 * S; i += NT) {
+    const int s = i / 320, k = i % 320;
+    const float v = active[s] ? (float)pcm[(size_t)slot[s] * 320 + k] * (1.0f / 32768.0f) : 0.0f;
+    X[(48 + k) * S + s] = v;
+  }
+  // prefix rows 0..4 of u: the 5 carried rows of encoder_0/simpleconv
+  for (int i = tid; i < 64 * 5 * S; i += NT) {
+    const int c = i / (5 * S), r = i % (5 * S);
+    u[(size_t)c * L::LDU + r] = st[EncStateA::kDown0 * S + i];
+  }
+  __syncthreads();
+  for (int i = tid; i < 48 * S; i += NT)
+    if (active[i % S]) st[EncStateA::kFirst * S + i] = X[320 * S + i];
+  // ---- first_layer: K = 64, stride 16, 1 -> 64 ; u = conv + bias (pre-activation residual stream)
+  {
+    const float* b = BlobPtr<float>(blob, P.first.bias);
+    GemmF32Tap<S, NT, 8, (S >= 16 ? 8 : 4), 16, true>(X, 0, 0, 16, 64, 1, 1, 20, 64, BlobPtr<float>(blob, P.first.w), wbuf, false,
+      [&](int t, int s0, int n0, float (&acc)[8][(S >= 16 ? 8 : 4)]) {
+#pragma unroll
+        for (int j = 0; j < (S >= 16 ? 8 : 4); ++j) {
+          float* o = u + (size_t)(n0 + j) * L::LDU + (5 + t) * S + s0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __fadd_rn(acc[i][j], b[n0 + j]);
+        }
+      });
+  }
+  // ---- encoder_0: three residual units, dilation 1/3/9
+  const int ring_off[3] = {EncStateA::kRing0, EncStateA::kRing1, EncStateA::kRing2};
+  const int dil[3] = {1, 3, 9};
+  for (int i = 0; i < 3; ++i)
+    ResUnitF32<S, NT, 8, (S >= 16 ? 8 : 4), (S >= 16 ? 8 : 4)>(blob, P.r0[i], u, L::LDU, 5, d, 64, 20, dil[i], 1,
+                                                              st + (size_t)ring_off[i] * S, n18, active, wbuf, i == 2);
+  // carried rows for the next frame: the last 5 activated rows
+  for (int i = tid; i < 64 * 5 * S; i += NT) {
+    const int c = i / (5 * S), r = i % (5 * S);
+    if (active[r % S]) st[EncStateA::kDown0 * S + i] = u[(size_t)c * L::LDU + 20 * S + r];
+  }
+  // ---- encoder_0/simpleconv: K = 10, stride 5, 64 -> 128 ; pre-activation output to HBM for kernel B
+  {
+    const float* b = BlobPtr<float>(blob, P.down0.bias);
+    float* out = mid + (size_t)tile * 128 * 4 * S;
+    GemmF32Tap<S, NT, 8, 4, 16, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), wbuf, false,
+      [&](int t, int s0, int n0, float (&acc)[8][4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float* o = out + ((size_t)(n0 + j) * 4 + t) * S + s0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __fadd_rn(acc[i][j], b[n0 + j]);
+        }
+      });
+  }
+  if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
+}
+
+// ================================================================================================
+//                                        ENCODER  B
+// ================================================================================================
+template <int S>
+struct EncB {
+  static constexpr int NT = 256;
+  static constexpr int LD1 = 6 * S;                       // u1: 2 carried rows + 4
+  static constexpr int kR0 = 0;                           // u1 f32 [128][6S]; later d2 f32 [256][2S]
+  static constexpr int kR1 = kR0 + 128 * LD1 * 4;         // d1 f32 [128][4S]; later hq, dq8, resq words [64][2S] each
+  static constexpr int kR2 = kR1 + 128 * 4 * S * 4;       // u2 f32 [256][2S]
+  static constexpr int kR3 = kR2 + 256 * 2 * S * 4;       // aq words [64][4S] (2 carried rows + 2), bq words [128][3S]
+  static constexpr int kW = kR3 + 64 * 4 * S * 4 + 128 * 3 * S * 4;
+  static constexpr int kI = kW + 2 * 16 * 256 * 4;
+  static constexpr int kSmemBytes = kI + 3 * S * 4;
+};
+
+template <int S>
+__global__ void __launch_bounds__(256, 1)
+EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, const float* __restrict__ mid,
+               float* __restrict__ state, int* __restrict__ n18g, float* __restrict__ features) {
+  using L = EncB<S>;
+  constexpr int NT = L::NT;
+  unsigned char* smem = LYRA_DYN_SMEM();
+  float* u1 = reinterpret_cast<float*>(smem + L::kR0);
+  float* d1 = reinterpret_cast<float*>(smem + L::kR1);
+  float* u2 = reinterpret_cast<float*>(smem + L::kR2);
+  float* d2 = reinterpret_cast<float*>(smem + L::kR0);
+  uint32_t* hq = reinterpret_cast<uint32_t*>(smem + L::kR1);
+  uint32_t* dq8 = hq + 64 * 2 * S;
+  uint32_t* resq = dq8 + 64 * 2 * S;
+  uint32_t* aq = reinterpret_cast<uint32_t*>(smem + L::kR3);
+  uint32_t* bq = aq + 64 * 4 * S;
+  float* wbuf = reinterpret_cast<float*>(smem + L::kW);
+  uint32_t* wbufq = reinterpret_cast<uint32_t*>(smem + L::kW);
+  int* slot = reinterpret_cast<int*>(smem + L::kI);
+  int* active = slot + S;
+  int* n18 = active + S;
+  int tile;
+  LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
+  uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * EncStateB::kUnits * S;
+  float* st = reinterpret_cast<float*>(stw);
+  const int tid = (int)threadIdx.x;
+
+  // ---- u1 <- kernel A output (rows 2..5), carried rows of encoder_1/simpleconv (rows 0..1)
+  {
+    const float* in = mid + (size_t)tile * 128 * 4 * S;
+    for (int i = tid; i < 128 * 4 * S; i += NT) { const int c = i / (4 * S), r = i % (4 * S); u1[(size_t)c * L::LD1 + 2 * S + r] = in[i]; }
+    for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); u1[(size_t)c * L::LD1 + r] = st[EncStateB::kDown1 * S + i]; }
+  }
+  __syncthreads();
+  // ---- encoder_1: three residual units @128 (second 1x1 has 2 groups)
+  const int ring_off[3] = {EncStateB::kRing0, EncStateB::kRing1, EncStateB::kRing2};
+  const int dil[3] = {1, 3, 9};
+  for (int i = 0; i < 3; ++i)
+    ResUnitF32<S, NT, 8, 4, 4>(blob, P.r1[i], u1, L::LD1, 2, d1, 128, 4, dil[i], 2, st + (size_t)ring_off[i] * S, n18, active, wbuf, i == 2);
+  for (int i = tid; i < 128 * 2 * S; i += NT) {
+    const int c = i / (2 * S), r = i % (2 * S);
+    if (active[r % S]) st[EncStateB::kDown1 * S + i] = u1[(size_t)c * L::LD1 + 4 * S + r];
+  }
+  // ---- encoder_1/simpleconv: K = 4, stride 2, 128 -> 256, 2 groups ; u2 = pre-activation
+  {
+    const float* b = BlobPtr<float>(blob, P.down1.bias);
+    GemmF32Tap<S, NT, 8, 4, 16, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, false,
+      [&](int t, int s0, int n0, float (&acc)[8][4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float* o = u2 + (size_t)(n0 + j) * 2 * S + t * S + s0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __fadd_rn(acc[i][j], b[n0 + j]);
+        }
+      });
+  }
+  // ---- encoder_2/resnet_0 (mixed): f32 depthwise + f32 1x1, QUANTIZE, int8 LeakyReLU, int8 1x1 (4 groups),
+  //      DEQUANTIZE + f32 residual, QUANTIZE, int8 LeakyReLU
+  constexpr int LD2 = 2 * S;
+  DwF32Ring<S, NT>(u2, LD2, 0, d2, LD2, 256, 2, 1, BlobPtr<float>(blob, P.m_dw.w), BlobPtr<float>(blob, P.m_dw.bias),
+                   st + (size_t)EncStateB::kRingM * S, n18, active);
+  {
+    const float* b = BlobPtr<float>(blob, P.m_pw1.bias);
+    const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
+    const QuantP q1 = P.m_q1;
+    GemmF32Tap<S, NT, 8, 4, 16, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, false,
+      [&](int t, int s0, int n0, float (&acc)[8][4]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int q[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = lut[QuantizeF32(__fadd_rn(acc[i][j], b[n0 + j]), q1.scale, q1.zp) + 128];
+          hq[(size_t)(n0 / 4) * LD2 + t * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
+        }
+      });
+  }
+  {
+    const int* bias = BlobPtr<int>(blob, P.m_pw2.bias);
+    const int* mult = BlobPtr<int>(blob, P.m_pw2.mult);
+    const int* shift = BlobPtr<int>(blob, P.m_pw2.shift);
+    const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
+    const QuantP dq = P.m_dq, q2 = P.m_q2;
+    const int out_zp = P.m_pw2.out_zp;
+    GemmI8Tap<S, NT, 8, 4, 8>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int r[4], a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int q = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
+            const float v = __fadd_rn(DequantizeI8(q, dq.scale, dq.zp), u2[(size_t)(n0 + j) * LD2 + t * S + s0 + i]);
+            r[j] = QuantizeF32(v, q2.scale, q2.zp);
+            a[j] = lut[r[j] + 128];
+          }
+          resq[(size_t)(n0 / 4) * LD2 + t * S + s0 + i] = PackI8x4(r[0], r[1], r[2], r[3]);
+          aq[(size_t)(n0 / 4) * 4 * S + (2 + t) * S + s0 + i] = PackI8x4(a[0], a[1], a[2], a[3]);
+        }
+      });
+  }
+  // ---- quant_encoder_2/resnet_{1,2}
+  ResUnitI8<S, NT>(blob, P.q[0], aq, 4 * S, 2, resq, dq8, hq, 3, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, wbufq);
+  ResUnitI8<S, NT>(blob, P.q[1], aq, 4 * S, 2, resq, dq8, hq, 9, stw + (size_t)EncStateB::kRingQ1 * S, n18, active, wbufq);
+  // ---- quant_encoder_2/simpleconv: K = 4, stride 2, 256 -> 512, 4 groups, then int8 LeakyReLU
+  for (int i = tid; i < 64 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); aq[(size_t)c * 4 * S + r] = stw[EncStateB::kDown2 * S + i]; }
+  for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); bq[(size_t)c * 3 * S + r] = stw[EncStateB::kBott * S + i]; }
+  __syncthreads();
+  for (int i = tid; i < 64 * 2 * S; i += NT) {
+    const int c = i / (2 * S), r = i % (2 * S);
+    if (active[r % S]) stw[EncStateB::kDown2 * S + i] = aq[(size_t)c * 4 * S + 2 * S + r];
+  }
+  {
+    const int* bias = BlobPtr<int>(blob, P.down2.bias);
+    const int* mult = BlobPtr<int>(blob, P.down2.mult);
+    const int* shift = BlobPtr<int>(blob, P.down2.shift);
+    const int8_t* lut = BlobPtr<int8_t>(blob, P.down2_lr.lut);
+    const int out_zp = P.down2.out_zp;
+    GemmI8Tap<S, NT, 8, 4, 8>(aq, 4 * S, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint32_t>(blob, P.down2.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+        (void)t;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int q[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
+          bq[(size_t)(n0 / 4) * 3 * S + 2 * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
+        }
+      });
+  }
+  // carried rows of quant_bottleneck_1: the two newest rows
+  for (int i = tid; i < 128 * 2 * S; i += NT) {
+    const int c = i / (2 * S), r = i % (2 * S);
+    if (active[r % S]) stw[EncStateB::kBott * S + i] = bq[(size_t)c * 3 * S + S + r];
+  }
+  // ---- quant_bottleneck_1: K = 3, 512 -> 64, 4 groups ; DEQUANTIZE -> features
+  {
+    const int* bias = BlobPtr<int>(blob, P.bott.bias);
+    const int* mult = BlobPtr<int>(blob, P.bott.mult);
+    const int* shift = BlobPtr<int>(blob, P.bott.shift);
+    const QuantP dq = P.out_dq;
+    const int out_zp = P.bott.out_zp;
+    GemmI8Tap<S, NT, 8, 4, 8>(bq, 3 * S, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint32_t>(blob, P.bott.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+        (void)t;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!active[s0 + i]) continue;
+          float* o = features + (size_t)slot[s0 + i] * 64 + n0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = DequantizeI8(RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp), dq.scale, dq.zp);
+        }
+      });
+  }
+  if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
+}
+
+// ================================================================================================
+//                                        DECODER  C
+// ================================================================================================
+template <int S>
+struct DecC {
+  static constexpr int NT = 256;
+  static constexpr int kF = 0;                              // F f32 [64][3S]
+  static constexpr int kXq = kF + 64 * 3 * S * 4;           // xq words [128][3S]  (pad, x0, pad)
+  static constexpr int kU = kXq + 128 * 3 * S * 4;          // u f32 [256][2S]; later u1 f32 [128][4S]
+  static constexpr int kAq = kU + 256 * 2 * S * 4;          // aq words [64][4S] (pad, t0, t1, pad)
+  static constexpr int kQ = kAq + 64 * 4 * S * 4;           // hq, dq8, resq words [64][2S] each; later d1 f32 [128][4S]
+  static constexpr int kW = kQ + 128 * 4 * S * 4;
+  static constexpr int kI = kW + 2 * 16 * 512 * 4;
+  static constexpr int kSmemBytes = kI + 3 * S * 4;
+};
+
+template <int S>
+__global__ void __launch_bounds__(256, 1)
+DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
+               const float* __restrict__ features, float* __restrict__ state, int* __restrict__ n18g,
+               float* __restrict__ mid) {
+  using L = DecC<S>;
+  constexpr int NT = L::NT;
+  unsigned char* smem = LYRA_DYN_SMEM();
+  float* F = reinterpret_cast<float*>(smem + L::kF);
+  uint32_t* xq = reinterpret_cast<uint32_t*>(smem + L::kXq);
+  float* u = reinterpret_cast<float*>(smem + L::kU);
+  float* u1 = u;
+  uint32_t* aq = reinterpret_cast<uint32_t*>(smem + L::kAq);
+  uint32_t* hq = reinterpret_cast<uint32_t*>(smem + L::kQ);
+  uint32_t* dq8 = hq + 64 * 2 * S;
+  uint32_t* resq = dq8 + 64 * 2 * S;
+  float* d1 = reinterpret_cast<float*>(smem + L::kQ);
+  float* wbuf = reinterpret_cast<float*>(smem + L::kW);
+  uint32_t* wbufq = reinterpret_cast<uint32_t*>(smem + L::kW);
+  int* slot = reinterpret_cast<int*>(smem + L::kI);
+  int* active = slot + S;
+  int* n18 = active + S;
+  int tile;
+  LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
+  uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * DecStateC::kUnits * S;
+  float* st = reinterpret_cast<float*>(stw);
+  const int tid = (int)threadIdx.x;
+  constexpr int LD2 = 2 * S;
+  const UpI8& up0 = P.up0;
+  const UpI8& up1 = P.up1;
+
+  // ---- F: 2 carried feature rows + the new one ; overlap states into u ; padding rows of xq
+  for (int i = tid; i < 64 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); F[(size_t)c * 3 * S + r] = st[DecStateC::kBott * S + i]; }
+  for (int i = tid; i < 64 * S; i += NT) {
+    const int s = i / 64, c = i % 64;
+    F[(size_t)c * 3 * S + 2 * S + s] = active[s] ? features[(size_t)slot[s] * 64 + c] : 0.0f;
+  }
+  for (int i = tid; i < 256 * 2 * S; i += NT) u[i] = st[DecStateC::kUp0 * S + i];
+  {
+    const uint32_t pad = PackI8x4(P.bott_q.zp, P.bott_q.zp, P.bott_q.zp, P.bott_q.zp);
+    for (int i = tid; i < 128 * S; i += NT) { const int c = i / S, s = i % S; xq[(size_t)c * 3 * S + s] = pad; xq[(size_t)c * 3 * S + 2 * S + s] = pad; }
+  }
+  __syncthreads();
+  for (int i = tid; i < 64 * 2 * S; i += NT) {
+    const int c = i / (2 * S), r = i % (2 * S);
+    if (active[r % S]) st[DecStateC::kBott * S + i] = F[(size_t)c * 3 * S + S + r];
+  }
+  // ---- bottleneck_2/simpleconv: K = 3, 64 -> 512, 4 groups ; LeakyReLU ; QUANTIZE
+  {
+    const float* b = BlobPtr<float>(blob, P.bott.bias);
+    const QuantP q = P.bott_q;
+    GemmF32Tap<S, NT, 8, 4, 16, false>(F, 3 * S, 0, 1, 3, 16, 4, 1, 512, BlobPtr<float>(blob, P.bott.w), wbuf, false,
+      [&](int t, int s0, int n0, float (&acc)[8][4]) {
+        (void)t;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = QuantizeF32(LeakyRelu(__fadd_rn(acc[i][j], b[n0 + j])), q.scale, q.zp);
+          xq[(size_t)(n0 / 4) * 3 * S + S + s0 + i] = PackI8x4(v[0], v[1], v[2], v[3]);
+        }
+      });
+  }
+  // ---- quant_decoder_0 upsample: 4 x TRANSPOSE_CONV (K = 4, stride 2, 128 -> 64), T 1 -> 2 (+2 tail rows)
+  {
+    const int* bias = BlobPtr<int>(blob, up0.g.bias);
+    const int* mult = BlobPtr<int>(blob, up0.g.mult);
+    const int* shift = BlobPtr<int>(blob, up0.g.shift);
+    float* tail = st + (size_t)DecStateC::kUp0 * S;
+    GemmI8Tap<S, NT, 8, 4, 8>(xq, 3 * S, 0, 1, 2, 128, 4, 2, 512, BlobPtr<uint32_t>(blob, up0.g.w), wbufq,
+      [&](int q, int s0, int n0, int (&acc)[8][4]) {
+        const int g = n0 / 128, r = (n0 % 128) / 64;
+        const float* bf = BlobPtr<float>(blob, up0.bias_f32[g]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int co = (n0 + j) % 64, ch = g * 64 + co;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int qv = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up0.out_zp[g]);
+            const float f = DequantizeI8(qv, up0.dq[g].scale, up0.dq[g].zp);
+            if (q == 0) {
+              float* o = u + (size_t)ch * LD2 + r * S + s0 + i;
+              *o = __fadd_rn(f, *o);
+            } else if (active[s0 + i]) {
+              tail[((size_t)ch * 2 + r) * S + s0 + i] = __fsub_rn(__fadd_rn(f, 0.0f), bf[co]);
+            }
+          }
+        }
+      });
+  }
+  // ---- LeakyReLU (f32) ; QUANTIZE -> aq rows 1..2
+  {
+    const QuantP q = P.up0_q;
+    for (int i = tid; i < 64 * 2 * S; i += NT) {
+      const int c4 = i / (2 * S), r = i % (2 * S);
+      int v[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[b] = QuantizeF32(LeakyRelu(u[(size_t)(c4 * 4 + b) * LD2 + r]), q.scale, q.zp);
+      aq[(size_t)c4 * 4 * S + S + r] = PackI8x4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  __syncthreads();
+  // ---- quant_decoder_0/resnet_0 (int8 body, f32 residual add)
+  DwI8Ring<S, NT>(aq, 4 * S, 1, dq8, LD2, 256, 2, 1, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18, active);
+  {
+    const int* bias = BlobPtr<int>(blob, P.m_pw1.bias);
+    const int* mult = BlobPtr<int>(blob, P.m_pw1.mult);
+    const int* shift = BlobPtr<int>(blob, P.m_pw1.shift);
+    const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
+    const int out_zp = P.m_pw1.out_zp;
+    GemmI8Tap<S, NT, 8, 4, 8>(dq8, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw1.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int q[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
+          hq[(size_t)(n0 / 4) * LD2 + t * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
+        }
+      });
+  }
+  {
+    const int* bias = BlobPtr<int>(blob, P.m_pw2.bias);
+    const int* mult = BlobPtr<int>(blob, P.m_pw2.mult);
+    const int* shift = BlobPtr<int>(blob, P.m_pw2.shift);
+    const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
+    const QuantP dq = P.m_dq, q2 = P.m_q2;
+    const int out_zp = P.m_pw2.out_zp;
+    GemmI8Tap<S, NT, 8, 4, 8>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int r[4], a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int q = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
+            const float v = __fadd_rn(DequantizeI8(q, dq.scale, dq.zp), u[(size_t)(n0 + j) * LD2 + t * S + s0 + i]);
+            r[j] = QuantizeF32(v, q2.scale, q2.zp);
+            a[j] = lut[r[j] + 128];
+          }
+          resq[(size_t)(n0 / 4) * LD2 + t * S + s0 + i] = PackI8x4(r[0], r[1], r[2], r[3]);
+          aq[(size_t)(n0 / 4) * 4 * S + (1 + t) * S + s0 + i] = PackI8x4(a[0], a[1], a[2], a[3]);
+        }
+      });
+  }
+  ResUnitI8<S, NT>(blob, P.q[0], aq, 4 * S, 1, resq, dq8, hq, 3, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, wbufq);
+  ResUnitI8<S, NT>(blob, P.q[1], aq, 4 * S, 1, resq, dq8, hq, 9, stw + (size_t)DecStateC::kRingQ1 * S, n18, active, wbufq);
+  // ---- quant_decoder_1 upsample: 2 x TRANSPOSE_CONV (K = 4, stride 2, 128 -> 64), T 2 -> 4 (+2 tail rows)
+  {
+    const uint32_t pad = PackI8x4(up1.g.in_zp, up1.g.in_zp, up1.g.in_zp, up1.g.in_zp);
+    for (int i = tid; i < 64 * S; i += NT) { const int c = i / S, s = i % S; aq[(size_t)c * 4 * S + s] = pad; aq[(size_t)c * 4 * S + 3 * S + s] = pad; }
+    // u1 [128][4S]: rows 0..1 carry the overlap, rows 2..3 start from +0 (the zeros of the reference's concat)
+    for (int i = tid; i < 128 * 4 * S; i += NT) {
+      const int c = i / (4 * S), r = i % (4 * S);
+      u1[i] = r < 2 * S ? st[DecStateC::kUp1 * S + (size_t)c * 2 * S + r] : 0.0f;
+    }
+  }
+  __syncthreads();
+  {
+    const int* bias = BlobPtr<int>(blob, up1.g.bias);
+    const int* mult = BlobPtr<int>(blob, up1.g.mult);
+    const int* shift = BlobPtr<int>(blob, up1.g.shift);
+    float* tail = st + (size_t)DecStateC::kUp1 * S;
+    GemmI8Tap<S, NT, 8, 4, 8>(aq, 4 * S, 0, 1, 2, 128, 2, 3, 256, BlobPtr<uint32_t>(blob, up1.g.w), wbufq,
+      [&](int q, int s0, int n0, int (&acc)[8][4]) {
+        const int g = n0 / 128, r = (n0 % 128) / 64;
+        const float* bf = BlobPtr<float>(blob, up1.bias_f32[g]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int co = (n0 + j) % 64, ch = g * 64 + co;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int qv = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up1.out_zp[g]);
+            const float f = DequantizeI8(qv, up1.dq[g].scale, up1.dq[g].zp);
+            if (q < 2) {
+              float* o = u1 + (size_t)ch * 4 * S + (2 * q + r) * S + s0 + i;
+              *o = __fadd_rn(f, *o);
+            } else if (active[s0 + i]) {
+              tail[((size_t)ch * 2 + r) * S + s0 + i] = __fsub_rn(__fadd_rn(f, 0.0f), bf[co]);
+            }
+          }
+        }
+      });
+  }
+  // ---- decoder_1: three fp32 residual units @128
+  const int ring_off[3] = {DecStateC::kRing0, DecStateC::kRing1, DecStateC::kRing2};
+  const int dil[3] = {1, 3, 9};
+  for (int i = 0; i < 3; ++i)
+    ResUnitF32<S, NT, 8, 4, 4>(blob, P.r1[i], u1, 4 * S, 0, d1, 128, 4, dil[i], 2, st + (size_t)ring_off[i] * S, n18, active, wbuf, i == 2);
+  {
+    float* out = mid + (size_t)tile * 128 * 4 * S;
+    for (int i = tid; i < 128 * 4 * S; i += NT) out[i] = u1[i];
+  }
+  if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
+}
+
+// ================================================================================================
+//                                        DECODER  D
+// ================================================================================================
+template <int S>
+struct DecD {
+  static constexpr int NT = 320;
+  static constexpr int LDU = 26 * S, LDD = 20 * S;          // u: 3 zero rows + 20 + 3 zero rows
+  static constexpr int kU = 0;
+  static constexpr int kD = kU + 64 * LDU * 4;              // d f32 [64][20S]; aliases X f32 [128][6S] and the PCM staging
+  static constexpr int kW = kD + 64 * LDD * 4;
+  static constexpr int kSl = kW + 2 * 8 * 320 * 4;          // carried tail of last_layer [48][S]
+  static constexpr int kI = kSl + 48 * S * 4;
+  static constexpr int kSmemBytes = kI + 3 * S * 4;
+  static_assert(128 * 6 * S <= 64 * LDD, "X must fit in d");
+};
+
+template <int S>
+__global__ void __launch_bounds__(320, 1)
+DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, const float* __restrict__ mid,
+               float* __restrict__ state, int* __restrict__ n18g, int16_t* __restrict__ pcm) {
+  using L = DecD<S>;
+  constexpr int NT = L::NT;
+  unsigned char* smem = LYRA_DYN_SMEM();
+  float* u = reinterpret_cast<float*>(smem + L::kU);
+  float* d = reinterpret_cast<float*>(smem + L::kD);
+  float* X = d;
+  float* wbuf = reinterpret_cast<float*>(smem + L::kW);
+  float* sl = reinterpret_cast<float*>(smem + L::kSl);
+  int* slot = reinterpret_cast<int*>(smem + L::kI);
+  int* active = slot + S;
+  int* n18 = active + S;
+  int tile;
+  LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
+  float* st = state + (size_t)tile * DecStateD::kUnits * S;
+  const int tid = (int)threadIdx.x;
+
+  // ---- X [128][6S]: zero row, 4 rows from kernel C, zero row
+  {
+    const float* in = mid + (size_t)tile * 128 * 4 * S;
+    for (int i = tid; i < 128 * 6 * S; i += NT) {
+      const int c = i / (6 * S), r = i % (6 * S);
+      X[i] = (r >= S && r < 5 * S) ? in[(size_t)c * 4 * S + (r - S)] : 0.0f;
+    }
+    // u rows: 3 zero rows | rows 0..4 carry the overlap of decoder_2/simple, rows 5..19 start from +0 | 3 zero rows
+    for (int i = tid; i < 64 * 26 * S; i += NT) {
+      const int c = i / (26 * S), r = i % (26 * S);
+      u[i] = (r >= 3 * S && r < 8 * S) ? st[DecStateD::kUp2 * S + (size_t)c * 5 * S + (r - 3 * S)] : 0.0f;
+    }
+    for (int i = tid; i < 48 * S; i += NT) sl[i] = st[DecStateD::kLast * S + i];
+  }
+  __syncthreads();
+  // ---- decoder_2/simple: TRANSPOSE_CONV K = 10, stride 5, 128 -> 64 ; T 4 -> 20 (+5 tail rows)
+  {
+    const float* b = BlobPtr<float>(blob, P.up2.bias);
+    float* tail = st + (size_t)DecStateD::kUp2 * S;
+    GemmF32Tap<S, NT, 8, 10, 8, false>(X, 6 * S, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float>(blob, P.up2.w), wbuf, false,
+      [&](int q, int s0, int n0, float (&acc)[8][10]) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          const int r = (n0 + j) / 64, co = (n0 + j) % 64;
+          const float bias = b[co];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float y = __fadd_rn(acc[i][j], bias);
+            if (q < 4) {
+              float* o = u + (size_t)co * L::LDU + (3 + 5 * q + r) * S + s0 + i;
+              *o = __fadd_rn(y, *o);
+            } else if (active[s0 + i]) {
+              tail[((size_t)co * 5 + r) * S + s0 + i] = __fsub_rn(__fadd_rn(y, 0.0f), bias);
+            }
+          }
+        }
+      });
+  }
+  // ---- decoder_2: three residual units @64, T = 20
+  const int ring_off[3] = {DecStateD::kRing0, DecStateD::kRing1, DecStateD::kRing2};
+  const int dil[3] = {1, 3, 9};
+  for (int i = 0; i < 3; ++i)
+    ResUnitF32<S, NT, 8, (S >= 16 ? 8 : 4), (S >= 16 ? 8 : 4)>(blob, P.r2[i], u, L::LDU, 3, d, 64, 20, dil[i], 1,
+                                                              st + (size_t)ring_off[i] * S, n18, active, wbuf, i == 2);
+  // ---- last_layer: TRANSPOSE_CONV K = 64, stride 16, 64 -> 1 ; T 20 -> 320 (+48 tail) ; float -> int16
+  {
+    const float bias = BlobPtr<float>(blob, P.last.bias)[0];
+    float* tail = st + (size_t)DecStateD::kLast * S;
+    int16_t* stage = reinterpret_cast<int16_t*>(d);      // [S][320]
+    GemmF32Tap<S, NT, 8, 4, 16, false>(u, L::LDU, 0, 1, 4, 64, 1, 23, 16, BlobPtr<float>(blob, P.last.w), wbuf, false,
+      [&](int q, int s0, int n0, float (&acc)[8][4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int t = 16 * q + n0 + j;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float y = __fadd_rn(__fadd_rn(acc[i][j], bias), t < 48 ? sl[t * S + s0 + i] : 0.0f);
+            if (t < 320) {
+              // UnitToInt16Scalar (dsp_utils.h:53-60,79-88): scale, clip in float, truncate
+              float v = __fmul_rn(y, 32768.0f);
+              v = v > -32768.0f ? v : -32768.0f;
+              v = v < 32767.0f ? v : 32767.0f;
+              stage[(s0 + i) * 320 + t] = (int16_t)(int)v;
+            } else if (active[s0 + i]) {
+              tail[(t - 320) * S + s0 + i] = __fsub_rn(y, bias);
+            }
+          }
+        }
+      });
+    for (int i = tid; i < S * 320; i += NT) {
+      const int s = i / 320;
+      if (active[s]) pcm[(size_t)slot[s] * 320 + (i % 320)] = stage[i];
+    }
+  }
+  if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
+}
+
+}  // namespace lyra_b200

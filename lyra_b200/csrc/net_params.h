@@ -1,0 +1,92 @@
+// Plain-old-data layer descriptors shared by the host-side spec builder (model_spec.cc) and the
+// kernels.  All weights live in ONE device blob; descriptors hold byte offsets into it.
+//
+// Layer naming follows the reference graphs:
+//   encoder: first_layer -> encoder_0 (3 res-units @64, T=20) -> encoder_0/simpleconv (K10 s5)
+//            -> encoder_1 (3 res-units @128, T=4) -> encoder_1/simpleconv (K4 s2, g2)
+//            -> encoder_2/resnet_0 (mixed f32/int8 @256, T=2) -> quant_encoder_2 (2 int8 res-units)
+//            -> quant_encoder_2/simpleconv (K4 s2, g4) -> quant_bottleneck_1 (K3, g4) -> f32[64]
+//   decoder: bottleneck_2 (K3, g4) -> quant_decoder_0 upsample (4 int8 transposed convs) -> 3 int8
+//            res-units @256 -> quant_decoder_1 upsample (2 int8 transposed convs) -> decoder_1
+//            (3 res-units @128, T=4) -> decoder_2/simple (transposed K10 s5) -> decoder_2
+//            (3 res-units @64, T=20) -> last_layer (transposed K64 s16) -> f32[320]
+#pragma once
+
+#include <stdint.h>
+
+namespace lyra_b200 {
+
+// fp32 GEMM-shaped convolution: weights [Ktot][N] k-major (k = tap*CinG + ci), bias [N]
+struct GemmF32 { uint32_t w, bias; };
+// int8 convolution: weights [Ktot/4][N] words (4 consecutive ci per word), bias folded with the
+// input zero point (bias + (-zp_in) * sum(w)), per-channel Q31 multiplier and shift
+struct GemmI8 { uint32_t w, bias, mult, shift; int32_t out_zp; int32_t in_zp; };
+struct DwF32 { uint32_t w, bias; };                       // w [3][C]
+struct DwI8 { uint32_t w, bias, mult, shift; int32_t out_zp; int32_t in_zp; };   // w [3][C] int32
+struct LReluQ { uint32_t lut; };                          // int8[256], index = q + 128
+struct AddQ { uint32_t lut1, lut2; int32_t m3, s3, out_zp; };   // int32[256] each
+struct QuantP { float scale; int32_t zp; };
+
+struct ResF32 { DwF32 dw; GemmF32 pw1, pw2; };
+struct ResI8 { DwI8 dw; GemmI8 pw1; LReluQ lr1; GemmI8 pw2; AddQ add; LReluQ lr2; };
+
+struct EncoderParams {
+  // ---- kernel A: T = 20, 64 channels
+  GemmF32 first;            // first_layer: K=64 s=16, 1 -> 64
+  ResF32 r0[3];             // encoder_0/resnet_{0,1,2}: dilation 1/3/9
+  GemmF32 down0;            // encoder_0/simpleconv: K=10 s=5, 64 -> 128
+  // ---- kernel B: T = 4 / 2 / 1
+  ResF32 r1[3];             // encoder_1/resnet_*: second 1x1 has groups = 2
+  GemmF32 down1;            // encoder_1/simpleconv: K=4 s=2, 128 -> 256, groups = 2
+  DwF32 m_dw;               // encoder_2/resnet_0 (mixed precision unit)
+  GemmF32 m_pw1;
+  QuantP m_q1; LReluQ m_lr1; GemmI8 m_pw2; QuantP m_dq; QuantP m_q2; LReluQ m_lr2;
+  ResI8 q[2];               // quant_encoder_2/resnet_{1,2}: dilation 3/9
+  GemmI8 down2; LReluQ down2_lr;   // quant_encoder_2/simpleconv: K=4 s=2, 256 -> 512, g = 4
+  GemmI8 bott; QuantP out_dq;      // quant_bottleneck_1: K=3, 512 -> 64, g = 4; DEQUANTIZE
+  // zero points used to initialise int8 state (real value 0): ring of q[0], q[1], down2, bott
+  int32_t zp_state[4];
+};
+
+// A bank of G parallel int8 TRANSPOSE_CONVs over a channel split (quant_decoder_{0,1}/simple_g*), fused
+// into one grouped tap-GEMM: weights [(j,ci)/4][g*128 + r*64 + co] words, per-column bias/mult/shift.
+struct UpI8 {
+  GemmI8 g;                 // out_zp unused (per group below); in_zp = zero point of the shared input
+  QuantP dq[4];             // DEQUANTIZE of each group's int8 output
+  int32_t out_zp[4];
+  uint32_t bias_f32[4];     // the f32 constants subtracted from the overlap tails (SUB ops), [64] each
+};
+
+struct DecoderParams {
+  // ---- kernel C: T = 1 / 2 / 4
+  GemmF32 bott;             // bottleneck_2/simpleconv: K=3, 64 -> 512, g = 4
+  QuantP bott_q;            // QUANTIZE after its LeakyReLU
+  UpI8 up0;                 // quant_decoder_0/simple_g{0..3}: K=4 s=2, 128 -> 64 each
+  QuantP up0_q;             // QUANTIZE of LeakyReLU(concat)
+  // quant_decoder_0/resnet_0 is mixed: int8 body, f32 residual add
+  DwI8 m_dw; GemmI8 m_pw1; LReluQ m_lr1; GemmI8 m_pw2; QuantP m_dq; QuantP m_q2; LReluQ m_lr2;
+  ResI8 q[2];               // quant_decoder_0/resnet_{1,2}
+  UpI8 up1;                 // quant_decoder_1/simple_g{0,1}: K=4 s=2, 128 -> 64 each
+  ResF32 r1[3];             // decoder_1/resnet_*: 128 ch, second 1x1 groups = 2
+  // ---- kernel D: T = 20
+  GemmF32 up2;              // decoder_2/simple: transposed K=10 s=5, 128 -> 64; weights [(j,ci)][(r,co)], bias [64]
+  ResF32 r2[3];             // decoder_2/resnet_*: 64 ch
+  GemmF32 last;             // last_layer: transposed K=64 s=16, 64 -> 1; weights [(j,ci)][r], bias [1]
+  int32_t zp_state[3];      // int8 ring zero points: m_dw ring, q[0], q[1]
+};
+
+struct RvqParams {
+  uint32_t codebooks_t;     // f32 [46][64][16]  (stage, dim, code): transposed for conflict-free lanes
+  uint32_t codebooks;       // f32 [46][16][64]
+  int32_t num_stages;       // 46
+};
+
+struct LogMelParams {
+  uint32_t window;          // f64 [640]
+  uint32_t twiddle;         // f64 [512][2]  cos, sin of -2*pi*k/1024
+  uint32_t weights;         // f64 [513]
+  uint32_t band;            // i32 [513]
+  int32_t start_index, end_index, num_mel, fft, window_len, hop;
+};
+
+}  // namespace lyra_b200

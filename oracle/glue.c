@@ -26,7 +26,9 @@ int lo_packet_size(int num_header_bits, int num_quantized_bits) {
 }
 
 int lo_packet_pack(const char* bits, int nh, int nq, uint8_t* bytes) {
-  if (nh + nq > 184 || nh < 0 || nq < 0) return -1;                             /* packet.h:41-48 */
+  /* Packet<MaxNumPacketBits>::Create rejects header + payload > MaxNumPacketBits (packet.h:41-48); Lyra
+     instantiates 184 (lyra_components.cc:33,57-60), packet_test.cc up to 204: the cap here is the buffer's */
+  if (nh + nq > 256 || nh < 0 || nq < 0) return -1;
   const int total = nh + nq, nb = lo_packet_size(nh, nq);
   memset(bytes, 0, (size_t)nb);
   /* header bits are all zero today (SetHeader, packet.h:160-170); payload follows MSB-first; the
