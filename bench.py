@@ -1,0 +1,317 @@
+#!/usr/bin/env python3
+"""Headline benchmark: 20 ms-frame encode+decode throughput (frames/s) at 16 kHz.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU arm
+
+One "step" = one 20 ms hop of every stream: PCM -> SoundStream encoder -> RVQ -> packet bytes -> RVQ decode ->
+LyraGAN -> PCM, for `--streams` (default 4096) concurrent 16 kHz streams per GPU.  One process per GPU (torchrun
+for N > 1); streams are independent, so ranks shard them with no data-path collective (weak scaling); NCCL is
+only used for the barrier and the max-over-ranks of the elapsed time.
+
+The CPU arm (`--impl reference`, and the `cpu_baseline` object of the normal run) is the plain-C restatement
+of the reference algorithm in oracle/ run on all host cores, one stream per thread like TFLite's
+num_threads = 1 (the reference binary itself cannot be built offline: no bazel / TFLite / abseil).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "20ms-frame encode+decode throughput (frames/s) @16kHz"
+UNIT = "frames/s"
+SEED = 0x4C595241
+
+# Algorithmic bytes per stream-frame (SURVEY.md §8d / BASELINE.md §2; fp32 state, read every state element once +
+# write the new rows, + PCM + packet), split by the kernel that owns the state:
+#   encoder: (13,808 + 6,128) * 4 = 79,744 B state + 640 B PCM + P B packet
+#   decoder: (12,912 + 5,680) * 4 = 74,368 B state + 640 B PCM + P B packet
+ALGO_BYTES = {
+    "EncoderKernelA": (2032 + 2032) * 4 + 640,                 # first_layer + encoder_0 rings + simpleconv carry, PCM in
+    "EncoderKernelB": (11776 + 4096) * 4,                      # the rest of the encoder state
+    "RvqEncodeKernel": 0,                                      # + P (added per run)
+    "RvqDecodeKernel": 0,                                      # + P
+    "DecoderKernelC": (10880 + 3648) * 4,                      # bottleneck_2 .. decoder_1 state
+    "DecoderKernelD": (2032 + 2032) * 4 + 640,                 # decoder_2 + last_layer state, PCM out
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_pcm_np(n, nbuf, seed):
+    """Seeded synthetic input: uniform noise at 0.25 full scale (the reference benchmark feeds uniform random audio,
+    lyra/lyra_benchmark_lib.cc:233-239); `nbuf` distinct hops are rotated through the steps."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    return rng.integers(-8192, 8192, size=(nbuf, n, 320), dtype=np.int16)
+
+
+def run_cpu_arm(streams, frames, bits, threads):
+    from oracle import oracle as O
+    from lyra_b200 import _capi
+    r = O.cpu_bench(_capi.MODEL_DIR, streams, frames, bits, threads, SEED)
+    return r
+
+
+def cpu_calibrated_sample(bits, threads, target_s):
+    """Pick (streams, frames) so the CPU arm runs for about target_s seconds on `threads` cores."""
+    probe = run_cpu_arm(threads, 4, bits, threads)
+    per_frame_s = probe["wall_s"] / 4.0                       # one frame of every thread's stream
+    frames = max(8, int(target_s / max(per_frame_s, 1e-6)))
+    return threads, frames
+
+
+def reference_arm(args, rank, world):
+    """`--impl reference`: the reference algorithm's CPU implementation (oracle port) on all host cores."""
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    bits = args.bits
+    streams, frames = cpu_calibrated_sample(bits, threads, max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        run_cpu_arm(streams, max(2, frames // 8), bits, threads)
+    t_total, f_total, stage = 0.0, 0, [0.0] * 4
+    for _ in range(args.steps):
+        r = run_cpu_arm(streams, frames, bits, threads)
+        t_total += r["wall_s"]
+        f_total += r["frames"]
+        stage = [a + b for a, b in zip(stage, r["stage_us"])]
+    value = f_total / t_total
+    sample = "%d streams x %d hops per step (one stream per thread), uniform noise 0.25 FS, %d bits" % (streams, frames, bits)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+i8", "data": "synthetic",
+        "config": {"workload": "%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode" % (args.streams, bits * 50 / 1000.0),
+                   "streams_per_gpu": args.streams, "bits_per_frame": bits,
+                   "note": "CPU arm: bounded sample of the same workload; the reference binary cannot be built offline, "
+                           "this is the oracle's C restatement of its algorithm (kind=port)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "stage_us_per_frame": {k: v / args.steps for k, v in zip(
+                             ["feature_extractor", "quantizer_quantize", "quantizer_decode", "model_decode"], stage)}},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
+    ap.add_argument("--bits", type=int, default=64, help="quantized bits per frame: 64 / 120 / 184 (3.2 / 6.0 / 9.2 kbps)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lyra_b200 import _capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, bits = args.streams, args.bits
+    P = (bits + 7) // 8
+    ctx = _capi.Context(n, device=local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    NBUF = 8
+    host = synth_pcm_np(n, NBUF, SEED + rank)
+    d_pcm = [torch.from_numpy(host[i]).cuda() for i in range(NBUF)]
+    d_pk = torch.zeros((n, P), dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros((n, 320), dtype=torch.int16, device="cuda")
+
+    def step_device(i):
+        ctx.encode_device(n, d_pcm[i % NBUF].data_ptr(), bits, d_pk.data_ptr())
+        ctx.decode_device(n, d_pk.data_ptr(), 0, bits, d_out.data_ptr())
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for i in range(max(3, args.warmup)):
+        step_device(i)
+    barrier()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    elapsed_ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    clocks = sampler.stop()
+    gpu_launches = ctx.launch_count - launches0
+    barrier()
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * n * args.steps / (elapsed_ms / 1e3)
+
+    # ---------------- end to end through the host-buffer C ABI (`e2e`) ----------------
+    pin_in = [torch.from_numpy(host[i]).pin_memory() for i in range(NBUF)]
+    pin_pk = torch.zeros((n, P), dtype=torch.uint8).pin_memory()
+    pin_out = torch.zeros((n, 320), dtype=torch.int16).pin_memory()
+    lib, h = ctx.api.lib, ctx.h
+    import ctypes as C
+
+    def step_host(i):
+        rc = lib.lyra_b200_encode(h, None, n, C.c_void_p(pin_in[i % NBUF].data_ptr()), bits, C.c_void_p(pin_pk.data_ptr()))
+        rc |= lib.lyra_b200_decode(h, None, n, C.c_void_p(pin_pk.data_ptr()), None, bits, C.c_void_p(pin_out.data_ptr()))
+        if rc:
+            raise RuntimeError("host API failed: %s" % lib.lyra_b200_last_error(h))
+
+    for i in range(3):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / float(t.item())
+    checksum = int(pin_out.to(torch.int64).sum().item())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kern = {}
+        for k, (ms, cnt) in prof.items():
+            if cnt:
+                ab = ALGO_BYTES.get(k, 0) + (P if k.startswith("Rvq") else 0)
+                kern[k] = {"ms_per_launch": ms / cnt, "launches": cnt, "algo_bytes_per_launch": ab * n,
+                           "achieved_gbs": ab * n / (ms / cnt * 1e-3) / 1e9}
+        dom = max(kern, key=lambda k: kern[k]["ms_per_launch"])
+        total_algo = (79744 + 640 + P) + (74368 + 640 + P)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "kernel_share_of_step": kern[dom]["ms_per_launch"] / sum(v["ms_per_launch"] for v in kern.values()),
+                    "whole_step": {"algo_bytes_per_frame": total_algo,
+                                   "achieved_gbs": total_algo * n * args.steps / (elapsed_ms / 1e3) / 1e9 if world == 1 else None,
+                                   "frac": (total_algo * n * args.steps / (elapsed_ms / 1e3) / 1e9) / peak if world == 1 else None},
+                    "kernels": kern}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            s, f = cpu_calibrated_sample(bits, threads, 12.0)
+            r = run_cpu_arm(s, f, bits, threads)
+            cpu = {"value": r["frames_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "%d streams x %d hops, one stream per thread, uniform noise 0.25 FS, %d bits" % (s, f, bits),
+                   "stage_us_per_frame": dict(zip(["feature_extractor", "quantizer_quantize", "quantizer_decode", "model_decode"], r["stage_us"]))}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i8", "data": "synthetic",
+            "config": {"workload": "%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode "
+                                   "(BASELINE configs[2] at %.1f kbps; the north_star target size)" % (n, bits * 50 / 1000.0, bits * 50 / 1000.0),
+                       "streams_per_gpu": n, "bits_per_frame": bits, "tile_streams": ctx.tile_streams,
+                       "real_time_factor": value / (50.0 * n * world),
+                       "l2": "no flush needed: per-step state working set %d x %.0f KB = %.0f MB exceeds the 126 MB L2; PCM inputs rotate over %d buffers"
+                             % (n, (EncDecStateBytes()) / 1024.0, n * EncDecStateBytes() / 1e6, NBUF),
+                       "parallelism": "streams sharded by rank, no data-path collective",
+                       "output_checksum": checksum},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (640 + P), "d2h_bytes_per_step": n * (P + 640)},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def EncDecStateBytes():
+    # bytes of streaming state this implementation keeps per stream (fp32 rings + packed int8 rings), 4 kernels
+    return 4 * (2032 + 6016 + 5888 + 2032)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -103,6 +103,14 @@ int lyra_b200_synchronize(lyra_b200_ctx* ctx);
 /* number of CUDA kernels this context has launched so far */
 uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx);
 
+/* ---- diagnostics: per-kernel device time measured with CUDA events on the launching stream.
+ *      Kernel order: 0 EncoderKernelA, 1 EncoderKernelB, 2 RvqEncodeKernel, 3 RvqDecodeKernel,
+ *      4 DecoderKernelC, 5 DecoderKernelD, 6 LogMelKernel.  profile_read synchronises the stream and
+ *      returns the accumulated milliseconds / launch counts since profiling was enabled. */
+#define LYRA_B200_NUM_KERNELS 7
+int lyra_b200_profile_enable(lyra_b200_ctx* ctx, int enable);
+int lyra_b200_profile_read(lyra_b200_ctx* ctx, double* ms_sum, uint64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

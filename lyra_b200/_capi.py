@@ -52,6 +52,8 @@ class CApi:
             "lyra_b200_decode_device": (ci, [vp, ci, vp, vp, ci, vp]),
             "lyra_b200_synchronize": (ci, [vp]),
             "lyra_b200_launch_count": (C.c_uint64, [vp]),
+            "lyra_b200_profile_enable": (ci, [vp, ci]),
+            "lyra_b200_profile_read": (ci, [vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)   # AttributeError here = the library does not export the declared ABI
@@ -64,7 +66,8 @@ class CApi:
                "lyra_b200_tile_streams", "lyra_b200_reset", "lyra_b200_encode", "lyra_b200_decode",
                "lyra_b200_extract_features", "lyra_b200_quantize", "lyra_b200_dequantize", "lyra_b200_generate",
                "lyra_b200_logmel", "lyra_b200_set_stream", "lyra_b200_encode_device", "lyra_b200_decode_device",
-               "lyra_b200_synchronize", "lyra_b200_launch_count"]
+               "lyra_b200_synchronize", "lyra_b200_launch_count", "lyra_b200_profile_enable",
+               "lyra_b200_profile_read"]
 
 
 _product = None
@@ -203,3 +206,16 @@ class Context:
 
     def synchronize(self):
         self._check(self.api.lib.lyra_b200_synchronize(self.h))
+
+    KERNEL_NAMES = ["EncoderKernelA", "EncoderKernelB", "RvqEncodeKernel", "RvqDecodeKernel", "DecoderKernelC",
+                    "DecoderKernelD", "LogMelKernel"]
+
+    def profile_enable(self, enable=True):
+        self._check(self.api.lib.lyra_b200_profile_enable(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> {kernel name: (total ms, launches)} since profiling was enabled (CUDA events on the launch stream)."""
+        ms = (C.c_double * 7)()
+        cnt = (C.c_uint64 * 7)()
+        self._check(self.api.lib.lyra_b200_profile_read(self.h, ms, cnt))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNEL_NAMES)}

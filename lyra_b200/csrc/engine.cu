@@ -57,11 +57,51 @@ struct lyra_b200_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   uint64_t launches = 0;
   std::string err;
+  // diagnostics: CUDA-event timing of every kernel launch
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[LYRA_B200_NUM_KERNELS];
+  size_t prof_used[LYRA_B200_NUM_KERNELS] = {0, 0, 0, 0, 0, 0, 0};
+  double prof_ms[LYRA_B200_NUM_KERNELS] = {0, 0, 0, 0, 0, 0, 0};
+  uint64_t prof_n[LYRA_B200_NUM_KERNELS] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
 
 int PacketBytes(int num_bits) { return (num_bits + 7) / 8; }
+
+// RAII pair of events around one kernel launch (no-op unless profiling is enabled)
+struct ProfScope {
+  lyra_b200_ctx* ctx;
+  int k;
+  cudaEvent_t stop = nullptr;
+  ProfScope(lyra_b200_ctx* c, int kernel) : ctx(c), k(kernel) {
+    if (!ctx->profiling) return;
+    auto& pool = ctx->prof_events[k];
+    if (ctx->prof_used[k] == pool.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      pool.emplace_back(a, b);
+    }
+    auto& ev = pool[ctx->prof_used[k]++];
+    cudaEventRecord(ev.first, ctx->stream);
+    stop = ev.second;
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, ctx->stream); }
+};
+
+void ProfDrain(lyra_b200_ctx* ctx) {
+  for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k) {
+    for (size_t i = 0; i < ctx->prof_used[k]; ++i) {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, ctx->prof_events[k][i].first, ctx->prof_events[k][i].second) == cudaSuccess) {
+        ctx->prof_ms[k] += ms;
+        ctx->prof_n[k] += 1;
+      }
+    }
+    ctx->prof_used[k] = 0;
+  }
+}
 
 bool BitsOk(lyra_b200_ctx* ctx, int num_bits) {
   // lyra/residual_vector_quantizer.cc:79-89,116-126
@@ -94,10 +134,12 @@ int PrepareMap(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
 
 int LaunchEncoderNets(lyra_b200_ctx* ctx, const int16_t* d_pcm, float* d_features) {
   const TileIo io{ctx->d_tile_list, ctx->d_slot_of};
+  { ProfScope ps(ctx, 0);
   LYRA_LAUNCH(EncoderKernelA<kS>, dim3((unsigned)ctx->active_tiles), dim3(EncA<kS>::NT), (size_t)EncA<kS>::kSmemBytes, ctx->stream,
-              ctx->d_blob, ctx->spec.enc, io, d_pcm, reinterpret_cast<float*>(ctx->d_state[0]), ctx->d_n18[0], ctx->d_mid_enc);
+              ctx->d_blob, ctx->spec.enc, io, d_pcm, reinterpret_cast<float*>(ctx->d_state[0]), ctx->d_n18[0], ctx->d_mid_enc); }
+  { ProfScope ps(ctx, 1);
   LYRA_LAUNCH(EncoderKernelB<kS>, dim3((unsigned)ctx->active_tiles), dim3(EncB<kS>::NT), (size_t)EncB<kS>::kSmemBytes, ctx->stream,
-              ctx->d_blob, ctx->spec.enc, io, ctx->d_mid_enc, reinterpret_cast<float*>(ctx->d_state[1]), ctx->d_n18[1], d_features);
+              ctx->d_blob, ctx->spec.enc, io, ctx->d_mid_enc, reinterpret_cast<float*>(ctx->d_state[1]), ctx->d_n18[1], d_features); }
   ctx->launches += 2;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
@@ -106,8 +148,9 @@ int LaunchEncoderNets(lyra_b200_ctx* ctx, const int16_t* d_pcm, float* d_feature
 int LaunchQuantize(lyra_b200_ctx* ctx, const float* d_features, int n, int num_bits, uint8_t* d_packets, int* d_indices) {
   const int nq = num_bits / ctx->spec.bits_per_stage;
   const int blocks = (n + kRvqSlotsPerBlock - 1) / kRvqSlotsPerBlock;
+  { ProfScope ps(ctx, 2);
   LYRA_LAUNCH(RvqEncodeKernel, dim3((unsigned)blocks), dim3(kRvqThreads), (size_t)(kRvqSlotsPerBlock * (64 * 4 + 48 * 4)), ctx->stream,
-              ctx->d_blob, ctx->spec.rvq, d_features, n, nq, d_packets, PacketBytes(num_bits), d_indices);
+              ctx->d_blob, ctx->spec.rvq, d_features, n, nq, d_packets, PacketBytes(num_bits), d_indices); }
   ctx->launches += 1;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
@@ -116,8 +159,9 @@ int LaunchQuantize(lyra_b200_ctx* ctx, const float* d_features, int n, int num_b
 int LaunchDequantize(lyra_b200_ctx* ctx, const uint8_t* d_packets, const uint8_t* d_received, int n, int num_bits, float* d_features) {
   const int nq = num_bits / ctx->spec.bits_per_stage;
   const int blocks = (n * 64 + 255) / 256;
+  { ProfScope ps(ctx, 3);
   LYRA_LAUNCH(RvqDecodeKernel, dim3((unsigned)blocks), dim3(256), (size_t)0, ctx->stream,
-              ctx->d_blob, ctx->spec.rvq, d_packets, PacketBytes(num_bits), d_received, n, nq, d_features);
+              ctx->d_blob, ctx->spec.rvq, d_packets, PacketBytes(num_bits), d_received, n, nq, d_features); }
   ctx->launches += 1;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
@@ -125,10 +169,12 @@ int LaunchDequantize(lyra_b200_ctx* ctx, const uint8_t* d_packets, const uint8_t
 
 int LaunchDecoderNets(lyra_b200_ctx* ctx, const float* d_features, int16_t* d_pcm) {
   const TileIo io{ctx->d_tile_list, ctx->d_slot_of};
+  { ProfScope ps(ctx, 4);
   LYRA_LAUNCH(DecoderKernelC<kS>, dim3((unsigned)ctx->active_tiles), dim3(DecC<kS>::NT), (size_t)DecC<kS>::kSmemBytes, ctx->stream,
-              ctx->d_blob, ctx->spec.dec, io, d_features, reinterpret_cast<float*>(ctx->d_state[2]), ctx->d_n18[2], ctx->d_mid_dec);
+              ctx->d_blob, ctx->spec.dec, io, d_features, reinterpret_cast<float*>(ctx->d_state[2]), ctx->d_n18[2], ctx->d_mid_dec); }
+  { ProfScope ps(ctx, 5);
   LYRA_LAUNCH(DecoderKernelD<kS>, dim3((unsigned)ctx->active_tiles), dim3(DecD<kS>::NT), (size_t)DecD<kS>::kSmemBytes, ctx->stream,
-              ctx->d_blob, ctx->spec.dec, io, ctx->d_mid_dec, reinterpret_cast<float*>(ctx->d_state[3]), ctx->d_n18[3], d_pcm);
+              ctx->d_blob, ctx->spec.dec, io, ctx->d_mid_dec, reinterpret_cast<float*>(ctx->d_state[3]), ctx->d_n18[3], d_pcm); }
   ctx->launches += 2;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
@@ -270,6 +316,8 @@ void lyra_b200_destroy(lyra_b200_ctx* ctx) {
   cudaFree(ctx->d_logmel_prev[0]); cudaFree(ctx->d_logmel_prev[1]);
   cudaFree(ctx->d_pcm); cudaFree(ctx->d_packets); cudaFree(ctx->d_received); cudaFree(ctx->d_features);
   cudaFree(ctx->d_melout); cudaFree(ctx->d_indices); cudaFree(ctx->d_ids); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_slot_of);
+  for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k)
+    for (auto& ev : ctx->prof_events[k]) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -278,6 +326,23 @@ const char* lyra_b200_last_error(const lyra_b200_ctx* ctx) { return ctx ? ctx->e
 int lyra_b200_max_streams(const lyra_b200_ctx* ctx) { return ctx ? ctx->max_streams : 0; }
 int lyra_b200_tile_streams(const lyra_b200_ctx* ctx) { return ctx ? kS : 0; }
 uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lyra_b200_profile_enable(lyra_b200_ctx* ctx, int enable) {
+  if (!ctx) return LYRA_B200_EINVAL;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ProfDrain(ctx);
+  ctx->profiling = enable != 0;
+  if (enable) for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_profile_read(lyra_b200_ctx* ctx, double* ms_sum, uint64_t* launches) {
+  if (!ctx || !ms_sum || !launches) return LYRA_B200_EINVAL;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ProfDrain(ctx);
+  for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k) { ms_sum[k] = ctx->prof_ms[k]; launches[k] = ctx->prof_n[k]; }
+  return LYRA_B200_OK;
+}
 
 int lyra_b200_reset(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n) {
   if (!ctx) return LYRA_B200_EINVAL;
@@ -408,8 +473,9 @@ int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* ids, int n, co
   const LogMelParams& P = num_mel_bins == 160 ? ctx->spec.logmel160 : ctx->spec.logmel64;
   CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   const size_t smem = sizeof(double) * (size_t)(2 * P.fft + P.fft / 2 + 1);
+  { ProfScope ps(ctx, 6);
   LYRA_LAUNCH(LogMelKernel, dim3((unsigned)n), dim3(256), smem, ctx->stream,
-              ctx->d_blob, P, d_ids, n, ctx->d_pcm, ctx->d_logmel_prev[bank], ctx->d_melout);
+              ctx->d_blob, P, d_ids, n, ctx->d_pcm, ctx->d_logmel_prev[bank], ctx->d_melout); }
   ctx->launches += 1;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, ctx->d_melout, sizeof(float) * (size_t)num_mel_bins * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));

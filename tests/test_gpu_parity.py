@@ -1,0 +1,136 @@
+"""GPU tier (B200): parity tests proper, through the C ABI of the nvcc-built library, against the oracle on the
+same seeded inputs; plus size-independent properties at BASELINE.json's full sizes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from conftest import GOLDEN_DIR
+from lyra_b200 import _capi
+
+pytestmark = pytest.mark.gpu
+
+
+def test_codec_parity_speech_with_loss(gpu_api, oracle, sample1):
+    pc.run_codec_parity(_capi.Context, gpu_api, oracle, max_streams=100, stream_ids=[0, 5, 17, 31, 32, 64, 99],
+                        frames=60, bits=64, wav=sample1, loss_every=6)
+
+
+@pytest.mark.parametrize("bits", [64, 120, 184])
+def test_codec_parity_noise_all_bitrates(gpu_api, oracle, bits):
+    pc.run_codec_parity(_capi.Context, gpu_api, oracle, max_streams=48, stream_ids=list(range(48)), frames=25, bits=bits,
+                        seed=bits, check=[0, 1, 15, 16, 33, 47])
+
+
+@pytest.mark.parametrize("kind", ["loud", "silence"])
+def test_codec_parity_extreme_inputs(gpu_api, oracle, kind):
+    pc.run_codec_parity(_capi.Context, gpu_api, oracle, max_streams=16, stream_ids=[3, 4, 9], frames=12, bits=120, kind=kind)
+
+
+def test_non_standard_bit_counts(gpu_api, oracle):
+    # any multiple of 4 up to 184 is accepted by Quantize (residual_vector_quantizer.cc:79-89)
+    for bits in (4, 60, 100, 180):
+        pc.run_codec_parity(_capi.Context, gpu_api, oracle, max_streams=4, stream_ids=[2], frames=2, bits=bits, seed=bits)
+
+
+def test_plugin_surface(gpu_api, oracle):
+    pc.run_plugin_surface_parity(_capi.Context, gpu_api, oracle, n=9, frames=4)
+
+
+def test_reset_and_isolation(gpu_api, oracle):
+    pc.run_reset_and_isolation(_capi.Context, gpu_api, oracle)
+
+
+def test_error_paths(gpu_api):
+    pc.run_error_paths(_capi.Context, gpu_api, _capi.LyraB200Error)
+
+
+def test_logmel(gpu_api, oracle, sample1):
+    pc.run_logmel_parity(_capi.Context, gpu_api, oracle, sample1, n=6, frames=8)
+
+
+def test_golden_fixture_packets(gpu_api, sample1):
+    """Committed fixtures (tests/golden/oracle_sample1.json): the GPU path reproduces them without the oracle present."""
+    with open(os.path.join(GOLDEN_DIR, "oracle_sample1.json")) as f:
+        g = json.load(f)
+    ctx = _capi.Context(3, capi=gpu_api)
+    for h in range(g["hops"]):
+        x = np.tile(sample1[320 * h:320 * h + 320], (3, 1))
+        for k, bits in enumerate((64, 120, 184)):
+            pkt = ctx.encode(x[k:k + 1], bits, stream_ids=np.array([k], dtype=np.int32))
+            assert bytes(pkt[0]).hex() == g["packets_%d" % bits][h], (bits, h)
+            pcm = ctx.decode(pkt, bits, stream_ids=np.array([k], dtype=np.int32))
+            assert int((pcm[0].astype(np.int64) * np.arange(1, 321)).sum()) == g["pcm_checksum_%d" % bits][h]
+    ctx.close()
+
+
+def test_integration_criterion_on_gpu(gpu_api, oracle, sample1):
+    """lyra/lyra_integration_test.cc:132-142 on the GPU path: every hop's log-spectral distance < 2.0."""
+    ctx = _capi.Context(3, capi=gpu_api)
+    hops = 150
+    worst = [0.0, 0.0, 0.0]
+    for h in range(hops):
+        x = sample1[320 * h:320 * h + 320]
+        for k, bits in enumerate((64, 120, 184)):
+            ids = np.array([k], dtype=np.int32)
+            y = ctx.decode(ctx.encode(x[None], bits, stream_ids=ids), bits, stream_ids=ids)[0]
+            a = ctx.logmel(x[None], num_mel_bins=64, bank=0, stream_ids=ids)[0]
+            b = ctx.logmel(y[None], num_mel_bins=64, bank=1, stream_ids=ids)[0]
+            worst[k] = max(worst[k], oracle.log_spectral_distance(a, b))
+    assert max(worst) < 2.0, worst
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,bits", [(1024, 64), (4096, 64), (4096, 120), (4096, 184)])
+def test_full_size_properties(gpu_api, oracle, n, bits):
+    """BASELINE configs 2/3 sizes.  Properties that need no per-stream oracle:
+    (1) batch independence: streams fed the same audio produce identical packets/PCM wherever they sit in the batch;
+    (2) a sample of streams with distinct audio matches the oracle bit for bit;
+    (3) packet -> dequantize -> quantize is idempotent on the decoded features' indices."""
+    ctx = _capi.Context(n, capi=gpu_api)
+    rng = np.random.default_rng(n + bits)
+    base = rng.integers(-8192, 8192, size=(6, 320), dtype=np.int16)
+    distinct = sorted(set([7, 100, n // 2 + 1, n - 2]))
+    refs = {k: oracle.Codec(_capi.MODEL_DIR) for k in distinct}
+    same_ref = oracle.Codec(_capi.MODEL_DIR)
+    for f in range(6):
+        pcm = np.tile(base[f], (n, 1))
+        other = rng.integers(-8192, 8192, size=(len(distinct), 320), dtype=np.int16)
+        for j, k in enumerate(distinct):
+            pcm[k] = other[j]
+        pk = ctx.encode(pcm, bits)
+        out = ctx.decode(pk, bits)
+        same = np.array([k for k in range(n) if k not in distinct])
+        assert (pk[same] == pk[same[0]]).all()
+        assert (out[same] == out[same[0]]).all()
+        opkt, _, _ = same_ref.encode(base[f], bits)
+        opcm, _, _ = same_ref.decode(opkt, bits)
+        assert bytes(pk[same[0]]) == opkt and np.array_equal(out[same[-1]], opcm)
+        for j, k in enumerate(distinct):
+            opkt, _, _ = refs[k].encode(pcm[k], bits)
+            opcm, _, _ = refs[k].decode(opkt, bits)
+            assert bytes(pk[k]) == opkt and np.array_equal(out[k], opcm)
+        feats = ctx.dequantize(pk[:64], bits)
+        assert (ctx.quantize(feats, 4)[:, 0] >> 4 == pk[:64, 0] >> 4).all()     # first-stage index is a fixed point
+    ctx.close()
+
+
+def test_decoder_only_concealment_4096(gpu_api, oracle):
+    """BASELINE config 4 (decoder-only PLC path): no packets at all, then Bernoulli(0.9) reception."""
+    n, bits = 4096, 64
+    ctx = _capi.Context(n, capi=gpu_api)
+    rng = np.random.default_rng(1234)
+    check = [0, 77, 2048, 4095]
+    refs = {k: oracle.Codec(_capi.MODEL_DIR) for k in check}
+    pk = rng.integers(0, 256, size=(n, 8), dtype=np.uint8)
+    for f in range(5):
+        rec = np.zeros(n, np.uint8) if f < 2 else (rng.random(n) < 0.9).astype(np.uint8)
+        out = ctx.decode(pk, bits, received=rec)
+        mel = ctx.logmel(out, num_mel_bins=160)                 # NoiseEstimator's extractor runs on every decoded hop
+        assert np.isfinite(mel).all()
+        for k in check:
+            opcm, _, _ = refs[k].decode(bytes(pk[k]) if rec[k] else None, bits)
+            assert np.array_equal(out[k], opcm)
+    ctx.close()
