@@ -1,6 +1,7 @@
 // Context + launch logic + the C ABI of include/lyra_b200.h.
 // Compiled by nvcc for sm_100a (product) and, for the CPU test tier only, by g++ with -DLYRA_EMU.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,7 +15,6 @@ using namespace lyra_b200;
 
 namespace {
 
-constexpr int kS = 16;   // streams per tile
 std::string g_create_error;
 
 #define CU(call)                                                                        \
@@ -31,6 +31,7 @@ std::string g_create_error;
 struct lyra_b200_ctx {
   ModelSpec spec;
   int device = 0, max_streams = 0, ntiles = 0, padded = 0;
+  int S = 8;                // streams per tile (8: two blocks per SM; 16: one)
   uint8_t* d_blob = nullptr;
   // streaming state, one block per kernel
   uint32_t* d_state[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -122,7 +123,7 @@ int PrepareMap(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
     if (id < 0 || id >= ctx->max_streams) { ctx->err = "stream id out of range"; ctx->map_dense_n = -1; return LYRA_B200_EINVAL; }
     if (ctx->h_slot_of[(size_t)id] != -1) { ctx->err = "duplicate stream id in one call"; ctx->map_dense_n = -1; return LYRA_B200_EINVAL; }
     ctx->h_slot_of[(size_t)id] = k;
-    if (!tile_used[(size_t)(id / kS)]) { tile_used[(size_t)(id / kS)] = 1; ctx->h_tile_list.push_back(id / kS); }
+    if (!tile_used[(size_t)(id / ctx->S)]) { tile_used[(size_t)(id / ctx->S)] = 1; ctx->h_tile_list.push_back(id / ctx->S); }
   }
   ctx->active_tiles = (int)ctx->h_tile_list.size();
   CU(cudaMemcpyAsync(ctx->d_slot_of, ctx->h_slot_of.data(), sizeof(int) * (size_t)ctx->padded, cudaMemcpyHostToDevice, ctx->stream));
@@ -132,7 +133,8 @@ int PrepareMap(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
   return LYRA_B200_OK;
 }
 
-int LaunchEncoderNets(lyra_b200_ctx* ctx, const int16_t* d_pcm, float* d_features) {
+template <int kS>
+int LaunchEncoderNetsT(lyra_b200_ctx* ctx, const int16_t* d_pcm, float* d_features) {
   const TileIo io{ctx->d_tile_list, ctx->d_slot_of};
   { ProfScope ps(ctx, 0);
   LYRA_LAUNCH(EncoderKernelA<kS>, dim3((unsigned)ctx->active_tiles), dim3(EncA<kS>::NT), (size_t)EncA<kS>::kSmemBytes, ctx->stream,
@@ -143,6 +145,9 @@ int LaunchEncoderNets(lyra_b200_ctx* ctx, const int16_t* d_pcm, float* d_feature
   ctx->launches += 2;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
+}
+int LaunchEncoderNets(lyra_b200_ctx* ctx, const int16_t* d_pcm, float* d_features) {
+  return ctx->S == 16 ? LaunchEncoderNetsT<16>(ctx, d_pcm, d_features) : LaunchEncoderNetsT<8>(ctx, d_pcm, d_features);
 }
 
 int LaunchQuantize(lyra_b200_ctx* ctx, const float* d_features, int n, int num_bits, uint8_t* d_packets, int* d_indices) {
@@ -167,7 +172,8 @@ int LaunchDequantize(lyra_b200_ctx* ctx, const uint8_t* d_packets, const uint8_t
   return LYRA_B200_OK;
 }
 
-int LaunchDecoderNets(lyra_b200_ctx* ctx, const float* d_features, int16_t* d_pcm) {
+template <int kS>
+int LaunchDecoderNetsT(lyra_b200_ctx* ctx, const float* d_features, int16_t* d_pcm) {
   const TileIo io{ctx->d_tile_list, ctx->d_slot_of};
   { ProfScope ps(ctx, 4);
   LYRA_LAUNCH(DecoderKernelC<kS>, dim3((unsigned)ctx->active_tiles), dim3(DecC<kS>::NT), (size_t)DecC<kS>::kSmemBytes, ctx->stream,
@@ -178,6 +184,15 @@ int LaunchDecoderNets(lyra_b200_ctx* ctx, const float* d_features, int16_t* d_pc
   ctx->launches += 2;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
+}
+int LaunchDecoderNets(lyra_b200_ctx* ctx, const float* d_features, int16_t* d_pcm) {
+  return ctx->S == 16 ? LaunchDecoderNetsT<16>(ctx, d_features, d_pcm) : LaunchDecoderNetsT<8>(ctx, d_features, d_pcm);
+}
+
+template <int kS>
+bool SetSmemLimits() {
+  return LYRA_SET_MAX_SMEM(EncoderKernelA<kS>, EncA<kS>::kSmemBytes) == 0 && LYRA_SET_MAX_SMEM(EncoderKernelB<kS>, EncB<kS>::kSmemBytes) == 0 &&
+         LYRA_SET_MAX_SMEM(DecoderKernelC<kS>, DecC<kS>::kSmemBytes) == 0 && LYRA_SET_MAX_SMEM(DecoderKernelD<kS>, DecD<kS>::kSmemBytes) == 0;
 }
 
 // initial value of every 4-byte state unit (all zero; int8 rings hold packed zero points)
@@ -214,7 +229,7 @@ int ResetImpl(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
   }
   for (int w = 0; w < 4; ++w) {
     LYRA_LAUNCH(ResetStateKernel, dim3((unsigned)n), dim3(256), (size_t)0, ctx->stream,
-                ctx->d_state[w], ctx->d_init[w], ctx->units[w], kS, d_ids, n, ctx->d_n18[w]);
+                ctx->d_state[w], ctx->d_init[w], ctx->units[w], ctx->S, d_ids, n, ctx->d_n18[w]);
     ctx->launches += 1;
   }
   CU(cudaGetLastError());
@@ -261,6 +276,12 @@ int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b2
   }
   ctx->device = device;
   ctx->max_streams = max_streams;
+  {
+    // streams per tile: 8 (default, two blocks per SM) or 16; LYRA_B200_TILE_STREAMS overrides for experiments
+    const char* e = std::getenv("LYRA_B200_TILE_STREAMS");
+    ctx->S = (e && std::atoi(e) == 16) ? 16 : 8;
+  }
+  const int kS = ctx->S;
   ctx->ntiles = (max_streams + kS - 1) / kS;
   ctx->padded = ctx->ntiles * kS;
   ctx->h_slot_of.assign((size_t)ctx->padded, -1);
@@ -290,10 +311,7 @@ int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b2
   ok = ok && DevAlloc(&ctx->d_ids, P) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_tile_list, (size_t)ctx->ntiles) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_slot_of, P) == cudaSuccess;
-  if (ok) {
-    ok = LYRA_SET_MAX_SMEM(EncoderKernelA<kS>, EncA<kS>::kSmemBytes) == 0 && LYRA_SET_MAX_SMEM(EncoderKernelB<kS>, EncB<kS>::kSmemBytes) == 0 &&
-         LYRA_SET_MAX_SMEM(DecoderKernelC<kS>, DecC<kS>::kSmemBytes) == 0 && LYRA_SET_MAX_SMEM(DecoderKernelD<kS>, DecD<kS>::kSmemBytes) == 0;
-  }
+  if (ok) ok = kS == 16 ? SetSmemLimits<16>() : SetSmemLimits<8>();
   if (!ok) {
     g_create_error = std::string("CUDA allocation / setup failed: ") + cudaGetErrorString(cudaGetLastError());
     lyra_b200_destroy(ctx);
@@ -324,7 +342,7 @@ void lyra_b200_destroy(lyra_b200_ctx* ctx) {
 
 const char* lyra_b200_last_error(const lyra_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 int lyra_b200_max_streams(const lyra_b200_ctx* ctx) { return ctx ? ctx->max_streams : 0; }
-int lyra_b200_tile_streams(const lyra_b200_ctx* ctx) { return ctx ? kS : 0; }
+int lyra_b200_tile_streams(const lyra_b200_ctx* ctx) { return ctx ? ctx->S : 0; }
 uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int lyra_b200_profile_enable(lyra_b200_ctx* ctx, int enable) {

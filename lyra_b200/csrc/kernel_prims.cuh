@@ -58,31 +58,52 @@ template <int NT>
 __device__ __forceinline__ void StageChunk(void* smem_dst, const void* gsrc, int n16) {
   for (int i = (int)threadIdx.x; i < n16; i += NT)
     lyra_cp_async16(reinterpret_cast<char*>(smem_dst) + 16 * i, reinterpret_cast<const char*>(gsrc) + 16 * i);
-  lyra_cp_async_commit();
 }
+
+constexpr int kStages = 3;   // cp.async ring depth of the weight stream (one block barrier per chunk)
+
+// Thread -> output tile mapping.  A warp covers WM m-groups x (32/WM) n-groups so that the A fragment is
+// shared by the lanes of one m-group and the W fragment by the lanes of one n-group (shared-memory
+// broadcast); warp tiles beyond NT/32 warps are handled in extra passes.
+template <int WM>
+struct TileMap {
+  int MGB, NGB, nwt;
+  __device__ __forceinline__ TileMap(int MG, int NG) {
+    MGB = (MG + WM - 1) / WM;
+    NGB = (NG + (32 / WM) - 1) / (32 / WM);
+    nwt = MGB * NGB;
+  }
+  __device__ __forceinline__ bool Locate(int wt, int MG, int NG, int& mg, int& ng) const {
+    const int lane = (int)threadIdx.x & 31;
+    mg = (wt % MGB) * WM + lane % WM;
+    ng = (wt / MGB) * (32 / WM) + lane / WM;
+    return wt < nwt && mg < MG && ng < NG;
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // fp32 tap-GEMM.   out[t][s][n] = sum_{tap < ntaps} sum_{ci < CinG} A[g*CinG + ci][rowA0 + t*row_stride + tap][s] * W[tap*CinG + ci][n]
 //   A: shared memory [channels][ldA]; if CIN1 the K loop runs over taps only (CinG == 1, single channel).
-//   W: global [ntaps*CinG][N];  wbuf: shared 2 * KC * N floats.
-//   Thread tile TM (streams) x TN (channels); tiles beyond NT are handled in extra passes.
-//   epi(t, s0, n0, acc) is called once per tile after the K loop (and after a block barrier when
-//   `sync_before_epi`, so epilogues may overwrite the A operand in place).
-template <int S, int NT, int TM, int TN, int KC, bool CIN1, typename Epi>
+//   W: global [ntaps*CinG][N];  wbuf: shared kStages * KC * N floats.
+//   Thread tile TM (streams) x TN (channels).
+//   epi(t, s0, n0, acc) is called once per tile after the K loop and a block barrier, so epilogues may
+//   overwrite the A operand in place.
+template <int S, int NT, int TM, int TN, int KC, int WM, bool CIN1, typename Epi>
 __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
                                            int groups, int T_out, int N, const float* __restrict__ Wg, float* wbuf,
-                                           bool sync_before_epi, Epi epi) {
-  static_assert(S % TM == 0 && TM % 4 == 0 && TN % 2 == 0, "tile shape");
+                                           Epi epi) {
+  static_assert(S % TM == 0 && TM % 4 == 0 && 32 % WM == 0, "tile shape");
   constexpr int MGS = S / TM;
-  const int MG = T_out * MGS, NG = N / TN, ntiles = MG * NG;
+  const int MG = T_out * MGS, NG = N / TN;
+  const TileMap<WM> map(MG, NG);
   const int Ktot = ntaps * CinG, nchunks = Ktot / KC;
   const int chunk16 = KC * N / 4;
   const int CoutG = N / groups;
-  for (int pass0 = 0; pass0 < ntiles; pass0 += NT) {
-    const int tile = pass0 + (int)threadIdx.x;
-    const bool active = tile < ntiles;
-    const int mg = active ? tile % MG : 0, ng = active ? tile / MG : 0;
-    const int t_out = mg / MGS, s0 = (mg % MGS) * TM, n0 = ng * TN;
+  const int warp = (int)threadIdx.x >> 5;
+  for (int wt0 = 0; wt0 < map.nwt; wt0 += NT / 32) {
+    int mg, ng;
+    const bool active = map.Locate(wt0 + warp, MG, NG, mg, ng);
+    const int t_out = active ? mg / MGS : 0, s0 = active ? (mg % MGS) * TM : 0, n0 = active ? ng * TN : 0;
     const int g = n0 / CoutG;
     const float* Abase = A + (size_t)(g * CinG) * ldA + (rowA0 + t_out * row_stride) * S + s0;
     float acc[TM][TN];
@@ -91,17 +112,22 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
-    StageChunk<NT>(wbuf, Wg, chunk16);
+    // prologue: chunks 0 .. kStages-2 in flight
+#pragma unroll
+    for (int p = 0; p < kStages - 1; ++p) {
+      if (p < nchunks) StageChunk<NT>(wbuf + p * (KC * N), Wg + (size_t)p * KC * N, chunk16);
+      lyra_cp_async_commit();
+    }
     for (int c = 0; c < nchunks; ++c) {
-      float* wcur = wbuf + (c & 1) * (KC * N);
-      if (c + 1 < nchunks) {
-        StageChunk<NT>(wbuf + ((c + 1) & 1) * (KC * N), Wg + (size_t)(c + 1) * KC * N, chunk16);
-        lyra_cp_async_wait<1>();
-      } else {
-        lyra_cp_async_wait<0>();
+      lyra_cp_async_wait<kStages - 2>();     // chunk c has landed (for this thread's copies)
+      __syncthreads();                       // ... for everyone's; and everyone is done with chunk c-1
+      {
+        const int nc = c + kStages - 1;
+        if (nc < nchunks) StageChunk<NT>(wbuf + (nc % kStages) * (KC * N), Wg + (size_t)nc * KC * N, chunk16);
+        lyra_cp_async_commit();
       }
-      __syncthreads();
       if (active) {
+        const float* wcur = wbuf + (c % kStages) * (KC * N);
         const int kk0 = c * KC;
         const float* Ap;
         int astep;
@@ -118,16 +144,19 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
           }
           if (TN % 4 == 0) {
 #pragma unroll
-            for (int j = 0; j < TN; j += 4) {
+            for (int j = 0; j + 3 < TN; j += 4) {
               const float4 v = *reinterpret_cast<const float4*>(wp + j);
               w[j] = v.x; w[j + 1] = v.y; w[j + 2] = v.z; w[j + 3] = v.w;
             }
-          } else {
+          } else if (TN % 2 == 0) {
 #pragma unroll
-            for (int j = 0; j < TN; j += 2) {
+            for (int j = 0; j + 1 < TN; j += 2) {
               const float2 v = *reinterpret_cast<const float2*>(wp + j);
               w[j] = v.x; w[j + 1] = v.y;
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) w[j] = wp[j];
           }
 #pragma unroll
           for (int i = 0; i < TM; ++i)
@@ -137,9 +166,8 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
           wp += N;
         }
       }
-      __syncthreads();
     }
-    (void)sync_before_epi;   // the loop above always ends with a block barrier
+    __syncthreads();   // every thread is past the K loop: A may be overwritten, the weight ring reused
     if (active) epi(t_out, s0, n0, acc);
   }
   __syncthreads();
@@ -147,22 +175,23 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 
 // ------------------------------------------------------------------------------------------------
 // int8 tap-GEMM with dp4a.  A words [CinTotal/4][ldA], W words [ntaps*CinG/4][N]; KC4 word-rows per chunk.
-template <int S, int NT, int TM, int TN, int KC4, typename Epi>
+template <int S, int NT, int TM, int TN, int KC4, int WM, typename Epi>
 __device__ __forceinline__ void GemmI8Tap(const uint32_t* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
                                           int groups, int T_out, int N, const uint32_t* __restrict__ Wg, uint32_t* wbuf,
                                           Epi epi) {
-  static_assert(S % TM == 0 && TM % 4 == 0 && TN % 4 == 0, "tile shape");
+  static_assert(S % TM == 0 && TM % 4 == 0 && TN % 4 == 0 && 32 % WM == 0, "tile shape");
   constexpr int MGS = S / TM;
   const int CinG4 = CinG / 4;
-  const int MG = T_out * MGS, NG = N / TN, ntiles = MG * NG;
+  const int MG = T_out * MGS, NG = N / TN;
+  const TileMap<WM> map(MG, NG);
   const int Ktot4 = ntaps * CinG4, nchunks = Ktot4 / KC4;
   const int chunk16 = KC4 * N / 4;
   const int CoutG = N / groups;
-  for (int pass0 = 0; pass0 < ntiles; pass0 += NT) {
-    const int tile = pass0 + (int)threadIdx.x;
-    const bool active = tile < ntiles;
-    const int mg = active ? tile % MG : 0, ng = active ? tile / MG : 0;
-    const int t_out = mg / MGS, s0 = (mg % MGS) * TM, n0 = ng * TN;
+  const int warp = (int)threadIdx.x >> 5;
+  for (int wt0 = 0; wt0 < map.nwt; wt0 += NT / 32) {
+    int mg, ng;
+    const bool active = map.Locate(wt0 + warp, MG, NG, mg, ng);
+    const int t_out = active ? mg / MGS : 0, s0 = active ? (mg % MGS) * TM : 0, n0 = active ? ng * TN : 0;
     const int g = n0 / CoutG;
     const uint32_t* Abase = A + (size_t)(g * CinG4) * ldA + (rowA0 + t_out * row_stride) * S + s0;
     int acc[TM][TN];
@@ -171,17 +200,21 @@ __device__ __forceinline__ void GemmI8Tap(const uint32_t* A, int ldA, int rowA0,
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = 0;
 
-    StageChunk<NT>(wbuf, Wg, chunk16);
+#pragma unroll
+    for (int p = 0; p < kStages - 1; ++p) {
+      if (p < nchunks) StageChunk<NT>(wbuf + p * (KC4 * N), Wg + (size_t)p * KC4 * N, chunk16);
+      lyra_cp_async_commit();
+    }
     for (int c = 0; c < nchunks; ++c) {
-      uint32_t* wcur = wbuf + (c & 1) * (KC4 * N);
-      if (c + 1 < nchunks) {
-        StageChunk<NT>(wbuf + ((c + 1) & 1) * (KC4 * N), Wg + (size_t)(c + 1) * KC4 * N, chunk16);
-        lyra_cp_async_wait<1>();
-      } else {
-        lyra_cp_async_wait<0>();
-      }
+      lyra_cp_async_wait<kStages - 2>();
       __syncthreads();
+      {
+        const int nc = c + kStages - 1;
+        if (nc < nchunks) StageChunk<NT>(wbuf + (nc % kStages) * (KC4 * N), Wg + (size_t)nc * KC4 * N, chunk16);
+        lyra_cp_async_commit();
+      }
       if (active) {
+        const uint32_t* wcur = wbuf + (c % kStages) * (KC4 * N);
         const int kk0 = c * KC4;
         const int tap = kk0 / CinG4, ci0 = kk0 - tap * CinG4;
         const uint32_t* Ap = Abase + (size_t)ci0 * ldA + tap * S;
@@ -207,8 +240,8 @@ __device__ __forceinline__ void GemmI8Tap(const uint32_t* A, int ldA, int rowA0,
           wp += N;
         }
       }
-      __syncthreads();
     }
+    __syncthreads();
     if (active) epi(t_out, s0, n0, acc);
   }
   __syncthreads();
@@ -221,6 +254,126 @@ __device__ __forceinline__ void GemmI8Tap(const uint32_t* A, int ldA, int rowA0,
 __device__ __forceinline__ int RingSlot(int base, int t, int R) {
   int v = (base + t) % R;
   return v < 0 ? v + R : v;
+}
+
+__device__ __forceinline__ float4 LeakyRelu4(float4 v) {
+  return make_float4(LeakyRelu(v.x), LeakyRelu(v.y), LeakyRelu(v.z), LeakyRelu(v.w));
+}
+
+// Fast path of DwF32Ring for tiles whose active streams share one frame counter (`n18u` >= 0): one thread
+// owns (channel, 4 streams); it first issues all R ring-row loads back to back (one exposed HBM/L2 latency
+// instead of one per element), then walks the T rows with compile-time indexing, and finally writes the
+// newest rows of its own ring column — no block barrier is needed because nobody else touches that column.
+template <int S, int NT, int C, int T, int DIL>
+__device__ __forceinline__ void DwF32RingFast(const float* u, int ldu, int row0u, float* dout, int ldd,
+                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                              float* __restrict__ ring, int n18u, const int* active) {
+  constexpr int R = 2 * DIL, Q = S / 4;
+  const int base = (n18u * T) % R;
+  for (int item = (int)threadIdx.x; item < C * Q; item += NT) {
+    const int c = item / Q, s4 = (item % Q) * 4;
+    float* rc = ring + (size_t)c * R * S + s4;
+    float4 rg[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) rg[j] = *reinterpret_cast<const float4*>(rc + ((base + j) % R) * S);
+    const float w0 = w[c], w1 = w[C + c], w2 = w[2 * C + c], b = bias[c];
+    const float* uc = u + (size_t)c * ldu + row0u * S + s4;
+    float* dc = dout + (size_t)c * ldd + s4;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float4 x2 = LeakyRelu4(*reinterpret_cast<const float4*>(uc + t * S));
+      float4 x1, x0;
+      if (t - DIL >= 0) x1 = LeakyRelu4(*reinterpret_cast<const float4*>(uc + (t - DIL) * S));
+      else x1 = rg[(t - DIL + R) % R];
+      if (t - 2 * DIL >= 0) x0 = LeakyRelu4(*reinterpret_cast<const float4*>(uc + (t - 2 * DIL) * S));
+      else x0 = rg[(t - 2 * DIL + R) % R];
+      float4 o;
+      o.x = __fadd_rn(__fmaf_rn(x2.x, w2, __fmaf_rn(x1.x, w1, __fmaf_rn(x0.x, w0, 0.0f))), b);
+      o.y = __fadd_rn(__fmaf_rn(x2.y, w2, __fmaf_rn(x1.y, w1, __fmaf_rn(x0.y, w0, 0.0f))), b);
+      o.z = __fadd_rn(__fmaf_rn(x2.z, w2, __fmaf_rn(x1.z, w1, __fmaf_rn(x0.z, w0, 0.0f))), b);
+      o.w = __fadd_rn(__fmaf_rn(x2.w, w2, __fmaf_rn(x1.w, w1, __fmaf_rn(x0.w, w0, 0.0f))), b);
+      *reinterpret_cast<float4*>(dc + t * S) = o;
+    }
+    constexpr int TF = T > R ? T - R : 0;
+    const bool all4 = active[s4] && active[s4 + 1] && active[s4 + 2] && active[s4 + 3];
+#pragma unroll
+    for (int t = TF; t < T; ++t) {
+      const float4 a = LeakyRelu4(*reinterpret_cast<const float4*>(uc + t * S));
+      float* dst = rc + ((base + t) % R) * S;
+      if (all4) {
+        *reinterpret_cast<float4*>(dst) = a;
+      } else {
+        if (active[s4]) dst[0] = a.x;
+        if (active[s4 + 1]) dst[1] = a.y;
+        if (active[s4 + 2]) dst[2] = a.z;
+        if (active[s4 + 3]) dst[3] = a.w;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// int8 analogue on packed words: one thread owns (4 channels, 4 streams).
+template <int S, int NT, int C, int T, int DIL>
+__device__ __forceinline__ void DwI8RingFast(const uint32_t* aq, int lda, int row0a, uint32_t* dq, int ldd,
+                                             const uint8_t* blob, const DwI8& p, uint32_t* __restrict__ ring, int n18u,
+                                             const int* active) {
+  constexpr int R = 2 * DIL, Q = S / 4, C4 = C / 4;
+  constexpr int NR = T < R ? 2 * T : R;          // ring rows actually read: (t - DIL), (t - 2 DIL) for t < T
+  const int base = (n18u * T) % R;
+  const int* w = BlobPtr<int>(blob, p.w);
+  const int* bias = BlobPtr<int>(blob, p.bias);
+  const int* mult = BlobPtr<int>(blob, p.mult);
+  const int* shift = BlobPtr<int>(blob, p.shift);
+  (void)NR;
+  for (int item = (int)threadIdx.x; item < C4 * Q; item += NT) {
+    const int c4 = item / Q, s4 = (item % Q) * 4;
+    uint32_t* rc = ring + (size_t)c4 * R * S + s4;
+    const uint32_t* ac = aq + (size_t)c4 * lda + row0a * S + s4;
+    uint4 x1[T], x0[T], x2[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      x2[t] = *reinterpret_cast<const uint4*>(ac + t * S);
+      if (t - DIL >= 0) x1[t] = *reinterpret_cast<const uint4*>(ac + (t - DIL) * S);
+      else x1[t] = *reinterpret_cast<const uint4*>(rc + ((base + t - DIL + 2 * R) % R) * S);
+      if (t - 2 * DIL >= 0) x0[t] = *reinterpret_cast<const uint4*>(ac + (t - 2 * DIL) * S);
+      else x0[t] = *reinterpret_cast<const uint4*>(rc + ((base + t - 2 * DIL + 2 * R) % R) * S);
+    }
+    int wk[3][4], bb[4], mm[4], sh[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int c = c4 * 4 + b;
+      wk[0][b] = w[c]; wk[1][b] = w[C + c]; wk[2][b] = w[2 * C + c];
+      bb[b] = bias[c]; mm[b] = mult[c]; sh[b] = shift[c];
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const uint32_t a0[4] = {x0[t].x, x0[t].y, x0[t].z, x0[t].w};
+      const uint32_t a1[4] = {x1[t].x, x1[t].y, x1[t].z, x1[t].w};
+      const uint32_t a2[4] = {x2[t].x, x2[t].y, x2[t].z, x2[t].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        int q[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int acc = UnpackI8(a0[l], b) * wk[0][b] + UnpackI8(a1[l], b) * wk[1][b] + UnpackI8(a2[l], b) * wk[2][b];
+          q[b] = RequantI8(acc, bb[b], mm[b], sh[b], p.out_zp);
+        }
+        o[l] = PackI8x4(q[0], q[1], q[2], q[3]);
+      }
+      *reinterpret_cast<uint4*>(dq + (size_t)c4 * ldd + t * S + s4) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    constexpr int TF = T > R ? T - R : 0;
+#pragma unroll
+    for (int t = TF; t < T; ++t) {
+      uint32_t* dst = rc + ((base + t) % R) * S;
+      const uint32_t v[4] = {x2[t].x, x2[t].y, x2[t].z, x2[t].w};
+#pragma unroll
+      for (int l = 0; l < 4; ++l) if (active[s4 + l]) dst[l] = v[l];
+    }
+  }
+  __syncthreads();
 }
 
 // fp32 depthwise conv over LeakyReLU(u).  u: shared [C][ldu] with the T new rows starting at row0u.

@@ -54,6 +54,8 @@ struct TileIo {
   const int* slot_of_stream;   // [max_streams] position of the stream in this call's I/O arrays, -1 = not in this call
 };
 
+// Per-tile metadata in shared memory: slot[S], active[S], n18[S] and n18[S] = the frame counter shared by all
+// active streams of the tile (or -1 if they differ, which selects the general ring path).
 template <int S>
 __device__ __forceinline__ void LoadTileMeta(const TileIo& io, const int* n18_global, int* slot, int* active, int* n18, int& tile) {
   tile = io.tile_list[blockIdx.x];
@@ -65,19 +67,29 @@ __device__ __forceinline__ void LoadTileMeta(const TileIo& io, const int* n18_gl
     n18[threadIdx.x] = n18_global[stream];
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    int u = -2;
+    for (int s = 0; s < S; ++s)
+      if (active[s]) u = (u == -2 || u == n18[s]) ? n18[s] : -1;
+    n18[S] = u < 0 ? -1 : u;
+  }
+  __syncthreads();
 }
 
 // One fp32 residual unit:  d = dw(lrelu(u)); h = lrelu(pw1(d)); u' = pw2(h) + u.
 // u lives at row offset row0u of a [C][ldu] buffer; d is a [C][T*S] scratch.  When `last`, lrelu(u') is stored.
-template <int S, int NT, int TM, int TN1, int TN2>
+template <int S, int NT, int TM, int TN1, int TN2, int WM, int KC, int C, int T, int DIL>
 __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p, float* u, int ldu, int row0u, float* d,
-                                           int C, int T, int dil, int groups2, float* ring, const int* n18,
+                                           int groups2, float* ring, const int* n18,
                                            const int* active, float* wbuf, bool last) {
-  const int ldd = T * S;
-  DwF32Ring<S, NT>(u, ldu, row0u, d, ldd, C, T, dil, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18, active);
+  constexpr int ldd = T * S;
+  if (n18[S] >= 0)
+    DwF32RingFast<S, NT, C, T, DIL>(u, ldu, row0u, d, ldd, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18[S], active);
+  else
+    DwF32Ring<S, NT>(u, ldu, row0u, d, ldd, C, T, DIL, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18, active);
   {
     const float* b1 = BlobPtr<float>(blob, p.pw1.bias);
-    GemmF32Tap<S, NT, TM, TN1, 16, false>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float>(blob, p.pw1.w), wbuf, true,
+    GemmF32Tap<S, NT, TM, TN1, KC, WM, false>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float>(blob, p.pw1.w), wbuf,
       [&](int t, int s0, int n0, float (&acc)[TM][TN1]) {
 #pragma unroll
         for (int j = 0; j < TN1; ++j) {
@@ -90,7 +102,7 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
   }
   {
     const float* b2 = BlobPtr<float>(blob, p.pw2.bias);
-    GemmF32Tap<S, NT, TM, TN2, 16, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float>(blob, p.pw2.w), wbuf, false,
+    GemmF32Tap<S, NT, TM, TN2, KC, WM, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float>(blob, p.pw2.w), wbuf,
       [&](int t, int s0, int n0, float (&acc)[TM][TN2]) {
 #pragma unroll
         for (int j = 0; j < TN2; ++j) {
@@ -108,22 +120,23 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
 
 // One int8 residual unit on packed activations (quant_encoder_2/resnet_{1,2}, quant_decoder_0/resnet_{1,2}).
 //   aq: LeakyReLU'd input (row offset row0a of [64][lda]); resq: the pre-activation residual; both updated in place.
-template <int S, int NT>
+template <int S, int NT, int TM, int DIL>
 __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, uint32_t* aq, int lda, int row0a,
-                                          uint32_t* resq, uint32_t* dq8, uint32_t* hq, int dil, uint32_t* ring,
+                                          uint32_t* resq, uint32_t* dq8, uint32_t* hq, uint32_t* ring,
                                           const int* n18, const int* active, uint32_t* wbuf) {
   constexpr int T = 2, C = 256, LD = T * S;
-  DwI8Ring<S, NT>(aq, lda, row0a, dq8, LD, C, T, dil, blob, p.dw, ring, n18, active);
+  if (n18[S] >= 0) DwI8RingFast<S, NT, C, T, DIL>(aq, lda, row0a, dq8, LD, blob, p.dw, ring, n18[S], active);
+  else DwI8Ring<S, NT>(aq, lda, row0a, dq8, LD, C, T, DIL, blob, p.dw, ring, n18, active);
   {
     const int* bias = BlobPtr<int>(blob, p.pw1.bias);
     const int* mult = BlobPtr<int>(blob, p.pw1.mult);
     const int* shift = BlobPtr<int>(blob, p.pw1.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, p.lr1.lut);
     const int out_zp = p.pw1.out_zp;
-    GemmI8Tap<S, NT, 8, 4, 8>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint32_t>(blob, p.pw1.w), wbuf,
-      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint32_t>(blob, p.pw1.w), wbuf,
+      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
           int q[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
@@ -139,10 +152,10 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
     const int* l2 = BlobPtr<int>(blob, p.add.lut2);
     const int8_t* lut = BlobPtr<int8_t>(blob, p.lr2.lut);
     const int out_zp = p.pw2.out_zp, m3 = p.add.m3, s3 = p.add.s3, add_zp = p.add.out_zp;
-    GemmI8Tap<S, NT, 8, 4, 8>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint32_t>(blob, p.pw2.w), wbuf,
-      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint32_t>(blob, p.pw2.w), wbuf,
+      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
           const size_t ro = (size_t)(n0 / 4) * LD + t * S + s0 + i;
           const uint32_t rw = resq[ro];
           int r[4], a[4];
@@ -165,17 +178,19 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
 template <int S>
 struct EncA {
   static constexpr int NT = 320;
+  static constexpr int kMinBlocks = S <= 8 ? 2 : 1;       // S = 8 tiles fit two blocks per SM
+  static constexpr int TN = S >= 16 ? 8 : 4;              // 1x1 / first-layer thread tile: 8 streams x TN channels
   static constexpr int LDU = 25 * S, LDD = 20 * S;
   static constexpr int kSmemU = 0;
   static constexpr int kSmemD = kSmemU + 64 * LDU * 4;
   static constexpr int kSmemW = kSmemD + 64 * LDD * 4;
-  static constexpr int kSmemI = kSmemW + 2 * 16 * 128 * 4;
-  static constexpr int kSmemBytes = kSmemI + 3 * S * 4;
+  static constexpr int kSmemI = kSmemW + kStages * 16 * 64 * 4;   // = kStages * 8 * 128 * 4 for simpleconv (KC = 8)
+  static constexpr int kSmemBytes = kSmemI + 3 * S * 4 + 16;
   static_assert(368 * S <= 64 * LDD, "first-layer input must fit in the d buffer");
 };
 
 template <int S>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(320, EncA<S>::kMinBlocks)
 EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, const int16_t* __restrict__ pcm,
                float* __restrict__ state, int* __restrict__ n18g, float* __restrict__ mid) {
   using L = EncA<S>;
@@ -211,10 +226,10 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   // ---- first_layer: K = 64, stride 16, 1 -> 64 ; u = conv + bias (pre-activation residual stream)
   {
     const float* b = BlobPtr<float>(blob, P.first.bias);
-    GemmF32Tap<S, NT, 8, (S >= 16 ? 8 : 4), 16, true>(X, 0, 0, 16, 64, 1, 1, 20, 64, BlobPtr<float>(blob, P.first.w), wbuf, false,
-      [&](int t, int s0, int n0, float (&acc)[8][(S >= 16 ? 8 : 4)]) {
+    GemmF32Tap<S, NT, 8, L::TN, 16, 4, true>(X, 0, 0, 16, 64, 1, 1, 20, 64, BlobPtr<float>(blob, P.first.w), wbuf,
+      [&](int t, int s0, int n0, float (&acc)[8][L::TN]) {
 #pragma unroll
-        for (int j = 0; j < (S >= 16 ? 8 : 4); ++j) {
+        for (int j = 0; j < L::TN; ++j) {
           float* o = u + (size_t)(n0 + j) * L::LDU + (5 + t) * S + s0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = __fadd_rn(acc[i][j], b[n0 + j]);
@@ -222,11 +237,9 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
       });
   }
   // ---- encoder_0: three residual units, dilation 1/3/9
-  const int ring_off[3] = {EncStateA::kRing0, EncStateA::kRing1, EncStateA::kRing2};
-  const int dil[3] = {1, 3, 9};
-  for (int i = 0; i < 3; ++i)
-    ResUnitF32<S, NT, 8, (S >= 16 ? 8 : 4), (S >= 16 ? 8 : 4)>(blob, P.r0[i], u, L::LDU, 5, d, 64, 20, dil[i], 1,
-                                                              st + (size_t)ring_off[i] * S, n18, active, wbuf, i == 2);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1>(blob, P.r0[0], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing0 * S, n18, active, wbuf, false);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3>(blob, P.r0[1], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing1 * S, n18, active, wbuf, false);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9>(blob, P.r0[2], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing2 * S, n18, active, wbuf, true);
   // carried rows for the next frame: the last 5 activated rows
   for (int i = tid; i < 64 * 5 * S; i += NT) {
     const int c = i / (5 * S), r = i % (5 * S);
@@ -236,7 +249,7 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   {
     const float* b = BlobPtr<float>(blob, P.down0.bias);
     float* out = mid + (size_t)tile * 128 * 4 * S;
-    GemmF32Tap<S, NT, 8, 4, 16, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), wbuf, false,
+    GemmF32Tap<S, NT, 8, 4, 8, 4, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), wbuf,
       [&](int t, int s0, int n0, float (&acc)[8][4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -255,22 +268,25 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 template <int S>
 struct EncB {
   static constexpr int NT = 256;
+  static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
+  static constexpr int TM = S >= 16 ? 8 : 4;              // streams per thread tile
   static constexpr int LD1 = 6 * S;                       // u1: 2 carried rows + 4
   static constexpr int kR0 = 0;                           // u1 f32 [128][6S]; later d2 f32 [256][2S]
   static constexpr int kR1 = kR0 + 128 * LD1 * 4;         // d1 f32 [128][4S]; later hq, dq8, resq words [64][2S] each
   static constexpr int kR2 = kR1 + 128 * 4 * S * 4;       // u2 f32 [256][2S]
   static constexpr int kR3 = kR2 + 256 * 2 * S * 4;       // aq words [64][4S] (2 carried rows + 2), bq words [128][3S]
   static constexpr int kW = kR3 + 64 * 4 * S * 4 + 128 * 3 * S * 4;
-  static constexpr int kI = kW + 2 * 16 * 256 * 4;
-  static constexpr int kSmemBytes = kI + 3 * S * 4;
+  static constexpr int kI = kW + kStages * 8 * 256 * 4;
+  static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
 };
 
 template <int S>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, EncB<S>::kMinBlocks)
 EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, const float* __restrict__ mid,
                float* __restrict__ state, int* __restrict__ n18g, float* __restrict__ features) {
   using L = EncB<S>;
   constexpr int NT = L::NT;
+  constexpr int TM = L::TM;
   unsigned char* smem = LYRA_DYN_SMEM();
   float* u1 = reinterpret_cast<float*>(smem + L::kR0);
   float* d1 = reinterpret_cast<float*>(smem + L::kR1);
@@ -300,10 +316,9 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   }
   __syncthreads();
   // ---- encoder_1: three residual units @128 (second 1x1 has 2 groups)
-  const int ring_off[3] = {EncStateB::kRing0, EncStateB::kRing1, EncStateB::kRing2};
-  const int dil[3] = {1, 3, 9};
-  for (int i = 0; i < 3; ++i)
-    ResUnitF32<S, NT, 8, 4, 4>(blob, P.r1[i], u1, L::LD1, 2, d1, 128, 4, dil[i], 2, st + (size_t)ring_off[i] * S, n18, active, wbuf, i == 2);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 1>(blob, P.r1[0], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf, false);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 3>(blob, P.r1[1], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing1 * S, n18, active, wbuf, false);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 9>(blob, P.r1[2], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing2 * S, n18, active, wbuf, true);
   for (int i = tid; i < 128 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
     if (active[r % S]) st[EncStateB::kDown1 * S + i] = u1[(size_t)c * L::LD1 + 4 * S + r];
@@ -311,29 +326,33 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   // ---- encoder_1/simpleconv: K = 4, stride 2, 128 -> 256, 2 groups ; u2 = pre-activation
   {
     const float* b = BlobPtr<float>(blob, P.down1.bias);
-    GemmF32Tap<S, NT, 8, 4, 16, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, false,
-      [&](int t, int s0, int n0, float (&acc)[8][4]) {
+    GemmF32Tap<S, NT, TM, 4, 8, 4, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf,
+      [&](int t, int s0, int n0, float (&acc)[TM][4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float* o = u2 + (size_t)(n0 + j) * 2 * S + t * S + s0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = __fadd_rn(acc[i][j], b[n0 + j]);
+          for (int i = 0; i < TM; ++i) o[i] = __fadd_rn(acc[i][j], b[n0 + j]);
         }
       });
   }
   // ---- encoder_2/resnet_0 (mixed): f32 depthwise + f32 1x1, QUANTIZE, int8 LeakyReLU, int8 1x1 (4 groups),
   //      DEQUANTIZE + f32 residual, QUANTIZE, int8 LeakyReLU
   constexpr int LD2 = 2 * S;
-  DwF32Ring<S, NT>(u2, LD2, 0, d2, LD2, 256, 2, 1, BlobPtr<float>(blob, P.m_dw.w), BlobPtr<float>(blob, P.m_dw.bias),
-                   st + (size_t)EncStateB::kRingM * S, n18, active);
+  if (n18[S] >= 0)
+    DwF32RingFast<S, NT, 256, 2, 1>(u2, LD2, 0, d2, LD2, BlobPtr<float>(blob, P.m_dw.w), BlobPtr<float>(blob, P.m_dw.bias),
+                                    st + (size_t)EncStateB::kRingM * S, n18[S], active);
+  else
+    DwF32Ring<S, NT>(u2, LD2, 0, d2, LD2, 256, 2, 1, BlobPtr<float>(blob, P.m_dw.w), BlobPtr<float>(blob, P.m_dw.bias),
+                     st + (size_t)EncStateB::kRingM * S, n18, active);
   {
     const float* b = BlobPtr<float>(blob, P.m_pw1.bias);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const QuantP q1 = P.m_q1;
-    GemmF32Tap<S, NT, 8, 4, 16, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, false,
-      [&](int t, int s0, int n0, float (&acc)[8][4]) {
+    GemmF32Tap<S, NT, TM, 4, 8, 4, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf,
+      [&](int t, int s0, int n0, float (&acc)[TM][4]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
           int q[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) q[j] = lut[QuantizeF32(__fadd_rn(acc[i][j], b[n0 + j]), q1.scale, q1.zp) + 128];
@@ -348,10 +367,10 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
     const QuantP dq = P.m_dq, q2 = P.m_q2;
     const int out_zp = P.m_pw2.out_zp;
-    GemmI8Tap<S, NT, 8, 4, 8>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq,
-      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
           int r[4], a[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -366,8 +385,8 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
       });
   }
   // ---- quant_encoder_2/resnet_{1,2}
-  ResUnitI8<S, NT>(blob, P.q[0], aq, 4 * S, 2, resq, dq8, hq, 3, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, wbufq);
-  ResUnitI8<S, NT>(blob, P.q[1], aq, 4 * S, 2, resq, dq8, hq, 9, stw + (size_t)EncStateB::kRingQ1 * S, n18, active, wbufq);
+  ResUnitI8<S, NT, TM, 3>(blob, P.q[0], aq, 4 * S, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, wbufq);
+  ResUnitI8<S, NT, TM, 9>(blob, P.q[1], aq, 4 * S, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ1 * S, n18, active, wbufq);
   // ---- quant_encoder_2/simpleconv: K = 4, stride 2, 256 -> 512, 4 groups, then int8 LeakyReLU
   for (int i = tid; i < 64 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); aq[(size_t)c * 4 * S + r] = stw[EncStateB::kDown2 * S + i]; }
   for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); bq[(size_t)c * 3 * S + r] = stw[EncStateB::kBott * S + i]; }
@@ -382,11 +401,11 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int* shift = BlobPtr<int>(blob, P.down2.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.down2_lr.lut);
     const int out_zp = P.down2.out_zp;
-    GemmI8Tap<S, NT, 8, 4, 8>(aq, 4 * S, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint32_t>(blob, P.down2.w), wbufq,
-      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+    GemmI8Tap<S, NT, TM, 4, 4, 2>(aq, 4 * S, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint32_t>(blob, P.down2.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
         (void)t;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
           int q[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
@@ -406,11 +425,11 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int* shift = BlobPtr<int>(blob, P.bott.shift);
     const QuantP dq = P.out_dq;
     const int out_zp = P.bott.out_zp;
-    GemmI8Tap<S, NT, 8, 4, 8>(bq, 3 * S, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint32_t>(blob, P.bott.w), wbufq,
-      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+    GemmI8Tap<S, NT, TM, 4, 8, 2>(bq, 3 * S, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint32_t>(blob, P.bott.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
         (void)t;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
           if (!active[s0 + i]) continue;
           float* o = features + (size_t)slot[s0 + i] * 64 + n0;
 #pragma unroll
@@ -428,23 +447,27 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 template <int S>
 struct DecC {
   static constexpr int NT = 256;
+  static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
+  static constexpr int TM = S >= 16 ? 8 : 4;
   static constexpr int kF = 0;                              // F f32 [64][3S]
   static constexpr int kXq = kF + 64 * 3 * S * 4;           // xq words [128][3S]  (pad, x0, pad)
   static constexpr int kU = kXq + 128 * 3 * S * 4;          // u f32 [256][2S]; later u1 f32 [128][4S]
   static constexpr int kAq = kU + 256 * 2 * S * 4;          // aq words [64][4S] (pad, t0, t1, pad)
   static constexpr int kQ = kAq + 64 * 4 * S * 4;           // hq, dq8, resq words [64][2S] each; later d1 f32 [128][4S]
   static constexpr int kW = kQ + 128 * 4 * S * 4;
-  static constexpr int kI = kW + 2 * 16 * 512 * 4;
-  static constexpr int kSmemBytes = kI + 3 * S * 4;
+  static constexpr int kI = kW + kStages * 4 * 512 * 4;
+  static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
 };
 
 template <int S>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, DecC<S>::kMinBlocks)
 DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
                const float* __restrict__ features, float* __restrict__ state, int* __restrict__ n18g,
                float* __restrict__ mid) {
   using L = DecC<S>;
   constexpr int NT = L::NT;
+  constexpr int TM = L::TM;
+  constexpr int TNU = 8;     // column tile of the transposed-conv banks
   unsigned char* smem = LYRA_DYN_SMEM();
   float* F = reinterpret_cast<float*>(smem + L::kF);
   uint32_t* xq = reinterpret_cast<uint32_t*>(smem + L::kXq);
@@ -489,11 +512,11 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   {
     const float* b = BlobPtr<float>(blob, P.bott.bias);
     const QuantP q = P.bott_q;
-    GemmF32Tap<S, NT, 8, 4, 16, false>(F, 3 * S, 0, 1, 3, 16, 4, 1, 512, BlobPtr<float>(blob, P.bott.w), wbuf, false,
-      [&](int t, int s0, int n0, float (&acc)[8][4]) {
+    GemmF32Tap<S, NT, TM, 4, 4, 2, false>(F, 3 * S, 0, 1, 3, 16, 4, 1, 512, BlobPtr<float>(blob, P.bott.w), wbuf,
+      [&](int t, int s0, int n0, float (&acc)[TM][4]) {
         (void)t;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
           int v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) v[j] = QuantizeF32(LeakyRelu(__fadd_rn(acc[i][j], b[n0 + j])), q.scale, q.zp);
@@ -507,15 +530,15 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int* mult = BlobPtr<int>(blob, up0.g.mult);
     const int* shift = BlobPtr<int>(blob, up0.g.shift);
     float* tail = st + (size_t)DecStateC::kUp0 * S;
-    GemmI8Tap<S, NT, 8, 4, 8>(xq, 3 * S, 0, 1, 2, 128, 4, 2, 512, BlobPtr<uint32_t>(blob, up0.g.w), wbufq,
-      [&](int q, int s0, int n0, int (&acc)[8][4]) {
+    GemmI8Tap<S, NT, TM, TNU, 4, 4>(xq, 3 * S, 0, 1, 2, 128, 4, 2, 512, BlobPtr<uint32_t>(blob, up0.g.w), wbufq,
+      [&](int q, int s0, int n0, int (&acc)[TM][TNU]) {
         const int g = n0 / 128, r = (n0 % 128) / 64;
         const float* bf = BlobPtr<float>(blob, up0.bias_f32[g]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < TNU; ++j) {
           const int co = (n0 + j) % 64, ch = g * 64 + co;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < TM; ++i) {
             const int qv = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up0.out_zp[g]);
             const float f = DequantizeI8(qv, up0.dq[g].scale, up0.dq[g].zp);
             if (q == 0) {
@@ -541,17 +564,18 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   }
   __syncthreads();
   // ---- quant_decoder_0/resnet_0 (int8 body, f32 residual add)
-  DwI8Ring<S, NT>(aq, 4 * S, 1, dq8, LD2, 256, 2, 1, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18, active);
+  if (n18[S] >= 0) DwI8RingFast<S, NT, 256, 2, 1>(aq, 4 * S, 1, dq8, LD2, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18[S], active);
+  else DwI8Ring<S, NT>(aq, 4 * S, 1, dq8, LD2, 256, 2, 1, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18, active);
   {
     const int* bias = BlobPtr<int>(blob, P.m_pw1.bias);
     const int* mult = BlobPtr<int>(blob, P.m_pw1.mult);
     const int* shift = BlobPtr<int>(blob, P.m_pw1.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const int out_zp = P.m_pw1.out_zp;
-    GemmI8Tap<S, NT, 8, 4, 8>(dq8, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw1.w), wbufq,
-      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(dq8, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw1.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
           int q[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
@@ -566,10 +590,10 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
     const QuantP dq = P.m_dq, q2 = P.m_q2;
     const int out_zp = P.m_pw2.out_zp;
-    GemmI8Tap<S, NT, 8, 4, 8>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq,
-      [&](int t, int s0, int n0, int (&acc)[8][4]) {
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq,
+      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TM; ++i) {
           int r[4], a[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -583,8 +607,8 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
         }
       });
   }
-  ResUnitI8<S, NT>(blob, P.q[0], aq, 4 * S, 1, resq, dq8, hq, 3, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, wbufq);
-  ResUnitI8<S, NT>(blob, P.q[1], aq, 4 * S, 1, resq, dq8, hq, 9, stw + (size_t)DecStateC::kRingQ1 * S, n18, active, wbufq);
+  ResUnitI8<S, NT, TM, 3>(blob, P.q[0], aq, 4 * S, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, wbufq);
+  ResUnitI8<S, NT, TM, 9>(blob, P.q[1], aq, 4 * S, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ1 * S, n18, active, wbufq);
   // ---- quant_decoder_1 upsample: 2 x TRANSPOSE_CONV (K = 4, stride 2, 128 -> 64), T 2 -> 4 (+2 tail rows)
   {
     const uint32_t pad = PackI8x4(up1.g.in_zp, up1.g.in_zp, up1.g.in_zp, up1.g.in_zp);
@@ -601,15 +625,15 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int* mult = BlobPtr<int>(blob, up1.g.mult);
     const int* shift = BlobPtr<int>(blob, up1.g.shift);
     float* tail = st + (size_t)DecStateC::kUp1 * S;
-    GemmI8Tap<S, NT, 8, 4, 8>(aq, 4 * S, 0, 1, 2, 128, 2, 3, 256, BlobPtr<uint32_t>(blob, up1.g.w), wbufq,
-      [&](int q, int s0, int n0, int (&acc)[8][4]) {
+    GemmI8Tap<S, NT, TM, TNU, 8, 2>(aq, 4 * S, 0, 1, 2, 128, 2, 3, 256, BlobPtr<uint32_t>(blob, up1.g.w), wbufq,
+      [&](int q, int s0, int n0, int (&acc)[TM][TNU]) {
         const int g = n0 / 128, r = (n0 % 128) / 64;
         const float* bf = BlobPtr<float>(blob, up1.bias_f32[g]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < TNU; ++j) {
           const int co = (n0 + j) % 64, ch = g * 64 + co;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < TM; ++i) {
             const int qv = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up1.out_zp[g]);
             const float f = DequantizeI8(qv, up1.dq[g].scale, up1.dq[g].zp);
             if (q < 2) {
@@ -623,10 +647,9 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
       });
   }
   // ---- decoder_1: three fp32 residual units @128
-  const int ring_off[3] = {DecStateC::kRing0, DecStateC::kRing1, DecStateC::kRing2};
-  const int dil[3] = {1, 3, 9};
-  for (int i = 0; i < 3; ++i)
-    ResUnitF32<S, NT, 8, 4, 4>(blob, P.r1[i], u1, 4 * S, 0, d1, 128, 4, dil[i], 2, st + (size_t)ring_off[i] * S, n18, active, wbuf, i == 2);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 1>(blob, P.r1[0], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, false);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 3>(blob, P.r1[1], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing1 * S, n18, active, wbuf, false);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 9>(blob, P.r1[2], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing2 * S, n18, active, wbuf, true);
   {
     float* out = mid + (size_t)tile * 128 * 4 * S;
     for (int i = tid; i < 128 * 4 * S; i += NT) out[i] = u1[i];
@@ -640,18 +663,25 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
 template <int S>
 struct DecD {
   static constexpr int NT = 320;
+  static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
+  static constexpr int TN = S >= 16 ? 8 : 4;              // 1x1 thread tile: 8 streams x TN channels
+  static constexpr int TNU = S >= 16 ? 10 : 5;            // decoder_2/simple column tile (320 columns)
+  static constexpr int WMU = S >= 16 ? 2 : 1;
+  static constexpr int KCU = S >= 16 ? 8 : 4;
+  static constexpr int TNL = S >= 16 ? 4 : 2;             // last_layer column tile (16 columns)
+  static constexpr int WML = S >= 16 ? 8 : 4;
   static constexpr int LDU = 26 * S, LDD = 20 * S;          // u: 3 zero rows + 20 + 3 zero rows
   static constexpr int kU = 0;
   static constexpr int kD = kU + 64 * LDU * 4;              // d f32 [64][20S]; aliases X f32 [128][6S] and the PCM staging
   static constexpr int kW = kD + 64 * LDD * 4;
-  static constexpr int kSl = kW + 2 * 8 * 320 * 4;          // carried tail of last_layer [48][S]
+  static constexpr int kSl = kW + kStages * KCU * 320 * 4;   // carried tail of last_layer [48][S]
   static constexpr int kI = kSl + 48 * S * 4;
-  static constexpr int kSmemBytes = kI + 3 * S * 4;
+  static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
   static_assert(128 * 6 * S <= 64 * LDD, "X must fit in d");
 };
 
 template <int S>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(320, DecD<S>::kMinBlocks)
 DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, const float* __restrict__ mid,
                float* __restrict__ state, int* __restrict__ n18g, int16_t* __restrict__ pcm) {
   using L = DecD<S>;
@@ -689,10 +719,10 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   {
     const float* b = BlobPtr<float>(blob, P.up2.bias);
     float* tail = st + (size_t)DecStateD::kUp2 * S;
-    GemmF32Tap<S, NT, 8, 10, 8, false>(X, 6 * S, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float>(blob, P.up2.w), wbuf, false,
-      [&](int q, int s0, int n0, float (&acc)[8][10]) {
+    GemmF32Tap<S, NT, 8, L::TNU, L::KCU, L::WMU, false>(X, 6 * S, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float>(blob, P.up2.w), wbuf,
+      [&](int q, int s0, int n0, float (&acc)[8][L::TNU]) {
 #pragma unroll
-        for (int j = 0; j < 10; ++j) {
+        for (int j = 0; j < L::TNU; ++j) {
           const int r = (n0 + j) / 64, co = (n0 + j) % 64;
           const float bias = b[co];
 #pragma unroll
@@ -709,20 +739,18 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
       });
   }
   // ---- decoder_2: three residual units @64, T = 20
-  const int ring_off[3] = {DecStateD::kRing0, DecStateD::kRing1, DecStateD::kRing2};
-  const int dil[3] = {1, 3, 9};
-  for (int i = 0; i < 3; ++i)
-    ResUnitF32<S, NT, 8, (S >= 16 ? 8 : 4), (S >= 16 ? 8 : 4)>(blob, P.r2[i], u, L::LDU, 3, d, 64, 20, dil[i], 1,
-                                                              st + (size_t)ring_off[i] * S, n18, active, wbuf, i == 2);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1>(blob, P.r2[0], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing0 * S, n18, active, wbuf, false);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3>(blob, P.r2[1], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing1 * S, n18, active, wbuf, false);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9>(blob, P.r2[2], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing2 * S, n18, active, wbuf, true);
   // ---- last_layer: TRANSPOSE_CONV K = 64, stride 16, 64 -> 1 ; T 20 -> 320 (+48 tail) ; float -> int16
   {
     const float bias = BlobPtr<float>(blob, P.last.bias)[0];
     float* tail = st + (size_t)DecStateD::kLast * S;
     int16_t* stage = reinterpret_cast<int16_t*>(d);      // [S][320]
-    GemmF32Tap<S, NT, 8, 4, 16, false>(u, L::LDU, 0, 1, 4, 64, 1, 23, 16, BlobPtr<float>(blob, P.last.w), wbuf, false,
-      [&](int q, int s0, int n0, float (&acc)[8][4]) {
+    GemmF32Tap<S, NT, 8, L::TNL, 16, L::WML, false>(u, L::LDU, 0, 1, 4, 64, 1, 23, 16, BlobPtr<float>(blob, P.last.w), wbuf,
+      [&](int q, int s0, int n0, float (&acc)[8][L::TNL]) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < L::TNL; ++j) {
           const int t = 16 * q + n0 + j;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
