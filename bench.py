@@ -97,6 +97,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """CPU cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def synth_pcm_np(n, nbuf, seed):
     """Seeded synthetic input: uniform noise at 0.25 full scale (the reference benchmark feeds uniform random audio,
     lyra/lyra_benchmark_lib.cc:233-239); `nbuf` distinct hops are rotated through the steps."""
@@ -124,7 +140,7 @@ def reference_arm(args, rank, world):
     """`--impl reference`: the reference algorithm's CPU implementation (oracle port) on all host cores."""
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    threads = host_cores()
     bits = args.bits
     streams, frames = cpu_calibrated_sample(bits, threads, max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup))))
     for _ in range(args.warmup):
@@ -158,7 +174,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
@@ -277,7 +293,7 @@ def main():
                     "kernels": kern}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = host_cores()
             s, f = cpu_calibrated_sample(bits, threads, 12.0)
             r = run_cpu_arm(s, f, bits, threads)
             cpu = {"value": r["frames_per_s"], "unit": UNIT, "cores": threads, "kind": "port",

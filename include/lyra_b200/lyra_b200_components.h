@@ -1,0 +1,369 @@
+// C++ host side above the C ABI: drop-in counterparts of the reference's plugin classes for the hot path,
+// with the reference's names, argument meaning and error behaviour (std::nullopt / false / nullptr, never
+// an exception, never an abort).  Header-only; link liblyra_b200.so.
+//
+//   reference class (lyra/…)                                    here
+//   SoundStreamEncoder          soundstream_encoder.{h,cc}       lyra_b200::SoundStreamEncoderB200
+//   ResidualVectorQuantizer     residual_vector_quantizer.{h,cc} lyra_b200::ResidualVectorQuantizerB200
+//   LyraGanModel                lyra_gan_model.{h,cc}            lyra_b200::LyraGanModelB200 (: GenerativeModel)
+//   LogMelSpectrogramExtractorImpl  log_mel_spectrogram_extractor_impl.{h,cc}   lyra_b200::LogMelSpectrogramExtractorB200
+//   Packet<184>                 packet.h                         lyra_b200::Packet184
+//   LyraEncoder / LyraDecoder   lyra_encoder.{h,cc} / lyra_decoder.{h,cc}       lyra_b200::LyraEncoderB200 / LyraDecoderB200
+//                                                                (16 kHz, no DTX; lost packets are concealed with zero
+//                                                                 features; comfort noise / fades are out of scope)
+//
+// The reference's interface headers need abseil, which is not available in this build environment, so the
+// three interfaces are restated below with std:: types (absl::Span<const T> -> pointer + size overloads on
+// std::vector).  INTEGRATION.md shows the 1:1 binding a maintainer adds inside the reference tree, where the
+// adapters derive from chromemedia::codec::{FeatureExtractorInterface, VectorQuantizerInterface, GenerativeModel}.
+//
+// Every object owns ONE stream id of a process-wide context (one context per device, created on first use with
+// LYRA_B200_MAX_STREAMS, default 4096, stream slots).  Per-object calls run the batched kernels with n = 1:
+// API-compatible but latency-bound; throughput users call the batched C ABI directly (include/lyra_b200.h).
+#pragma once
+
+#include <cstdint>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "../lyra_b200.h"
+
+namespace lyra_b200 {
+
+// ---- the three plugin interfaces (lyra/feature_extractor_interface.h:32-39, lyra/vector_quantizer_interface.h:28-41,
+//      lyra/generative_model_interface.h:32-42) ---------------------------------------------------------------------
+class FeatureExtractorInterface {
+ public:
+  virtual ~FeatureExtractorInterface() {}
+  virtual std::optional<std::vector<float>> Extract(const std::vector<int16_t>& audio) = 0;
+};
+
+class VectorQuantizerInterface {
+ public:
+  virtual ~VectorQuantizerInterface() {}
+  virtual std::optional<std::string> Quantize(const std::vector<float>& features, int num_bits) const = 0;
+  virtual std::optional<std::vector<float>> DecodeToLossyFeatures(const std::string& quantized_features) const = 0;
+};
+
+class GenerativeModelInterface {
+ public:
+  virtual ~GenerativeModelInterface() {}
+  virtual bool AddFeatures(const std::vector<float>& features) = 0;
+  virtual std::optional<std::vector<int16_t>> GenerateSamples(int num_samples) = 0;
+  virtual int num_samples_available() const = 0;
+};
+
+// lyra/generative_model_interface.h:45-134: FIFO of feature vectors + partial-hop bookkeeping
+class GenerativeModel : public GenerativeModelInterface {
+ public:
+  bool AddFeatures(const std::vector<float>& features) final {
+    if ((int)features.size() != num_features_) return false;
+    features_queue_.push(features);
+    return true;
+  }
+  std::optional<std::vector<int16_t>> GenerateSamples(int num_samples) final {
+    if (num_samples < 0) return std::nullopt;
+    if (num_samples == 0) return std::vector<int16_t>(0);
+    if (num_samples_available() == 0) return std::nullopt;
+    if (next_sample_in_hop_ == 0 && !RunConditioning(features_queue_.front())) return std::nullopt;
+    if (num_samples > num_samples_per_hop_ - next_sample_in_hop_) return std::nullopt;
+    auto samples = RunModel(num_samples);
+    if (samples.has_value()) {
+      next_sample_in_hop_ += (int)samples->size();
+      if (next_sample_in_hop_ == num_samples_per_hop_) { next_sample_in_hop_ = 0; features_queue_.pop(); }
+    }
+    return samples;
+  }
+  int num_samples_available() const final { return (int)features_queue_.size() * num_samples_per_hop_ - next_sample_in_hop_; }
+
+ protected:
+  GenerativeModel(int num_samples_per_hop, int num_features)
+      : num_samples_per_hop_(num_samples_per_hop), num_features_(num_features), next_sample_in_hop_(0) {}
+  virtual bool RunConditioning(const std::vector<float>& features) = 0;
+  virtual std::optional<std::vector<int16_t>> RunModel(int num_samples) = 0;
+  int next_sample_in_hop() const { return next_sample_in_hop_; }
+
+ private:
+  const int num_samples_per_hop_;
+  const int num_features_;
+  int next_sample_in_hop_;
+  std::queue<std::vector<float>> features_queue_;
+};
+
+// ---- process-wide context + stream-id allocator ------------------------------------------------------------------
+class Session {
+ public:
+  // nullptr when the context cannot be created (no GPU, bad model directory): factories then return nullptr,
+  // like the reference's Create() functions (e.g. lyra/soundstream_encoder.cc:36-46).
+  static std::shared_ptr<Session> Get(const std::string& model_path, int device = 0) {
+    static std::mutex mu;
+    static std::weak_ptr<Session> cached;
+    static std::string cached_path;
+    std::lock_guard<std::mutex> lock(mu);
+    if (auto s = cached.lock()) if (cached_path == model_path) return s;
+    int max_streams = 4096;
+    if (const char* e = std::getenv("LYRA_B200_MAX_STREAMS")) max_streams = std::atoi(e) > 0 ? std::atoi(e) : max_streams;
+    lyra_b200_ctx* ctx = nullptr;
+    if (lyra_b200_create(model_path.c_str(), device, max_streams, &ctx) != LYRA_B200_OK) return nullptr;
+    std::shared_ptr<Session> s(new Session(ctx, max_streams));
+    cached = s;
+    cached_path = model_path;
+    return s;
+  }
+  ~Session() { lyra_b200_destroy(ctx_); }
+  lyra_b200_ctx* ctx() const { return ctx_; }
+  std::mutex& mutex() { return mu_; }   // calls on one context are serialised
+  int Acquire() {
+    std::lock_guard<std::mutex> lock(mu_);
+    int id;
+    if (!free_.empty()) { id = free_.back(); free_.pop_back(); }
+    else if (next_ < max_streams_) id = next_++;
+    else return -1;
+    lyra_b200_reset(ctx_, &id, 1);
+    return id;
+  }
+  void Release(int id) { std::lock_guard<std::mutex> lock(mu_); free_.push_back(id); }
+
+ private:
+  Session(lyra_b200_ctx* c, int n) : ctx_(c), max_streams_(n) {}
+  lyra_b200_ctx* ctx_;
+  int max_streams_, next_ = 0;
+  std::vector<int> free_;
+  std::mutex mu_;
+};
+
+// ---- SoundStreamEncoder (lyra/soundstream_encoder.cc:36-64) --------------------------------------------------------
+class SoundStreamEncoderB200 : public FeatureExtractorInterface {
+ public:
+  static std::unique_ptr<SoundStreamEncoderB200> Create(const std::string& model_path) {
+    auto s = Session::Get(model_path);
+    if (!s) return nullptr;
+    const int id = s->Acquire();
+    if (id < 0) return nullptr;
+    return std::unique_ptr<SoundStreamEncoderB200>(new SoundStreamEncoderB200(std::move(s), id));
+  }
+  ~SoundStreamEncoderB200() override { session_->Release(id_); }
+  std::optional<std::vector<float>> Extract(const std::vector<int16_t>& audio) override {
+    if ((int)audio.size() != LYRA_B200_HOP) return std::nullopt;
+    std::vector<float> out(LYRA_B200_NUM_FEATURES);
+    std::lock_guard<std::mutex> lock(session_->mutex());
+    if (lyra_b200_extract_features(session_->ctx(), &id_, 1, audio.data(), out.data()) != LYRA_B200_OK) return std::nullopt;
+    return out;
+  }
+
+ private:
+  SoundStreamEncoderB200(std::shared_ptr<Session> s, int id) : session_(std::move(s)), id_(id) {}
+  std::shared_ptr<Session> session_;
+  int id_;
+};
+
+// ---- Packet<184> with 0 header bits (lyra/packet.h:56-146, lyra/lyra_components.cc:57-60) --------------------------
+struct Packet184 {
+  static int PacketSize(int num_quantized_bits) { return (num_quantized_bits + 7) / 8; }
+  static std::vector<uint8_t> PackQuantized(const std::string& bits) {
+    std::vector<uint8_t> bytes((size_t)PacketSize((int)bits.size()), 0);
+    for (size_t i = 0; i < bits.size(); ++i) if (bits[i] == '1') bytes[i >> 3] |= (uint8_t)(0x80u >> (i & 7));
+    return bytes;
+  }
+  static std::optional<std::string> UnpackPacket(const std::vector<uint8_t>& packet, int num_quantized_bits) {
+    if ((int)packet.size() != PacketSize(num_quantized_bits)) return std::nullopt;
+    std::string bits((size_t)num_quantized_bits, '0');
+    for (int i = 0; i < num_quantized_bits; ++i) if ((packet[(size_t)i >> 3] >> (7 - (i & 7))) & 1) bits[(size_t)i] = '1';
+    return bits;
+  }
+};
+
+// ---- ResidualVectorQuantizer (lyra/residual_vector_quantizer.cc:36-168) --------------------------------------------
+class ResidualVectorQuantizerB200 : public VectorQuantizerInterface {
+ public:
+  static std::unique_ptr<ResidualVectorQuantizerB200> Create(const std::string& model_path) {
+    auto s = Session::Get(model_path);
+    if (!s) return nullptr;
+    return std::unique_ptr<ResidualVectorQuantizerB200>(new ResidualVectorQuantizerB200(std::move(s)));
+  }
+  std::optional<std::string> Quantize(const std::vector<float>& features, int num_bits) const override {
+    if ((int)features.size() != LYRA_B200_NUM_FEATURES) return std::nullopt;
+    std::vector<uint8_t> packet((size_t)Packet184::PacketSize(num_bits > 0 ? num_bits : 0) + 1);
+    {
+      std::lock_guard<std::mutex> lock(session_->mutex());
+      if (lyra_b200_quantize(session_->ctx(), 1, features.data(), num_bits, packet.data(), nullptr) != LYRA_B200_OK) return std::nullopt;
+    }
+    packet.resize((size_t)Packet184::PacketSize(num_bits));
+    return Packet184::UnpackPacket(packet, num_bits);
+  }
+  std::optional<std::vector<float>> DecodeToLossyFeatures(const std::string& quantized_features) const override {
+    const int num_bits = (int)quantized_features.size();
+    if (num_bits > LYRA_B200_MAX_BITS || num_bits % 4 != 0 || num_bits == 0) return std::nullopt;
+    const std::vector<uint8_t> packet = Packet184::PackQuantized(quantized_features);
+    std::vector<float> out(LYRA_B200_NUM_FEATURES);
+    std::lock_guard<std::mutex> lock(session_->mutex());
+    if (lyra_b200_dequantize(session_->ctx(), 1, packet.data(), num_bits, out.data()) != LYRA_B200_OK) return std::nullopt;
+    return out;
+  }
+
+ private:
+  explicit ResidualVectorQuantizerB200(std::shared_ptr<Session> s) : session_(std::move(s)) {}
+  std::shared_ptr<Session> session_;
+};
+
+// ---- LyraGanModel (lyra/lyra_gan_model.cc:36-64) ------------------------------------------------------------------
+class LyraGanModelB200 : public GenerativeModel {
+ public:
+  static std::unique_ptr<LyraGanModelB200> Create(const std::string& model_path, int num_features) {
+    if (num_features != LYRA_B200_NUM_FEATURES) return nullptr;
+    auto s = Session::Get(model_path);
+    if (!s) return nullptr;
+    const int id = s->Acquire();
+    if (id < 0) return nullptr;
+    return std::unique_ptr<LyraGanModelB200>(new LyraGanModelB200(std::move(s), id));
+  }
+  ~LyraGanModelB200() override { session_->Release(id_); }
+
+ protected:
+  bool RunConditioning(const std::vector<float>& features) override {
+    std::lock_guard<std::mutex> lock(session_->mutex());
+    // like the reference (lyra_gan_model.cc:53-58) the hop is generated in one go; RunModel slices it
+    return lyra_b200_generate(session_->ctx(), &id_, 1, features.data(), hop_) == LYRA_B200_OK;
+  }
+  std::optional<std::vector<int16_t>> RunModel(int num_samples) override {
+    return std::vector<int16_t>(hop_ + next_sample_in_hop(), hop_ + next_sample_in_hop() + num_samples);
+  }
+
+ private:
+  LyraGanModelB200(std::shared_ptr<Session> s, int id) : GenerativeModel(LYRA_B200_HOP, LYRA_B200_NUM_FEATURES), session_(std::move(s)), id_(id) {}
+  std::shared_ptr<Session> session_;
+  int id_;
+  int16_t hop_[LYRA_B200_HOP] = {0};
+};
+
+// ---- LogMelSpectrogramExtractorImpl at (16 kHz, hop 320, window 640) (lyra/log_mel_spectrogram_extractor_impl.cc:53-126)
+class LogMelSpectrogramExtractorB200 : public FeatureExtractorInterface {
+ public:
+  // bank: which of the context's two independent extractor states this object advances (0 or 1)
+  static std::unique_ptr<LogMelSpectrogramExtractorB200> Create(const std::string& model_path, int sample_rate_hz, int hop_length_samples,
+                                                                int window_length_samples, int num_mel_bins, int bank = 0) {
+    if (sample_rate_hz != 16000 || hop_length_samples != 320 || window_length_samples != 640) return nullptr;
+    if (num_mel_bins != 160 && num_mel_bins != 64) return nullptr;
+    auto s = Session::Get(model_path);
+    if (!s) return nullptr;
+    const int id = s->Acquire();
+    if (id < 0) return nullptr;
+    return std::unique_ptr<LogMelSpectrogramExtractorB200>(new LogMelSpectrogramExtractorB200(std::move(s), id, num_mel_bins, bank));
+  }
+  ~LogMelSpectrogramExtractorB200() override { session_->Release(id_); }
+  std::optional<std::vector<float>> Extract(const std::vector<int16_t>& audio) override {
+    if ((int)audio.size() != LYRA_B200_HOP) return std::nullopt;
+    std::vector<float> out((size_t)num_mel_);
+    std::lock_guard<std::mutex> lock(session_->mutex());
+    if (lyra_b200_logmel(session_->ctx(), bank_, &id_, 1, audio.data(), num_mel_, out.data()) != LYRA_B200_OK) return std::nullopt;
+    return out;
+  }
+
+ private:
+  LogMelSpectrogramExtractorB200(std::shared_ptr<Session> s, int id, int nmel, int bank)
+      : session_(std::move(s)), id_(id), num_mel_(nmel), bank_(bank) {}
+  std::shared_ptr<Session> session_;
+  int id_, num_mel_, bank_;
+};
+
+// ---- factories with the reference's names (lyra/lyra_components.cc:42-60) ------------------------------------------
+inline std::unique_ptr<VectorQuantizerInterface> CreateQuantizer(const std::string& model_path) { return ResidualVectorQuantizerB200::Create(model_path); }
+inline std::unique_ptr<GenerativeModelInterface> CreateGenerativeModel(int num_output_features, const std::string& model_path) {
+  return LyraGanModelB200::Create(model_path, num_output_features);
+}
+inline std::unique_ptr<FeatureExtractorInterface> CreateFeatureExtractor(const std::string& model_path) { return SoundStreamEncoderB200::Create(model_path); }
+
+// lyra/lyra_config.h:79-115
+inline int GetPacketSize(int num_quantized_bits) { return (num_quantized_bits + 7) / 8; }
+inline int BitrateToNumQuantizedBits(int bitrate) { return bitrate == 3200 ? 64 : bitrate == 6000 ? 120 : bitrate == 9200 ? 184 : -1; }
+inline int PacketSizeToNumQuantizedBits(int packet_size) { return packet_size == 8 ? 64 : packet_size == 15 ? 120 : packet_size == 23 ? 184 : -1; }
+
+// ---- LyraEncoder at 16 kHz, mono, no DTX (lyra/lyra_encoder.h:44-122, lyra/lyra_encoder.cc:43-156) --------------------
+class LyraEncoderB200 {
+ public:
+  static std::unique_ptr<LyraEncoderB200> Create(int sample_rate_hz, int num_channels, int bitrate, bool enable_dtx, const std::string& model_path) {
+    if (sample_rate_hz != 16000 || num_channels != 1 || enable_dtx) return nullptr;   // resamplers / DTX are out of scope here
+    const int bits = BitrateToNumQuantizedBits(bitrate);
+    if (bits < 0) return nullptr;
+    auto fe = CreateFeatureExtractor(model_path);
+    auto vq = CreateQuantizer(model_path);
+    if (!fe || !vq) return nullptr;
+    return std::unique_ptr<LyraEncoderB200>(new LyraEncoderB200(std::move(fe), std::move(vq), bits));
+  }
+  std::optional<std::vector<uint8_t>> Encode(const std::vector<int16_t>& audio) {
+    if ((int)audio.size() != LYRA_B200_HOP) return std::nullopt;                      // lyra_encoder.cc:124-129
+    auto features = feature_extractor_->Extract(audio);
+    if (!features.has_value()) return std::nullopt;
+    auto quantized = vector_quantizer_->Quantize(features.value(), num_quantized_bits_);
+    if (!quantized.has_value()) return std::nullopt;
+    return Packet184::PackQuantized(quantized.value());
+  }
+  bool set_bitrate(int bitrate) {
+    const int bits = BitrateToNumQuantizedBits(bitrate);
+    if (bits < 0) return false;
+    num_quantized_bits_ = bits;
+    return true;
+  }
+  int sample_rate_hz() const { return 16000; }
+  int num_channels() const { return 1; }
+  int bitrate() const { return GetPacketSize(num_quantized_bits_) * 8 * 50; }
+  int frame_rate() const { return 50; }
+
+ private:
+  LyraEncoderB200(std::unique_ptr<FeatureExtractorInterface> fe, std::unique_ptr<VectorQuantizerInterface> vq, int bits)
+      : feature_extractor_(std::move(fe)), vector_quantizer_(std::move(vq)), num_quantized_bits_(bits) {}
+  std::unique_ptr<FeatureExtractorInterface> feature_extractor_;
+  std::unique_ptr<VectorQuantizerInterface> vector_quantizer_;
+  int num_quantized_bits_;
+};
+
+// ---- LyraDecoder at 16 kHz (lyra/lyra_decoder.h:41-163): SetEncodedPacket + DecodeSamples.  A hop requested
+//      without a packet is concealed by feeding 64 zero features (ZeroFeatureEstimator, lyra_decoder.cc:317-326);
+//      the comfort-noise / fade state machine (lyra_decoder.cc:228-373) is out of scope. -----------
+class LyraDecoderB200 {
+ public:
+  static std::unique_ptr<LyraDecoderB200> Create(int sample_rate_hz, int num_channels, const std::string& model_path) {
+    if (sample_rate_hz != 16000 || num_channels != 1) return nullptr;
+    auto gm = CreateGenerativeModel(LYRA_B200_NUM_FEATURES, model_path);
+    auto vq = CreateQuantizer(model_path);
+    if (!gm || !vq) return nullptr;
+    return std::unique_ptr<LyraDecoderB200>(new LyraDecoderB200(std::move(gm), std::move(vq)));
+  }
+  bool SetEncodedPacket(const std::vector<uint8_t>& encoded) {
+    const int bits = PacketSizeToNumQuantizedBits((int)encoded.size());
+    if (bits < 0) return false;                                                         // lyra_decoder.cc:173-178
+    const auto unpacked = Packet184::UnpackPacket(encoded, bits);
+    if (!unpacked.has_value()) return false;
+    auto features = vector_quantizer_->DecodeToLossyFeatures(unpacked.value());
+    if (!features.has_value()) return false;
+    return generative_model_->AddFeatures(features.value());
+  }
+  std::optional<std::vector<int16_t>> DecodeSamples(int num_samples) {
+    if (num_samples < 0) return std::nullopt;
+    std::vector<int16_t> result;
+    while ((int)result.size() < num_samples) {
+      if (generative_model_->num_samples_available() == 0)
+        generative_model_->AddFeatures(std::vector<float>(LYRA_B200_NUM_FEATURES, 0.0f));   // packet-loss concealment
+      const int want = num_samples - (int)result.size();
+      const int in_hop = (generative_model_->num_samples_available() - 1) % LYRA_B200_HOP + 1;   // left in the current hop
+      const int take = want < in_hop ? want : in_hop;
+      auto s = generative_model_->GenerateSamples(take);
+      if (!s.has_value()) return std::nullopt;
+      result.insert(result.end(), s->begin(), s->end());
+    }
+    return result;
+  }
+
+ private:
+  LyraDecoderB200(std::unique_ptr<GenerativeModelInterface> gm, std::unique_ptr<VectorQuantizerInterface> vq)
+      : generative_model_(std::move(gm)), vector_quantizer_(std::move(vq)) {}
+  std::unique_ptr<GenerativeModelInterface> generative_model_;
+  std::unique_ptr<VectorQuantizerInterface> vector_quantizer_;
+};
+
+}  // namespace lyra_b200

@@ -134,3 +134,17 @@ def test_decoder_only_concealment_4096(gpu_api, oracle):
             opcm, _, _ = refs[k].decode(bytes(pk[k]) if rec[k] else None, bits)
             assert np.array_equal(out[k], opcm)
     ctx.close()
+
+
+def test_cpp_components_against_oracle(gpu_api, oracle, tmp_path):
+    """include/lyra_b200/lyra_b200_components.h: the reference's plugin classes re-hosted on the C ABI (C++)."""
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "test_components")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                           os.path.join(ROOT, "tests", "cpp", "test_components.cc"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "lyra_b200"), "-llyra_b200", "-L" + os.path.join(ROOT, "oracle", "_build"), "-llyra_oracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "lyra_b200"), "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build"), "-lpthread"])
+    env = dict(os.environ, LYRA_B200_MAX_STREAMS="64")
+    out = subprocess.run([exe, _capi.MODEL_DIR], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
