@@ -62,6 +62,30 @@ __device__ __forceinline__ void StageChunk(void* smem_dst, const void* gsrc, int
 
 constexpr int kStages = 3;   // cp.async ring depth of the weight stream (one block barrier per chunk)
 
+// Description of a GEMM's weight stream, used to issue its first kStages-1 chunks EARLY (right after the previous
+// GEMM's K loop, before that GEMM's epilogue and any element-wise pass in between) so the L2 latency of the
+// first chunk is never exposed.
+struct WNext {
+  const void* w;      // global weights (nullptr: nothing to prefetch)
+  int chunk_words;    // 4-byte words per chunk (KC * N)
+  int nchunks;
+};
+__device__ __forceinline__ WNext NoNext() { return WNext{nullptr, 0, 0}; }
+__device__ __forceinline__ WNext NextF32(const float* w, int KC, int N, int Ktot) { return WNext{w, KC * N, Ktot / KC}; }
+__device__ __forceinline__ WNext NextI8(const uint32_t* w, int KC4, int N, int Ktot4) { return WNext{w, KC4 * N, Ktot4 / KC4}; }
+
+template <int NT>
+__device__ __forceinline__ void IssuePrologue(void* wbuf, const WNext& nx) {
+  if (nx.w == nullptr) return;
+#pragma unroll
+  for (int p = 0; p < kStages - 1; ++p) {
+    if (p < nx.nchunks)
+      StageChunk<NT>(reinterpret_cast<uint32_t*>(wbuf) + (size_t)p * nx.chunk_words,
+                     reinterpret_cast<const uint32_t*>(nx.w) + (size_t)p * nx.chunk_words, nx.chunk_words / 4);
+    lyra_cp_async_commit();
+  }
+}
+
 // Thread -> output tile mapping.  A warp covers WM m-groups x (32/WM) n-groups so that the A fragment is
 // shared by the lanes of one m-group and the W fragment by the lanes of one n-group (shared-memory
 // broadcast); warp tiles beyond NT/32 warps are handled in extra passes.
@@ -91,7 +115,7 @@ struct TileMap {
 template <int S, int NT, int TM, int TN, int KC, int WM, bool CIN1, typename Epi>
 __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
                                            int groups, int T_out, int N, const float* __restrict__ Wg, float* wbuf,
-                                           Epi epi) {
+                                           bool pre, const WNext& nxt, Epi epi) {
   static_assert(S % TM == 0 && TM % 4 == 0 && 32 % WM == 0, "tile shape");
   constexpr int MGS = S / TM;
   const int MG = T_out * MGS, NG = N / TN;
@@ -112,11 +136,13 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
-    // prologue: chunks 0 .. kStages-2 in flight
+    // prologue: chunks 0 .. kStages-2 in flight (already issued by the previous GEMM when `pre`)
+    if (!(pre && wt0 == 0)) {
 #pragma unroll
-    for (int p = 0; p < kStages - 1; ++p) {
-      if (p < nchunks) StageChunk<NT>(wbuf + p * (KC * N), Wg + (size_t)p * KC * N, chunk16);
-      lyra_cp_async_commit();
+      for (int p = 0; p < kStages - 1; ++p) {
+        if (p < nchunks) StageChunk<NT>(wbuf + p * (KC * N), Wg + (size_t)p * KC * N, chunk16);
+        lyra_cp_async_commit();
+      }
     }
     for (int c = 0; c < nchunks; ++c) {
       lyra_cp_async_wait<kStages - 2>();     // chunk c has landed (for this thread's copies)
@@ -131,7 +157,7 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
         const int kk0 = c * KC;
         const float* Ap;
         int astep;
-        if (CIN1) { Ap = Abase + kk0 * S; astep = S; }
+        if (CIN1) { Ap = Abase + (kk0 + (kk0 >> 4)) * S; astep = S; }   // first_layer: rows skewed by one per 16 (KC == 16)
         else { const int tap = kk0 / CinG, ci0 = kk0 - tap * CinG; Ap = Abase + (size_t)ci0 * ldA + tap * S; astep = ldA; }
         const float* wp = wcur + n0;
 #pragma unroll 4
@@ -168,6 +194,7 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
       }
     }
     __syncthreads();   // every thread is past the K loop: A may be overwritten, the weight ring reused
+    if (wt0 + NT / 32 >= map.nwt) IssuePrologue<NT>(wbuf, nxt);   // last pass: start the next GEMM's weight stream
     if (active) epi(t_out, s0, n0, acc);
   }
   __syncthreads();
@@ -178,7 +205,7 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 template <int S, int NT, int TM, int TN, int KC4, int WM, typename Epi>
 __device__ __forceinline__ void GemmI8Tap(const uint32_t* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
                                           int groups, int T_out, int N, const uint32_t* __restrict__ Wg, uint32_t* wbuf,
-                                          Epi epi) {
+                                          bool pre, const WNext& nxt, Epi epi) {
   static_assert(S % TM == 0 && TM % 4 == 0 && TN % 4 == 0 && 32 % WM == 0, "tile shape");
   constexpr int MGS = S / TM;
   const int CinG4 = CinG / 4;
@@ -200,10 +227,12 @@ __device__ __forceinline__ void GemmI8Tap(const uint32_t* A, int ldA, int rowA0,
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = 0;
 
+    if (!(pre && wt0 == 0)) {
 #pragma unroll
-    for (int p = 0; p < kStages - 1; ++p) {
-      if (p < nchunks) StageChunk<NT>(wbuf + p * (KC4 * N), Wg + (size_t)p * KC4 * N, chunk16);
-      lyra_cp_async_commit();
+      for (int p = 0; p < kStages - 1; ++p) {
+        if (p < nchunks) StageChunk<NT>(wbuf + p * (KC4 * N), Wg + (size_t)p * KC4 * N, chunk16);
+        lyra_cp_async_commit();
+      }
     }
     for (int c = 0; c < nchunks; ++c) {
       lyra_cp_async_wait<kStages - 2>();
@@ -242,6 +271,7 @@ __device__ __forceinline__ void GemmI8Tap(const uint32_t* A, int ldA, int rowA0,
       }
     }
     __syncthreads();
+    if (wt0 + NT / 32 >= map.nwt) IssuePrologue<NT>(wbuf, nxt);
     if (active) epi(t_out, s0, n0, acc);
   }
   __syncthreads();

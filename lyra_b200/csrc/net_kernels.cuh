@@ -15,6 +15,14 @@
 
 namespace lyra_b200 {
 
+// Development aid (-DLYRA_PHASE_PROF): thread 0 of every block stamps clock64() at phase boundaries.
+#if defined(LYRA_PHASE_PROF) && !defined(LYRA_EMU)
+__device__ long long* g_phase_prof = nullptr;
+#define LYRA_PHASE(k, ph) do { if (threadIdx.x == 0 && g_phase_prof && blockIdx.x < 1024) g_phase_prof[((size_t)(k) * 1024 + blockIdx.x) * 48 + (ph)] = clock64(); ++(ph); } while (0)
+#else
+#define LYRA_PHASE(k, ph) do { (void)(ph); } while (0)
+#endif
+
 // ---- per-tile state layouts, in 4-byte units (each unit is S lanes wide) ----
 struct EncStateA {
   static constexpr int kFirst = 0;                               // [48]
@@ -81,15 +89,18 @@ __device__ __forceinline__ void LoadTileMeta(const TileIo& io, const int* n18_gl
 template <int S, int NT, int TM, int TN1, int TN2, int WM, int KC, int C, int T, int DIL>
 __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p, float* u, int ldu, int row0u, float* d,
                                            int groups2, float* ring, const int* n18,
-                                           const int* active, float* wbuf, bool last) {
+                                           const int* active, float* wbuf, bool last, const WNext& after, int pk, int& ph) {
   constexpr int ldd = T * S;
+  // pw1's weight stream is started by whoever ran before this unit (previous GEMM or the kernel prologue)
   if (n18[S] >= 0)
     DwF32RingFast<S, NT, C, T, DIL>(u, ldu, row0u, d, ldd, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18[S], active);
   else
     DwF32Ring<S, NT>(u, ldu, row0u, d, ldd, C, T, DIL, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18, active);
+  LYRA_PHASE(pk, ph);
   {
     const float* b1 = BlobPtr<float>(blob, p.pw1.bias);
-    GemmF32Tap<S, NT, TM, TN1, KC, WM, false>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float>(blob, p.pw1.w), wbuf,
+    GemmF32Tap<S, NT, TM, TN1, KC, WM, false>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float>(blob, p.pw1.w), wbuf, true,
+      NextF32(BlobPtr<float>(blob, p.pw2.w), KC, C, C / groups2),
       [&](int t, int s0, int n0, float (&acc)[TM][TN1]) {
 #pragma unroll
         for (int j = 0; j < TN1; ++j) {
@@ -100,9 +111,10 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
         }
       });
   }
+  LYRA_PHASE(pk, ph);
   {
     const float* b2 = BlobPtr<float>(blob, p.pw2.bias);
-    GemmF32Tap<S, NT, TM, TN2, KC, WM, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float>(blob, p.pw2.w), wbuf,
+    GemmF32Tap<S, NT, TM, TN2, KC, WM, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float>(blob, p.pw2.w), wbuf, true, after,
       [&](int t, int s0, int n0, float (&acc)[TM][TN2]) {
 #pragma unroll
         for (int j = 0; j < TN2; ++j) {
@@ -116,6 +128,7 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
         }
       });
   }
+  LYRA_PHASE(pk, ph);
 }
 
 // One int8 residual unit on packed activations (quant_encoder_2/resnet_{1,2}, quant_decoder_0/resnet_{1,2}).
@@ -123,17 +136,19 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
 template <int S, int NT, int TM, int DIL>
 __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, uint32_t* aq, int lda, int row0a,
                                           uint32_t* resq, uint32_t* dq8, uint32_t* hq, uint32_t* ring,
-                                          const int* n18, const int* active, uint32_t* wbuf) {
+                                          const int* n18, const int* active, uint32_t* wbuf, const WNext& after, int pk, int& ph) {
   constexpr int T = 2, C = 256, LD = T * S;
   if (n18[S] >= 0) DwI8RingFast<S, NT, C, T, DIL>(aq, lda, row0a, dq8, LD, blob, p.dw, ring, n18[S], active);
   else DwI8Ring<S, NT>(aq, lda, row0a, dq8, LD, C, T, DIL, blob, p.dw, ring, n18, active);
+  LYRA_PHASE(pk, ph);
   {
     const int* bias = BlobPtr<int>(blob, p.pw1.bias);
     const int* mult = BlobPtr<int>(blob, p.pw1.mult);
     const int* shift = BlobPtr<int>(blob, p.pw1.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, p.lr1.lut);
     const int out_zp = p.pw1.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint32_t>(blob, p.pw1.w), wbuf,
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint32_t>(blob, p.pw1.w), wbuf, true,
+      NextI8(BlobPtr<uint32_t>(blob, p.pw2.w), 8, C, C / 16),
       [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
@@ -152,7 +167,7 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
     const int* l2 = BlobPtr<int>(blob, p.add.lut2);
     const int8_t* lut = BlobPtr<int8_t>(blob, p.lr2.lut);
     const int out_zp = p.pw2.out_zp, m3 = p.add.m3, s3 = p.add.s3, add_zp = p.add.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint32_t>(blob, p.pw2.w), wbuf,
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint32_t>(blob, p.pw2.w), wbuf, true, after,
       [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
@@ -170,6 +185,7 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
         }
       });
   }
+  LYRA_PHASE(pk, ph);
 }
 
 // ================================================================================================
@@ -177,20 +193,25 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
 // ================================================================================================
 template <int S>
 struct EncA {
+#ifndef LYRA_TILE_8x8
   static constexpr int NT = 320;
+  static constexpr int TN = S >= 16 ? 8 : 4;
+#else
+  static constexpr int NT = S >= 16 ? 320 : 160;          // 8 x 8 thread tiles: 20*S tiles of the T = 20 layers
+  static constexpr int TN = 8;                            // 1x1 / first-layer thread tile: 8 streams x 8 channels
+#endif
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;       // S = 8 tiles fit two blocks per SM
-  static constexpr int TN = S >= 16 ? 8 : 4;              // 1x1 / first-layer thread tile: 8 streams x TN channels
   static constexpr int LDU = 25 * S, LDD = 20 * S;
   static constexpr int kSmemU = 0;
   static constexpr int kSmemD = kSmemU + 64 * LDU * 4;
   static constexpr int kSmemW = kSmemD + 64 * LDD * 4;
   static constexpr int kSmemI = kSmemW + kStages * 16 * 64 * 4;   // = kStages * 8 * 128 * 4 for simpleconv (KC = 8)
   static constexpr int kSmemBytes = kSmemI + 3 * S * 4 + 16;
-  static_assert(368 * S <= 64 * LDD, "first-layer input must fit in the d buffer");
+  static_assert(391 * S <= 64 * LDD, "first-layer input (368 rows + 23 skew rows) must fit in the d buffer");
 };
 
 template <int S>
-__global__ void __launch_bounds__(320, EncA<S>::kMinBlocks)
+__global__ void __launch_bounds__(EncA<S>::NT, EncA<S>::kMinBlocks)
 EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, const int16_t* __restrict__ pcm,
                float* __restrict__ state, int* __restrict__ n18g, float* __restrict__ mid) {
   using L = EncA<S>;
@@ -206,14 +227,19 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
   float* st = state + (size_t)tile * EncStateA::kUnits * S;
   const int tid = (int)threadIdx.x;
+  IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.first.w), 16, 64, 64));
+  int ph = 0;
+  LYRA_PHASE(0, ph);
 
   // ---- input window X[368][S] (aliases d): 48 carried samples + 320 new ones as unit floats (dsp_utils.h:104-108)
   float* X = d;
-  for (int i = tid; i < 48 * S; i += NT) X[i] = st[EncStateA::kFirst * S + i];
+  // rows are skewed by one pad row per 16 (row r lives at r + r/16) so the 4 time rows a warp reads per tap hit
+  // different banks (their distance would otherwise be 16*S words = a multiple of 32 banks)
+  for (int i = tid; i < 48 * S; i += NT) { const int r = i / S; X[(r + (r >> 4)) * S + i % S] = st[EncStateA::kFirst * S + i]; }
   for (int i = tid; i < 320 * S; i += NT) {
     const int s = i / 320, k = i % 320;
     const float v = active[s] ? (float)pcm[(size_t)slot[s] * 320 + k] * (1.0f / 32768.0f) : 0.0f;
-    X[(48 + k) * S + s] = v;
+    X[(48 + k + ((48 + k) >> 4)) * S + s] = v;
   }
   // prefix rows 0..4 of u: the 5 carried rows of encoder_0/simpleconv
   for (int i = tid; i < 64 * 5 * S; i += NT) {
@@ -222,11 +248,13 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   }
   __syncthreads();
   for (int i = tid; i < 48 * S; i += NT)
-    if (active[i % S]) st[EncStateA::kFirst * S + i] = X[320 * S + i];
+    if (active[i % S]) { const int r = 320 + i / S; st[EncStateA::kFirst * S + i] = X[(r + (r >> 4)) * S + i % S]; }
+  LYRA_PHASE(0, ph);
   // ---- first_layer: K = 64, stride 16, 1 -> 64 ; u = conv + bias (pre-activation residual stream)
   {
     const float* b = BlobPtr<float>(blob, P.first.bias);
-    GemmF32Tap<S, NT, 8, L::TN, 16, 4, true>(X, 0, 0, 16, 64, 1, 1, 20, 64, BlobPtr<float>(blob, P.first.w), wbuf,
+    GemmF32Tap<S, NT, 8, L::TN, 16, 4, true>(X, 0, 0, 17, 64, 1, 1, 20, 64, BlobPtr<float>(blob, P.first.w), wbuf, true,
+      NextF32(BlobPtr<float>(blob, P.r0[0].pw1.w), 16, 64, 64),
       [&](int t, int s0, int n0, float (&acc)[8][L::TN]) {
 #pragma unroll
         for (int j = 0; j < L::TN; ++j) {
@@ -237,19 +265,24 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
       });
   }
   // ---- encoder_0: three residual units, dilation 1/3/9
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1>(blob, P.r0[0], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing0 * S, n18, active, wbuf, false);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3>(blob, P.r0[1], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing1 * S, n18, active, wbuf, false);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9>(blob, P.r0[2], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing2 * S, n18, active, wbuf, true);
+  LYRA_PHASE(0, ph);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1>(blob, P.r0[0], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing0 * S, n18, active, wbuf, false,
+                                                       NextF32(BlobPtr<float>(blob, P.r0[1].pw1.w), 16, 64, 64), 0, ph);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3>(blob, P.r0[1], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing1 * S, n18, active, wbuf, false,
+                                                       NextF32(BlobPtr<float>(blob, P.r0[2].pw1.w), 16, 64, 64), 0, ph);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9>(blob, P.r0[2], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing2 * S, n18, active, wbuf, true,
+                                                       NextF32(BlobPtr<float>(blob, P.down0.w), 8, 128, 640), 0, ph);
   // carried rows for the next frame: the last 5 activated rows
   for (int i = tid; i < 64 * 5 * S; i += NT) {
     const int c = i / (5 * S), r = i % (5 * S);
     if (active[r % S]) st[EncStateA::kDown0 * S + i] = u[(size_t)c * L::LDU + 20 * S + r];
   }
   // ---- encoder_0/simpleconv: K = 10, stride 5, 64 -> 128 ; pre-activation output to HBM for kernel B
+  LYRA_PHASE(0, ph);
   {
     const float* b = BlobPtr<float>(blob, P.down0.bias);
     float* out = mid + (size_t)tile * 128 * 4 * S;
-    GemmF32Tap<S, NT, 8, 4, 8, 4, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), wbuf,
+    GemmF32Tap<S, NT, 8, 4, 8, 4, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), wbuf, true, NoNext(),
       [&](int t, int s0, int n0, float (&acc)[8][4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -260,6 +293,7 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
       });
   }
   if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
+  LYRA_PHASE(0, ph);
 }
 
 // ================================================================================================
@@ -307,6 +341,9 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * EncStateB::kUnits * S;
   float* st = reinterpret_cast<float*>(stw);
   const int tid = (int)threadIdx.x;
+  IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128));
+  int ph = 0;
+  LYRA_PHASE(1, ph);
 
   // ---- u1 <- kernel A output (rows 2..5), carried rows of encoder_1/simpleconv (rows 0..1)
   {
@@ -316,17 +353,23 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   }
   __syncthreads();
   // ---- encoder_1: three residual units @128 (second 1x1 has 2 groups)
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 1>(blob, P.r1[0], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf, false);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 3>(blob, P.r1[1], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing1 * S, n18, active, wbuf, false);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 9>(blob, P.r1[2], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing2 * S, n18, active, wbuf, true);
+  LYRA_PHASE(1, ph);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 1>(blob, P.r1[0], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf, false,
+                                                NextF32(BlobPtr<float>(blob, P.r1[1].pw1.w), 16, 128, 128), 1, ph);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 3>(blob, P.r1[1], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing1 * S, n18, active, wbuf, false,
+                                                NextF32(BlobPtr<float>(blob, P.r1[2].pw1.w), 16, 128, 128), 1, ph);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 9>(blob, P.r1[2], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing2 * S, n18, active, wbuf, true,
+                                                NextF32(BlobPtr<float>(blob, P.down1.w), 8, 256, 256), 1, ph);
   for (int i = tid; i < 128 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
     if (active[r % S]) st[EncStateB::kDown1 * S + i] = u1[(size_t)c * L::LD1 + 4 * S + r];
   }
   // ---- encoder_1/simpleconv: K = 4, stride 2, 128 -> 256, 2 groups ; u2 = pre-activation
+  LYRA_PHASE(1, ph);
   {
     const float* b = BlobPtr<float>(blob, P.down1.bias);
-    GemmF32Tap<S, NT, TM, 4, 8, 4, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf,
+    GemmF32Tap<S, NT, TM, 4, 8, 4, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, true,
+      NextF32(BlobPtr<float>(blob, P.m_pw1.w), 8, 256, 256),
       [&](int t, int s0, int n0, float (&acc)[TM][4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -339,6 +382,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   // ---- encoder_2/resnet_0 (mixed): f32 depthwise + f32 1x1, QUANTIZE, int8 LeakyReLU, int8 1x1 (4 groups),
   //      DEQUANTIZE + f32 residual, QUANTIZE, int8 LeakyReLU
   constexpr int LD2 = 2 * S;
+  LYRA_PHASE(1, ph);
   if (n18[S] >= 0)
     DwF32RingFast<S, NT, 256, 2, 1>(u2, LD2, 0, d2, LD2, BlobPtr<float>(blob, P.m_dw.w), BlobPtr<float>(blob, P.m_dw.bias),
                                     st + (size_t)EncStateB::kRingM * S, n18[S], active);
@@ -349,7 +393,8 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const float* b = BlobPtr<float>(blob, P.m_pw1.bias);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const QuantP q1 = P.m_q1;
-    GemmF32Tap<S, NT, TM, 4, 8, 4, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf,
+    GemmF32Tap<S, NT, TM, 4, 8, 4, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, true,
+      NextI8(BlobPtr<uint32_t>(blob, P.m_pw2.w), 8, 256, 16),
       [&](int t, int s0, int n0, float (&acc)[TM][4]) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
@@ -367,7 +412,8 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
     const QuantP dq = P.m_dq, q2 = P.m_q2;
     const int out_zp = P.m_pw2.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq,
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq, true,
+      NextI8(BlobPtr<uint32_t>(blob, P.q[0].pw1.w), 8, 256, 64),
       [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
@@ -385,9 +431,13 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
       });
   }
   // ---- quant_encoder_2/resnet_{1,2}
-  ResUnitI8<S, NT, TM, 3>(blob, P.q[0], aq, 4 * S, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, wbufq);
-  ResUnitI8<S, NT, TM, 9>(blob, P.q[1], aq, 4 * S, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ1 * S, n18, active, wbufq);
+  LYRA_PHASE(1, ph);
+  ResUnitI8<S, NT, TM, 3>(blob, P.q[0], aq, 4 * S, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, wbufq,
+                          NextI8(BlobPtr<uint32_t>(blob, P.q[1].pw1.w), 8, 256, 64), 1, ph);
+  ResUnitI8<S, NT, TM, 9>(blob, P.q[1], aq, 4 * S, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ1 * S, n18, active, wbufq,
+                          NextI8(BlobPtr<uint32_t>(blob, P.down2.w), 4, 512, 64), 1, ph);
   // ---- quant_encoder_2/simpleconv: K = 4, stride 2, 256 -> 512, 4 groups, then int8 LeakyReLU
+  LYRA_PHASE(1, ph);
   for (int i = tid; i < 64 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); aq[(size_t)c * 4 * S + r] = stw[EncStateB::kDown2 * S + i]; }
   for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); bq[(size_t)c * 3 * S + r] = stw[EncStateB::kBott * S + i]; }
   __syncthreads();
@@ -401,7 +451,8 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int* shift = BlobPtr<int>(blob, P.down2.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.down2_lr.lut);
     const int out_zp = P.down2.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 4, 2>(aq, 4 * S, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint32_t>(blob, P.down2.w), wbufq,
+    GemmI8Tap<S, NT, TM, 4, 4, 2>(aq, 4 * S, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint32_t>(blob, P.down2.w), wbufq, true,
+      NextI8(BlobPtr<uint32_t>(blob, P.bott.w), 8, 64, 96),
       [&](int t, int s0, int n0, int (&acc)[TM][4]) {
         (void)t;
 #pragma unroll
@@ -419,13 +470,14 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     if (active[r % S]) stw[EncStateB::kBott * S + i] = bq[(size_t)c * 3 * S + S + r];
   }
   // ---- quant_bottleneck_1: K = 3, 512 -> 64, 4 groups ; DEQUANTIZE -> features
+  LYRA_PHASE(1, ph);
   {
     const int* bias = BlobPtr<int>(blob, P.bott.bias);
     const int* mult = BlobPtr<int>(blob, P.bott.mult);
     const int* shift = BlobPtr<int>(blob, P.bott.shift);
     const QuantP dq = P.out_dq;
     const int out_zp = P.bott.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 2>(bq, 3 * S, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint32_t>(blob, P.bott.w), wbufq,
+    GemmI8Tap<S, NT, TM, 4, 8, 2>(bq, 3 * S, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint32_t>(blob, P.bott.w), wbufq, true, NoNext(),
       [&](int t, int s0, int n0, int (&acc)[TM][4]) {
         (void)t;
 #pragma unroll
@@ -439,6 +491,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
       });
   }
   if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
+  LYRA_PHASE(1, ph);
 }
 
 // ================================================================================================
@@ -491,6 +544,9 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   constexpr int LD2 = 2 * S;
   const UpI8& up0 = P.up0;
   const UpI8& up1 = P.up1;
+  IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.bott.w), 4, 512, 48));
+  int ph = 0;
+  LYRA_PHASE(2, ph);
 
   // ---- F: 2 carried feature rows + the new one ; overlap states into u ; padding rows of xq
   for (int i = tid; i < 64 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); F[(size_t)c * 3 * S + r] = st[DecStateC::kBott * S + i]; }
@@ -509,10 +565,12 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     if (active[r % S]) st[DecStateC::kBott * S + i] = F[(size_t)c * 3 * S + S + r];
   }
   // ---- bottleneck_2/simpleconv: K = 3, 64 -> 512, 4 groups ; LeakyReLU ; QUANTIZE
+  LYRA_PHASE(2, ph);
   {
     const float* b = BlobPtr<float>(blob, P.bott.bias);
     const QuantP q = P.bott_q;
-    GemmF32Tap<S, NT, TM, 4, 4, 2, false>(F, 3 * S, 0, 1, 3, 16, 4, 1, 512, BlobPtr<float>(blob, P.bott.w), wbuf,
+    GemmF32Tap<S, NT, TM, 4, 4, 2, false>(F, 3 * S, 0, 1, 3, 16, 4, 1, 512, BlobPtr<float>(blob, P.bott.w), wbuf, true,
+      NextI8(BlobPtr<uint32_t>(blob, P.up0.g.w), 4, 512, 64),
       [&](int t, int s0, int n0, float (&acc)[TM][4]) {
         (void)t;
 #pragma unroll
@@ -525,12 +583,14 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
       });
   }
   // ---- quant_decoder_0 upsample: 4 x TRANSPOSE_CONV (K = 4, stride 2, 128 -> 64), T 1 -> 2 (+2 tail rows)
+  LYRA_PHASE(2, ph);
   {
     const int* bias = BlobPtr<int>(blob, up0.g.bias);
     const int* mult = BlobPtr<int>(blob, up0.g.mult);
     const int* shift = BlobPtr<int>(blob, up0.g.shift);
     float* tail = st + (size_t)DecStateC::kUp0 * S;
-    GemmI8Tap<S, NT, TM, TNU, 4, 4>(xq, 3 * S, 0, 1, 2, 128, 4, 2, 512, BlobPtr<uint32_t>(blob, up0.g.w), wbufq,
+    GemmI8Tap<S, NT, TM, TNU, 4, 4>(xq, 3 * S, 0, 1, 2, 128, 4, 2, 512, BlobPtr<uint32_t>(blob, up0.g.w), wbufq, true,
+      NextI8(BlobPtr<uint32_t>(blob, P.m_pw1.w), 8, 256, 64),
       [&](int q, int s0, int n0, int (&acc)[TM][TNU]) {
         const int g = n0 / 128, r = (n0 % 128) / 64;
         const float* bf = BlobPtr<float>(blob, up0.bias_f32[g]);
@@ -552,6 +612,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
       });
   }
   // ---- LeakyReLU (f32) ; QUANTIZE -> aq rows 1..2
+  LYRA_PHASE(2, ph);
   {
     const QuantP q = P.up0_q;
     for (int i = tid; i < 64 * 2 * S; i += NT) {
@@ -564,6 +625,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   }
   __syncthreads();
   // ---- quant_decoder_0/resnet_0 (int8 body, f32 residual add)
+  LYRA_PHASE(2, ph);
   if (n18[S] >= 0) DwI8RingFast<S, NT, 256, 2, 1>(aq, 4 * S, 1, dq8, LD2, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18[S], active);
   else DwI8Ring<S, NT>(aq, 4 * S, 1, dq8, LD2, 256, 2, 1, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18, active);
   {
@@ -572,7 +634,8 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int* shift = BlobPtr<int>(blob, P.m_pw1.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const int out_zp = P.m_pw1.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(dq8, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw1.w), wbufq,
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(dq8, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw1.w), wbufq, true,
+      NextI8(BlobPtr<uint32_t>(blob, P.m_pw2.w), 8, 256, 16),
       [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
@@ -590,7 +653,8 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
     const QuantP dq = P.m_dq, q2 = P.m_q2;
     const int out_zp = P.m_pw2.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq,
+    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq, true,
+      NextI8(BlobPtr<uint32_t>(blob, P.q[0].pw1.w), 8, 256, 64),
       [&](int t, int s0, int n0, int (&acc)[TM][4]) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
@@ -607,9 +671,13 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
         }
       });
   }
-  ResUnitI8<S, NT, TM, 3>(blob, P.q[0], aq, 4 * S, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, wbufq);
-  ResUnitI8<S, NT, TM, 9>(blob, P.q[1], aq, 4 * S, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ1 * S, n18, active, wbufq);
+  LYRA_PHASE(2, ph);
+  ResUnitI8<S, NT, TM, 3>(blob, P.q[0], aq, 4 * S, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, wbufq,
+                          NextI8(BlobPtr<uint32_t>(blob, P.q[1].pw1.w), 8, 256, 64), 2, ph);
+  ResUnitI8<S, NT, TM, 9>(blob, P.q[1], aq, 4 * S, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ1 * S, n18, active, wbufq,
+                          NextI8(BlobPtr<uint32_t>(blob, P.up1.g.w), 8, 256, 64), 2, ph);
   // ---- quant_decoder_1 upsample: 2 x TRANSPOSE_CONV (K = 4, stride 2, 128 -> 64), T 2 -> 4 (+2 tail rows)
+  LYRA_PHASE(2, ph);
   {
     const uint32_t pad = PackI8x4(up1.g.in_zp, up1.g.in_zp, up1.g.in_zp, up1.g.in_zp);
     for (int i = tid; i < 64 * S; i += NT) { const int c = i / S, s = i % S; aq[(size_t)c * 4 * S + s] = pad; aq[(size_t)c * 4 * S + 3 * S + s] = pad; }
@@ -625,7 +693,8 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int* mult = BlobPtr<int>(blob, up1.g.mult);
     const int* shift = BlobPtr<int>(blob, up1.g.shift);
     float* tail = st + (size_t)DecStateC::kUp1 * S;
-    GemmI8Tap<S, NT, TM, TNU, 8, 2>(aq, 4 * S, 0, 1, 2, 128, 2, 3, 256, BlobPtr<uint32_t>(blob, up1.g.w), wbufq,
+    GemmI8Tap<S, NT, TM, TNU, 8, 2>(aq, 4 * S, 0, 1, 2, 128, 2, 3, 256, BlobPtr<uint32_t>(blob, up1.g.w), wbufq, true,
+      NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128),
       [&](int q, int s0, int n0, int (&acc)[TM][TNU]) {
         const int g = n0 / 128, r = (n0 % 128) / 64;
         const float* bf = BlobPtr<float>(blob, up1.bias_f32[g]);
@@ -647,14 +716,18 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
       });
   }
   // ---- decoder_1: three fp32 residual units @128
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 1>(blob, P.r1[0], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, false);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 3>(blob, P.r1[1], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing1 * S, n18, active, wbuf, false);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 9>(blob, P.r1[2], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing2 * S, n18, active, wbuf, true);
+  LYRA_PHASE(2, ph);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 1>(blob, P.r1[0], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, false,
+                                                NextF32(BlobPtr<float>(blob, P.r1[1].pw1.w), 16, 128, 128), 2, ph);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 3>(blob, P.r1[1], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing1 * S, n18, active, wbuf, false,
+                                                NextF32(BlobPtr<float>(blob, P.r1[2].pw1.w), 16, 128, 128), 2, ph);
+  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 9>(blob, P.r1[2], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing2 * S, n18, active, wbuf, true, NoNext(), 2, ph);
   {
     float* out = mid + (size_t)tile * 128 * 4 * S;
     for (int i = tid; i < 128 * 4 * S; i += NT) out[i] = u1[i];
   }
   if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
+  LYRA_PHASE(2, ph);
 }
 
 // ================================================================================================
@@ -662,14 +735,25 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
 // ================================================================================================
 template <int S>
 struct DecD {
+#ifndef LYRA_TILE_8x8
   static constexpr int NT = 320;
+  static constexpr int TN = S >= 16 ? 8 : 4;
+#else
+  static constexpr int NT = S >= 16 ? 320 : 160;
+  static constexpr int TN = 8;                            // 1x1 thread tile: 8 streams x 8 channels
+#endif
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
-  static constexpr int TN = S >= 16 ? 8 : 4;              // 1x1 thread tile: 8 streams x TN channels
+#ifndef LYRA_TILE_8x8
   static constexpr int TNU = S >= 16 ? 10 : 5;            // decoder_2/simple column tile (320 columns)
-  static constexpr int WMU = S >= 16 ? 2 : 1;
-  static constexpr int KCU = S >= 16 ? 8 : 4;
   static constexpr int TNL = S >= 16 ? 4 : 2;             // last_layer column tile (16 columns)
   static constexpr int WML = S >= 16 ? 8 : 4;
+#else
+  static constexpr int TNU = 10;
+  static constexpr int TNL = 4;
+  static constexpr int WML = 8;
+#endif
+  static constexpr int WMU = S >= 16 ? 2 : 1;
+  static constexpr int KCU = S >= 16 ? 8 : 4;
   static constexpr int LDU = 26 * S, LDD = 20 * S;          // u: 3 zero rows + 20 + 3 zero rows
   static constexpr int kU = 0;
   static constexpr int kD = kU + 64 * LDU * 4;              // d f32 [64][20S]; aliases X f32 [128][6S] and the PCM staging
@@ -681,7 +765,7 @@ struct DecD {
 };
 
 template <int S>
-__global__ void __launch_bounds__(320, DecD<S>::kMinBlocks)
+__global__ void __launch_bounds__(DecD<S>::NT, DecD<S>::kMinBlocks)
 DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, const float* __restrict__ mid,
                float* __restrict__ state, int* __restrict__ n18g, int16_t* __restrict__ pcm) {
   using L = DecD<S>;
@@ -699,6 +783,9 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const int tid = (int)threadIdx.x;
+  IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.up2.w), L::KCU, 320, 256));
+  int ph = 0;
+  LYRA_PHASE(3, ph);
 
   // ---- X [128][6S]: zero row, 4 rows from kernel C, zero row
   {
@@ -716,10 +803,12 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   }
   __syncthreads();
   // ---- decoder_2/simple: TRANSPOSE_CONV K = 10, stride 5, 128 -> 64 ; T 4 -> 20 (+5 tail rows)
+  LYRA_PHASE(3, ph);
   {
     const float* b = BlobPtr<float>(blob, P.up2.bias);
     float* tail = st + (size_t)DecStateD::kUp2 * S;
-    GemmF32Tap<S, NT, 8, L::TNU, L::KCU, L::WMU, false>(X, 6 * S, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float>(blob, P.up2.w), wbuf,
+    GemmF32Tap<S, NT, 8, L::TNU, L::KCU, L::WMU, false>(X, 6 * S, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float>(blob, P.up2.w), wbuf, true,
+      NextF32(BlobPtr<float>(blob, P.r2[0].pw1.w), 16, 64, 64),
       [&](int q, int s0, int n0, float (&acc)[8][L::TNU]) {
 #pragma unroll
         for (int j = 0; j < L::TNU; ++j) {
@@ -739,15 +828,20 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
       });
   }
   // ---- decoder_2: three residual units @64, T = 20
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1>(blob, P.r2[0], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing0 * S, n18, active, wbuf, false);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3>(blob, P.r2[1], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing1 * S, n18, active, wbuf, false);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9>(blob, P.r2[2], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing2 * S, n18, active, wbuf, true);
+  LYRA_PHASE(3, ph);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1>(blob, P.r2[0], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing0 * S, n18, active, wbuf, false,
+                                                       NextF32(BlobPtr<float>(blob, P.r2[1].pw1.w), 16, 64, 64), 3, ph);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3>(blob, P.r2[1], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing1 * S, n18, active, wbuf, false,
+                                                       NextF32(BlobPtr<float>(blob, P.r2[2].pw1.w), 16, 64, 64), 3, ph);
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9>(blob, P.r2[2], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing2 * S, n18, active, wbuf, true,
+                                                       NextF32(BlobPtr<float>(blob, P.last.w), 16, 16, 256), 3, ph);
   // ---- last_layer: TRANSPOSE_CONV K = 64, stride 16, 64 -> 1 ; T 20 -> 320 (+48 tail) ; float -> int16
+  LYRA_PHASE(3, ph);
   {
     const float bias = BlobPtr<float>(blob, P.last.bias)[0];
     float* tail = st + (size_t)DecStateD::kLast * S;
     int16_t* stage = reinterpret_cast<int16_t*>(d);      // [S][320]
-    GemmF32Tap<S, NT, 8, L::TNL, 16, L::WML, false>(u, L::LDU, 0, 1, 4, 64, 1, 23, 16, BlobPtr<float>(blob, P.last.w), wbuf,
+    GemmF32Tap<S, NT, 8, L::TNL, 16, L::WML, false>(u, L::LDU, 0, 1, 4, 64, 1, 23, 16, BlobPtr<float>(blob, P.last.w), wbuf, true, NoNext(),
       [&](int q, int s0, int n0, float (&acc)[8][L::TNL]) {
 #pragma unroll
         for (int j = 0; j < L::TNL; ++j) {
@@ -773,6 +867,7 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
     }
   }
   if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
+  LYRA_PHASE(3, ph);
 }
 
 }  // namespace lyra_b200
