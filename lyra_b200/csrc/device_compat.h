@@ -39,3 +39,38 @@ __device__ __forceinline__ void lyra_cp_async_commit() { asm volatile("cp.async.
 template <int N>
 __device__ __forceinline__ void lyra_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif
+
+// ---- warp-level int8 tensor-core MMA: D(16x8,s32) += A(16x32,s8,row) * B(32x8,s8,col), fragments as in the PTX ISA
+//      (mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32).  Integer accumulation is exact, so results are
+//      bit-identical to the dp4a / scalar formulation whatever the internal order.
+#if defined(LYRA_EMU)
+static inline void lyra_mma_s8_16x8x32(int (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  const uint32_t mine[6] = {a[0], a[1], a[2], a[3], b[0], b[1]};
+  const uint32_t (*all)[8] = cuda_emu::warp_gather(mine, 6);
+  const int lane = (int)(threadIdx.x & 31), g = lane >> 2, t = lane & 3;
+  auto A = [&](int row, int k) {      // row 0..15, k 0..31
+    const int src = (row & 7) * 4 + (k & 15) / 4;
+    const int reg = (row >> 3) + 2 * (k >> 4);
+    return (int)(int8_t)((all[src][reg] >> (8 * (k & 3))) & 0xff);
+  };
+  auto B = [&](int k, int col) {
+    const int src = col * 4 + (k & 15) / 4;
+    return (int)(int8_t)((all[src][4 + (k >> 4)] >> (8 * (k & 3))) & 0xff);
+  };
+  int d[4] = {c[0], c[1], c[2], c[3]};
+  for (int k = 0; k < 32; ++k) {
+    d[0] += A(g, k) * B(k, 2 * t);
+    d[1] += A(g, k) * B(k, 2 * t + 1);
+    d[2] += A(g + 8, k) * B(k, 2 * t);
+    d[3] += A(g + 8, k) * B(k, 2 * t + 1);
+  }
+  cuda_emu::warp_barrier();             // keep the table alive until every lane has read it
+  c[0] = d[0]; c[1] = d[1]; c[2] = d[2]; c[3] = d[3];
+}
+#elif defined(__CUDACC__)
+__device__ __forceinline__ void lyra_mma_s8_16x8x32(int (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+#endif

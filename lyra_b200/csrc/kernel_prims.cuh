@@ -201,80 +201,87 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// int8 tap-GEMM with dp4a.  A words [CinTotal/4][ldA], W words [ntaps*CinG/4][N]; KC4 word-rows per chunk.
-template <int S, int NT, int TM, int TN, int KC4, int WM, typename Epi>
-__device__ __forceinline__ void GemmI8Tap(const uint32_t* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
-                                          int groups, int T_out, int N, const uint32_t* __restrict__ Wg, uint32_t* wbuf,
-                                          bool pre, const WNext& nxt, Epi epi) {
-  static_assert(S % TM == 0 && TM % 4 == 0 && TN % 4 == 0 && 32 % WM == 0, "tile shape");
-  constexpr int MGS = S / TM;
-  const int CinG4 = CinG / 4;
-  const int MG = T_out * MGS, NG = N / TN;
-  const TileMap<WM> map(MG, NG);
-  const int Ktot4 = ntaps * CinG4, nchunks = Ktot4 / KC4;
-  const int chunk16 = KC4 * N / 4;
-  const int CoutG = N / groups;
-  const int warp = (int)threadIdx.x >> 5;
-  for (int wt0 = 0; wt0 < map.nwt; wt0 += NT / 32) {
-    int mg, ng;
-    const bool active = map.Locate(wt0 + warp, MG, NG, mg, ng);
-    const int t_out = active ? mg / MGS : 0, s0 = active ? (mg % MGS) * TM : 0, n0 = active ? ng * TN : 0;
-    const int g = n0 / CoutG;
-    const uint32_t* Abase = A + (size_t)(g * CinG4) * ldA + (rowA0 + t_out * row_stride) * S + s0;
-    int acc[TM][TN];
+// int8 tap-GEMM on the tensor cores (mma.sync m16n8k32, s8 x s8 -> s32; exact integer arithmetic).
+//   out[t][s][n] = sum_{tap} sum_{ci} A[g*CinG + ci][rowA0 + t*row_stride + tap][s] * W[tap*CinG + ci][n]
+//   A: shared-memory words [CinTotal/4][ldA] (4 consecutive channels per word); ldA mod 32 must be 8 or 24 so
+//      that the 4 k-words x 8 rows of a fragment load hit 32 different banks.
+//   W: global memory in FRAGMENT ORDER [k-step][n-tile][lane] x uint2 (see model_spec.cc PackMmaB): every lane's
+//      B fragment of one (k-step, n-tile) is one coalesced 8-byte load; each weight is read exactly once per
+//      block, straight from L2 into registers (no shared-memory staging, no barriers in the K loop), with a
+//      PD-deep register prefetch.
+//   A warp owns one 16-row m-tile (rows m = t*S + s) and NTW consecutive 8-column n-tiles.
+//   epi(t, s, n4, acc) is called per output row and group of 4 consecutive channels n4..n4+3 (acc is [1][4]),
+//   after neighbouring lanes have exchanged their halves of the accumulator tile.
+template <int S, int NT, int NTW, typename Epi>
+__device__ __forceinline__ void GemmI8Mma(const uint32_t* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
+                                          int groups, int T_out, int N, const uint2* __restrict__ Wf, Epi epi) {
+  constexpr int PD = 4;
+  const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+  const int M = T_out * S, MT = (M + 15) / 16, NTILES = N / 8, NWT = MT * (NTILES / NTW);
+  const int CinG4 = CinG / 4, KS = ntaps * CinG4 / 8, CoutG = N / groups;
+  for (int wt = warp; wt < NWT; wt += NT / 32) {
+    const int mt = wt % MT, nt0 = (wt / MT) * NTW;
+    const int m0 = mt * 16 + g, m1 = m0 + 8;
+    const bool valid0 = m0 < M, valid1 = m1 < M;
+    const int tr0 = valid0 ? m0 / S : T_out - 1, tr1 = valid1 ? m1 / S : T_out - 1;   // clamp: rows past M only feed discarded outputs
+    const int s0 = m0 % S, s1 = m1 % S;
+    const int grp = (nt0 * 8) / CoutG;
+    const uint32_t* pa0 = A + (size_t)(grp * CinG4) * ldA + (rowA0 + tr0 * row_stride) * S + s0;
+    const uint32_t* pa1 = A + (size_t)(grp * CinG4) * ldA + (rowA0 + tr1 * row_stride) * S + s1;
+    const uint2* wp = Wf + (size_t)nt0 * 32 + lane;
+    const size_t ks_stride = (size_t)NTILES * 32;
+    int acc[NTW][4];
 #pragma unroll
-    for (int i = 0; i < TM; ++i)
+    for (int j = 0; j < NTW; ++j) { acc[j][0] = 0; acc[j][1] = 0; acc[j][2] = 0; acc[j][3] = 0; }
+    uint2 bf[PD][NTW];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = 0;
-
-    if (!(pre && wt0 == 0)) {
+    for (int p = 0; p < PD; ++p)
+      if (p < KS) {
 #pragma unroll
-      for (int p = 0; p < kStages - 1; ++p) {
-        if (p < nchunks) StageChunk<NT>(wbuf + p * (KC4 * N), Wg + (size_t)p * KC4 * N, chunk16);
-        lyra_cp_async_commit();
+        for (int j = 0; j < NTW; ++j) bf[p][j] = __ldg(wp + p * ks_stride + j * 32);
       }
-    }
-    for (int c = 0; c < nchunks; ++c) {
-      lyra_cp_async_wait<kStages - 2>();
-      __syncthreads();
-      {
-        const int nc = c + kStages - 1;
-        if (nc < nchunks) StageChunk<NT>(wbuf + (nc % kStages) * (KC4 * N), Wg + (size_t)nc * KC4 * N, chunk16);
-        lyra_cp_async_commit();
-      }
-      if (active) {
-        const uint32_t* wcur = wbuf + (c % kStages) * (KC4 * N);
-        const int kk0 = c * KC4;
-        const int tap = kk0 / CinG4, ci0 = kk0 - tap * CinG4;
-        const uint32_t* Ap = Abase + (size_t)ci0 * ldA + tap * S;
-        const uint32_t* wp = wcur + n0;
-#pragma unroll 4
-        for (int kk = 0; kk < KC4; ++kk) {
-          uint32_t a[TM], w[TN];
+    for (int ks0 = 0; ks0 < KS; ks0 += PD) {
 #pragma unroll
-          for (int i = 0; i < TM; i += 4) {
-            const uint4 v = *reinterpret_cast<const uint4*>(Ap + i);
-            a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+      for (int p = 0; p < PD; ++p) {
+        const int ks = ks0 + p;
+        if (ks < KS) {
+          const int kw = ks * 8, tap = kw / CinG4, kw0 = kw - tap * CinG4;
+          const size_t off = (size_t)(kw0 + t4) * ldA + tap * S;
+          uint32_t a[4];
+          a[0] = pa0[off]; a[1] = pa1[off]; a[2] = pa0[off + 4 * (size_t)ldA]; a[3] = pa1[off + 4 * (size_t)ldA];
+#pragma unroll
+          for (int j = 0; j < NTW; ++j) {
+            const uint32_t b[2] = {bf[p][j].x, bf[p][j].y};
+            lyra_mma_s8_16x8x32(acc[j], a, b);
           }
+          if (ks + PD < KS) {
 #pragma unroll
-          for (int j = 0; j < TN; j += 4) {
-            const uint4 v = *reinterpret_cast<const uint4*>(wp + j);
-            w[j] = v.x; w[j + 1] = v.y; w[j + 2] = v.z; w[j + 3] = v.w;
+            for (int j = 0; j < NTW; ++j) bf[p][j] = __ldg(wp + (size_t)(ks + PD) * ks_stride + j * 32);
           }
-#pragma unroll
-          for (int i = 0; i < TM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = __dp4a((int)a[i], (int)w[j], acc[i][j]);
-          Ap += ldA;
-          wp += N;
         }
       }
     }
-    __syncthreads();
-    if (wt0 + NT / 32 >= map.nwt) IssuePrologue<NT>(wbuf, nxt);
-    if (active) epi(t_out, s0, n0, acc);
+    // lanes (2p, 2p+1) of a quad hold columns 4p..4p+1 / 4p+2..4p+3 of rows g and g+8: after one exchange the even
+    // lane owns row g, the odd lane row g+8, each with 4 consecutive channels
+    const bool even = (t4 & 1) == 0;
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) {
+      const int r0 = __shfl_xor_sync(0xffffffffu, even ? acc[j][2] : acc[j][0], 1);
+      const int r1 = __shfl_xor_sync(0xffffffffu, even ? acc[j][3] : acc[j][1], 1);
+      int out[1][4];
+      if (even) { out[0][0] = acc[j][0]; out[0][1] = acc[j][1]; out[0][2] = r0; out[0][3] = r1; }
+      else { out[0][0] = r0; out[0][1] = r1; out[0][2] = acc[j][2]; out[0][3] = acc[j][3]; }
+      const int n4 = (nt0 + j) * 8 + (t4 >> 1) * 4;
+      if (even ? valid0 : valid1) epi(even ? tr0 : tr1, even ? s0 : s1, n4, out);
+    }
   }
   __syncthreads();
+}
+
+// smallest stride >= x (multiple of 4 words) whose residue mod 32 is 8 or 24: conflict-free MMA A-fragment loads
+__host__ __device__ constexpr int PadLd(int x) {
+  while (!(x % 4 == 0 && (x % 32 == 8 || x % 32 == 24))) ++x;
+  return x;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -58,6 +58,28 @@ uint32_t Append(std::vector<uint8_t>* blob, const std::vector<T>& v) {
   return (uint32_t)off;
 }
 
+// B operand of mma.sync.m16n8k32 (s8) in fragment order: for k-step ks (32 k-values), n-tile nt (8 columns) and
+// lane L (g = L / 4, t = L % 4) two words: {B[32ks + 4t .. +3][8nt + g], B[32ks + 16 + 4t .. +3][8nt + g]}, bytes in
+// ascending k.  `b` is the dense [K][N] int8 matrix (k-major).
+std::vector<uint32_t> PackMmaB(const std::vector<int8_t>& b, int K, int N) {
+  SPEC_CHECK(K % 32 == 0 && N % 8 == 0, "MMA operand: K must be a multiple of 32 and N of 8");
+  std::vector<uint32_t> out((size_t)(K / 32) * (N / 8) * 64, 0u);
+  for (int ks = 0; ks < K / 32; ++ks)
+    for (int nt = 0; nt < N / 8; ++nt)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane / 4, t = lane % 4;
+        for (int half = 0; half < 2; ++half) {
+          uint32_t w = 0;
+          for (int byte = 0; byte < 4; ++byte) {
+            const int k = 32 * ks + 16 * half + 4 * t + byte;
+            w |= (uint32_t)(uint8_t)b[(size_t)k * N + 8 * nt + g] << (8 * byte);
+          }
+          out[(((size_t)ks * (N / 8) + nt) * 32 + lane) * 2 + half] = w;
+        }
+      }
+  return out;
+}
+
 struct Net {
   const TflModel& m;
   const TflSubgraph& g;
@@ -153,9 +175,8 @@ struct Net {
     const TflTensor& x = T(in_tensor(o));
     const TflTensor& y = T(o.outputs[0]);
     const int Cout = w.shape[0], K = w.shape[1], CinG = w.shape[3];
-    SPEC_CHECK(CinG % 4 == 0, "int8 conv: CinG must be a multiple of 4");
-    const int K4 = K * CinG / 4;
-    std::vector<uint32_t> wt((size_t)K4 * Cout, 0u);
+    SPEC_CHECK(CinG % 32 == 0, "int8 conv: CinG must be a multiple of 32");
+    std::vector<int8_t> dense((size_t)K * CinG * Cout);
     std::vector<int32_t> bias(Cout), mult, shift;
     const int8_t* src = w.as<int8_t>();
     const int32_t* bsrc = b.as<int32_t>();
@@ -166,43 +187,12 @@ struct Net {
         for (int ci = 0; ci < CinG; ++ci) {
           const int8_t v = src[((size_t)co * K + k) * CinG + ci];
           wsum += v;
-          const size_t kk = (size_t)k * CinG + ci;
-          wt[(kk / 4) * Cout + co] |= (uint32_t)(uint8_t)v << (8 * (kk % 4));
+          dense[((size_t)k * CinG + ci) * Cout + co] = v;
         }
       bias[co] = (int32_t)(bsrc[co] - (int64_t)in_zp * wsum);
     }
     RequantArrays(x, w, y, Cout, 1, &mult, &shift);
-    return GemmI8{Append(blob, wt), Append(blob, bias), Append(blob, mult), Append(blob, shift), y.zp0(), in_zp};
-  }
-
-  GemmI8 PackTconvI8(const TflOp& o, int stride) const {
-    const TflTensor& w = T(w_tensor(o));
-    const TflTensor& b = T(b_tensor(o));
-    const TflTensor& x = T(in_tensor(o));
-    const TflTensor& y = T(o.outputs[0]);
-    const int Cout = w.shape[0], K = w.shape[1], Cin = w.shape[3];
-    SPEC_CHECK(K % stride == 0 && Cin % 4 == 0, "int8 transposed conv geometry");
-    const int J = K / stride, N = stride * Cout, K4 = J * Cin / 4;
-    std::vector<uint32_t> wt((size_t)K4 * N, 0u);
-    std::vector<int32_t> bias(N), mult, shift;
-    const int8_t* src = w.as<int8_t>();
-    const int32_t* bsrc = b.as<int32_t>();
-    const int in_zp = x.zp0();
-    for (int r = 0; r < stride; ++r)
-      for (int co = 0; co < Cout; ++co) {
-        int64_t wsum = 0;
-        for (int j = 0; j < J; ++j)
-          for (int ci = 0; ci < Cin; ++ci) {
-            const int8_t v = src[((size_t)co * K + (r + stride * (J - 1 - j))) * Cin + ci];
-            wsum += v;
-            const size_t kk = (size_t)j * Cin + ci;
-            wt[(kk / 4) * N + (size_t)r * Cout + co] |= (uint32_t)(uint8_t)v << (8 * (kk % 4));
-          }
-        // rows outside the input are padded with the zero point, so the fold uses all J taps
-        bias[(size_t)r * Cout + co] = (int32_t)(bsrc[co] - (int64_t)in_zp * wsum);
-      }
-    RequantArrays(x, w, y, Cout, stride, &mult, &shift);
-    return GemmI8{Append(blob, wt), Append(blob, bias), Append(blob, mult), Append(blob, shift), y.zp0(), in_zp};
+    return GemmI8{Append(blob, PackMmaB(dense, K * CinG, Cout)), Append(blob, bias), Append(blob, mult), Append(blob, shift), y.zp0(), in_zp};
   }
 
   DwF32 PackDwF32(const TflOp& o) const {
@@ -376,8 +366,8 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
     UpI8 up;
     std::memset(&up, 0, sizeof(up));
     const int stride = 2, K = 4, Cin = 128, Cout = 64, J = K / stride;
-    const int NG = stride * Cout, N = G * NG, K4 = J * Cin / 4;
-    std::vector<uint32_t> wt((size_t)K4 * N, 0u);
+    const int NG = stride * Cout, N = G * NG;
+    std::vector<int8_t> dense((size_t)J * Cin * N);
     std::vector<int32_t> bias((size_t)N), mult((size_t)N), shift((size_t)N);
     int in_zp = 0;
     for (int gi = 0; gi < G; ++gi) {
@@ -398,8 +388,7 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
             for (int ci = 0; ci < Cin; ++ci) {
               const int8_t v = src[((size_t)co * K + (r + stride * (J - 1 - j))) * Cin + ci];
               wsum += v;
-              const size_t kk = (size_t)j * Cin + ci;
-              wt[(kk / 4) * N + col] |= (uint32_t)(uint8_t)v << (8 * (kk % 4));
+              dense[((size_t)j * Cin + ci) * N + col] = v;
             }
           // rows outside the input are padded with the zero point, so the fold uses all J taps
           bias[col] = (int32_t)(b.as<int32_t>()[co] - (int64_t)in_zp * wsum);
@@ -424,7 +413,7 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
       SPEC_CHECK(bf.data && bf.count() == 64 && bf.type == DType::F32, "transposed conv: f32 bias constant");
       up.bias_f32[gi] = Append(blob, std::vector<float>(bf.as<float>(), bf.as<float>() + 64));
     }
-    up.g = GemmI8{Append(blob, wt), Append(blob, bias), Append(blob, mult), Append(blob, shift), 0, in_zp};
+    up.g = GemmI8{Append(blob, PackMmaB(dense, J * Cin, N)), Append(blob, bias), Append(blob, mult), Append(blob, shift), 0, in_zp};
     return up;
   };
   p.up0 = pack_up(1, 4);

@@ -131,13 +131,15 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
   LYRA_PHASE(pk, ph);
 }
 
-// One int8 residual unit on packed activations (quant_encoder_2/resnet_{1,2}, quant_decoder_0/resnet_{1,2}).
+// One int8 residual unit on packed activations (quant_encoder_2/resnet_{1,2}, quant_decoder_0/resnet_{1,2}); the two
+// 1x1 convolutions run on the tensor cores.
 //   aq: LeakyReLU'd input (row offset row0a of [64][lda]); resq: the pre-activation residual; both updated in place.
-template <int S, int NT, int TM, int DIL>
+template <int S, int NT, int DIL>
 __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, uint32_t* aq, int lda, int row0a,
                                           uint32_t* resq, uint32_t* dq8, uint32_t* hq, uint32_t* ring,
-                                          const int* n18, const int* active, uint32_t* wbuf, const WNext& after, int pk, int& ph) {
-  constexpr int T = 2, C = 256, LD = T * S;
+                                          const int* n18, const int* active, int pk, int& ph) {
+  constexpr int T = 2, C = 256, LD = PadLd(T * S);
+  constexpr int NTW = S >= 16 ? 8 : 4;
   if (n18[S] >= 0) DwI8RingFast<S, NT, C, T, DIL>(aq, lda, row0a, dq8, LD, blob, p.dw, ring, n18[S], active);
   else DwI8Ring<S, NT>(aq, lda, row0a, dq8, LD, C, T, DIL, blob, p.dw, ring, n18, active);
   LYRA_PHASE(pk, ph);
@@ -147,18 +149,15 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
     const int* shift = BlobPtr<int>(blob, p.pw1.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, p.lr1.lut);
     const int out_zp = p.pw1.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint32_t>(blob, p.pw1.w), wbuf, true,
-      NextI8(BlobPtr<uint32_t>(blob, p.pw2.w), 8, C, C / 16),
-      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
+    GemmI8Mma<S, NT, NTW>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint2>(blob, p.pw1.w),
+      [&](int t, int s, int n0, int (&acc)[1][4]) {
+        int q[4];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          int q[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
-          hq[(size_t)(n0 / 4) * LD + t * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
-        }
+        for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
+        hq[(size_t)(n0 / 4) * LD + t * S + s] = PackI8x4(q[0], q[1], q[2], q[3]);
       });
   }
+  LYRA_PHASE(pk, ph);
   {
     const int* bias = BlobPtr<int>(blob, p.pw2.bias);
     const int* mult = BlobPtr<int>(blob, p.pw2.mult);
@@ -167,22 +166,19 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
     const int* l2 = BlobPtr<int>(blob, p.add.lut2);
     const int8_t* lut = BlobPtr<int8_t>(blob, p.lr2.lut);
     const int out_zp = p.pw2.out_zp, m3 = p.add.m3, s3 = p.add.s3, add_zp = p.add.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint32_t>(blob, p.pw2.w), wbuf, true, after,
-      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
+    GemmI8Mma<S, NT, NTW>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint2>(blob, p.pw2.w),
+      [&](int t, int s, int n0, int (&acc)[1][4]) {
+        const size_t ro = (size_t)(n0 / 4) * LD + t * S + s;
+        const uint32_t rw = resq[ro];
+        int r[4], a[4];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          const size_t ro = (size_t)(n0 / 4) * LD + t * S + s0 + i;
-          const uint32_t rw = resq[ro];
-          int r[4], a[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int q = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
-            r[j] = ClampI8(Mbqm(l1[q + 128] + l2[UnpackI8(rw, j) + 128], m3, s3) + add_zp);
-            a[j] = lut[r[j] + 128];
-          }
-          resq[ro] = PackI8x4(r[0], r[1], r[2], r[3]);
-          aq[(size_t)(n0 / 4) * lda + (row0a + t) * S + s0 + i] = PackI8x4(a[0], a[1], a[2], a[3]);
+        for (int j = 0; j < 4; ++j) {
+          const int q = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
+          r[j] = ClampI8(Mbqm(l1[q + 128] + l2[UnpackI8(rw, j) + 128], m3, s3) + add_zp);
+          a[j] = lut[r[j] + 128];
         }
+        resq[ro] = PackI8x4(r[0], r[1], r[2], r[3]);
+        aq[(size_t)(n0 / 4) * lda + (row0a + t) * S + s] = PackI8x4(a[0], a[1], a[2], a[3]);
       });
   }
   LYRA_PHASE(pk, ph);
@@ -306,10 +302,12 @@ struct EncB {
   static constexpr int TM = S >= 16 ? 8 : 4;              // streams per thread tile
   static constexpr int LD1 = 6 * S;                       // u1: 2 carried rows + 4
   static constexpr int kR0 = 0;                           // u1 f32 [128][6S]; later d2 f32 [256][2S]
-  static constexpr int kR1 = kR0 + 128 * LD1 * 4;         // d1 f32 [128][4S]; later hq, dq8, resq words [64][2S] each
-  static constexpr int kR2 = kR1 + 128 * 4 * S * 4;       // u2 f32 [256][2S]
-  static constexpr int kR3 = kR2 + 256 * 2 * S * 4;       // aq words [64][4S] (2 carried rows + 2), bq words [128][3S]
-  static constexpr int kW = kR3 + 64 * 4 * S * 4 + 128 * 3 * S * 4;
+  static constexpr int LQ2 = PadLd(2 * S), LQA = PadLd(4 * S), LQB = PadLd(3 * S);   // padded int8 word strides (MMA A operand)
+  static constexpr int kR1 = kR0 + 128 * LD1 * 4;         // d1 f32 [128][4S]; later hq, dq8, resq words [64][LQ2] each
+  static constexpr int kR1Bytes = 128 * 4 * S * 4 > 3 * 64 * LQ2 * 4 ? 128 * 4 * S * 4 : 3 * 64 * LQ2 * 4;
+  static constexpr int kR2 = kR1 + kR1Bytes;              // u2 f32 [256][2S]
+  static constexpr int kR3 = kR2 + 256 * 2 * S * 4;       // aq words [64][LQA] (2 carried rows + 2), bq words [128][LQB]
+  static constexpr int kW = kR3 + 64 * LQA * 4 + 128 * LQB * 4;
   static constexpr int kI = kW + kStages * 8 * 256 * 4;
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
 };
@@ -327,12 +325,12 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   float* u2 = reinterpret_cast<float*>(smem + L::kR2);
   float* d2 = reinterpret_cast<float*>(smem + L::kR0);
   uint32_t* hq = reinterpret_cast<uint32_t*>(smem + L::kR1);
-  uint32_t* dq8 = hq + 64 * 2 * S;
-  uint32_t* resq = dq8 + 64 * 2 * S;
+  constexpr int LQ2 = L::LQ2, LQA = L::LQA, LQB = L::LQB;
+  uint32_t* dq8 = hq + 64 * LQ2;
+  uint32_t* resq = dq8 + 64 * LQ2;
   uint32_t* aq = reinterpret_cast<uint32_t*>(smem + L::kR3);
-  uint32_t* bq = aq + 64 * 4 * S;
+  uint32_t* bq = aq + 64 * LQA;
   float* wbuf = reinterpret_cast<float*>(smem + L::kW);
-  uint32_t* wbufq = reinterpret_cast<uint32_t*>(smem + L::kW);
   int* slot = reinterpret_cast<int*>(smem + L::kI);
   int* active = slot + S;
   int* n18 = active + S;
@@ -394,14 +392,14 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const QuantP q1 = P.m_q1;
     GemmF32Tap<S, NT, TM, 4, 8, 4, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, true,
-      NextI8(BlobPtr<uint32_t>(blob, P.m_pw2.w), 8, 256, 16),
+      NoNext(),
       [&](int t, int s0, int n0, float (&acc)[TM][4]) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
           int q[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) q[j] = lut[QuantizeF32(__fadd_rn(acc[i][j], b[n0 + j]), q1.scale, q1.zp) + 128];
-          hq[(size_t)(n0 / 4) * LD2 + t * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
+          hq[(size_t)(n0 / 4) * LQ2 + t * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
         }
       });
   }
@@ -412,38 +410,32 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
     const QuantP dq = P.m_dq, q2 = P.m_q2;
     const int out_zp = P.m_pw2.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq, true,
-      NextI8(BlobPtr<uint32_t>(blob, P.q[0].pw1.w), 8, 256, 64),
-      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
+    GemmI8Mma<S, NT, (S >= 16 ? 8 : 4)>(hq, LQ2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint2>(blob, P.m_pw2.w),
+      [&](int t, int s, int n0, int (&acc)[1][4]) {
+        int r[4], a[4];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          int r[4], a[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int q = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
-            const float v = __fadd_rn(DequantizeI8(q, dq.scale, dq.zp), u2[(size_t)(n0 + j) * LD2 + t * S + s0 + i]);
-            r[j] = QuantizeF32(v, q2.scale, q2.zp);
-            a[j] = lut[r[j] + 128];
-          }
-          resq[(size_t)(n0 / 4) * LD2 + t * S + s0 + i] = PackI8x4(r[0], r[1], r[2], r[3]);
-          aq[(size_t)(n0 / 4) * 4 * S + (2 + t) * S + s0 + i] = PackI8x4(a[0], a[1], a[2], a[3]);
+        for (int j = 0; j < 4; ++j) {
+          const int q = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
+          const float v = __fadd_rn(DequantizeI8(q, dq.scale, dq.zp), u2[(size_t)(n0 + j) * LD2 + t * S + s]);
+          r[j] = QuantizeF32(v, q2.scale, q2.zp);
+          a[j] = lut[r[j] + 128];
         }
+        resq[(size_t)(n0 / 4) * LQ2 + t * S + s] = PackI8x4(r[0], r[1], r[2], r[3]);
+        aq[(size_t)(n0 / 4) * LQA + (2 + t) * S + s] = PackI8x4(a[0], a[1], a[2], a[3]);
       });
   }
   // ---- quant_encoder_2/resnet_{1,2}
   LYRA_PHASE(1, ph);
-  ResUnitI8<S, NT, TM, 3>(blob, P.q[0], aq, 4 * S, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, wbufq,
-                          NextI8(BlobPtr<uint32_t>(blob, P.q[1].pw1.w), 8, 256, 64), 1, ph);
-  ResUnitI8<S, NT, TM, 9>(blob, P.q[1], aq, 4 * S, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ1 * S, n18, active, wbufq,
-                          NextI8(BlobPtr<uint32_t>(blob, P.down2.w), 4, 512, 64), 1, ph);
+  ResUnitI8<S, NT, 3>(blob, P.q[0], aq, LQA, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, 1, ph);
+  ResUnitI8<S, NT, 9>(blob, P.q[1], aq, LQA, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ1 * S, n18, active, 1, ph);
   // ---- quant_encoder_2/simpleconv: K = 4, stride 2, 256 -> 512, 4 groups, then int8 LeakyReLU
   LYRA_PHASE(1, ph);
-  for (int i = tid; i < 64 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); aq[(size_t)c * 4 * S + r] = stw[EncStateB::kDown2 * S + i]; }
-  for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); bq[(size_t)c * 3 * S + r] = stw[EncStateB::kBott * S + i]; }
+  for (int i = tid; i < 64 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); aq[(size_t)c * LQA + r] = stw[EncStateB::kDown2 * S + i]; }
+  for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); bq[(size_t)c * LQB + r] = stw[EncStateB::kBott * S + i]; }
   __syncthreads();
   for (int i = tid; i < 64 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
-    if (active[r % S]) stw[EncStateB::kDown2 * S + i] = aq[(size_t)c * 4 * S + 2 * S + r];
+    if (active[r % S]) stw[EncStateB::kDown2 * S + i] = aq[(size_t)c * LQA + 2 * S + r];
   }
   {
     const int* bias = BlobPtr<int>(blob, P.down2.bias);
@@ -451,23 +443,19 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int* shift = BlobPtr<int>(blob, P.down2.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.down2_lr.lut);
     const int out_zp = P.down2.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 4, 2>(aq, 4 * S, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint32_t>(blob, P.down2.w), wbufq, true,
-      NextI8(BlobPtr<uint32_t>(blob, P.bott.w), 8, 64, 96),
-      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
+    GemmI8Mma<S, NT, 8>(aq, LQA, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint2>(blob, P.down2.w),
+      [&](int t, int s, int n0, int (&acc)[1][4]) {
         (void)t;
+        int q[4];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          int q[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
-          bq[(size_t)(n0 / 4) * 3 * S + 2 * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
-        }
+        for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
+        bq[(size_t)(n0 / 4) * LQB + 2 * S + s] = PackI8x4(q[0], q[1], q[2], q[3]);
       });
   }
   // carried rows of quant_bottleneck_1: the two newest rows
   for (int i = tid; i < 128 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
-    if (active[r % S]) stw[EncStateB::kBott * S + i] = bq[(size_t)c * 3 * S + S + r];
+    if (active[r % S]) stw[EncStateB::kBott * S + i] = bq[(size_t)c * LQB + S + r];
   }
   // ---- quant_bottleneck_1: K = 3, 512 -> 64, 4 groups ; DEQUANTIZE -> features
   LYRA_PHASE(1, ph);
@@ -477,17 +465,14 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int* shift = BlobPtr<int>(blob, P.bott.shift);
     const QuantP dq = P.out_dq;
     const int out_zp = P.bott.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 2>(bq, 3 * S, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint32_t>(blob, P.bott.w), wbufq, true, NoNext(),
-      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
+    GemmI8Mma<S, NT, 1>(bq, LQB, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint2>(blob, P.bott.w),
+      [&](int t, int s, int n0, int (&acc)[1][4]) {
         (void)t;
+        if (!active[s]) return;
+        float* o = features + (size_t)slot[s] * 64 + n0;
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          if (!active[s0 + i]) continue;
-          float* o = features + (size_t)slot[s0 + i] * 64 + n0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = DequantizeI8(RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp), dq.scale, dq.zp);
-        }
+        for (int j = 0; j < 4; ++j)
+          o[j] = DequantizeI8(RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp), dq.scale, dq.zp);
       });
   }
   if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
@@ -503,11 +488,13 @@ struct DecC {
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
   static constexpr int TM = S >= 16 ? 8 : 4;
   static constexpr int kF = 0;                              // F f32 [64][3S]
-  static constexpr int kXq = kF + 64 * 3 * S * 4;           // xq words [128][3S]  (pad, x0, pad)
-  static constexpr int kU = kXq + 128 * 3 * S * 4;          // u f32 [256][2S]; later u1 f32 [128][4S]
-  static constexpr int kAq = kU + 256 * 2 * S * 4;          // aq words [64][4S] (pad, t0, t1, pad)
-  static constexpr int kQ = kAq + 64 * 4 * S * 4;           // hq, dq8, resq words [64][2S] each; later d1 f32 [128][4S]
-  static constexpr int kW = kQ + 128 * 4 * S * 4;
+  static constexpr int LQ2 = PadLd(2 * S), LQA = PadLd(4 * S), LQB = PadLd(3 * S);   // padded int8 word strides (MMA A operand)
+  static constexpr int kXq = kF + 64 * 3 * S * 4;           // xq words [128][LQB]  (pad, x0, pad)
+  static constexpr int kU = kXq + 128 * LQB * 4;            // u f32 [256][2S]; later u1 f32 [128][4S]
+  static constexpr int kAq = kU + 256 * 2 * S * 4;          // aq words [64][LQA] (pad, t0, t1, pad)
+  static constexpr int kQ = kAq + 64 * LQA * 4;             // hq, dq8, resq words [64][LQ2] each; later d1 f32 [128][4S]
+  static constexpr int kQBytes = 128 * 4 * S * 4 > 3 * 64 * LQ2 * 4 ? 128 * 4 * S * 4 : 3 * 64 * LQ2 * 4;
+  static constexpr int kW = kQ + kQBytes;
   static constexpr int kI = kW + kStages * 4 * 512 * 4;
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
 };
@@ -520,7 +507,6 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   using L = DecC<S>;
   constexpr int NT = L::NT;
   constexpr int TM = L::TM;
-  constexpr int TNU = 8;     // column tile of the transposed-conv banks
   unsigned char* smem = LYRA_DYN_SMEM();
   float* F = reinterpret_cast<float*>(smem + L::kF);
   uint32_t* xq = reinterpret_cast<uint32_t*>(smem + L::kXq);
@@ -528,11 +514,11 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   float* u1 = u;
   uint32_t* aq = reinterpret_cast<uint32_t*>(smem + L::kAq);
   uint32_t* hq = reinterpret_cast<uint32_t*>(smem + L::kQ);
-  uint32_t* dq8 = hq + 64 * 2 * S;
-  uint32_t* resq = dq8 + 64 * 2 * S;
+  constexpr int LQ2 = L::LQ2, LQA = L::LQA, LQB = L::LQB;
+  uint32_t* dq8 = hq + 64 * LQ2;
+  uint32_t* resq = dq8 + 64 * LQ2;
   float* d1 = reinterpret_cast<float*>(smem + L::kQ);
   float* wbuf = reinterpret_cast<float*>(smem + L::kW);
-  uint32_t* wbufq = reinterpret_cast<uint32_t*>(smem + L::kW);
   int* slot = reinterpret_cast<int*>(smem + L::kI);
   int* active = slot + S;
   int* n18 = active + S;
@@ -557,7 +543,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   for (int i = tid; i < 256 * 2 * S; i += NT) u[i] = st[DecStateC::kUp0 * S + i];
   {
     const uint32_t pad = PackI8x4(P.bott_q.zp, P.bott_q.zp, P.bott_q.zp, P.bott_q.zp);
-    for (int i = tid; i < 128 * S; i += NT) { const int c = i / S, s = i % S; xq[(size_t)c * 3 * S + s] = pad; xq[(size_t)c * 3 * S + 2 * S + s] = pad; }
+    for (int i = tid; i < 128 * S; i += NT) { const int c = i / S, s = i % S; xq[(size_t)c * LQB + s] = pad; xq[(size_t)c * LQB + 2 * S + s] = pad; }
   }
   __syncthreads();
   for (int i = tid; i < 64 * 2 * S; i += NT) {
@@ -570,7 +556,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const float* b = BlobPtr<float>(blob, P.bott.bias);
     const QuantP q = P.bott_q;
     GemmF32Tap<S, NT, TM, 4, 4, 2, false>(F, 3 * S, 0, 1, 3, 16, 4, 1, 512, BlobPtr<float>(blob, P.bott.w), wbuf, true,
-      NextI8(BlobPtr<uint32_t>(blob, P.up0.g.w), 4, 512, 64),
+      NoNext(),
       [&](int t, int s0, int n0, float (&acc)[TM][4]) {
         (void)t;
 #pragma unroll
@@ -578,7 +564,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
           int v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) v[j] = QuantizeF32(LeakyRelu(__fadd_rn(acc[i][j], b[n0 + j])), q.scale, q.zp);
-          xq[(size_t)(n0 / 4) * 3 * S + S + s0 + i] = PackI8x4(v[0], v[1], v[2], v[3]);
+          xq[(size_t)(n0 / 4) * LQB + S + s0 + i] = PackI8x4(v[0], v[1], v[2], v[3]);
         }
       });
   }
@@ -589,24 +575,20 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int* mult = BlobPtr<int>(blob, up0.g.mult);
     const int* shift = BlobPtr<int>(blob, up0.g.shift);
     float* tail = st + (size_t)DecStateC::kUp0 * S;
-    GemmI8Tap<S, NT, TM, TNU, 4, 4>(xq, 3 * S, 0, 1, 2, 128, 4, 2, 512, BlobPtr<uint32_t>(blob, up0.g.w), wbufq, true,
-      NextI8(BlobPtr<uint32_t>(blob, P.m_pw1.w), 8, 256, 64),
-      [&](int q, int s0, int n0, int (&acc)[TM][TNU]) {
+    GemmI8Mma<S, NT, 8>(xq, LQB, 0, 1, 2, 128, 4, 2, 512, BlobPtr<uint2>(blob, up0.g.w),
+      [&](int q, int s, int n0, int (&acc)[1][4]) {
         const int g = n0 / 128, r = (n0 % 128) / 64;
         const float* bf = BlobPtr<float>(blob, up0.bias_f32[g]);
 #pragma unroll
-        for (int j = 0; j < TNU; ++j) {
+        for (int j = 0; j < 4; ++j) {
           const int co = (n0 + j) % 64, ch = g * 64 + co;
-#pragma unroll
-          for (int i = 0; i < TM; ++i) {
-            const int qv = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up0.out_zp[g]);
-            const float f = DequantizeI8(qv, up0.dq[g].scale, up0.dq[g].zp);
-            if (q == 0) {
-              float* o = u + (size_t)ch * LD2 + r * S + s0 + i;
-              *o = __fadd_rn(f, *o);
-            } else if (active[s0 + i]) {
-              tail[((size_t)ch * 2 + r) * S + s0 + i] = __fsub_rn(__fadd_rn(f, 0.0f), bf[co]);
-            }
+          const int qv = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up0.out_zp[g]);
+          const float f = DequantizeI8(qv, up0.dq[g].scale, up0.dq[g].zp);
+          if (q == 0) {
+            float* o = u + (size_t)ch * LD2 + r * S + s;
+            *o = __fadd_rn(f, *o);
+          } else if (active[s]) {
+            tail[((size_t)ch * 2 + r) * S + s] = __fsub_rn(__fadd_rn(f, 0.0f), bf[co]);
           }
         }
       });
@@ -620,30 +602,26 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
       int v[4];
 #pragma unroll
       for (int b = 0; b < 4; ++b) v[b] = QuantizeF32(LeakyRelu(u[(size_t)(c4 * 4 + b) * LD2 + r]), q.scale, q.zp);
-      aq[(size_t)c4 * 4 * S + S + r] = PackI8x4(v[0], v[1], v[2], v[3]);
+      aq[(size_t)c4 * LQA + S + r] = PackI8x4(v[0], v[1], v[2], v[3]);
     }
   }
   __syncthreads();
   // ---- quant_decoder_0/resnet_0 (int8 body, f32 residual add)
   LYRA_PHASE(2, ph);
-  if (n18[S] >= 0) DwI8RingFast<S, NT, 256, 2, 1>(aq, 4 * S, 1, dq8, LD2, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18[S], active);
-  else DwI8Ring<S, NT>(aq, 4 * S, 1, dq8, LD2, 256, 2, 1, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18, active);
+  if (n18[S] >= 0) DwI8RingFast<S, NT, 256, 2, 1>(aq, LQA, 1, dq8, LQ2, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18[S], active);
+  else DwI8Ring<S, NT>(aq, LQA, 1, dq8, LQ2, 256, 2, 1, blob, P.m_dw, stw + (size_t)DecStateC::kRingM * S, n18, active);
   {
     const int* bias = BlobPtr<int>(blob, P.m_pw1.bias);
     const int* mult = BlobPtr<int>(blob, P.m_pw1.mult);
     const int* shift = BlobPtr<int>(blob, P.m_pw1.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const int out_zp = P.m_pw1.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(dq8, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw1.w), wbufq, true,
-      NextI8(BlobPtr<uint32_t>(blob, P.m_pw2.w), 8, 256, 16),
-      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
+    GemmI8Mma<S, NT, (S >= 16 ? 8 : 4)>(dq8, LQ2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint2>(blob, P.m_pw1.w),
+      [&](int t, int s, int n0, int (&acc)[1][4]) {
+        int q[4];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          int q[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
-          hq[(size_t)(n0 / 4) * LD2 + t * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
-        }
+        for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
+        hq[(size_t)(n0 / 4) * LQ2 + t * S + s] = PackI8x4(q[0], q[1], q[2], q[3]);
       });
   }
   {
@@ -653,34 +631,28 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
     const QuantP dq = P.m_dq, q2 = P.m_q2;
     const int out_zp = P.m_pw2.out_zp;
-    GemmI8Tap<S, NT, TM, 4, 8, 4>(hq, LD2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint32_t>(blob, P.m_pw2.w), wbufq, true,
-      NextI8(BlobPtr<uint32_t>(blob, P.q[0].pw1.w), 8, 256, 64),
-      [&](int t, int s0, int n0, int (&acc)[TM][4]) {
+    GemmI8Mma<S, NT, (S >= 16 ? 8 : 4)>(hq, LQ2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint2>(blob, P.m_pw2.w),
+      [&](int t, int s, int n0, int (&acc)[1][4]) {
+        int r[4], a[4];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          int r[4], a[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int q = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
-            const float v = __fadd_rn(DequantizeI8(q, dq.scale, dq.zp), u[(size_t)(n0 + j) * LD2 + t * S + s0 + i]);
-            r[j] = QuantizeF32(v, q2.scale, q2.zp);
-            a[j] = lut[r[j] + 128];
-          }
-          resq[(size_t)(n0 / 4) * LD2 + t * S + s0 + i] = PackI8x4(r[0], r[1], r[2], r[3]);
-          aq[(size_t)(n0 / 4) * 4 * S + (1 + t) * S + s0 + i] = PackI8x4(a[0], a[1], a[2], a[3]);
+        for (int j = 0; j < 4; ++j) {
+          const int q = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
+          const float v = __fadd_rn(DequantizeI8(q, dq.scale, dq.zp), u[(size_t)(n0 + j) * LD2 + t * S + s]);
+          r[j] = QuantizeF32(v, q2.scale, q2.zp);
+          a[j] = lut[r[j] + 128];
         }
+        resq[(size_t)(n0 / 4) * LQ2 + t * S + s] = PackI8x4(r[0], r[1], r[2], r[3]);
+        aq[(size_t)(n0 / 4) * LQA + (1 + t) * S + s] = PackI8x4(a[0], a[1], a[2], a[3]);
       });
   }
   LYRA_PHASE(2, ph);
-  ResUnitI8<S, NT, TM, 3>(blob, P.q[0], aq, 4 * S, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, wbufq,
-                          NextI8(BlobPtr<uint32_t>(blob, P.q[1].pw1.w), 8, 256, 64), 2, ph);
-  ResUnitI8<S, NT, TM, 9>(blob, P.q[1], aq, 4 * S, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ1 * S, n18, active, wbufq,
-                          NextI8(BlobPtr<uint32_t>(blob, P.up1.g.w), 8, 256, 64), 2, ph);
+  ResUnitI8<S, NT, 3>(blob, P.q[0], aq, LQA, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, 2, ph);
+  ResUnitI8<S, NT, 9>(blob, P.q[1], aq, LQA, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ1 * S, n18, active, 2, ph);
   // ---- quant_decoder_1 upsample: 2 x TRANSPOSE_CONV (K = 4, stride 2, 128 -> 64), T 2 -> 4 (+2 tail rows)
   LYRA_PHASE(2, ph);
   {
     const uint32_t pad = PackI8x4(up1.g.in_zp, up1.g.in_zp, up1.g.in_zp, up1.g.in_zp);
-    for (int i = tid; i < 64 * S; i += NT) { const int c = i / S, s = i % S; aq[(size_t)c * 4 * S + s] = pad; aq[(size_t)c * 4 * S + 3 * S + s] = pad; }
+    for (int i = tid; i < 64 * S; i += NT) { const int c = i / S, s = i % S; aq[(size_t)c * LQA + s] = pad; aq[(size_t)c * LQA + 3 * S + s] = pad; }
     // u1 [128][4S]: rows 0..1 carry the overlap, rows 2..3 start from +0 (the zeros of the reference's concat)
     for (int i = tid; i < 128 * 4 * S; i += NT) {
       const int c = i / (4 * S), r = i % (4 * S);
@@ -693,24 +665,21 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int* mult = BlobPtr<int>(blob, up1.g.mult);
     const int* shift = BlobPtr<int>(blob, up1.g.shift);
     float* tail = st + (size_t)DecStateC::kUp1 * S;
-    GemmI8Tap<S, NT, TM, TNU, 8, 2>(aq, 4 * S, 0, 1, 2, 128, 2, 3, 256, BlobPtr<uint32_t>(blob, up1.g.w), wbufq, true,
-      NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128),
-      [&](int q, int s0, int n0, int (&acc)[TM][TNU]) {
+    IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128));
+    GemmI8Mma<S, NT, 8>(aq, LQA, 0, 1, 2, 128, 2, 3, 256, BlobPtr<uint2>(blob, up1.g.w),
+      [&](int q, int s, int n0, int (&acc)[1][4]) {
         const int g = n0 / 128, r = (n0 % 128) / 64;
         const float* bf = BlobPtr<float>(blob, up1.bias_f32[g]);
 #pragma unroll
-        for (int j = 0; j < TNU; ++j) {
+        for (int j = 0; j < 4; ++j) {
           const int co = (n0 + j) % 64, ch = g * 64 + co;
-#pragma unroll
-          for (int i = 0; i < TM; ++i) {
-            const int qv = RequantI8(acc[i][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up1.out_zp[g]);
-            const float f = DequantizeI8(qv, up1.dq[g].scale, up1.dq[g].zp);
-            if (q < 2) {
-              float* o = u1 + (size_t)ch * 4 * S + (2 * q + r) * S + s0 + i;
-              *o = __fadd_rn(f, *o);
-            } else if (active[s0 + i]) {
-              tail[((size_t)ch * 2 + r) * S + s0 + i] = __fsub_rn(__fadd_rn(f, 0.0f), bf[co]);
-            }
+          const int qv = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up1.out_zp[g]);
+          const float f = DequantizeI8(qv, up1.dq[g].scale, up1.dq[g].zp);
+          if (q < 2) {
+            float* o = u1 + (size_t)ch * 4 * S + (2 * q + r) * S + s;
+            *o = __fadd_rn(f, *o);
+          } else if (active[s]) {
+            tail[((size_t)ch * 2 + r) * S + s] = __fsub_rn(__fadd_rn(f, 0.0f), bf[co]);
           }
         }
       });

@@ -18,8 +18,9 @@ namespace lyra_b200 {
 
 // fp32 GEMM-shaped convolution: weights [Ktot][N] k-major (k = tap*CinG + ci), bias [N]
 struct GemmF32 { uint32_t w, bias; };
-// int8 convolution: weights [Ktot/4][N] words (4 consecutive ci per word), bias folded with the
-// input zero point (bias + (-zp_in) * sum(w)), per-channel Q31 multiplier and shift
+// int8 convolution: weights in mma.sync m16n8k32 B-fragment order [Ktot/32][N/8][32 lanes][2 words]
+// (k = tap*CinG + ci), bias folded with the input zero point (bias + (-zp_in) * sum(w)), per-channel Q31
+// multiplier and shift
 struct GemmI8 { uint32_t w, bias, mult, shift; int32_t out_zp; int32_t in_zp; };
 struct DwF32 { uint32_t w, bias; };                       // w [3][C]
 struct DwI8 { uint32_t w, bias, mult, shift; int32_t out_zp; int32_t in_zp; };   // w [3][C] int32
@@ -49,7 +50,7 @@ struct EncoderParams {
 };
 
 // A bank of G parallel int8 TRANSPOSE_CONVs over a channel split (quant_decoder_{0,1}/simple_g*), fused
-// into one grouped tap-GEMM: weights [(j,ci)/4][g*128 + r*64 + co] words, per-column bias/mult/shift.
+// into one grouped tap-GEMM: B-fragment-order weights over k = (j,ci), columns g*128 + r*64 + co, per-column bias/mult/shift.
 struct UpI8 {
   GemmI8 g;                 // out_zp unused (per group below); in_zp = zero point of the shared input
   QuantP dq[4];             // DEQUANTIZE of each group's int8 output

@@ -48,6 +48,15 @@ uint64_t warp_exchange(uint64_t v, int src_lane) {
   return r;
 }
 
+const uint32_t (*warp_gather(const uint32_t* vals, int n))[8] {
+  BlockState* b = g_blk;
+  const unsigned w = b->cur / 32, lane = b->cur % 32;
+  warp_barrier();                       // previous readers of the table are done
+  for (int i = 0; i < n; ++i) b->warp_scratch[w][lane][i] = vals[i];
+  warp_barrier();
+  return b->warp_scratch[w];
+}
+
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
   BlockState b;
   const unsigned nt = block.x * block.y * block.z;

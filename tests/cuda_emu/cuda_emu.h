@@ -61,6 +61,7 @@ struct BlockState {
   std::vector<unsigned> warp_arrived;
   std::vector<unsigned> warp_live;
   uint64_t warp_xchg[64][32];
+  uint32_t warp_scratch[64][32][8];
   char* smem = nullptr;
   std::function<void()> body;
 };
@@ -73,6 +74,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 void block_barrier();
 void warp_barrier();
 uint64_t warp_exchange(uint64_t v, int src_lane);
+// every lane deposits n (<= 8) words; after the call `all` points at the warp's [32][8] table (valid until the next barrier)
+const uint32_t (*warp_gather(const uint32_t* vals, int n))[8];
 
 }  // namespace cuda_emu
 
