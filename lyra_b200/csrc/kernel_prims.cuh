@@ -53,6 +53,20 @@ __device__ __forceinline__ uint32_t PackI8x4(int a, int b, int c, int d) {
 __device__ __forceinline__ int UnpackI8(uint32_t w, int i) { return (int)(int8_t)((w >> (8 * i)) & 0xff); }
 
 // ------------------------------------------------------------------------------------------------
+// Element-wise loop whose loads are batched: every thread first issues up to U independent loads (one exposed
+// memory latency instead of U), then runs the stores.  ld(i) -> T, st(i, T).
+template <int NT, int U, typename T, typename LoadFn, typename StoreFn>
+__device__ __forceinline__ void BatchedLoop(int n, LoadFn ld, StoreFn st) {
+  for (int i0 = (int)threadIdx.x; i0 < n; i0 += NT * U) {
+    T v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) { const int i = i0 + k * NT; if (i < n) v[k] = ld(i); }
+#pragma unroll
+    for (int k = 0; k < U; ++k) { const int i = i0 + k * NT; if (i < n) st(i, v[k]); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Weight chunk copy: `n16` 16-byte packets, contiguous in global memory, by all NT threads.
 template <int NT>
 __device__ __forceinline__ void StageChunk(void* smem_dst, const void* gsrc, int n16) {
@@ -350,31 +364,28 @@ __device__ __forceinline__ void DwF32RingFast(const float* u, int ldu, int row0u
   __syncthreads();
 }
 
-// int8 analogue on packed words: one thread owns (4 channels, 4 streams).
+// int8 analogue on packed words: one thread owns (4 channels, 1 stream) for all T rows (C/4 * S work items, so a
+// 256-channel T = 2 layer keeps every thread of the block busy with 8 requantisations each).
 template <int S, int NT, int C, int T, int DIL>
 __device__ __forceinline__ void DwI8RingFast(const uint32_t* aq, int lda, int row0a, uint32_t* dq, int ldd,
                                              const uint8_t* blob, const DwI8& p, uint32_t* __restrict__ ring, int n18u,
                                              const int* active) {
-  constexpr int R = 2 * DIL, Q = S / 4, C4 = C / 4;
-  constexpr int NR = T < R ? 2 * T : R;          // ring rows actually read: (t - DIL), (t - 2 DIL) for t < T
+  constexpr int R = 2 * DIL, C4 = C / 4;
   const int base = (n18u * T) % R;
   const int* w = BlobPtr<int>(blob, p.w);
   const int* bias = BlobPtr<int>(blob, p.bias);
   const int* mult = BlobPtr<int>(blob, p.mult);
   const int* shift = BlobPtr<int>(blob, p.shift);
-  (void)NR;
-  for (int item = (int)threadIdx.x; item < C4 * Q; item += NT) {
-    const int c4 = item / Q, s4 = (item % Q) * 4;
-    uint32_t* rc = ring + (size_t)c4 * R * S + s4;
-    const uint32_t* ac = aq + (size_t)c4 * lda + row0a * S + s4;
-    uint4 x1[T], x0[T], x2[T];
+  for (int item = (int)threadIdx.x; item < C4 * S; item += NT) {
+    const int c4 = item / S, s = item % S;
+    uint32_t* rc = ring + (size_t)c4 * R * S + s;
+    const uint32_t* ac = aq + (size_t)c4 * lda + row0a * S + s;
+    uint32_t x0[T], x1[T], x2[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      x2[t] = *reinterpret_cast<const uint4*>(ac + t * S);
-      if (t - DIL >= 0) x1[t] = *reinterpret_cast<const uint4*>(ac + (t - DIL) * S);
-      else x1[t] = *reinterpret_cast<const uint4*>(rc + ((base + t - DIL + 2 * R) % R) * S);
-      if (t - 2 * DIL >= 0) x0[t] = *reinterpret_cast<const uint4*>(ac + (t - 2 * DIL) * S);
-      else x0[t] = *reinterpret_cast<const uint4*>(rc + ((base + t - 2 * DIL + 2 * R) % R) * S);
+      x2[t] = ac[t * S];
+      x1[t] = t - DIL >= 0 ? ac[(t - DIL) * S] : rc[((base + t - DIL + 2 * R) % R) * S];
+      x0[t] = t - 2 * DIL >= 0 ? ac[(t - 2 * DIL) * S] : rc[((base + t - 2 * DIL + 2 * R) % R) * S];
     }
     int wk[3][4], bb[4], mm[4], sh[4];
 #pragma unroll
@@ -385,29 +396,18 @@ __device__ __forceinline__ void DwI8RingFast(const uint32_t* aq, int lda, int ro
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      const uint32_t a0[4] = {x0[t].x, x0[t].y, x0[t].z, x0[t].w};
-      const uint32_t a1[4] = {x1[t].x, x1[t].y, x1[t].z, x1[t].w};
-      const uint32_t a2[4] = {x2[t].x, x2[t].y, x2[t].z, x2[t].w};
-      uint32_t o[4];
+      int q[4];
 #pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        int q[4];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int acc = UnpackI8(a0[l], b) * wk[0][b] + UnpackI8(a1[l], b) * wk[1][b] + UnpackI8(a2[l], b) * wk[2][b];
-          q[b] = RequantI8(acc, bb[b], mm[b], sh[b], p.out_zp);
-        }
-        o[l] = PackI8x4(q[0], q[1], q[2], q[3]);
+      for (int b = 0; b < 4; ++b) {
+        const int acc = UnpackI8(x0[t], b) * wk[0][b] + UnpackI8(x1[t], b) * wk[1][b] + UnpackI8(x2[t], b) * wk[2][b];
+        q[b] = RequantI8(acc, bb[b], mm[b], sh[b], p.out_zp);
       }
-      *reinterpret_cast<uint4*>(dq + (size_t)c4 * ldd + t * S + s4) = make_uint4(o[0], o[1], o[2], o[3]);
+      dq[(size_t)c4 * ldd + t * S + s] = PackI8x4(q[0], q[1], q[2], q[3]);
     }
     constexpr int TF = T > R ? T - R : 0;
+    if (active[s]) {
 #pragma unroll
-    for (int t = TF; t < T; ++t) {
-      uint32_t* dst = rc + ((base + t) % R) * S;
-      const uint32_t v[4] = {x2[t].x, x2[t].y, x2[t].z, x2[t].w};
-#pragma unroll
-      for (int l = 0; l < 4; ++l) if (active[s4 + l]) dst[l] = v[l];
+      for (int t = TF; t < T; ++t) rc[((base + t) % R) * S] = x2[t];
     }
   }
   __syncthreads();

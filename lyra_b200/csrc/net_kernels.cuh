@@ -231,17 +231,14 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   float* X = d;
   // rows are skewed by one pad row per 16 (row r lives at r + r/16) so the 4 time rows a warp reads per tap hit
   // different banks (their distance would otherwise be 16*S words = a multiple of 32 banks)
-  for (int i = tid; i < 48 * S; i += NT) { const int r = i / S; X[(r + (r >> 4)) * S + i % S] = st[EncStateA::kFirst * S + i]; }
-  for (int i = tid; i < 320 * S; i += NT) {
-    const int s = i / 320, k = i % 320;
-    const float v = active[s] ? (float)pcm[(size_t)slot[s] * 320 + k] * (1.0f / 32768.0f) : 0.0f;
-    X[(48 + k + ((48 + k) >> 4)) * S + s] = v;
-  }
+  BatchedLoop<NT, 2, float>(48 * S, [&](int i) { return st[EncStateA::kFirst * S + i]; },
+                            [&](int i, float v) { const int r = i / S; X[(r + (r >> 4)) * S + i % S] = v; });
+  BatchedLoop<NT, 8, float>(320 * S,
+    [&](int i) { const int s = i / 320, k = i % 320; return active[s] ? (float)pcm[(size_t)slot[s] * 320 + k] * (1.0f / 32768.0f) : 0.0f; },
+    [&](int i, float v) { const int s = i / 320, k = i % 320; X[(48 + k + ((48 + k) >> 4)) * S + s] = v; });
   // prefix rows 0..4 of u: the 5 carried rows of encoder_0/simpleconv
-  for (int i = tid; i < 64 * 5 * S; i += NT) {
-    const int c = i / (5 * S), r = i % (5 * S);
-    u[(size_t)c * L::LDU + r] = st[EncStateA::kDown0 * S + i];
-  }
+  BatchedLoop<NT, 8, float>(64 * 5 * S, [&](int i) { return st[EncStateA::kDown0 * S + i]; },
+                            [&](int i, float v) { const int c = i / (5 * S), r = i % (5 * S); u[(size_t)c * L::LDU + r] = v; });
   __syncthreads();
   for (int i = tid; i < 48 * S; i += NT)
     if (active[i % S]) { const int r = 320 + i / S; st[EncStateA::kFirst * S + i] = X[(r + (r >> 4)) * S + i % S]; }
@@ -346,8 +343,10 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   // ---- u1 <- kernel A output (rows 2..5), carried rows of encoder_1/simpleconv (rows 0..1)
   {
     const float* in = mid + (size_t)tile * 128 * 4 * S;
-    for (int i = tid; i < 128 * 4 * S; i += NT) { const int c = i / (4 * S), r = i % (4 * S); u1[(size_t)c * L::LD1 + 2 * S + r] = in[i]; }
-    for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); u1[(size_t)c * L::LD1 + r] = st[EncStateB::kDown1 * S + i]; }
+    BatchedLoop<NT, 4, float4>(128 * S, [&](int i) { return reinterpret_cast<const float4*>(in)[i]; },
+      [&](int i, float4 v) { const int c = i / S, r = (i % S) * 4; *reinterpret_cast<float4*>(u1 + (size_t)c * L::LD1 + 2 * S + r) = v; });
+    BatchedLoop<NT, 8, float>(128 * 2 * S, [&](int i) { return st[EncStateB::kDown1 * S + i]; },
+      [&](int i, float v) { const int c = i / (2 * S), r = i % (2 * S); u1[(size_t)c * L::LD1 + r] = v; });
   }
   __syncthreads();
   // ---- encoder_1: three residual units @128 (second 1x1 has 2 groups)
@@ -430,8 +429,10 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   ResUnitI8<S, NT, 9>(blob, P.q[1], aq, LQA, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ1 * S, n18, active, 1, ph);
   // ---- quant_encoder_2/simpleconv: K = 4, stride 2, 256 -> 512, 4 groups, then int8 LeakyReLU
   LYRA_PHASE(1, ph);
-  for (int i = tid; i < 64 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); aq[(size_t)c * LQA + r] = stw[EncStateB::kDown2 * S + i]; }
-  for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); bq[(size_t)c * LQB + r] = stw[EncStateB::kBott * S + i]; }
+  BatchedLoop<NT, 4, uint32_t>(64 * 2 * S, [&](int i) { return stw[EncStateB::kDown2 * S + i]; },
+    [&](int i, uint32_t v) { const int c = i / (2 * S), r = i % (2 * S); aq[(size_t)c * LQA + r] = v; });
+  BatchedLoop<NT, 8, uint32_t>(128 * 2 * S, [&](int i) { return stw[EncStateB::kBott * S + i]; },
+    [&](int i, uint32_t v) { const int c = i / (2 * S), r = i % (2 * S); bq[(size_t)c * LQB + r] = v; });
   __syncthreads();
   for (int i = tid; i < 64 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
@@ -535,12 +536,12 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   LYRA_PHASE(2, ph);
 
   // ---- F: 2 carried feature rows + the new one ; overlap states into u ; padding rows of xq
-  for (int i = tid; i < 64 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); F[(size_t)c * 3 * S + r] = st[DecStateC::kBott * S + i]; }
-  for (int i = tid; i < 64 * S; i += NT) {
-    const int s = i / 64, c = i % 64;
-    F[(size_t)c * 3 * S + 2 * S + s] = active[s] ? features[(size_t)slot[s] * 64 + c] : 0.0f;
-  }
-  for (int i = tid; i < 256 * 2 * S; i += NT) u[i] = st[DecStateC::kUp0 * S + i];
+  BatchedLoop<NT, 4, float>(64 * 2 * S, [&](int i) { return st[DecStateC::kBott * S + i]; },
+    [&](int i, float v) { const int c = i / (2 * S), r = i % (2 * S); F[(size_t)c * 3 * S + r] = v; });
+  BatchedLoop<NT, 2, float>(64 * S, [&](int i) { const int s = i / 64, c = i % 64; return active[s] ? features[(size_t)slot[s] * 64 + c] : 0.0f; },
+    [&](int i, float v) { const int s = i / 64, c = i % 64; F[(size_t)c * 3 * S + 2 * S + s] = v; });
+  BatchedLoop<NT, 4, float4>(256 * 2 * S / 4, [&](int i) { return reinterpret_cast<const float4*>(st + (size_t)DecStateC::kUp0 * S)[i]; },
+    [&](int i, float4 v) { reinterpret_cast<float4*>(u)[i] = v; });
   {
     const uint32_t pad = PackI8x4(P.bott_q.zp, P.bott_q.zp, P.bott_q.zp, P.bott_q.zp);
     for (int i = tid; i < 128 * S; i += NT) { const int c = i / S, s = i % S; xq[(size_t)c * LQB + s] = pad; xq[(size_t)c * LQB + 2 * S + s] = pad; }
@@ -654,10 +655,9 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const uint32_t pad = PackI8x4(up1.g.in_zp, up1.g.in_zp, up1.g.in_zp, up1.g.in_zp);
     for (int i = tid; i < 64 * S; i += NT) { const int c = i / S, s = i % S; aq[(size_t)c * LQA + s] = pad; aq[(size_t)c * LQA + 3 * S + s] = pad; }
     // u1 [128][4S]: rows 0..1 carry the overlap, rows 2..3 start from +0 (the zeros of the reference's concat)
-    for (int i = tid; i < 128 * 4 * S; i += NT) {
-      const int c = i / (4 * S), r = i % (4 * S);
-      u1[i] = r < 2 * S ? st[DecStateC::kUp1 * S + (size_t)c * 2 * S + r] : 0.0f;
-    }
+    BatchedLoop<NT, 8, float>(128 * 4 * S,
+      [&](int i) { const int c = i / (4 * S), r = i % (4 * S); return r < 2 * S ? st[DecStateC::kUp1 * S + (size_t)c * 2 * S + r] : 0.0f; },
+      [&](int i, float v) { u1[i] = v; });
   }
   __syncthreads();
   {
@@ -759,16 +759,17 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   // ---- X [128][6S]: zero row, 4 rows from kernel C, zero row
   {
     const float* in = mid + (size_t)tile * 128 * 4 * S;
-    for (int i = tid; i < 128 * 6 * S; i += NT) {
-      const int c = i / (6 * S), r = i % (6 * S);
-      X[i] = (r >= S && r < 5 * S) ? in[(size_t)c * 4 * S + (r - S)] : 0.0f;
-    }
+    BatchedLoop<NT, 4, float4>(128 * S, [&](int i) { return reinterpret_cast<const float4*>(in)[i]; },
+      [&](int i, float4 v) { const int c = i / S, r = (i % S) * 4; *reinterpret_cast<float4*>(X + (size_t)c * 6 * S + S + r) = v; });
+    for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); X[(size_t)c * 6 * S + (r < S ? r : 4 * S + r)] = 0.0f; }
     // u rows: 3 zero rows | rows 0..4 carry the overlap of decoder_2/simple, rows 5..19 start from +0 | 3 zero rows
-    for (int i = tid; i < 64 * 26 * S; i += NT) {
-      const int c = i / (26 * S), r = i % (26 * S);
-      u[i] = (r >= 3 * S && r < 8 * S) ? st[DecStateD::kUp2 * S + (size_t)c * 5 * S + (r - 3 * S)] : 0.0f;
+    for (int i = tid; i < 64 * 26 * S / 4; i += NT) {
+      const int r = (i * 4) % (26 * S);
+      if (!(r >= 3 * S && r < 8 * S)) reinterpret_cast<float4*>(u)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
-    for (int i = tid; i < 48 * S; i += NT) sl[i] = st[DecStateD::kLast * S + i];
+    BatchedLoop<NT, 8, float>(64 * 5 * S, [&](int i) { return st[DecStateD::kUp2 * S + i]; },
+      [&](int i, float v) { const int c = i / (5 * S), r = i % (5 * S); u[(size_t)c * 26 * S + 3 * S + r] = v; });
+    BatchedLoop<NT, 2, float>(48 * S, [&](int i) { return st[DecStateD::kLast * S + i]; }, [&](int i, float v) { sl[i] = v; });
   }
   __syncthreads();
   // ---- decoder_2/simple: TRANSPOSE_CONV K = 10, stride 5, 128 -> 64 ; T 4 -> 20 (+5 tail rows)

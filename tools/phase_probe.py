@@ -15,7 +15,7 @@ from lyra_b200 import _capi  # noqa
 NAMES = {
     0: ["loads(X,prefix,state)", "first_layer", "u0.dw", "u0.pw1", "u0.pw2", "u1.dw", "u1.pw1", "u1.pw2", "u2.dw", "u2.pw1", "u2.pw2", "down0.state", "down0 gemm+end"],
     1: ["loads", "r0.dw", "r0.pw1", "r0.pw2", "r1.dw", "r1.pw1", "r1.pw2", "r2.dw", "r2.pw1", "r2.pw2", "down1 state", "down1", "m.dw+pw1+pw2",
-        "q0.dw", "q0.pw1", "q0.pw2", "q1.dw", "q1.pw1", "q1.pw2", "down2 state", "down2", "bott"],
+        "q0.dw", "q0.pw1", "q0.pw2", "q1.dw", "q1.pw1", "q1.pw2", "down2 state+gemm", "bott state", "bott"],
     2: ["loads", "bott", "up0", "lrelu+quant", "m.dw+pw1+pw2", "q0.dw", "q0.pw1", "q0.pw2", "q1.dw", "q1.pw1", "q1.pw2", "up1 prep", "up1",
         "r0.dw", "r0.pw1", "r0.pw2", "r1.dw", "r1.pw1", "r1.pw2", "r2.dw", "r2.pw1", "r2.pw2", "store"],
     3: ["loads", "up2", "u0.dw", "u0.pw1", "u0.pw2", "u1.dw", "u1.pw1", "u1.pw2", "u2.dw", "u2.pw1", "u2.pw2", "last+store"],
