@@ -83,14 +83,15 @@ struct WNext {
   const void* w;      // global weights (nullptr: nothing to prefetch)
   int chunk_words;    // 4-byte words per chunk (KC * N)
   int nchunks;
+  void* ring;         // shared-memory ring of the next GEMM when it is not the caller's (nullptr: same ring)
 };
-__device__ __forceinline__ WNext NoNext() { return WNext{nullptr, 0, 0}; }
-__device__ __forceinline__ WNext NextF32(const float* w, int KC, int N, int Ktot) { return WNext{w, KC * N, Ktot / KC}; }
-__device__ __forceinline__ WNext NextI8(const uint32_t* w, int KC4, int N, int Ktot4) { return WNext{w, KC4 * N, Ktot4 / KC4}; }
+__device__ __forceinline__ WNext NoNext() { return WNext{nullptr, 0, 0, nullptr}; }
+__device__ __forceinline__ WNext NextF32(const float* w, int KC, int N, int Ktot, void* ring = nullptr) { return WNext{w, KC * N, Ktot / KC, ring}; }
 
 template <int NT>
-__device__ __forceinline__ void IssuePrologue(void* wbuf, const WNext& nx) {
+__device__ __forceinline__ void IssuePrologue(void* wbuf_default, const WNext& nx) {
   if (nx.w == nullptr) return;
+  void* wbuf = nx.ring ? nx.ring : wbuf_default;
 #pragma unroll
   for (int p = 0; p < kStages - 1; ++p) {
     if (p < nx.nchunks)

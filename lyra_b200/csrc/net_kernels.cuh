@@ -201,7 +201,7 @@ struct EncA {
   static constexpr int kSmemU = 0;
   static constexpr int kSmemD = kSmemU + 64 * LDU * 4;
   static constexpr int kSmemW = kSmemD + 64 * LDD * 4;
-  static constexpr int kSmemI = kSmemW + kStages * 16 * 64 * 4;   // = kStages * 8 * 128 * 4 for simpleconv (KC = 8)
+  static constexpr int kSmemI = kSmemW + kStages * 16 * 64 * 4;   // ring of the 64-channel layers (simpleconv's ring lives in d)
   static constexpr int kSmemBytes = kSmemI + 3 * S * 4 + 16;
   static_assert(391 * S <= 64 * LDD, "first-layer input (368 rows + 23 skew rows) must fit in the d buffer");
 };
@@ -264,7 +264,7 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3>(blob, P.r0[1], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing1 * S, n18, active, wbuf, false,
                                                        NextF32(BlobPtr<float>(blob, P.r0[2].pw1.w), 16, 64, 64), 0, ph);
   ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9>(blob, P.r0[2], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing2 * S, n18, active, wbuf, true,
-                                                       NextF32(BlobPtr<float>(blob, P.down0.w), 8, 128, 640), 0, ph);
+                                                       NextF32(BlobPtr<float>(blob, P.down0.w), 16, 128, 640, d), 0, ph);
   // carried rows for the next frame: the last 5 activated rows
   for (int i = tid; i < 64 * 5 * S; i += NT) {
     const int c = i / (5 * S), r = i % (5 * S);
@@ -275,7 +275,10 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   {
     const float* b = BlobPtr<float>(blob, P.down0.bias);
     float* out = mid + (size_t)tile * 128 * 4 * S;
-    GemmF32Tap<S, NT, 8, 4, 8, 4, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), wbuf, true, NoNext(),
+    // the d buffer is free from here on: it hosts this GEMM's weight ring (3 x 16 x 128 floats), twice the chunk the
+    // regular ring could hold, which halves the number of block barriers of this K = 640 layer
+    static_assert(kStages * 16 * 128 * 4 <= 64 * L::LDD * 4, "simpleconv weight ring must fit in d");
+    GemmF32Tap<S, NT, 8, 4, 16, 4, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), d, true, NoNext(),
       [&](int t, int s0, int n0, float (&acc)[8][4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -722,12 +725,14 @@ struct DecD {
   static constexpr int WML = 8;
 #endif
   static constexpr int WMU = S >= 16 ? 2 : 1;
-  static constexpr int KCU = S >= 16 ? 8 : 4;
+  static constexpr int KCU = 8;                           // its ring starts right behind X inside d and runs into the regular ring
   static constexpr int LDU = 26 * S, LDD = 20 * S;          // u: 3 zero rows + 20 + 3 zero rows
   static constexpr int kU = 0;
   static constexpr int kD = kU + 64 * LDU * 4;              // d f32 [64][20S]; aliases X f32 [128][6S] and the PCM staging
   static constexpr int kW = kD + 64 * LDD * 4;
-  static constexpr int kSl = kW + kStages * KCU * 320 * 4;   // carried tail of last_layer [48][S]
+  static constexpr int kWBytes = kStages * 16 * 64 * 4 + 2048;   // regular ring (64-channel layers) + slack for the decoder_2/simple ring
+  static constexpr int kSl = kW + kWBytes;                  // carried tail of last_layer [48][S]
+  static_assert(128 * 6 * S * 4 + kStages * KCU * 320 * 4 <= 64 * LDD * 4 + kWBytes, "decoder_2/simple ring must fit behind X");
   static constexpr int kI = kSl + 48 * S * 4;
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
   static_assert(128 * 6 * S <= 64 * LDD, "X must fit in d");
@@ -752,7 +757,8 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const int tid = (int)threadIdx.x;
-  IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.up2.w), L::KCU, 320, 256));
+  float* wbuf_up2 = X + 128 * 6 * S;     // free tail of d + the regular ring
+  IssuePrologue<NT>(wbuf_up2, NextF32(BlobPtr<float>(blob, P.up2.w), L::KCU, 320, 256));
   int ph = 0;
   LYRA_PHASE(3, ph);
 
@@ -777,8 +783,8 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   {
     const float* b = BlobPtr<float>(blob, P.up2.bias);
     float* tail = st + (size_t)DecStateD::kUp2 * S;
-    GemmF32Tap<S, NT, 8, L::TNU, L::KCU, L::WMU, false>(X, 6 * S, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float>(blob, P.up2.w), wbuf, true,
-      NextF32(BlobPtr<float>(blob, P.r2[0].pw1.w), 16, 64, 64),
+    GemmF32Tap<S, NT, 8, L::TNU, L::KCU, L::WMU, false>(X, 6 * S, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float>(blob, P.up2.w), wbuf_up2, true,
+      NextF32(BlobPtr<float>(blob, P.r2[0].pw1.w), 16, 64, 64, wbuf),
       [&](int q, int s0, int n0, float (&acc)[8][L::TNU]) {
 #pragma unroll
         for (int j = 0; j < L::TNU; ++j) {
