@@ -299,7 +299,14 @@ template <int S>
 struct EncB {
   static constexpr int NT = 256;
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
+#ifdef LYRA_BC_TM4
   static constexpr int TM = S >= 16 ? 8 : 4;              // streams per thread tile
+#else
+  static constexpr int TM = 8;                            // streams per fp32 thread tile (8 x 4 tiles: fewer smem wavefronts per FMA)
+#endif
+  static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
+  static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;
+  static constexpr int WM1 = 1 * S / TM >= 4 ? 4 : 1 * S / TM;
   static constexpr int LD1 = 6 * S;                       // u1: 2 carried rows + 4
   static constexpr int kR0 = 0;                           // u1 f32 [128][6S]; later d2 f32 [256][2S]
   static constexpr int LQ2 = PadLd(2 * S), LQA = PadLd(4 * S), LQB = PadLd(3 * S);   // padded int8 word strides (MMA A operand)
@@ -354,11 +361,11 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   __syncthreads();
   // ---- encoder_1: three residual units @128 (second 1x1 has 2 groups)
   LYRA_PHASE(1, ph);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 1>(blob, P.r1[0], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf, false,
+  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 1>(blob, P.r1[0], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf, false,
                                                 NextF32(BlobPtr<float>(blob, P.r1[1].pw1.w), 16, 128, 128), 1, ph);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 3>(blob, P.r1[1], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing1 * S, n18, active, wbuf, false,
+  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 3>(blob, P.r1[1], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing1 * S, n18, active, wbuf, false,
                                                 NextF32(BlobPtr<float>(blob, P.r1[2].pw1.w), 16, 128, 128), 1, ph);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 9>(blob, P.r1[2], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing2 * S, n18, active, wbuf, true,
+  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 9>(blob, P.r1[2], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing2 * S, n18, active, wbuf, true,
                                                 NextF32(BlobPtr<float>(blob, P.down1.w), 8, 256, 256), 1, ph);
   for (int i = tid; i < 128 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
@@ -368,7 +375,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   LYRA_PHASE(1, ph);
   {
     const float* b = BlobPtr<float>(blob, P.down1.bias);
-    GemmF32Tap<S, NT, TM, 4, 8, 4, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, true,
+    GemmF32Tap<S, NT, TM, 4, 8, L::WM2, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, true,
       NextF32(BlobPtr<float>(blob, P.m_pw1.w), 8, 256, 256),
       [&](int t, int s0, int n0, float (&acc)[TM][4]) {
 #pragma unroll
@@ -393,7 +400,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const float* b = BlobPtr<float>(blob, P.m_pw1.bias);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const QuantP q1 = P.m_q1;
-    GemmF32Tap<S, NT, TM, 4, 8, 4, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, true,
+    GemmF32Tap<S, NT, TM, 4, 8, L::WM2, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, true,
       NoNext(),
       [&](int t, int s0, int n0, float (&acc)[TM][4]) {
 #pragma unroll
@@ -490,7 +497,14 @@ template <int S>
 struct DecC {
   static constexpr int NT = 256;
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
-  static constexpr int TM = S >= 16 ? 8 : 4;
+#ifdef LYRA_BC_TM4
+  static constexpr int TM = S >= 16 ? 8 : 4;              // streams per thread tile
+#else
+  static constexpr int TM = 8;                            // streams per fp32 thread tile (8 x 4 tiles: fewer smem wavefronts per FMA)
+#endif
+  static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
+  static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;
+  static constexpr int WM1 = 1 * S / TM >= 4 ? 4 : 1 * S / TM;
   static constexpr int kF = 0;                              // F f32 [64][3S]
   static constexpr int LQ2 = PadLd(2 * S), LQA = PadLd(4 * S), LQB = PadLd(3 * S);   // padded int8 word strides (MMA A operand)
   static constexpr int kXq = kF + 64 * 3 * S * 4;           // xq words [128][LQB]  (pad, x0, pad)
@@ -559,7 +573,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   {
     const float* b = BlobPtr<float>(blob, P.bott.bias);
     const QuantP q = P.bott_q;
-    GemmF32Tap<S, NT, TM, 4, 4, 2, false>(F, 3 * S, 0, 1, 3, 16, 4, 1, 512, BlobPtr<float>(blob, P.bott.w), wbuf, true,
+    GemmF32Tap<S, NT, TM, 4, 4, L::WM1, false>(F, 3 * S, 0, 1, 3, 16, 4, 1, 512, BlobPtr<float>(blob, P.bott.w), wbuf, true,
       NoNext(),
       [&](int t, int s0, int n0, float (&acc)[TM][4]) {
         (void)t;
@@ -689,11 +703,11 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   }
   // ---- decoder_1: three fp32 residual units @128
   LYRA_PHASE(2, ph);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 1>(blob, P.r1[0], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, false,
+  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 1>(blob, P.r1[0], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, false,
                                                 NextF32(BlobPtr<float>(blob, P.r1[1].pw1.w), 16, 128, 128), 2, ph);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 3>(blob, P.r1[1], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing1 * S, n18, active, wbuf, false,
+  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 3>(blob, P.r1[1], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing1 * S, n18, active, wbuf, false,
                                                 NextF32(BlobPtr<float>(blob, P.r1[2].pw1.w), 16, 128, 128), 2, ph);
-  ResUnitF32<S, NT, TM, 4, 4, 4, 16, 128, 4, 9>(blob, P.r1[2], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing2 * S, n18, active, wbuf, true, NoNext(), 2, ph);
+  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 9>(blob, P.r1[2], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing2 * S, n18, active, wbuf, true, NoNext(), 2, ph);
   {
     float* out = mid + (size_t)tile * 128 * 4 * S;
     for (int i = tid; i < 128 * 4 * S; i += NT) out[i] = u1[i];
