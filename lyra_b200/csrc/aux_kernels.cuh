@@ -20,21 +20,31 @@ __global__ void __launch_bounds__(kRvqThreads)
 RvqEncodeKernel(const uint8_t* __restrict__ blob, RvqParams P, const float* __restrict__ features, int n, int nq,
                 uint8_t* __restrict__ packets, int packet_bytes, int* __restrict__ indices_out) {
   unsigned char* smem = LYRA_DYN_SMEM();
-  float* rs = reinterpret_cast<float*>(smem);                       // [slots][64]
-  int* idxs = reinterpret_cast<int*>(smem + kRvqSlotsPerBlock * 64 * 4);   // [slots][48]
+  float* cbs = reinterpret_cast<float*>(smem);                                  // [2][64][16] stage codebooks (double buffer)
+  float* rs = cbs + 2 * 1024;                                                   // [slots][64] residuals
+  int* idxs = reinterpret_cast<int*>(rs + kRvqSlotsPerBlock * 64);              // [slots][48]
   const int tid = (int)threadIdx.x, grp = tid / 16, c = tid % 16;
   const int slot = (int)blockIdx.x * kRvqSlotsPerBlock + grp;
   const bool valid = slot < n;
   float* r = rs + grp * 64;
   int* idx = idxs + grp * 48;
   const float* cbt = BlobPtr<float>(blob, P.codebooks_t);
-  const float* cb = BlobPtr<float>(blob, P.codebooks);
+  // stage 0 codebook -> buffer 0 (4 KB = 256 x 16 B, two packets per thread)
+  for (int i = tid; i < 256; i += kRvqThreads) lyra_cp_async16(cbs + 4 * i, cbt + 4 * i);
+  lyra_cp_async_commit();
   for (int jj = 0; jj < 4; ++jj) r[c + 16 * jj] = valid ? features[(size_t)slot * 64 + c + 16 * jj] : 0.0f;
-  __syncwarp();
   for (int s = 0; s < nq; ++s) {
-    const float* cs = cbt + (size_t)s * 1024 + c;
+    lyra_cp_async_wait<0>();
+    __syncthreads();                       // codebook s landed; everyone finished stage s-1 (its buffer is free again)
+    if (s + 1 < nq) {
+      float* dst = cbs + ((s + 1) & 1) * 1024;
+      const float* src = cbt + (size_t)(s + 1) * 1024;
+      for (int i = tid; i < 256; i += kRvqThreads) lyra_cp_async16(dst + 4 * i, src + 4 * i);
+    }
+    lyra_cp_async_commit();
+    const float* cs = cbs + (s & 1) * 1024 + c;
     float d = 0.0f;
-#pragma unroll 8
+#pragma unroll 16
     for (int j = 0; j < 64; ++j) {
       const float df = __fsub_rn(r[j], cs[j * 16]);
       d = __fadd_rn(d, __fmul_rn(df, df));
@@ -47,18 +57,18 @@ RvqEncodeKernel(const uint8_t* __restrict__ blob, RvqParams P, const float* __re
       if (od < d || (od == d && oi < best)) { d = od; best = oi; }
     }
     __syncwarp();
-    const float* q = cb + ((size_t)s * 16 + best) * 64;
+    const float* q = cbs + (s & 1) * 1024 + best;      // q[j] = codebook[best][j] at q[j * 16]
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int j = c + 16 * jj;
       const float rj = r[j];
-      const float t = __fsub_rn(q[j], rj);
+      const float t = __fsub_rn(q[j * 16], rj);
       const float u = __fadd_rn(rj, t);
       r[j] = __fsub_rn(rj, u);
     }
     if (c == 0) idx[s] = best;
-    __syncwarp();
   }
+  __syncthreads();
   if (valid) {
     // first quantizer in the most significant bits (residual_vector_quantizer.cc:101-109), bytes MSB-first
     for (int b = c; b < packet_bytes; b += 16) {

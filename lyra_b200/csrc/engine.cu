@@ -154,7 +154,7 @@ int LaunchQuantize(lyra_b200_ctx* ctx, const float* d_features, int n, int num_b
   const int nq = num_bits / ctx->spec.bits_per_stage;
   const int blocks = (n + kRvqSlotsPerBlock - 1) / kRvqSlotsPerBlock;
   { ProfScope ps(ctx, 2);
-  LYRA_LAUNCH(RvqEncodeKernel, dim3((unsigned)blocks), dim3(kRvqThreads), (size_t)(kRvqSlotsPerBlock * (64 * 4 + 48 * 4)), ctx->stream,
+  LYRA_LAUNCH(RvqEncodeKernel, dim3((unsigned)blocks), dim3(kRvqThreads), (size_t)(2 * 1024 * 4 + kRvqSlotsPerBlock * (64 * 4 + 48 * 4)), ctx->stream,
               ctx->d_blob, ctx->spec.rvq, d_features, n, nq, d_packets, PacketBytes(num_bits), d_indices); }
   ctx->launches += 1;
   CU(cudaGetLastError());
