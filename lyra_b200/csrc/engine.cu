@@ -56,6 +56,10 @@ struct lyra_b200_ctx {
   int map_dense_n = -1;     // >= 0: the device map currently describes streams 0..n-1
   int active_tiles = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  static constexpr int kMaxSplit = 4;
+  cudaStream_t aux_stream[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
+  int nsplit = 2;
   uint64_t launches = 0;
   std::string err;
   // diagnostics: CUDA-event timing of every kernel launch
@@ -75,7 +79,8 @@ struct ProfScope {
   lyra_b200_ctx* ctx;
   int k;
   cudaEvent_t stop = nullptr;
-  ProfScope(lyra_b200_ctx* c, int kernel) : ctx(c), k(kernel) {
+  cudaStream_t st;
+  ProfScope(lyra_b200_ctx* c, int kernel, cudaStream_t stream) : ctx(c), k(kernel), st(stream) {
     if (!ctx->profiling) return;
     auto& pool = ctx->prof_events[k];
     if (ctx->prof_used[k] == pool.size()) {
@@ -85,10 +90,10 @@ struct ProfScope {
       pool.emplace_back(a, b);
     }
     auto& ev = pool[ctx->prof_used[k]++];
-    cudaEventRecord(ev.first, ctx->stream);
+    cudaEventRecord(ev.first, st);
     stop = ev.second;
   }
-  ~ProfScope() { if (stop) cudaEventRecord(stop, ctx->stream); }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
 };
 
 void ProfDrain(lyra_b200_ctx* ctx) {
@@ -133,60 +138,120 @@ int PrepareMap(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
   return LYRA_B200_OK;
 }
 
+// A contiguous part of the current call: tiles [tile0, tile0 + ntiles) of the tile list, I/O slots
+// [slot0, slot0 + nslots), launched on stream `st`.
+struct Part {
+  int tile0, ntiles, slot0, nslots;
+  cudaStream_t st;
+};
+Part WholeCall(lyra_b200_ctx* ctx, int n) { return Part{0, ctx->active_tiles, 0, n, ctx->stream}; }
+
 template <int kS>
-int LaunchEncoderNetsT(lyra_b200_ctx* ctx, const int16_t* d_pcm, float* d_features) {
-  const TileIo io{ctx->d_tile_list, ctx->d_slot_of};
-  { ProfScope ps(ctx, 0);
-  LYRA_LAUNCH(EncoderKernelA<kS>, dim3((unsigned)ctx->active_tiles), dim3(EncA<kS>::NT), (size_t)EncA<kS>::kSmemBytes, ctx->stream,
+int LaunchEncoderNetsT(lyra_b200_ctx* ctx, const Part& p, const int16_t* d_pcm, float* d_features) {
+  const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of};
+  { ProfScope ps(ctx, 0, p.st);
+  LYRA_LAUNCH(EncoderKernelA<kS>, dim3((unsigned)p.ntiles), dim3(EncA<kS>::NT), (size_t)EncA<kS>::kSmemBytes, p.st,
               ctx->d_blob, ctx->spec.enc, io, d_pcm, reinterpret_cast<float*>(ctx->d_state[0]), ctx->d_n18[0], ctx->d_mid_enc); }
-  { ProfScope ps(ctx, 1);
-  LYRA_LAUNCH(EncoderKernelB<kS>, dim3((unsigned)ctx->active_tiles), dim3(EncB<kS>::NT), (size_t)EncB<kS>::kSmemBytes, ctx->stream,
+  { ProfScope ps(ctx, 1, p.st);
+  LYRA_LAUNCH(EncoderKernelB<kS>, dim3((unsigned)p.ntiles), dim3(EncB<kS>::NT), (size_t)EncB<kS>::kSmemBytes, p.st,
               ctx->d_blob, ctx->spec.enc, io, ctx->d_mid_enc, reinterpret_cast<float*>(ctx->d_state[1]), ctx->d_n18[1], d_features); }
   ctx->launches += 2;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
 }
-int LaunchEncoderNets(lyra_b200_ctx* ctx, const int16_t* d_pcm, float* d_features) {
-  return ctx->S == 16 ? LaunchEncoderNetsT<16>(ctx, d_pcm, d_features) : LaunchEncoderNetsT<8>(ctx, d_pcm, d_features);
+int LaunchEncoderNets(lyra_b200_ctx* ctx, const Part& p, const int16_t* d_pcm, float* d_features) {
+  return ctx->S == 16 ? LaunchEncoderNetsT<16>(ctx, p, d_pcm, d_features) : LaunchEncoderNetsT<8>(ctx, p, d_pcm, d_features);
 }
 
-int LaunchQuantize(lyra_b200_ctx* ctx, const float* d_features, int n, int num_bits, uint8_t* d_packets, int* d_indices) {
-  const int nq = num_bits / ctx->spec.bits_per_stage;
-  const int blocks = (n + kRvqSlotsPerBlock - 1) / kRvqSlotsPerBlock;
-  { ProfScope ps(ctx, 2);
-  LYRA_LAUNCH(RvqEncodeKernel, dim3((unsigned)blocks), dim3(kRvqThreads), (size_t)(2 * 1024 * 4 + kRvqSlotsPerBlock * (64 * 4 + 48 * 4)), ctx->stream,
-              ctx->d_blob, ctx->spec.rvq, d_features, n, nq, d_packets, PacketBytes(num_bits), d_indices); }
+int LaunchQuantize(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int num_bits, uint8_t* d_packets, int* d_indices) {
+  const int nq = num_bits / ctx->spec.bits_per_stage, pb = PacketBytes(num_bits);
+  const int blocks = (p.nslots + kRvqSlotsPerBlock - 1) / kRvqSlotsPerBlock;
+  { ProfScope ps(ctx, 2, p.st);
+  LYRA_LAUNCH(RvqEncodeKernel, dim3((unsigned)blocks), dim3(kRvqThreads), (size_t)(2 * 1024 * 4 + kRvqSlotsPerBlock * (64 * 4 + 48 * 4)), p.st,
+              ctx->d_blob, ctx->spec.rvq, d_features + (size_t)p.slot0 * 64, p.nslots, nq, d_packets + (size_t)p.slot0 * pb, pb,
+              d_indices ? d_indices + (size_t)p.slot0 * 46 : nullptr); }
   ctx->launches += 1;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
 }
 
-int LaunchDequantize(lyra_b200_ctx* ctx, const uint8_t* d_packets, const uint8_t* d_received, int n, int num_bits, float* d_features) {
-  const int nq = num_bits / ctx->spec.bits_per_stage;
-  const int blocks = (n * 64 + 255) / 256;
-  { ProfScope ps(ctx, 3);
-  LYRA_LAUNCH(RvqDecodeKernel, dim3((unsigned)blocks), dim3(256), (size_t)0, ctx->stream,
-              ctx->d_blob, ctx->spec.rvq, d_packets, PacketBytes(num_bits), d_received, n, nq, d_features); }
+int LaunchDequantize(lyra_b200_ctx* ctx, const Part& p, const uint8_t* d_packets, const uint8_t* d_received, int num_bits, float* d_features) {
+  const int nq = num_bits / ctx->spec.bits_per_stage, pb = PacketBytes(num_bits);
+  const int blocks = (p.nslots * 64 + 255) / 256;
+  { ProfScope ps(ctx, 3, p.st);
+  LYRA_LAUNCH(RvqDecodeKernel, dim3((unsigned)blocks), dim3(256), (size_t)0, p.st,
+              ctx->d_blob, ctx->spec.rvq, d_packets + (size_t)p.slot0 * pb, pb, d_received ? d_received + p.slot0 : nullptr, p.nslots, nq,
+              d_features + (size_t)p.slot0 * 64); }
   ctx->launches += 1;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
 }
 
 template <int kS>
-int LaunchDecoderNetsT(lyra_b200_ctx* ctx, const float* d_features, int16_t* d_pcm) {
-  const TileIo io{ctx->d_tile_list, ctx->d_slot_of};
-  { ProfScope ps(ctx, 4);
-  LYRA_LAUNCH(DecoderKernelC<kS>, dim3((unsigned)ctx->active_tiles), dim3(DecC<kS>::NT), (size_t)DecC<kS>::kSmemBytes, ctx->stream,
+int LaunchDecoderNetsT(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int16_t* d_pcm) {
+  const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of};
+  { ProfScope ps(ctx, 4, p.st);
+  LYRA_LAUNCH(DecoderKernelC<kS>, dim3((unsigned)p.ntiles), dim3(DecC<kS>::NT), (size_t)DecC<kS>::kSmemBytes, p.st,
               ctx->d_blob, ctx->spec.dec, io, d_features, reinterpret_cast<float*>(ctx->d_state[2]), ctx->d_n18[2], ctx->d_mid_dec); }
-  { ProfScope ps(ctx, 5);
-  LYRA_LAUNCH(DecoderKernelD<kS>, dim3((unsigned)ctx->active_tiles), dim3(DecD<kS>::NT), (size_t)DecD<kS>::kSmemBytes, ctx->stream,
+  { ProfScope ps(ctx, 5, p.st);
+  LYRA_LAUNCH(DecoderKernelD<kS>, dim3((unsigned)p.ntiles), dim3(DecD<kS>::NT), (size_t)DecD<kS>::kSmemBytes, p.st,
               ctx->d_blob, ctx->spec.dec, io, ctx->d_mid_dec, reinterpret_cast<float*>(ctx->d_state[3]), ctx->d_n18[3], d_pcm); }
   ctx->launches += 2;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
 }
-int LaunchDecoderNets(lyra_b200_ctx* ctx, const float* d_features, int16_t* d_pcm) {
-  return ctx->S == 16 ? LaunchDecoderNetsT<16>(ctx, d_features, d_pcm) : LaunchDecoderNetsT<8>(ctx, d_features, d_pcm);
+int LaunchDecoderNets(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int16_t* d_pcm) {
+  return ctx->S == 16 ? LaunchDecoderNetsT<16>(ctx, p, d_features, d_pcm) : LaunchDecoderNetsT<8>(ctx, p, d_features, d_pcm);
+}
+
+// Dense calls over many tiles are cut into two halves that run on two CUDA streams: the block scheduler then
+// fills the partial last wave of one half's kernel with blocks of the other half (independent streams, so no
+// ordering between them), which removes most of the wave-quantisation loss of 512 tiles on 2 x 148 block slots.
+int SplitParts(lyra_b200_ctx* ctx, int n, Part* parts) {
+  int np = ctx->nsplit < 1 ? 1 : (ctx->nsplit > lyra_b200_ctx::kMaxSplit ? lyra_b200_ctx::kMaxSplit : ctx->nsplit);
+  if (!(ctx->map_dense_n == n && ctx->active_tiles >= 64 * np)) np = 1;
+  if (np == 1) { parts[0] = WholeCall(ctx, n); return 1; }
+  for (int i = 0; i < np; ++i) {
+    const int t0 = (int)((long long)ctx->active_tiles * i / np), t1 = (int)((long long)ctx->active_tiles * (i + 1) / np);
+    const int s0 = t0 * ctx->S, s1 = i + 1 == np ? n : t1 * ctx->S;
+    parts[i] = Part{t0, t1 - t0, s0, s1 - s0, i == 0 ? ctx->stream : ctx->aux_stream[i - 1]};
+  }
+  return np;
+}
+int Fork(lyra_b200_ctx* ctx, int nparts) {
+  if (nparts < 2) return LYRA_B200_OK;
+  CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  for (int i = 1; i < nparts; ++i) CU(cudaStreamWaitEvent(ctx->aux_stream[i - 1], ctx->ev_fork, 0));
+  return LYRA_B200_OK;
+}
+int Join(lyra_b200_ctx* ctx, int nparts) {
+  for (int i = 1; i < nparts; ++i) {
+    CU(cudaEventRecord(ctx->ev_join[i - 1], ctx->aux_stream[i - 1]));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i - 1], 0));
+  }
+  return LYRA_B200_OK;
+}
+
+int RunEncode(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets) {
+  Part parts[lyra_b200_ctx::kMaxSplit];
+  const int np = SplitParts(ctx, n, parts);
+  int rc = Fork(ctx, np);
+  for (int i = 0; i < np && !rc; ++i) {
+    if ((rc = LaunchEncoderNets(ctx, parts[i], d_pcm, ctx->d_features))) break;
+    rc = LaunchQuantize(ctx, parts[i], ctx->d_features, num_bits, d_packets, nullptr);
+  }
+  return rc ? rc : Join(ctx, np);
+}
+
+int RunDecode(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits, int16_t* d_pcm) {
+  Part parts[lyra_b200_ctx::kMaxSplit];
+  const int np = SplitParts(ctx, n, parts);
+  int rc = Fork(ctx, np);
+  for (int i = 0; i < np && !rc; ++i) {
+    if ((rc = LaunchDequantize(ctx, parts[i], d_packets, d_received, num_bits, ctx->d_features))) break;
+    rc = LaunchDecoderNets(ctx, parts[i], ctx->d_features, d_pcm);
+  }
+  return rc ? rc : Join(ctx, np);
 }
 
 template <int kS>
@@ -305,6 +370,12 @@ int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b2
   const size_t P = (size_t)ctx->padded;
   bool ok = cudaSetDevice(device) == cudaSuccess;
   ok = ok && cudaStreamCreate(&ctx->own_stream) == cudaSuccess;
+  for (int i = 0; i < lyra_b200_ctx::kMaxSplit - 1; ++i) {
+    ok = ok && cudaStreamCreate(&ctx->aux_stream[i]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  if (const char* e = std::getenv("LYRA_B200_SPLIT")) ctx->nsplit = std::atoi(e);
   ctx->stream = ctx->own_stream;
   ok = ok && DevAlloc(&ctx->d_blob, ctx->spec.blob.size()) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->d_blob, ctx->spec.blob.data(), ctx->spec.blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -353,6 +424,11 @@ void lyra_b200_destroy(lyra_b200_ctx* ctx) {
   cudaFree(ctx->d_melout); cudaFree(ctx->d_indices); cudaFree(ctx->d_ids); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_slot_of);
   for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k)
     for (auto& ev : ctx->prof_events[k]) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < lyra_b200_ctx::kMaxSplit - 1; ++i) {
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -401,8 +477,7 @@ int lyra_b200_encode_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, nullptr, n);
   if (rc) return rc;
-  if ((rc = LaunchEncoderNets(ctx, d_pcm, ctx->d_features))) return rc;
-  return LaunchQuantize(ctx, ctx->d_features, n, num_bits, d_packets, nullptr);
+  return RunEncode(ctx, n, d_pcm, num_bits, d_packets);
 }
 
 int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits,
@@ -411,8 +486,7 @@ int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets,
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, nullptr, n);
   if (rc) return rc;
-  if ((rc = LaunchDequantize(ctx, d_packets, d_received, n, num_bits, ctx->d_features))) return rc;
-  return LaunchDecoderNets(ctx, ctx->d_features, d_pcm);
+  return RunDecode(ctx, n, d_packets, d_received, num_bits, d_pcm);
 }
 
 int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, int num_bits, uint8_t* packets) {
@@ -421,8 +495,7 @@ int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = LaunchEncoderNets(ctx, ctx->d_pcm, ctx->d_features))) return rc;
-  if ((rc = LaunchQuantize(ctx, ctx->d_features, n, num_bits, ctx->d_packets, nullptr))) return rc;
+  if ((rc = RunEncode(ctx, n, ctx->d_pcm, num_bits, ctx->d_packets))) return rc;
   CU(cudaMemcpyAsync(packets, ctx->d_packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return LYRA_B200_OK;
@@ -436,8 +509,7 @@ int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_
   if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->d_packets, packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   if (received) CU(cudaMemcpyAsync(ctx->d_received, received, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = LaunchDequantize(ctx, ctx->d_packets, received ? ctx->d_received : nullptr, n, num_bits, ctx->d_features))) return rc;
-  if ((rc = LaunchDecoderNets(ctx, ctx->d_features, ctx->d_pcm))) return rc;
+  if ((rc = RunDecode(ctx, n, ctx->d_packets, received ? ctx->d_received : nullptr, num_bits, ctx->d_pcm))) return rc;
   CU(cudaMemcpyAsync(pcm, ctx->d_pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return LYRA_B200_OK;
@@ -448,7 +520,7 @@ int lyra_b200_extract_features(lyra_b200_ctx* ctx, const int32_t* ids, int n, co
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = LaunchEncoderNets(ctx, ctx->d_pcm, ctx->d_features))) return rc;
+  if ((rc = LaunchEncoderNets(ctx, WholeCall(ctx, n), ctx->d_pcm, ctx->d_features))) return rc;
   CU(cudaMemcpyAsync(features, ctx->d_features, sizeof(float) * 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return LYRA_B200_OK;
@@ -459,7 +531,8 @@ int lyra_b200_quantize(lyra_b200_ctx* ctx, int n, const float* features, int num
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "count out of range"; return LYRA_B200_EINVAL; }
   CU(cudaMemcpyAsync(ctx->d_features, features, sizeof(float) * 64 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = LaunchQuantize(ctx, ctx->d_features, n, num_bits, ctx->d_packets, indices ? ctx->d_indices : nullptr);
+  const Part whole{0, 0, 0, n, ctx->stream};
+  int rc = LaunchQuantize(ctx, whole, ctx->d_features, num_bits, ctx->d_packets, indices ? ctx->d_indices : nullptr);
   if (rc) return rc;
   CU(cudaMemcpyAsync(packets, ctx->d_packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   if (indices) CU(cudaMemcpyAsync(indices, ctx->d_indices, sizeof(int) * 46 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -472,7 +545,8 @@ int lyra_b200_dequantize(lyra_b200_ctx* ctx, int n, const uint8_t* packets, int 
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "count out of range"; return LYRA_B200_EINVAL; }
   CU(cudaMemcpyAsync(ctx->d_packets, packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = LaunchDequantize(ctx, ctx->d_packets, nullptr, n, num_bits, ctx->d_features);
+  const Part whole{0, 0, 0, n, ctx->stream};
+  int rc = LaunchDequantize(ctx, whole, ctx->d_packets, nullptr, num_bits, ctx->d_features);
   if (rc) return rc;
   CU(cudaMemcpyAsync(features, ctx->d_features, sizeof(float) * 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -484,7 +558,7 @@ int lyra_b200_generate(lyra_b200_ctx* ctx, const int32_t* ids, int n, const floa
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->d_features, features, sizeof(float) * 64 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = LaunchDecoderNets(ctx, ctx->d_features, ctx->d_pcm))) return rc;
+  if ((rc = LaunchDecoderNets(ctx, WholeCall(ctx, n), ctx->d_features, ctx->d_pcm))) return rc;
   CU(cudaMemcpyAsync(pcm, ctx->d_pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return LYRA_B200_OK;
@@ -508,7 +582,7 @@ int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* ids, int n, co
   const LogMelParams& P = num_mel_bins == 160 ? ctx->spec.logmel160 : ctx->spec.logmel64;
   CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   const size_t smem = sizeof(double) * (size_t)(2 * P.fft + P.fft / 2 + 1);
-  { ProfScope ps(ctx, 6);
+  { ProfScope ps(ctx, 6, ctx->stream);
   LYRA_LAUNCH(LogMelKernel, dim3((unsigned)n), dim3(256), smem, ctx->stream,
               ctx->d_blob, P, d_ids, n, ctx->d_pcm, ctx->d_logmel_prev[bank], ctx->d_melout); }
   ctx->launches += 1;
