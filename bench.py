@@ -43,6 +43,19 @@ ALGO_BYTES = {
 }
 
 
+def ncu_traffic(kernel, streams):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        if d.get("streams") == streams and kernel in d:
+            return d[kernel]
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -227,7 +240,6 @@ def main():
     launches0 = ctx.launch_count
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ctx.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
@@ -235,10 +247,20 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize()
     elapsed_ms = e0.elapsed_time(e1)
-    prof = ctx.profile_read()
-    ctx.profile_enable(False)
     clocks = sampler.stop()
     gpu_launches = ctx.launch_count - launches0
+    barrier()
+    # per-kernel roofline pass: the same steps with the kernels serialised (one launch per kernel and step over all
+    # streams, no concurrent sub-batches) and CUDA events around every launch on the launching stream
+    ctx.set_split(1)
+    for i in range(3):
+        step_device(i)
+    ctx.profile_enable(True)
+    for i in range(args.steps):
+        step_device(i)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    ctx.set_split(2)
     barrier()
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -285,7 +307,7 @@ def main():
         dom = max(kern, key=lambda k: kern[k]["ms_per_launch"])
         total_algo = (79744 + 640 + P) + (74368 + 640 + P)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": ncu_traffic(dom, n), "peak_source": peak_src,
                     "kernel_share_of_step": kern[dom]["ms_per_launch"] / sum(v["ms_per_launch"] for v in kern.values()),
                     "whole_step": {"algo_bytes_per_frame": total_algo,
                                    "achieved_gbs": total_algo * n * args.steps / (elapsed_ms / 1e3) / 1e9 if world == 1 else None,

@@ -100,6 +100,10 @@ int lyra_b200_encode_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int
 int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received,
                             int num_bits, int16_t* d_pcm);
 int lyra_b200_synchronize(lyra_b200_ctx* ctx);
+/* Dense calls (stream_ids == NULL / *_device) over many tiles are cut into `parts` (1..4, default 2) sub-batches that
+ * run concurrently on internal CUDA streams so partial waves of one kernel are filled by another's blocks.
+ * parts = 1 serialises the kernels (used by bench.py's per-kernel roofline pass). */
+int lyra_b200_set_split(lyra_b200_ctx* ctx, int parts);
 /* number of CUDA kernels this context has launched so far */
 uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx);
 

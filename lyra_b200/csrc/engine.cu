@@ -466,6 +466,12 @@ int lyra_b200_set_stream(lyra_b200_ctx* ctx, void* cuda_stream) {
   return LYRA_B200_OK;
 }
 
+int lyra_b200_set_split(lyra_b200_ctx* ctx, int parts) {
+  if (!ctx || parts < 1 || parts > lyra_b200_ctx::kMaxSplit) return LYRA_B200_EINVAL;
+  ctx->nsplit = parts;
+  return LYRA_B200_OK;
+}
+
 int lyra_b200_synchronize(lyra_b200_ctx* ctx) {
   if (!ctx) return LYRA_B200_EINVAL;
   CU(cudaStreamSynchronize(ctx->stream));
