@@ -297,8 +297,16 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 // ================================================================================================
 template <int S>
 struct EncB {
+#ifdef LYRA_BC_NT128
+  static constexpr int NT = 128;
+#else
   static constexpr int NT = 256;
+#endif
+#ifdef LYRA_BC_2BLOCKS
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
+#else
+  static constexpr int kMinBlocks = S <= 8 ? 3 : 1;
+#endif
 #ifdef LYRA_BC_TM4
   static constexpr int TM = S >= 16 ? 8 : 4;              // streams per thread tile
 #else
@@ -308,36 +316,43 @@ struct EncB {
   static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;
   static constexpr int WM1 = 1 * S / TM >= 4 ? 4 : 1 * S / TM;
   static constexpr int LD1 = 6 * S;                       // u1: 2 carried rows + 4
-  static constexpr int kR0 = 0;                           // u1 f32 [128][6S]; later d2 f32 [256][2S]
   static constexpr int LQ2 = PadLd(2 * S), LQA = PadLd(4 * S), LQB = PadLd(3 * S);   // padded int8 word strides (MMA A operand)
-  static constexpr int kR1 = kR0 + 128 * LD1 * 4;         // d1 f32 [128][4S]; later hq, dq8, resq words [64][LQ2] each
-  static constexpr int kR1Bytes = 128 * 4 * S * 4 > 3 * 64 * LQ2 * 4 ? 128 * 4 * S * 4 : 3 * 64 * LQ2 * 4;
-  static constexpr int kR2 = kR1 + kR1Bytes;              // u2 f32 [256][2S]
-  static constexpr int kR3 = kR2 + 256 * 2 * S * 4;       // aq words [64][LQA] (2 carried rows + 2), bq words [128][LQB]
-  static constexpr int kW = kR3 + 64 * LQA * 4 + 128 * LQB * 4;
-  static constexpr int kI = kW + kStages * 8 * 256 * 4;
+  // Shared memory is reused along the layer sequence (72 KB at S = 8, so three blocks share an SM):
+  //   region A: u1 f32 [128][6S]  ->  d2 f32 [256][2S]  ->  aq words [64][LQA] + bq words [128][LQB]
+  //   region B: d1 f32 [128][4S]  ->  u2 f32 [256][2S]
+  //   region C: hq words [64][LQ2]
+  //   region W: fp32 weight ring  ->  (after the last fp32 GEMM) dq8, resq words [64][LQ2] each
+  static constexpr int kMax(int a, int b) { return a > b ? a : b; }
+  static constexpr int kRA = 0;
+  static constexpr int kRABytes = kMax(kMax(128 * LD1 * 4, 256 * 2 * S * 4), 64 * LQA * 4 + 128 * LQB * 4);
+  static constexpr int kRB = kRA + kRABytes;
+  static constexpr int kRBBytes = kMax(128 * 4 * S * 4, 256 * 2 * S * 4);
+  static constexpr int kRC = kRB + kRBBytes;
+  static constexpr int kW = kRC + 64 * LQ2 * 4;
+  static constexpr int kWBytes = kMax(kStages * 8 * 256 * 4, 2 * 64 * LQ2 * 4);
+  static constexpr int kI = kW + kWBytes;
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
 };
 
 template <int S>
-__global__ void __launch_bounds__(256, EncB<S>::kMinBlocks)
+__global__ void __launch_bounds__(EncB<S>::NT, EncB<S>::kMinBlocks)
 EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, const float* __restrict__ mid,
                float* __restrict__ state, int* __restrict__ n18g, float* __restrict__ features) {
   using L = EncB<S>;
   constexpr int NT = L::NT;
   constexpr int TM = L::TM;
   unsigned char* smem = LYRA_DYN_SMEM();
-  float* u1 = reinterpret_cast<float*>(smem + L::kR0);
-  float* d1 = reinterpret_cast<float*>(smem + L::kR1);
-  float* u2 = reinterpret_cast<float*>(smem + L::kR2);
-  float* d2 = reinterpret_cast<float*>(smem + L::kR0);
-  uint32_t* hq = reinterpret_cast<uint32_t*>(smem + L::kR1);
   constexpr int LQ2 = L::LQ2, LQA = L::LQA, LQB = L::LQB;
-  uint32_t* dq8 = hq + 64 * LQ2;
-  uint32_t* resq = dq8 + 64 * LQ2;
-  uint32_t* aq = reinterpret_cast<uint32_t*>(smem + L::kR3);
+  float* u1 = reinterpret_cast<float*>(smem + L::kRA);
+  float* d2 = reinterpret_cast<float*>(smem + L::kRA);          // after encoder_1/simpleconv has consumed u1
+  uint32_t* aq = reinterpret_cast<uint32_t*>(smem + L::kRA);    // after the mixed unit's fp32 1x1 has consumed d2
   uint32_t* bq = aq + 64 * LQA;
+  float* d1 = reinterpret_cast<float*>(smem + L::kRB);
+  float* u2 = reinterpret_cast<float*>(smem + L::kRB);          // d1 is dead once encoder_1's last unit is done
+  uint32_t* hq = reinterpret_cast<uint32_t*>(smem + L::kRC);
   float* wbuf = reinterpret_cast<float*>(smem + L::kW);
+  uint32_t* dq8 = reinterpret_cast<uint32_t*>(smem + L::kW);    // the fp32 weight ring is idle after the mixed unit's fp32 1x1
+  uint32_t* resq = dq8 + 64 * LQ2;
   int* slot = reinterpret_cast<int*>(smem + L::kI);
   int* active = slot + S;
   int* n18 = active + S;
@@ -495,8 +510,16 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 // ================================================================================================
 template <int S>
 struct DecC {
+#ifdef LYRA_BC_NT128
+  static constexpr int NT = 128;
+#else
   static constexpr int NT = 256;
+#endif
+#ifdef LYRA_BC_2BLOCKS
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
+#else
+  static constexpr int kMinBlocks = S <= 8 ? 3 : 1;
+#endif
 #ifdef LYRA_BC_TM4
   static constexpr int TM = S >= 16 ? 8 : 4;              // streams per thread tile
 #else
@@ -505,20 +528,24 @@ struct DecC {
   static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
   static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;
   static constexpr int WM1 = 1 * S / TM >= 4 ? 4 : 1 * S / TM;
-  static constexpr int kF = 0;                              // F f32 [64][3S]
   static constexpr int LQ2 = PadLd(2 * S), LQA = PadLd(4 * S), LQB = PadLd(3 * S);   // padded int8 word strides (MMA A operand)
-  static constexpr int kXq = kF + 64 * 3 * S * 4;           // xq words [128][LQB]  (pad, x0, pad)
-  static constexpr int kU = kXq + 128 * LQB * 4;            // u f32 [256][2S]; later u1 f32 [128][4S]
-  static constexpr int kAq = kU + 256 * 2 * S * 4;          // aq words [64][LQA] (pad, t0, t1, pad)
-  static constexpr int kQ = kAq + 64 * LQA * 4;             // hq, dq8, resq words [64][LQ2] each; later d1 f32 [128][4S]
-  static constexpr int kQBytes = 128 * 4 * S * 4 > 3 * 64 * LQ2 * 4 ? 128 * 4 * S * 4 : 3 * 64 * LQ2 * 4;
-  static constexpr int kW = kQ + kQBytes;
-  static constexpr int kI = kW + kStages * 4 * 512 * 4;
+  // Shared memory is reused along the layer sequence (59 KB at S = 8, so three blocks share an SM):
+  //   region 1: F f32 [64][3S] + xq words [128][LQB]  ->  aq words [64][LQA]  ->  d1 f32 [128][4S]
+  //   region 2: u f32 [256][2S]  ->  u1 f32 [128][4S]
+  //   region W: fp32 weight ring (bottleneck_2, decoder_1)  <->  hq, dq8, resq words [64][LQ2] each (int8 phases)
+  static constexpr int kMax(int a, int b) { return a > b ? a : b; }
+  static constexpr int kF = 0;
+  static constexpr int kXq = kF + 64 * 3 * S * 4;
+  static constexpr int kR1Bytes = kMax(kMax(64 * 3 * S * 4 + 128 * LQB * 4, 64 * LQA * 4), 128 * 4 * S * 4);
+  static constexpr int kU = kF + kR1Bytes;
+  static constexpr int kW = kU + 256 * 2 * S * 4;
+  static constexpr int kWBytes = kMax(kStages * 4 * 512 * 4, 3 * 64 * LQ2 * 4);
+  static constexpr int kI = kW + kWBytes;
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
 };
 
 template <int S>
-__global__ void __launch_bounds__(256, DecC<S>::kMinBlocks)
+__global__ void __launch_bounds__(DecC<S>::NT, DecC<S>::kMinBlocks)
 DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
                const float* __restrict__ features, float* __restrict__ state, int* __restrict__ n18g,
                float* __restrict__ mid) {
@@ -530,13 +557,13 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   uint32_t* xq = reinterpret_cast<uint32_t*>(smem + L::kXq);
   float* u = reinterpret_cast<float*>(smem + L::kU);
   float* u1 = u;
-  uint32_t* aq = reinterpret_cast<uint32_t*>(smem + L::kAq);
-  uint32_t* hq = reinterpret_cast<uint32_t*>(smem + L::kQ);
   constexpr int LQ2 = L::LQ2, LQA = L::LQA, LQB = L::LQB;
+  uint32_t* aq = reinterpret_cast<uint32_t*>(smem + L::kF);     // F and xq are dead once the first upsampler has run
+  float* d1 = reinterpret_cast<float*>(smem + L::kF);           // aq is dead once the second upsampler has run
+  float* wbuf = reinterpret_cast<float*>(smem + L::kW);
+  uint32_t* hq = reinterpret_cast<uint32_t*>(smem + L::kW);     // the fp32 weight ring is idle during the int8 phases
   uint32_t* dq8 = hq + 64 * LQ2;
   uint32_t* resq = dq8 + 64 * LQ2;
-  float* d1 = reinterpret_cast<float*>(smem + L::kQ);
-  float* wbuf = reinterpret_cast<float*>(smem + L::kW);
   int* slot = reinterpret_cast<int*>(smem + L::kI);
   int* active = slot + S;
   int* n18 = active + S;
