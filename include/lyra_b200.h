@@ -104,6 +104,19 @@ int lyra_b200_synchronize(lyra_b200_ctx* ctx);
  * run concurrently on internal CUDA streams so partial waves of one kernel are filled by another's blocks.
  * parts = 1 serialises the kernels (used by bench.py's per-kernel roofline pass). */
 int lyra_b200_set_split(lyra_b200_ctx* ctx, int parts);
+/* Arithmetic of the decoder's fp32 convolutions (decoder_1, decoder_2/simple, decoder_2, last_layer of lyragan.tflite):
+ *   LYRA_B200_DECODER_EXACT  (default) every output is one fp32 fmaf chain in the canonical order: decoded PCM is
+ *                            bit-identical to the CPU restatement of the reference graph;
+ *   LYRA_B200_DECODER_TENSOR the same layers as split-precision TF32 tensor-core MMAs (fp32-level accuracy, different
+ *                            rounding): decoded PCM stays within a few int16 LSB of the exact mode (bound stated and
+ *                            tested in tests/test_gpu_parity.py), well inside the 1e-3 full-scale tolerance the
+ *                            drop-in target allows.  The encoder, the quantizer and every int8 layer are exact in
+ *                            both modes, so packets / RVQ indices never depend on this switch.
+ * The reference has one arithmetic (TFLite's, lyra/lyra_gan_model.cc:53-64); this switch is an extension. */
+#define LYRA_B200_DECODER_EXACT 0
+#define LYRA_B200_DECODER_TENSOR 1
+int lyra_b200_set_decoder_mode(lyra_b200_ctx* ctx, int mode);
+int lyra_b200_decoder_mode(const lyra_b200_ctx* ctx);
 /* number of CUDA kernels this context has launched so far */
 uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx);
 

@@ -52,6 +52,8 @@ class CApi:
             "lyra_b200_decode_device": (ci, [vp, ci, vp, vp, ci, vp]),
             "lyra_b200_synchronize": (ci, [vp]),
             "lyra_b200_set_split": (ci, [vp, ci]),
+            "lyra_b200_set_decoder_mode": (ci, [vp, ci]),
+            "lyra_b200_decoder_mode": (ci, [vp]),
             "lyra_b200_launch_count": (C.c_uint64, [vp]),
             "lyra_b200_profile_enable": (ci, [vp, ci]),
             "lyra_b200_profile_read": (ci, [vp, vp, vp]),
@@ -67,7 +69,7 @@ class CApi:
                "lyra_b200_tile_streams", "lyra_b200_reset", "lyra_b200_encode", "lyra_b200_decode",
                "lyra_b200_extract_features", "lyra_b200_quantize", "lyra_b200_dequantize", "lyra_b200_generate",
                "lyra_b200_logmel", "lyra_b200_set_stream", "lyra_b200_encode_device", "lyra_b200_decode_device",
-               "lyra_b200_synchronize", "lyra_b200_set_split", "lyra_b200_launch_count", "lyra_b200_profile_enable",
+               "lyra_b200_synchronize", "lyra_b200_set_split", "lyra_b200_set_decoder_mode", "lyra_b200_decoder_mode", "lyra_b200_launch_count", "lyra_b200_profile_enable",
                "lyra_b200_profile_read"]
 
 
@@ -207,6 +209,10 @@ class Context:
 
     def synchronize(self):
         self._check(self.api.lib.lyra_b200_synchronize(self.h))
+
+    def set_decoder_mode(self, mode):
+        """mode: "exact" (bit-identical PCM, default) or "tensor" (split-precision TF32 tensor-core decoder)."""
+        self._check(self.api.lib.lyra_b200_set_decoder_mode(self.h, {"exact": 0, "tensor": 1}[mode]))
 
     def set_split(self, parts):
         self._check(self.api.lib.lyra_b200_set_split(self.h, int(parts)))

@@ -11,12 +11,14 @@
   cuda_emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define LYRA_SET_MAX_SMEM(kernel, bytes) (0)
 #define LYRA_DEVICE_CODE 1
+#define LYRA_TRAP() std::abort()
 #else
 #include <cuda_runtime.h>
 #define LYRA_DYN_SMEM() (lyra_dyn_smem_raw)
 #define LYRA_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define LYRA_SET_MAX_SMEM(kernel, bytes) \
   cudaFuncSetAttribute((kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#define LYRA_TRAP() __trap()
 #ifdef __CUDACC__
 extern __shared__ __align__(1024) unsigned char lyra_dyn_smem_raw[];
 #endif
@@ -71,6 +73,42 @@ static inline void lyra_mma_s8_16x8x32(int (&c)[4], const uint32_t (&a)[4], cons
 __device__ __forceinline__ void lyra_mma_s8_16x8x32(int (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+#endif
+
+// ---- warp-level TF32 tensor-core MMA: D(16x8,f32) += A(16x8,tf32,row) * B(8x8,tf32,col)
+//      (mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32).  Used only by the decoder's opt-in tensor-core mode
+//      (split-precision "3xTF32": fp32-equivalent accuracy, not bit-identical to the fmaf chain).
+//      Fragments (g = lane / 4, t = lane % 4): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4); b0 (k=t, n=g) b1 (k=t+4, n=g);
+//      c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
+#if defined(LYRA_EMU)
+static inline float lyra_emu_tf32(uint32_t bits) {          // the tensor core reads the top 19 bits of each operand
+  bits &= 0xffffe000u;
+  float f;
+  std::memcpy(&f, &bits, 4);
+  return f;
+}
+static inline void lyra_mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  const uint32_t mine[6] = {a[0], a[1], a[2], a[3], b[0], b[1]};
+  const uint32_t (*all)[8] = cuda_emu::warp_gather(mine, 6);
+  const int lane = (int)(threadIdx.x & 31), g = lane >> 2, t = lane & 3;
+  auto A = [&](int row, int k) { return (double)lyra_emu_tf32(all[(row & 7) * 4 + (k & 3)][(row >> 3) + 2 * (k >> 2)]); };
+  auto B = [&](int k, int col) { return (double)lyra_emu_tf32(all[col * 4 + (k & 3)][4 + (k >> 2)]); };
+  double d[4] = {c[0], c[1], c[2], c[3]};
+  for (int k = 0; k < 8; ++k) {
+    d[0] += A(g, k) * B(k, 2 * t);
+    d[1] += A(g, k) * B(k, 2 * t + 1);
+    d[2] += A(g + 8, k) * B(k, 2 * t);
+    d[3] += A(g + 8, k) * B(k, 2 * t + 1);
+  }
+  cuda_emu::warp_barrier();
+  c[0] = (float)d[0]; c[1] = (float)d[1]; c[2] = (float)d[2]; c[3] = (float)d[3];
+}
+#elif defined(__CUDACC__)
+__device__ __forceinline__ void lyra_mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 #endif

@@ -60,6 +60,7 @@ struct lyra_b200_ctx {
   cudaStream_t aux_stream[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   int nsplit = 2;
+  int decoder_mode = LYRA_B200_DECODER_EXACT;   // lyra_b200_set_decoder_mode
   uint64_t launches = 0;
   std::string err;
   // diagnostics: CUDA-event timing of every kernel launch
@@ -187,21 +188,25 @@ int LaunchDequantize(lyra_b200_ctx* ctx, const Part& p, const uint8_t* d_packets
   return LYRA_B200_OK;
 }
 
-template <int kS>
+template <int kS, bool kTC>
 int LaunchDecoderNetsT(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int16_t* d_pcm) {
   const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of};
+  using LC = DecC<kS, kTC>;
+  using LD = DecD<kS, kTC>;
   { ProfScope ps(ctx, 4, p.st);
-  LYRA_LAUNCH(DecoderKernelC<kS>, dim3((unsigned)p.ntiles), dim3(DecC<kS>::NT), (size_t)DecC<kS>::kSmemBytes, p.st,
+  LYRA_LAUNCH((DecoderKernelC<kS, kTC>), dim3((unsigned)p.ntiles), dim3(LC::NT), (size_t)LC::kSmemBytes, p.st,
               ctx->d_blob, ctx->spec.dec, io, d_features, reinterpret_cast<float*>(ctx->d_state[2]), ctx->d_n18[2], ctx->d_mid_dec); }
   { ProfScope ps(ctx, 5, p.st);
-  LYRA_LAUNCH(DecoderKernelD<kS>, dim3((unsigned)p.ntiles), dim3(DecD<kS>::NT), (size_t)DecD<kS>::kSmemBytes, p.st,
+  LYRA_LAUNCH((DecoderKernelD<kS, kTC>), dim3((unsigned)p.ntiles), dim3(LD::NT), (size_t)LD::kSmemBytes, p.st,
               ctx->d_blob, ctx->spec.dec, io, ctx->d_mid_dec, reinterpret_cast<float*>(ctx->d_state[3]), ctx->d_n18[3], d_pcm); }
   ctx->launches += 2;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
 }
 int LaunchDecoderNets(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int16_t* d_pcm) {
-  return ctx->S == 16 ? LaunchDecoderNetsT<16>(ctx, p, d_features, d_pcm) : LaunchDecoderNetsT<8>(ctx, p, d_features, d_pcm);
+  const bool tc = ctx->decoder_mode == LYRA_B200_DECODER_TENSOR;
+  if (ctx->S == 16) return tc ? LaunchDecoderNetsT<16, true>(ctx, p, d_features, d_pcm) : LaunchDecoderNetsT<16, false>(ctx, p, d_features, d_pcm);
+  return tc ? LaunchDecoderNetsT<8, true>(ctx, p, d_features, d_pcm) : LaunchDecoderNetsT<8, false>(ctx, p, d_features, d_pcm);
 }
 
 // Dense calls over many tiles are cut into two halves that run on two CUDA streams: the block scheduler then
@@ -257,7 +262,10 @@ int RunDecode(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t
 template <int kS>
 bool SetSmemLimits() {
   return LYRA_SET_MAX_SMEM(EncoderKernelA<kS>, EncA<kS>::kSmemBytes) == 0 && LYRA_SET_MAX_SMEM(EncoderKernelB<kS>, EncB<kS>::kSmemBytes) == 0 &&
-         LYRA_SET_MAX_SMEM(DecoderKernelC<kS>, DecC<kS>::kSmemBytes) == 0 && LYRA_SET_MAX_SMEM(DecoderKernelD<kS>, DecD<kS>::kSmemBytes) == 0;
+         LYRA_SET_MAX_SMEM((DecoderKernelC<kS, false>), (DecC<kS, false>::kSmemBytes)) == 0 &&
+         LYRA_SET_MAX_SMEM((DecoderKernelD<kS, false>), (DecD<kS, false>::kSmemBytes)) == 0 &&
+         LYRA_SET_MAX_SMEM((DecoderKernelC<kS, true>), (DecC<kS, true>::kSmemBytes)) == 0 &&
+         LYRA_SET_MAX_SMEM((DecoderKernelD<kS, true>), (DecD<kS, true>::kSmemBytes)) == 0;
 }
 
 // initial value of every 4-byte state unit (all zero; int8 rings hold packed zero points)
@@ -376,6 +384,7 @@ int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b2
   }
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   if (const char* e = std::getenv("LYRA_B200_SPLIT")) ctx->nsplit = std::atoi(e);
+  if (const char* e = std::getenv("LYRA_B200_DECODER_MODE")) ctx->decoder_mode = std::strcmp(e, "tensor") == 0 ? LYRA_B200_DECODER_TENSOR : LYRA_B200_DECODER_EXACT;
   ctx->stream = ctx->own_stream;
   ok = ok && DevAlloc(&ctx->d_blob, ctx->spec.blob.size()) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->d_blob, ctx->spec.blob.data(), ctx->spec.blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -471,6 +480,14 @@ int lyra_b200_set_split(lyra_b200_ctx* ctx, int parts) {
   ctx->nsplit = parts;
   return LYRA_B200_OK;
 }
+
+int lyra_b200_set_decoder_mode(lyra_b200_ctx* ctx, int mode) {
+  if (!ctx || (mode != LYRA_B200_DECODER_EXACT && mode != LYRA_B200_DECODER_TENSOR)) return LYRA_B200_EINVAL;
+  ctx->decoder_mode = mode;
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_decoder_mode(const lyra_b200_ctx* ctx) { return ctx ? ctx->decoder_mode : LYRA_B200_EINVAL; }
 
 int lyra_b200_synchronize(lyra_b200_ctx* ctx) {
   if (!ctx) return LYRA_B200_EINVAL;

@@ -304,6 +304,131 @@ __host__ __device__ constexpr int PadLd(int x) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32 tap-GEMM on the tensor cores in split precision ("3xTF32"); decoder tensor-core mode only.
+//   x = hi + lo with hi = the top 19 bits of x (what a TF32 operand keeps) and lo = x - hi (exact in fp32);
+//   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, accumulated in fp32 by mma.sync m16n8k8 (small terms first).
+//   The dropped a_lo*b_lo term and the TF32 truncation of lo are both below 2^-21 relative, i.e. the result
+//   carries fp32-level accuracy but NOT the oracle's exact fmaf-chain rounding: outputs of this mode are
+//   compared with a tolerance (tests/test_gpu_parity.py), never bit-for-bit.
+//   Same operand conventions as GemmF32Tap / GemmI8Mma:
+//   A: shared memory [channels][ldA] floats, rows m = t*S + s; ldA mod 32 should be 8 or 24 (PadLd) so the
+//      4 k-rows x 8 m-rows of a fragment load hit 32 different banks.
+//   W: global memory in FRAGMENT ORDER [Ktot/8][N/8][lane] x float2 = {W[8ks + t][8nt + g], W[8ks + t + 4][8nt + g]}
+//      (model_spec.cc PackMmaBTf32), loaded straight from L2 with a PD-deep register prefetch.
+//   A warp owns WTM m-tiles (16 rows each) x WTN n-tiles (8 columns each).
+//   epi(t, s, n2, acc) is called per output row and pair of channels n2, n2+1 (acc is float[1][2]).
+//   SYNC_EPI: the epilogue may overwrite the A operand in place: every warp owns at most one warp tile and a block
+//   barrier separates the K loops from the epilogues.
+__device__ __forceinline__ void SplitTf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(__fsub_rn(x, __uint_as_float(hi)));
+}
+
+template <int S, int NT, int WTM, int WTN, bool SYNC_EPI, typename Epi>
+__device__ __forceinline__ void GemmTf32Mma(const float* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
+                                            int groups, int T_out, int N, const float2* __restrict__ Wf, Epi epi) {
+  constexpr int PD = 2;
+  constexpr int NW = NT / 32;
+  const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+  const int M = T_out * S, MT = (M + 15) / 16, MTW = (MT + WTM - 1) / WTM, NTILES = N / 8, NWT = MTW * (NTILES / WTN);
+  const int KS = ntaps * CinG / 8, CoutG = N / groups;
+  const size_t ks_stride = (size_t)NTILES * 32;
+  float acc[WTM][WTN][4];
+  int tr[WTM][2], sr[WTM][2];
+  bool vr[WTM][2];
+  int nt0 = 0;
+
+  auto kloop = [&](int wt) {
+    const int mtb = (wt % MTW) * WTM;
+    nt0 = (wt / MTW) * WTN;
+    const int grp = (nt0 * 8) / CoutG;
+    const float* pa[WTM][2];
+#pragma unroll
+    for (int i = 0; i < WTM; ++i)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = (mtb + i) * 16 + g + 8 * h;
+        vr[i][h] = m < M;
+        tr[i][h] = vr[i][h] ? m / S : T_out - 1;      // clamp: rows past M only feed discarded outputs
+        sr[i][h] = m % S;
+        pa[i][h] = A + (size_t)(grp * CinG) * ldA + (rowA0 + tr[i][h] * row_stride) * S + sr[i][h];
+      }
+#pragma unroll
+    for (int i = 0; i < WTM; ++i)
+#pragma unroll
+      for (int j = 0; j < WTN; ++j) { acc[i][j][0] = 0.0f; acc[i][j][1] = 0.0f; acc[i][j][2] = 0.0f; acc[i][j][3] = 0.0f; }
+    const float2* wp = Wf + (size_t)nt0 * 32 + lane;
+    float2 bf[PD][WTN];
+#pragma unroll
+    for (int p = 0; p < PD; ++p)
+      if (p < KS) {
+#pragma unroll
+        for (int j = 0; j < WTN; ++j) bf[p][j] = __ldg(wp + p * ks_stride + j * 32);
+      }
+    for (int ks0 = 0; ks0 < KS; ks0 += PD) {
+#pragma unroll
+      for (int p = 0; p < PD; ++p) {
+        const int ks = ks0 + p;
+        if (ks < KS) {
+          const int k0 = ks * 8, tap = k0 / CinG, c0 = k0 - tap * CinG;
+          const size_t off = (size_t)(c0 + t4) * ldA + tap * S, off4 = off + 4 * (size_t)ldA;
+          uint32_t ahi[WTM][4], alo[WTM][4];
+#pragma unroll
+          for (int i = 0; i < WTM; ++i) {
+            SplitTf32(pa[i][0][off], ahi[i][0], alo[i][0]);
+            SplitTf32(pa[i][1][off], ahi[i][1], alo[i][1]);
+            SplitTf32(pa[i][0][off4], ahi[i][2], alo[i][2]);
+            SplitTf32(pa[i][1][off4], ahi[i][3], alo[i][3]);
+          }
+#pragma unroll
+          for (int j = 0; j < WTN; ++j) {
+            uint32_t bhi[2], blo[2];
+            SplitTf32(bf[p][j].x, bhi[0], blo[0]);
+            SplitTf32(bf[p][j].y, bhi[1], blo[1]);
+#pragma unroll
+            for (int i = 0; i < WTM; ++i) {
+              lyra_mma_tf32_16x8x8(acc[i][j], alo[i], bhi);
+              lyra_mma_tf32_16x8x8(acc[i][j], ahi[i], blo);
+              lyra_mma_tf32_16x8x8(acc[i][j], ahi[i], bhi);
+            }
+          }
+          if (ks + PD < KS) {
+#pragma unroll
+            for (int j = 0; j < WTN; ++j) bf[p][j] = __ldg(wp + (size_t)(ks + PD) * ks_stride + j * 32);
+          }
+        }
+      }
+    }
+  };
+  auto epilogue = [&]() {
+#pragma unroll
+    for (int i = 0; i < WTM; ++i)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (vr[i][h]) {
+#pragma unroll
+          for (int j = 0; j < WTN; ++j) {
+            float o[1][2] = {{acc[i][j][2 * h], acc[i][j][2 * h + 1]}};
+            epi(tr[i][h], sr[i][h], (nt0 + j) * 8 + 2 * t4, o);
+          }
+        }
+  };
+  if (SYNC_EPI) {
+    if (NWT > NW) LYRA_TRAP();          // callers size the warp tile so that every warp owns at most one
+    const bool has = warp < NWT;
+    if (has) kloop(warp);
+    __syncthreads();
+    if (has) epilogue();
+  } else {
+    for (int wt = warp; wt < NWT; wt += NW) {
+      kloop(wt);
+      epilogue();
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Ring addressing.  A dilated depthwise conv (k = 3, dilation d) needs a(i - 2d), a(i - d), a(i) for
 // absolute row i; the last R = 2d rows of every stream live in a global ring [C][R][S] (slot = i mod R).
 // frame counters are kept modulo 18 (every R divides 18), so base = (n18 * T) mod R.

@@ -80,7 +80,24 @@ std::vector<uint32_t> PackMmaB(const std::vector<int8_t>& b, int K, int N) {
   return out;
 }
 
+// fp32 GEMM B operand ([K][N], k-major) in mma.sync m16n8k8 (tf32) fragment order: for every k-step ks (8 k) and n-tile
+// nt (8 n), lane L (g = L / 4, t = L % 4) holds {B[8ks + t][8nt + g], B[8ks + t + 4][8nt + g]}.
+std::vector<float> PackMmaBTf32(const std::vector<float>& b, int K, int N) {
+  SPEC_CHECK(K % 8 == 0 && N % 8 == 0, "TF32 MMA operand: K and N must be multiples of 8");
+  std::vector<float> out((size_t)(K / 8) * (N / 8) * 64, 0.0f);
+  for (int ks = 0; ks < K / 8; ++ks)
+    for (int nt = 0; nt < N / 8; ++nt)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane / 4, t = lane % 4;
+        float* o = &out[(((size_t)ks * (N / 8) + nt) * 32 + lane) * 2];
+        o[0] = b[(size_t)(8 * ks + t) * N + 8 * nt + g];
+        o[1] = b[(size_t)(8 * ks + t + 4) * N + 8 * nt + g];
+      }
+  return out;
+}
+
 struct Net {
+  bool pack_tc = false;     // also emit tensor-core fragment-order copies of the fp32 GEMM weights (decoder)
   const TflModel& m;
   const TflSubgraph& g;
   std::vector<int> convs;   // CONV_2D / DEPTHWISE_CONV_2D / TRANSPOSE_CONV ops in graph order
@@ -134,7 +151,8 @@ struct Net {
           wt[((size_t)k * CinG + ci) * Cout + co] = src[((size_t)co * K + k) * CinG + ci];
     SPEC_CHECK((int)b.count() == Cout && b.data, "conv bias");
     std::vector<float> bias(b.as<float>(), b.as<float>() + Cout);
-    return GemmF32{Append(blob, wt), Append(blob, bias)};
+    const uint32_t wf = pack_tc && (K * CinG) % 8 == 0 && Cout % 8 == 0 ? Append(blob, PackMmaBTf32(wt, K * CinG, Cout)) : 0u;
+    return GemmF32{Append(blob, wt), Append(blob, bias), wf};
   }
 
   // transposed conv as a J-tap GEMM over (r, co) outputs: W'[(j,ci)][(r,co)] = W[co][r + s*(J-1-j)][ci]
@@ -152,7 +170,8 @@ struct Net {
           for (int co = 0; co < Cout; ++co)
             wt[((size_t)j * Cin + ci) * N + (size_t)r * Cout + co] = src[((size_t)co * K + (r + stride * (J - 1 - j))) * Cin + ci];
     std::vector<float> bias(b.as<float>(), b.as<float>() + Cout);
-    return GemmF32{Append(blob, wt), Append(blob, bias)};
+    const uint32_t wf = pack_tc && (J * Cin) % 8 == 0 && N % 8 == 0 ? Append(blob, PackMmaBTf32(wt, J * Cin, N)) : 0u;
+    return GemmF32{Append(blob, wt), Append(blob, bias), wf};
   }
 
   void RequantArrays(const TflTensor& x, const TflTensor& w, const TflTensor& y, int n, int repeat,
@@ -351,6 +370,7 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
   int sg = m.SignatureSubgraph("serving_default");
   if (sg < 0) sg = 0;
   Net n(m, sg, blob);
+  n.pack_tc = true;
   SPEC_CHECK(n.convs.size() == 36, "decoder: expected 36 convolution ops");
   DecoderParams p;
   std::memset(&p, 0, sizeof(p));

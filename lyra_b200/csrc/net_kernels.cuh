@@ -85,12 +85,16 @@ __device__ __forceinline__ void LoadTileMeta(const TileIo& io, const int* n18_gl
 }
 
 // One fp32 residual unit:  d = dw(lrelu(u)); h = lrelu(pw1(d)); u' = pw2(h) + u.
-// u lives at row offset row0u of a [C][ldu] buffer; d is a [C][T*S] scratch.  When `last`, lrelu(u') is stored.
-template <int S, int NT, int TM, int TN1, int TN2, int WM, int KC, int C, int T, int DIL>
+// u lives at row offset row0u of a [C][ldu] buffer; d is a [C][LDD] scratch.  When `last`, lrelu(u') is stored.
+// TC (decoder tensor-core mode): the two 1x1 convolutions run as split-precision TF32 MMAs with warp tiles of
+// WTM x WTN fragments (sized so that every warp owns at most one tile: pw1 rewrites its operand in place); the weight
+// ring and its prefetch chain are not used in that mode.
+template <int S, int NT, int TM, int TN1, int TN2, int WM, int KC, int C, int T, int DIL, bool TC = false, int LDD = T * S,
+          int WTM = 1, int WTN = 1>
 __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p, float* u, int ldu, int row0u, float* d,
                                            int groups2, float* ring, const int* n18,
                                            const int* active, float* wbuf, bool last, const WNext& after, int pk, int& ph) {
-  constexpr int ldd = T * S;
+  constexpr int ldd = LDD;
   // pw1's weight stream is started by whoever ran before this unit (previous GEMM or the kernel prologue)
   if (n18[S] >= 0)
     DwF32RingFast<S, NT, C, T, DIL>(u, ldu, row0u, d, ldd, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18[S], active);
@@ -99,34 +103,42 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
   LYRA_PHASE(pk, ph);
   {
     const float* b1 = BlobPtr<float>(blob, p.pw1.bias);
-    GemmF32Tap<S, NT, TM, TN1, KC, WM, false>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float>(blob, p.pw1.w), wbuf, true,
-      NextF32(BlobPtr<float>(blob, p.pw2.w), KC, C, C / groups2),
-      [&](int t, int s0, int n0, float (&acc)[TM][TN1]) {
+    auto epi1 = [&](int t, int s0, int n0, auto& acc) {
+      constexpr int TMx = sizeof(acc) / sizeof(acc[0]), TNx = sizeof(acc[0]) / sizeof(float);
 #pragma unroll
-        for (int j = 0; j < TN1; ++j) {
-          const float b = b1[n0 + j];
-          float* o = d + (size_t)(n0 + j) * ldd + t * S + s0;
+      for (int j = 0; j < TNx; ++j) {
+        const float b = b1[n0 + j];
+        float* o = d + (size_t)(n0 + j) * ldd + t * S + s0;
 #pragma unroll
-          for (int i = 0; i < TM; ++i) o[i] = LeakyRelu(__fadd_rn(acc[i][j], b));
-        }
-      });
+        for (int i = 0; i < TMx; ++i) o[i] = LeakyRelu(__fadd_rn(acc[i][j], b));
+      }
+    };
+    if constexpr (TC)
+      GemmTf32Mma<S, NT, WTM, WTN, true>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float2>(blob, p.pw1.wf), epi1);
+    else
+      GemmF32Tap<S, NT, TM, TN1, KC, WM, false>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float>(blob, p.pw1.w), wbuf, true,
+                                                NextF32(BlobPtr<float>(blob, p.pw2.w), KC, C, C / groups2), epi1);
   }
   LYRA_PHASE(pk, ph);
   {
     const float* b2 = BlobPtr<float>(blob, p.pw2.bias);
-    GemmF32Tap<S, NT, TM, TN2, KC, WM, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float>(blob, p.pw2.w), wbuf, true, after,
-      [&](int t, int s0, int n0, float (&acc)[TM][TN2]) {
+    auto epi2 = [&](int t, int s0, int n0, auto& acc) {
+      constexpr int TMx = sizeof(acc) / sizeof(acc[0]), TNx = sizeof(acc[0]) / sizeof(float);
 #pragma unroll
-        for (int j = 0; j < TN2; ++j) {
-          const float b = b2[n0 + j];
-          float* o = u + (size_t)(n0 + j) * ldu + (row0u + t) * S + s0;
+      for (int j = 0; j < TNx; ++j) {
+        const float b = b2[n0 + j];
+        float* o = u + (size_t)(n0 + j) * ldu + (row0u + t) * S + s0;
 #pragma unroll
-          for (int i = 0; i < TM; ++i) {
-            const float v = __fadd_rn(__fadd_rn(acc[i][j], b), o[i]);
-            o[i] = last ? LeakyRelu(v) : v;
-          }
+        for (int i = 0; i < TMx; ++i) {
+          const float v = __fadd_rn(__fadd_rn(acc[i][j], b), o[i]);
+          o[i] = last ? LeakyRelu(v) : v;
         }
-      });
+      }
+    };
+    if constexpr (TC)
+      GemmTf32Mma<S, NT, WTM, WTN, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float2>(blob, p.pw2.wf), epi2);
+    else
+      GemmF32Tap<S, NT, TM, TN2, KC, WM, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float>(blob, p.pw2.w), wbuf, true, after, epi2);
   }
   LYRA_PHASE(pk, ph);
 }
@@ -508,7 +520,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 // ================================================================================================
 //                                        DECODER  C
 // ================================================================================================
-template <int S>
+template <int S, bool TC = false>
 struct DecC {
 #ifdef LYRA_BC_NT128
   static constexpr int NT = 128;
@@ -536,7 +548,11 @@ struct DecC {
   static constexpr int kMax(int a, int b) { return a > b ? a : b; }
   static constexpr int kF = 0;
   static constexpr int kXq = kF + 64 * 3 * S * 4;
-  static constexpr int kR1Bytes = kMax(kMax(64 * 3 * S * 4 + 128 * LQB * 4, 64 * LQA * 4), 128 * 4 * S * 4);
+  // tensor-core mode: d1 is an MMA A operand (padded stride); decoder_1 warp tiles: 2 m-tiles x RWN n-tiles
+  static constexpr int LD1 = TC ? PadLd(4 * S) : 4 * S;
+  static constexpr int RWM = 2, RWN = S >= 16 ? 4 : 2;
+  static_assert(!TC || ((4 * S + 31) / 32) * (16 / RWN) <= NT / 32, "decoder_1: one warp tile per warp");
+  static constexpr int kR1Bytes = kMax(kMax(64 * 3 * S * 4 + 128 * LQB * 4, 64 * LQA * 4), 128 * LD1 * 4);
   static constexpr int kU = kF + kR1Bytes;
   static constexpr int kW = kU + 256 * 2 * S * 4;
   static constexpr int kWBytes = kMax(kStages * 4 * 512 * 4, 3 * 64 * LQ2 * 4);
@@ -544,12 +560,12 @@ struct DecC {
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
 };
 
-template <int S>
-__global__ void __launch_bounds__(DecC<S>::NT, DecC<S>::kMinBlocks)
+template <int S, bool TC>
+__global__ void __launch_bounds__(DecC<S, TC>::NT, DecC<S, TC>::kMinBlocks)
 DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
                const float* __restrict__ features, float* __restrict__ state, int* __restrict__ n18g,
                float* __restrict__ mid) {
-  using L = DecC<S>;
+  using L = DecC<S, TC>;
   constexpr int NT = L::NT;
   constexpr int TM = L::TM;
   unsigned char* smem = LYRA_DYN_SMEM();
@@ -709,7 +725,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int* mult = BlobPtr<int>(blob, up1.g.mult);
     const int* shift = BlobPtr<int>(blob, up1.g.shift);
     float* tail = st + (size_t)DecStateC::kUp1 * S;
-    IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128));
+    if (!TC) IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128));
     GemmI8Mma<S, NT, 8>(aq, LQA, 0, 1, 2, 128, 2, 3, 256, BlobPtr<uint2>(blob, up1.g.w),
       [&](int q, int s, int n0, int (&acc)[1][4]) {
         const int g = n0 / 128, r = (n0 % 128) / 64;
@@ -730,11 +746,14 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   }
   // ---- decoder_1: three fp32 residual units @128
   LYRA_PHASE(2, ph);
-  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 1>(blob, P.r1[0], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, false,
-                                                NextF32(BlobPtr<float>(blob, P.r1[1].pw1.w), 16, 128, 128), 2, ph);
-  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 3>(blob, P.r1[1], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing1 * S, n18, active, wbuf, false,
-                                                NextF32(BlobPtr<float>(blob, P.r1[2].pw1.w), 16, 128, 128), 2, ph);
-  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 9>(blob, P.r1[2], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing2 * S, n18, active, wbuf, true, NoNext(), 2, ph);
+  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 1, TC, L::LD1, L::RWM, L::RWN>(
+      blob, P.r1[0], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, false,
+      NextF32(BlobPtr<float>(blob, P.r1[1].pw1.w), 16, 128, 128), 2, ph);
+  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 3, TC, L::LD1, L::RWM, L::RWN>(
+      blob, P.r1[1], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing1 * S, n18, active, wbuf, false,
+      NextF32(BlobPtr<float>(blob, P.r1[2].pw1.w), 16, 128, 128), 2, ph);
+  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 9, TC, L::LD1, L::RWM, L::RWN>(
+      blob, P.r1[2], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing2 * S, n18, active, wbuf, true, NoNext(), 2, ph);
   {
     float* out = mid + (size_t)tile * 128 * 4 * S;
     for (int i = tid; i < 128 * 4 * S; i += NT) out[i] = u1[i];
@@ -746,7 +765,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
 // ================================================================================================
 //                                        DECODER  D
 // ================================================================================================
-template <int S>
+template <int S, bool TC = false>
 struct DecD {
 #ifndef LYRA_TILE_8x8
   static constexpr int NT = 320;
@@ -767,23 +786,30 @@ struct DecD {
 #endif
   static constexpr int WMU = S >= 16 ? 2 : 1;
   static constexpr int KCU = 8;                           // its ring starts right behind X inside d and runs into the regular ring
-  static constexpr int LDU = 26 * S, LDD = 20 * S;          // u: 3 zero rows + 20 + 3 zero rows
+  // u: 3 zero rows + 20 + 3 zero rows.  Tensor-core mode pads the strides of the MMA A operands (u, d, X) and
+  // needs no weight ring (weights go from L2 straight into fragments).
+  static constexpr int LDU = TC ? PadLd(26 * S) : 26 * S, LDD = TC ? PadLd(20 * S) : 20 * S, LDX = TC ? PadLd(6 * S) : 6 * S;
   static constexpr int kU = 0;
-  static constexpr int kD = kU + 64 * LDU * 4;              // d f32 [64][20S]; aliases X f32 [128][6S] and the PCM staging
+  static constexpr int kD = kU + 64 * LDU * 4;              // d f32 [64][LDD]; aliases X f32 [128][LDX] and the PCM staging
   static constexpr int kW = kD + 64 * LDD * 4;
-  static constexpr int kWBytes = kStages * 16 * 64 * 4 + 2048;   // regular ring (64-channel layers) + slack for the decoder_2/simple ring
+  static constexpr int kWBytes = TC ? 0 : kStages * 16 * 64 * 4 + 2048;   // regular ring (64-channel layers) + slack for the decoder_2/simple ring
   static constexpr int kSl = kW + kWBytes;                  // carried tail of last_layer [48][S]
-  static_assert(128 * 6 * S * 4 + kStages * KCU * 320 * 4 <= 64 * LDD * 4 + kWBytes, "decoder_2/simple ring must fit behind X");
+  static_assert(TC || 128 * 6 * S * 4 + kStages * KCU * 320 * 4 <= 64 * LDD * 4 + kWBytes, "decoder_2/simple ring must fit behind X");
   static constexpr int kI = kSl + 48 * S * 4;
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
-  static_assert(128 * 6 * S <= 64 * LDD, "X must fit in d");
+  static_assert(128 * LDX <= 64 * LDD, "X must fit in d");
+  static_assert(S * 320 * 2 <= 64 * LDD * 4, "PCM staging must fit in d");
+  // tensor-core warp tiles: decoder_2 res-units RWM x RWN (one per warp), decoder_2/simple UWM x 2, last_layer 1 x 1
+  static constexpr int RWM = S >= 16 ? 4 : 2, RWN = 4;
+  static constexpr int UWM = (5 * S + 15) / 16;
+  static_assert(!TC || ((20 * S / 16 + RWM - 1) / RWM) * (8 / RWN) <= NT / 32, "decoder_2: one warp tile per warp");
 };
 
-template <int S>
-__global__ void __launch_bounds__(DecD<S>::NT, DecD<S>::kMinBlocks)
+template <int S, bool TC>
+__global__ void __launch_bounds__(DecD<S, TC>::NT, DecD<S, TC>::kMinBlocks)
 DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, const float* __restrict__ mid,
                float* __restrict__ state, int* __restrict__ n18g, int16_t* __restrict__ pcm) {
-  using L = DecD<S>;
+  using L = DecD<S, TC>;
   constexpr int NT = L::NT;
   unsigned char* smem = LYRA_DYN_SMEM();
   float* u = reinterpret_cast<float*>(smem + L::kU);
@@ -798,8 +824,9 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const int tid = (int)threadIdx.x;
-  float* wbuf_up2 = X + 128 * 6 * S;     // free tail of d + the regular ring
-  IssuePrologue<NT>(wbuf_up2, NextF32(BlobPtr<float>(blob, P.up2.w), L::KCU, 320, 256));
+  constexpr int LDX = L::LDX;
+  float* wbuf_up2 = X + 128 * LDX;       // free tail of d + the regular ring
+  if (!TC) IssuePrologue<NT>(wbuf_up2, NextF32(BlobPtr<float>(blob, P.up2.w), L::KCU, 320, 256));
   int ph = 0;
   LYRA_PHASE(3, ph);
 
@@ -807,15 +834,15 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   {
     const float* in = mid + (size_t)tile * 128 * 4 * S;
     BatchedLoop<NT, 4, float4>(128 * S, [&](int i) { return reinterpret_cast<const float4*>(in)[i]; },
-      [&](int i, float4 v) { const int c = i / S, r = (i % S) * 4; *reinterpret_cast<float4*>(X + (size_t)c * 6 * S + S + r) = v; });
-    for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); X[(size_t)c * 6 * S + (r < S ? r : 4 * S + r)] = 0.0f; }
+      [&](int i, float4 v) { const int c = i / S, r = (i % S) * 4; *reinterpret_cast<float4*>(X + (size_t)c * LDX + S + r) = v; });
+    for (int i = tid; i < 128 * 2 * S; i += NT) { const int c = i / (2 * S), r = i % (2 * S); X[(size_t)c * LDX + (r < S ? r : 4 * S + r)] = 0.0f; }
     // u rows: 3 zero rows | rows 0..4 carry the overlap of decoder_2/simple, rows 5..19 start from +0 | 3 zero rows
     for (int i = tid; i < 64 * 26 * S / 4; i += NT) {
-      const int r = (i * 4) % (26 * S);
-      if (!(r >= 3 * S && r < 8 * S)) reinterpret_cast<float4*>(u)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      const int c = (i * 4) / (26 * S), r = (i * 4) % (26 * S);
+      if (!(r >= 3 * S && r < 8 * S)) *reinterpret_cast<float4*>(u + (size_t)c * L::LDU + r) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     BatchedLoop<NT, 8, float>(64 * 5 * S, [&](int i) { return st[DecStateD::kUp2 * S + i]; },
-      [&](int i, float v) { const int c = i / (5 * S), r = i % (5 * S); u[(size_t)c * 26 * S + 3 * S + r] = v; });
+      [&](int i, float v) { const int c = i / (5 * S), r = i % (5 * S); u[(size_t)c * L::LDU + 3 * S + r] = v; });
     BatchedLoop<NT, 2, float>(48 * S, [&](int i) { return st[DecStateD::kLast * S + i]; }, [&](int i, float v) { sl[i] = v; });
   }
   __syncthreads();
@@ -824,33 +851,37 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   {
     const float* b = BlobPtr<float>(blob, P.up2.bias);
     float* tail = st + (size_t)DecStateD::kUp2 * S;
-    GemmF32Tap<S, NT, 8, L::TNU, L::KCU, L::WMU, false>(X, 6 * S, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float>(blob, P.up2.w), wbuf_up2, true,
-      NextF32(BlobPtr<float>(blob, P.r2[0].pw1.w), 16, 64, 64, wbuf),
-      [&](int q, int s0, int n0, float (&acc)[8][L::TNU]) {
+    auto epi_up = [&](int q, int s0, int n0, auto& acc) {
+      constexpr int TMx = sizeof(acc) / sizeof(acc[0]), TNx = sizeof(acc[0]) / sizeof(float);
 #pragma unroll
-        for (int j = 0; j < L::TNU; ++j) {
-          const int r = (n0 + j) / 64, co = (n0 + j) % 64;
-          const float bias = b[co];
+      for (int j = 0; j < TNx; ++j) {
+        const int r = (n0 + j) / 64, co = (n0 + j) % 64;
+        const float bias = b[co];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float y = __fadd_rn(acc[i][j], bias);
-            if (q < 4) {
-              float* o = u + (size_t)co * L::LDU + (3 + 5 * q + r) * S + s0 + i;
-              *o = __fadd_rn(y, *o);
-            } else if (active[s0 + i]) {
-              tail[((size_t)co * 5 + r) * S + s0 + i] = __fsub_rn(__fadd_rn(y, 0.0f), bias);
-            }
+        for (int i = 0; i < TMx; ++i) {
+          const float y = __fadd_rn(acc[i][j], bias);
+          if (q < 4) {
+            float* o = u + (size_t)co * L::LDU + (3 + 5 * q + r) * S + s0 + i;
+            *o = __fadd_rn(y, *o);
+          } else if (active[s0 + i]) {
+            tail[((size_t)co * 5 + r) * S + s0 + i] = __fsub_rn(__fadd_rn(y, 0.0f), bias);
           }
         }
-      });
+      }
+    };
+    if constexpr (TC)
+      GemmTf32Mma<S, NT, L::UWM, 2, false>(X, LDX, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float2>(blob, P.up2.wf), epi_up);
+    else
+      GemmF32Tap<S, NT, 8, L::TNU, L::KCU, L::WMU, false>(X, LDX, 0, 1, 2, 128, 1, 5, 320, BlobPtr<float>(blob, P.up2.w), wbuf_up2, true,
+                                                          NextF32(BlobPtr<float>(blob, P.r2[0].pw1.w), 16, 64, 64, wbuf), epi_up);
   }
   // ---- decoder_2: three residual units @64, T = 20
   LYRA_PHASE(3, ph);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1>(blob, P.r2[0], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing0 * S, n18, active, wbuf, false,
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1, TC, L::LDD, L::RWM, L::RWN>(blob, P.r2[0], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing0 * S, n18, active, wbuf, false,
                                                        NextF32(BlobPtr<float>(blob, P.r2[1].pw1.w), 16, 64, 64), 3, ph);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3>(blob, P.r2[1], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing1 * S, n18, active, wbuf, false,
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3, TC, L::LDD, L::RWM, L::RWN>(blob, P.r2[1], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing1 * S, n18, active, wbuf, false,
                                                        NextF32(BlobPtr<float>(blob, P.r2[2].pw1.w), 16, 64, 64), 3, ph);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9>(blob, P.r2[2], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing2 * S, n18, active, wbuf, true,
+  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9, TC, L::LDD, L::RWM, L::RWN>(blob, P.r2[2], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing2 * S, n18, active, wbuf, true,
                                                        NextF32(BlobPtr<float>(blob, P.last.w), 16, 16, 256), 3, ph);
   // ---- last_layer: TRANSPOSE_CONV K = 64, stride 16, 64 -> 1 ; T 20 -> 320 (+48 tail) ; float -> int16
   LYRA_PHASE(3, ph);
@@ -858,26 +889,30 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
     const float bias = BlobPtr<float>(blob, P.last.bias)[0];
     float* tail = st + (size_t)DecStateD::kLast * S;
     int16_t* stage = reinterpret_cast<int16_t*>(d);      // [S][320]
-    GemmF32Tap<S, NT, 8, L::TNL, 16, L::WML, false>(u, L::LDU, 0, 1, 4, 64, 1, 23, 16, BlobPtr<float>(blob, P.last.w), wbuf, true, NoNext(),
-      [&](int q, int s0, int n0, float (&acc)[8][L::TNL]) {
+    auto epi_last = [&](int q, int s0, int n0, auto& acc) {
+      constexpr int TMx = sizeof(acc) / sizeof(acc[0]), TNx = sizeof(acc[0]) / sizeof(float);
 #pragma unroll
-        for (int j = 0; j < L::TNL; ++j) {
-          const int t = 16 * q + n0 + j;
+      for (int j = 0; j < TNx; ++j) {
+        const int t = 16 * q + n0 + j;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float y = __fadd_rn(__fadd_rn(acc[i][j], bias), t < 48 ? sl[t * S + s0 + i] : 0.0f);
-            if (t < 320) {
-              // UnitToInt16Scalar (dsp_utils.h:53-60,79-88): scale, clip in float, truncate
-              float v = __fmul_rn(y, 32768.0f);
-              v = v > -32768.0f ? v : -32768.0f;
-              v = v < 32767.0f ? v : 32767.0f;
-              stage[(s0 + i) * 320 + t] = (int16_t)(int)v;
-            } else if (active[s0 + i]) {
-              tail[(t - 320) * S + s0 + i] = __fsub_rn(y, bias);
-            }
+        for (int i = 0; i < TMx; ++i) {
+          const float y = __fadd_rn(__fadd_rn(acc[i][j], bias), t < 48 ? sl[t * S + s0 + i] : 0.0f);
+          if (t < 320) {
+            // UnitToInt16Scalar (dsp_utils.h:53-60,79-88): scale, clip in float, truncate
+            float v = __fmul_rn(y, 32768.0f);
+            v = v > -32768.0f ? v : -32768.0f;
+            v = v < 32767.0f ? v : 32767.0f;
+            stage[(s0 + i) * 320 + t] = (int16_t)(int)v;
+          } else if (active[s0 + i]) {
+            tail[(t - 320) * S + s0 + i] = __fsub_rn(y, bias);
           }
         }
-      });
+      }
+    };
+    if constexpr (TC)
+      GemmTf32Mma<S, NT, 1, 1, false>(u, L::LDU, 0, 1, 4, 64, 1, 23, 16, BlobPtr<float2>(blob, P.last.wf), epi_last);
+    else
+      GemmF32Tap<S, NT, 8, L::TNL, 16, L::WML, false>(u, L::LDU, 0, 1, 4, 64, 1, 23, 16, BlobPtr<float>(blob, P.last.w), wbuf, true, NoNext(), epi_last);
     for (int i = tid; i < S * 320; i += NT) {
       const int s = i / 320;
       if (active[s]) pcm[(size_t)slot[s] * 320 + (i % 320)] = stage[i];

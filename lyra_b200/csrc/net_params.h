@@ -17,7 +17,9 @@
 namespace lyra_b200 {
 
 // fp32 GEMM-shaped convolution: weights [Ktot][N] k-major (k = tap*CinG + ci), bias [N]
-struct GemmF32 { uint32_t w, bias; };
+// wf: the same [K][N] matrix in mma.sync m16n8k8 B-fragment order [K/8][N/8][32 lanes] x float2 (decoder layers only;
+// 0 = not packed) for the decoder's tensor-core mode
+struct GemmF32 { uint32_t w, bias, wf; };
 // int8 convolution: weights in mma.sync m16n8k32 B-fragment order [Ktot/32][N/8][32 lanes][2 words]
 // (k = tap*CinG + ci), bias folded with the input zero point (bias + (-zp_in) * sum(w)), per-channel Q31
 // multiplier and shift

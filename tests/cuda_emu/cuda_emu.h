@@ -132,6 +132,8 @@ static inline int __dp4a(int a, int b, int c) {
   return c;
 }
 static inline int __float2int_rz(float v) { return (int)v; }
+static inline uint32_t __float_as_uint(float v) { uint32_t b; std::memcpy(&b, &v, 4); return b; }
+static inline float __uint_as_float(uint32_t b) { float v; std::memcpy(&v, &b, 4); return v; }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 static inline long long __mul64hi(long long a, long long b) { return (long long)(((__int128)a * b) >> 64); }

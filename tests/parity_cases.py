@@ -1,9 +1,16 @@
 """Parity cases shared by the CPU tier (emulated kernels) and the GPU tier (real kernels): every case drives
 the C ABI and compares with the oracle on the same seeded inputs.  Bar: bit-exact packets, RVQ indices,
-features and int16 PCM; log-mel within 2e-6 absolute (float log)."""
+features and int16 PCM; log-mel within 2e-6 absolute (float log).
+
+The decoder's opt-in tensor-core mode (lyra_b200_set_decoder_mode, split-precision TF32) is the one floating-point
+path that is compared with a tolerance: decoded int16 PCM within TENSOR_PCM_TOL_LSB of the oracle (the drop-in
+target in BASELINE.json allows 1e-3 of full scale = 32.8 LSB); packets stay bit-exact in that mode too."""
 import numpy as np
 
 from conftest import MODEL_DIR
+
+
+TENSOR_PCM_TOL_LSB = 4      # |PCM_tensor - PCM_oracle| <= 4 int16 LSB = 1.2e-4 of full scale
 
 
 def synth_pcm(rng, n, kind="noise"):
@@ -17,9 +24,13 @@ def synth_pcm(rng, n, kind="noise"):
 
 
 def run_codec_parity(Context, api, O, *, max_streams, stream_ids, frames, bits, kind="noise", seed=0, loss_every=0,
-                     wav=None, check=None):
-    """Encode+decode `frames` hops of the listed streams; compare `check` (default: all) against per-stream oracles."""
+                     wav=None, check=None, decoder_mode="exact"):
+    """Encode+decode `frames` hops of the listed streams; compare `check` (default: all) against per-stream oracles.
+    Returns the largest |PCM difference| seen (0 unless decoder_mode == "tensor")."""
     ctx = Context(max_streams, capi=api)
+    ctx.set_decoder_mode(decoder_mode)
+    pcm_tol = TENSOR_PCM_TOL_LSB if decoder_mode == "tensor" else 0
+    worst = 0
     ids = np.asarray(stream_ids, dtype=np.int32)
     n = len(ids)
     check = list(range(n)) if check is None else check
@@ -40,9 +51,11 @@ def run_codec_parity(Context, api, O, *, max_streams, stream_ids, frames, bits, 
             lost = received is not None and received[k] == 0
             opcm, _, _ = codecs[k].decode(None if lost else opkt, bits)
             assert bytes(packets[k]) == opkt, "packet mismatch frame %d stream %d" % (f, ids[k])
-            assert np.array_equal(out[k], opcm), "PCM mismatch frame %d stream %d (max |d| %d)" % (
-                f, ids[k], np.abs(out[k].astype(int) - opcm.astype(int)).max())
+            diff = int(np.abs(out[k].astype(int) - opcm.astype(int)).max())
+            worst = max(worst, diff)
+            assert diff <= pcm_tol, "PCM mismatch frame %d stream %d (max |d| %d, allowed %d)" % (f, ids[k], diff, pcm_tol)
     ctx.close()
+    return worst
 
 
 def run_plugin_surface_parity(Context, api, O, *, n=5, frames=3, seed=1):

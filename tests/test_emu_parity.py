@@ -22,6 +22,15 @@ def test_emu_loud_and_silent_input(emu_api, oracle):
     pc.run_codec_parity(_capi.Context, emu_api, oracle, max_streams=16, stream_ids=[4], frames=2, bits=64, kind="silence")
 
 
+def test_emu_tensor_decoder_mode(emu_api, oracle, sample1):
+    # split-precision TF32 decoder: packets bit-exact, PCM within the stated tolerance, over a ring wrap, with loss
+    worst = pc.run_codec_parity(_capi.Context, emu_api, oracle, max_streams=16, stream_ids=[0, 9], frames=20, bits=64,
+                                wav=sample1, loss_every=7, decoder_mode="tensor")
+    assert worst <= pc.TENSOR_PCM_TOL_LSB
+    pc.run_codec_parity(_capi.Context, emu_api, oracle, max_streams=8, stream_ids=[3], frames=3, bits=184, kind="loud",
+                        decoder_mode="tensor")
+
+
 def test_emu_plugin_surface(emu_api, oracle):
     pc.run_plugin_surface_parity(_capi.Context, emu_api, oracle, n=3, frames=2)
 

@@ -29,6 +29,35 @@ def test_codec_parity_extreme_inputs(gpu_api, oracle, kind):
     pc.run_codec_parity(_capi.Context, gpu_api, oracle, max_streams=16, stream_ids=[3, 4, 9], frames=12, bits=120, kind=kind)
 
 
+@pytest.mark.parametrize("kind", ["speech", "noise", "loud"])
+def test_tensor_decoder_mode_within_tolerance(gpu_api, oracle, sample1, kind):
+    # opt-in split-precision TF32 decoder: packets stay bit-exact, PCM within TENSOR_PCM_TOL_LSB of the oracle
+    worst = pc.run_codec_parity(_capi.Context, gpu_api, oracle, max_streams=40, stream_ids=[0, 7, 8, 21, 39], frames=60,
+                                bits=64 if kind != "loud" else 184, wav=sample1 if kind == "speech" else None,
+                                kind="noise" if kind == "speech" else kind, loss_every=9, decoder_mode="tensor", seed=5)
+    print("tensor-mode decoder, %s: worst |PCM - oracle| = %d LSB" % (kind, worst))
+    assert worst <= pc.TENSOR_PCM_TOL_LSB
+
+
+def test_tensor_decoder_mode_full_size_matches_exact_mode(gpu_api):
+    # 4096 streams x 20 frames: the tensor-mode PCM stays within the tolerance of the exact-mode PCM on every stream
+    n = 4096
+    rng = np.random.default_rng(11)
+    a = _capi.Context(n, capi=gpu_api)
+    b = _capi.Context(n, capi=gpu_api)
+    b.set_decoder_mode("tensor")
+    worst = 0
+    for f in range(20):
+        pcm = pc.synth_pcm(rng, n, "noise")
+        pk = a.encode(pcm, 64)
+        assert np.array_equal(pk, b.encode(pcm, 64))
+        worst = max(worst, int(np.abs(a.decode(pk, 64).astype(int) - b.decode(pk, 64).astype(int)).max()))
+    a.close()
+    b.close()
+    print("tensor vs exact decoder, 4096 streams: worst |dPCM| = %d LSB" % worst)
+    assert worst <= pc.TENSOR_PCM_TOL_LSB
+
+
 def test_non_standard_bit_counts(gpu_api, oracle):
     # any multiple of 4 up to 184 is accepted by Quantize (residual_vector_quantizer.cc:79-89)
     for bits in (4, 60, 100, 180):
