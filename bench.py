@@ -193,6 +193,10 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--bits", type=int, default=64, help="quantized bits per frame: 64 / 120 / 184 (3.2 / 6.0 / 9.2 kbps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
+    ap.add_argument("--e2e-split", type=int, default=2, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
+    ap.add_argument("--decoder-mode", default="exact", choices=["exact", "tensor"],
+                    help="exact: decoded PCM bit-identical to the oracle (default); tensor: split-precision TF32 tensor-core decoder")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -215,6 +219,8 @@ def main():
     n, bits = args.streams, args.bits
     P = (bits + 7) // 8
     ctx = _capi.Context(n, device=local_rank)
+    ctx.set_decoder_mode(args.decoder_mode)
+    ctx.set_split(args.split)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -260,7 +266,7 @@ def main():
         step_device(i)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
-    ctx.set_split(2)
+    ctx.set_split(args.e2e_split)
     barrier()
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -328,6 +334,7 @@ def main():
             "config": {"workload": "%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode "
                                    "(BASELINE configs[2] at %.1f kbps; the north_star target size)" % (n, bits * 50 / 1000.0, bits * 50 / 1000.0),
                        "streams_per_gpu": n, "bits_per_frame": bits, "tile_streams": ctx.tile_streams,
+                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split},
                        "real_time_factor": value / (50.0 * n * world),
                        "l2": "no flush needed: per-step state working set %d x %.0f KB = %.0f MB exceeds the 126 MB L2; PCM inputs rotate over %d buffers"
                              % (n, (EncDecStateBytes()) / 1024.0, n * EncDecStateBytes() / 1e6, NBUF),

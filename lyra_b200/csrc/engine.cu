@@ -237,24 +237,44 @@ int Join(lyra_b200_ctx* ctx, int nparts) {
   return LYRA_B200_OK;
 }
 
-int RunEncode(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets) {
+// h_pcm / h_packets (host-buffer API): each part copies its own slice in on its own stream before its kernels and
+// its result out right after them, so the copies of one part overlap the kernels of the others.
+int RunEncode(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets,
+              const int16_t* h_pcm = nullptr, uint8_t* h_packets = nullptr) {
   Part parts[lyra_b200_ctx::kMaxSplit];
   const int np = SplitParts(ctx, n, parts);
+  const size_t pb = (size_t)PacketBytes(num_bits);
   int rc = Fork(ctx, np);
   for (int i = 0; i < np && !rc; ++i) {
-    if ((rc = LaunchEncoderNets(ctx, parts[i], d_pcm, ctx->d_features))) break;
-    rc = LaunchQuantize(ctx, parts[i], ctx->d_features, num_bits, d_packets, nullptr);
+    const Part& p = parts[i];
+    if (h_pcm)
+      CU(cudaMemcpyAsync(ctx->d_pcm + (size_t)p.slot0 * 320, h_pcm + (size_t)p.slot0 * 320, sizeof(int16_t) * 320 * (size_t)p.nslots,
+                         cudaMemcpyHostToDevice, p.st));
+    if ((rc = LaunchEncoderNets(ctx, p, d_pcm, ctx->d_features))) break;
+    if ((rc = LaunchQuantize(ctx, p, ctx->d_features, num_bits, d_packets, nullptr))) break;
+    if (h_packets)
+      CU(cudaMemcpyAsync(h_packets + (size_t)p.slot0 * pb, d_packets + (size_t)p.slot0 * pb, pb * (size_t)p.nslots, cudaMemcpyDeviceToHost, p.st));
   }
   return rc ? rc : Join(ctx, np);
 }
 
-int RunDecode(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits, int16_t* d_pcm) {
+int RunDecode(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits, int16_t* d_pcm,
+              const uint8_t* h_packets = nullptr, const uint8_t* h_received = nullptr, int16_t* h_pcm = nullptr) {
   Part parts[lyra_b200_ctx::kMaxSplit];
   const int np = SplitParts(ctx, n, parts);
+  const size_t pb = (size_t)PacketBytes(num_bits);
   int rc = Fork(ctx, np);
   for (int i = 0; i < np && !rc; ++i) {
-    if ((rc = LaunchDequantize(ctx, parts[i], d_packets, d_received, num_bits, ctx->d_features))) break;
-    rc = LaunchDecoderNets(ctx, parts[i], ctx->d_features, d_pcm);
+    const Part& p = parts[i];
+    if (h_packets)
+      CU(cudaMemcpyAsync(ctx->d_packets + (size_t)p.slot0 * pb, h_packets + (size_t)p.slot0 * pb, pb * (size_t)p.nslots, cudaMemcpyHostToDevice, p.st));
+    if (h_received)
+      CU(cudaMemcpyAsync(ctx->d_received + p.slot0, h_received + p.slot0, (size_t)p.nslots, cudaMemcpyHostToDevice, p.st));
+    if ((rc = LaunchDequantize(ctx, p, d_packets, d_received, num_bits, ctx->d_features))) break;
+    if ((rc = LaunchDecoderNets(ctx, p, ctx->d_features, d_pcm))) break;
+    if (h_pcm)
+      CU(cudaMemcpyAsync(h_pcm + (size_t)p.slot0 * 320, d_pcm + (size_t)p.slot0 * 320, sizeof(int16_t) * 320 * (size_t)p.nslots,
+                         cudaMemcpyDeviceToHost, p.st));
   }
   return rc ? rc : Join(ctx, np);
 }
@@ -517,9 +537,7 @@ int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = RunEncode(ctx, n, ctx->d_pcm, num_bits, ctx->d_packets))) return rc;
-  CU(cudaMemcpyAsync(packets, ctx->d_packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = RunEncode(ctx, n, ctx->d_pcm, num_bits, ctx->d_packets, pcm, packets))) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   return LYRA_B200_OK;
 }
@@ -530,10 +548,7 @@ int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(ctx->d_packets, packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  if (received) CU(cudaMemcpyAsync(ctx->d_received, received, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = RunDecode(ctx, n, ctx->d_packets, received ? ctx->d_received : nullptr, num_bits, ctx->d_pcm))) return rc;
-  CU(cudaMemcpyAsync(pcm, ctx->d_pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = RunDecode(ctx, n, ctx->d_packets, received ? ctx->d_received : nullptr, num_bits, ctx->d_pcm, packets, received, pcm))) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   return LYRA_B200_OK;
 }
