@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "20ms-frame encode+decode throughput (frames/s) @16kHz"
+METRIC_PLC = "20ms-frame decode throughput with packet-loss concealment and noise tracking (frames/s) @16kHz"
 UNIT = "frames/s"
 SEED = 0x4C595241
 
@@ -40,6 +41,8 @@ ALGO_BYTES = {
     "RvqDecodeKernel": 0,                                      # + P
     "DecoderKernelC": (10880 + 3648) * 4,                      # bottleneck_2 .. decoder_1 state
     "DecoderKernelD": (2032 + 2032) * 4 + 640,                 # decoder_2 + last_layer state, PCM out
+    "LogMelKernel": 640 + 2 * 640 + 160 * 4,                   # PCM in, carried hop read + written, 160 mel bins out
+    "NoiseEstimatorKernel": 160 * 4 + 2 * 5 * 160 * 4 + 1,     # mel in, 5 x 160 floats of state read + written, flag out
 }
 
 
@@ -193,6 +196,10 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--bits", type=int, default=64, help="quantized bits per frame: 64 / 120 / 184 (3.2 / 6.0 / 9.2 kbps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="codec", choices=["codec", "decode_plc"],
+                    help="codec: encode+decode (the headline metric). decode_plc: BASELINE configs[3], decoder only with a received "
+                         "mask (lost packets are concealed from zero features) + log-mel and noise-estimator update of the decoded hop")
+    ap.add_argument("--loss", type=float, default=0.1, help="decode_plc: packet loss probability (Bernoulli, seed 1234); 1.0 = all lost")
     ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
     ap.add_argument("--e2e-split", type=int, default=2, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
     ap.add_argument("--decoder-mode", default="exact", choices=["exact", "tensor"],
@@ -235,7 +242,22 @@ def main():
     d_pk = torch.zeros((n, P), dtype=torch.uint8, device="cuda")
     d_out = torch.zeros((n, 320), dtype=torch.int16, device="cuda")
 
+    plc = args.workload == "decode_plc"
+    if plc:
+        # packets of NBUF encoded hops + Bernoulli received masks
+        d_pks = [torch.zeros((n, P), dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
+        for i in range(NBUF):
+            ctx.encode_device(n, d_pcm[i].data_ptr(), bits, d_pks[i].data_ptr())
+        ctx.synchronize()
+        mrng = np.random.default_rng(1234 + rank)
+        h_masks = [(mrng.random(n) >= args.loss).astype(np.uint8) for _ in range(NBUF)]
+        d_masks = [torch.from_numpy(m).cuda() for m in h_masks]
+        d_flags = torch.zeros(n, dtype=torch.uint8, device="cuda")
+
     def step_device(i):
+        if plc:
+            ctx.decode_track_noise_device(n, d_pks[i % NBUF].data_ptr(), d_masks[i % NBUF].data_ptr(), bits, d_out.data_ptr(), d_flags.data_ptr())
+            return
         ctx.encode_device(n, d_pcm[i % NBUF].data_ptr(), bits, d_pk.data_ptr())
         ctx.decode_device(n, d_pk.data_ptr(), 0, bits, d_out.data_ptr())
 
@@ -281,7 +303,18 @@ def main():
     lib, h = ctx.api.lib, ctx.h
     import ctypes as C
 
+    if plc:
+        pin_pks = [d_pks[i].cpu().pin_memory() for i in range(NBUF)]
+        pin_masks = [torch.from_numpy(h_masks[i]).pin_memory() for i in range(NBUF)]
+        pin_flags = torch.zeros(n, dtype=torch.uint8).pin_memory()
+
     def step_host(i):
+        if plc:
+            rc = lib.lyra_b200_decode_track_noise(h, None, n, C.c_void_p(pin_pks[i % NBUF].data_ptr()), C.c_void_p(pin_masks[i % NBUF].data_ptr()),
+                                                  bits, C.c_void_p(pin_out.data_ptr()), C.c_void_p(pin_flags.data_ptr()))
+            if rc:
+                raise RuntimeError("host API failed: %s" % lib.lyra_b200_last_error(h))
+            return
         rc = lib.lyra_b200_encode(h, None, n, C.c_void_p(pin_in[i % NBUF].data_ptr()), bits, C.c_void_p(pin_pk.data_ptr()))
         rc |= lib.lyra_b200_decode(h, None, n, C.c_void_p(pin_pk.data_ptr()), None, bits, C.c_void_p(pin_out.data_ptr()))
         if rc:
@@ -311,7 +344,8 @@ def main():
                 kern[k] = {"ms_per_launch": ms / cnt, "launches": cnt, "algo_bytes_per_launch": ab * n,
                            "achieved_gbs": ab * n / (ms / cnt * 1e-3) / 1e9}
         dom = max(kern, key=lambda k: kern[k]["ms_per_launch"])
-        total_algo = (79744 + 640 + P) + (74368 + 640 + P)
+        # decode_plc: decoder state traffic + PCM + packet + the estimator's state (5 x 160 floats read and written) and carried hop
+        total_algo = (74368 + 640 + P + 1 + 2 * 5 * 160 * 4 + 2 * 640) if plc else (79744 + 640 + P) + (74368 + 640 + P)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["achieved_gbs"] / peak, "traffic": ncu_traffic(dom, n), "peak_source": peak_src,
                     "kernel_share_of_step": kern[dom]["ms_per_launch"] / sum(v["ms_per_launch"] for v in kern.values()),
@@ -324,14 +358,19 @@ def main():
             threads = host_cores()
             s, f = cpu_calibrated_sample(bits, threads, 12.0)
             r = run_cpu_arm(s, f, bits, threads)
+            if plc:   # decoder stages only (dequantize + generative model), the part of the CPU port this workload runs
+                r["frames_per_s"] = threads * 1e6 / (r["stage_us"][2] + r["stage_us"][3])
             cpu = {"value": r["frames_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "%d streams x %d hops, one stream per thread, uniform noise 0.25 FS, %d bits" % (s, f, bits),
                    "stage_us_per_frame": dict(zip(["feature_extractor", "quantizer_quantize", "quantizer_decode", "model_decode"], r["stage_us"]))}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC_PLC if plc else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+i8", "data": "synthetic",
-            "config": {"workload": "%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode "
+            "config": {"workload": ("%d concurrent 16kHz streams per GPU, %.1f kbps, decoder only with packet-loss concealment "
+                                    "(BASELINE configs[3]): received mask Bernoulli(%.2f, seed 1234), log-mel + noise estimator on the decoded hop"
+                                    % (n, bits * 50 / 1000.0, 1.0 - args.loss)) if plc else
+                                   "%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode "
                                    "(BASELINE configs[2] at %.1f kbps; the north_star target size)" % (n, bits * 50 / 1000.0, bits * 50 / 1000.0),
                        "streams_per_gpu": n, "bits_per_frame": bits, "tile_streams": ctx.tile_streams,
                        "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split},
@@ -340,7 +379,8 @@ def main():
                              % (n, (EncDecStateBytes()) / 1024.0, n * EncDecStateBytes() / 1e6, NBUF),
                        "parallelism": "streams sharded by rank, no data-path collective",
                        "output_checksum": checksum},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (640 + P), "d2h_bytes_per_step": n * (P + 640)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (P + 1) if plc else n * (640 + P),
+                    "d2h_bytes_per_step": n * (640 + 1) if plc else n * (P + 640)},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": roofline,

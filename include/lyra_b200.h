@@ -92,6 +92,23 @@ int lyra_b200_generate(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, con
 int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* stream_ids, int n, const int16_t* pcm,
                      int num_mel_bins, float* out);
 
+/* NoiseEstimator::ReceiveSamples(one whole hop) + is_noise() + noise_estimate() (lyra/noise_estimator.h:44-62,
+ * lyra/noise_estimator.cc:144-245; 160 features, the decoder's configuration lyra/lyra_decoder.cc:98-104), one
+ * estimator per stream with its own log-mel extractor.  pcm[n][320] is the decoded hop; update_mask[n] (NULL = all
+ * ones) is 1 for streams whose hop came from a received packet: only those feed the estimator
+ * (LyraDecoder::DecodeSamplesInternal, lyra/lyra_decoder.cc:306-311), the others only report.  Outputs (either may
+ * be NULL): is_noise[n] (1 = the last fed hop was classified as noise; 1 for a fresh estimator) and
+ * noise_estimate[n][160].  State is cleared by lyra_b200_reset. */
+int lyra_b200_noise_update(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const int16_t* pcm,
+                           const uint8_t* update_mask, uint8_t* is_noise, float* noise_estimate);
+
+/* lyra_b200_decode followed, on the device and per sub-batch, by the noise-estimator update of every stream whose
+ * packet was received — what LyraDecoder::DecodeSamplesInternal does after RunGenerativeModel
+ * (lyra/lyra_decoder.cc:306-311) — without moving the decoded audio or the 160-bin spectra off the GPU.
+ * is_noise[n] may be NULL; the estimate itself is read with lyra_b200_noise_update(update_mask = zeros). */
+int lyra_b200_decode_track_noise(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const uint8_t* packets,
+                                 const uint8_t* received, int num_bits, int16_t* pcm, uint8_t* is_noise);
+
 /* ---- device-resident variants (pointers are CUDA device pointers; asynchronous on the context's
  *      stream; streams 0..n-1).  Used by bench.py for the HBM-resident `value` measurement and by
  *      callers that keep audio on the GPU. ---------------------------------------------------------- */
@@ -99,6 +116,10 @@ int lyra_b200_set_stream(lyra_b200_ctx* ctx, void* cuda_stream); /* NULL restore
 int lyra_b200_encode_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets);
 int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received,
                             int num_bits, int16_t* d_pcm);
+int lyra_b200_decode_track_noise_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received,
+                                        int num_bits, int16_t* d_pcm, uint8_t* d_is_noise);
+int lyra_b200_noise_update_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, const uint8_t* d_update_mask,
+                                  uint8_t* d_is_noise, float* d_noise_estimate);
 int lyra_b200_synchronize(lyra_b200_ctx* ctx);
 /* Dense calls (stream_ids == NULL / *_device) over many tiles are cut into `parts` (1..4, default 2) sub-batches that
  * run concurrently on internal CUDA streams so partial waves of one kernel are filled by another's blocks.
@@ -122,9 +143,9 @@ uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx);
 
 /* ---- diagnostics: per-kernel device time measured with CUDA events on the launching stream.
  *      Kernel order: 0 EncoderKernelA, 1 EncoderKernelB, 2 RvqEncodeKernel, 3 RvqDecodeKernel,
- *      4 DecoderKernelC, 5 DecoderKernelD, 6 LogMelKernel.  profile_read synchronises the stream and
+ *      4 DecoderKernelC, 5 DecoderKernelD, 6 LogMelKernel, 7 NoiseEstimatorKernel.  profile_read synchronises the stream and
  *      returns the accumulated milliseconds / launch counts since profiling was enabled. */
-#define LYRA_B200_NUM_KERNELS 7
+#define LYRA_B200_NUM_KERNELS 8
 int lyra_b200_profile_enable(lyra_b200_ctx* ctx, int enable);
 int lyra_b200_profile_read(lyra_b200_ctx* ctx, double* ms_sum, uint64_t* launches);
 

@@ -51,6 +51,10 @@ class CApi:
             "lyra_b200_encode_device": (ci, [vp, ci, vp, ci, vp]),
             "lyra_b200_decode_device": (ci, [vp, ci, vp, vp, ci, vp]),
             "lyra_b200_synchronize": (ci, [vp]),
+            "lyra_b200_noise_update": (ci, [vp, vp, ci, vp, vp, vp, vp]),
+            "lyra_b200_decode_track_noise": (ci, [vp, vp, ci, vp, vp, ci, vp, vp]),
+            "lyra_b200_decode_track_noise_device": (ci, [vp, ci, vp, vp, ci, vp, vp]),
+            "lyra_b200_noise_update_device": (ci, [vp, ci, vp, vp, vp, vp]),
             "lyra_b200_set_split": (ci, [vp, ci]),
             "lyra_b200_set_decoder_mode": (ci, [vp, ci]),
             "lyra_b200_decoder_mode": (ci, [vp]),
@@ -69,7 +73,8 @@ class CApi:
                "lyra_b200_tile_streams", "lyra_b200_reset", "lyra_b200_encode", "lyra_b200_decode",
                "lyra_b200_extract_features", "lyra_b200_quantize", "lyra_b200_dequantize", "lyra_b200_generate",
                "lyra_b200_logmel", "lyra_b200_set_stream", "lyra_b200_encode_device", "lyra_b200_decode_device",
-               "lyra_b200_synchronize", "lyra_b200_set_split", "lyra_b200_set_decoder_mode", "lyra_b200_decoder_mode", "lyra_b200_launch_count", "lyra_b200_profile_enable",
+               "lyra_b200_synchronize", "lyra_b200_noise_update", "lyra_b200_noise_update_device", "lyra_b200_decode_track_noise",
+               "lyra_b200_decode_track_noise_device", "lyra_b200_set_split", "lyra_b200_set_decoder_mode", "lyra_b200_decoder_mode", "lyra_b200_launch_count", "lyra_b200_profile_enable",
                "lyra_b200_profile_read"]
 
 
@@ -200,6 +205,36 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         self._check(self.api.lib.lyra_b200_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
 
+    def decode_track_noise(self, packets, num_bits, stream_ids=None, received=None):
+        """decode() + noise-estimator update of the received streams on the device -> (pcm[n][320], is_noise[n])."""
+        packets = np.ascontiguousarray(packets, dtype=np.uint8).reshape(-1, packet_bytes(num_bits))
+        n = packets.shape[0]
+        ids = _ids(stream_ids, n)
+        rec = None if received is None else np.ascontiguousarray(received, dtype=np.uint8)
+        out = np.empty((n, HOP), dtype=np.int16)
+        flags = np.empty(n, dtype=np.uint8)
+        self._check(self.api.lib.lyra_b200_decode_track_noise(self.h, _ptr(ids), n, _ptr(packets), _ptr(rec), num_bits, _ptr(out), _ptr(flags)))
+        return out, flags.astype(bool)
+
+    def decode_track_noise_device(self, n, d_packets, d_received, num_bits, d_pcm, d_is_noise=0):
+        self._check(self.api.lib.lyra_b200_decode_track_noise_device(self.h, n, C.c_void_p(d_packets), C.c_void_p(d_received or 0),
+                                                                     num_bits, C.c_void_p(d_pcm), C.c_void_p(d_is_noise or 0)))
+
+    def noise_update(self, pcm, stream_ids=None, update_mask=None):
+        """NoiseEstimator::ReceiveSamples on one decoded hop per stream -> (is_noise[n] bool, noise_estimate[n][160])."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, HOP)
+        n = pcm.shape[0]
+        ids = _ids(stream_ids, n)
+        mask = None if update_mask is None else np.ascontiguousarray(update_mask, dtype=np.uint8)
+        flags = np.empty(n, dtype=np.uint8)
+        est = np.empty((n, 160), dtype=np.float32)
+        self._check(self.api.lib.lyra_b200_noise_update(self.h, _ptr(ids), n, _ptr(pcm), _ptr(mask), _ptr(flags), _ptr(est)))
+        return flags.astype(bool), est
+
+    def noise_update_device(self, n, d_pcm, d_mask, d_is_noise, d_estimate):
+        self._check(self.api.lib.lyra_b200_noise_update_device(self.h, n, C.c_void_p(d_pcm), C.c_void_p(d_mask or 0),
+                                                               C.c_void_p(d_is_noise or 0), C.c_void_p(d_estimate or 0)))
+
     def encode_device(self, n, d_pcm, num_bits, d_packets):
         self._check(self.api.lib.lyra_b200_encode_device(self.h, n, C.c_void_p(d_pcm), num_bits, C.c_void_p(d_packets)))
 
@@ -218,14 +253,14 @@ class Context:
         self._check(self.api.lib.lyra_b200_set_split(self.h, int(parts)))
 
     KERNEL_NAMES = ["EncoderKernelA", "EncoderKernelB", "RvqEncodeKernel", "RvqDecodeKernel", "DecoderKernelC",
-                    "DecoderKernelD", "LogMelKernel"]
+                    "DecoderKernelD", "LogMelKernel", "NoiseEstimatorKernel"]
 
     def profile_enable(self, enable=True):
         self._check(self.api.lib.lyra_b200_profile_enable(self.h, 1 if enable else 0))
 
     def profile_read(self):
         """-> {kernel name: (total ms, launches)} since profiling was enabled (CUDA events on the launch stream)."""
-        ms = (C.c_double * 7)()
-        cnt = (C.c_uint64 * 7)()
+        ms = (C.c_double * len(self.KERNEL_NAMES))()
+        cnt = (C.c_uint64 * len(self.KERNEL_NAMES))()
         self._check(self.api.lib.lyra_b200_profile_read(self.h, ms, cnt))
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNEL_NAMES)}

@@ -127,37 +127,79 @@ ResetStateKernel(uint32_t* __restrict__ state, const uint32_t* __restrict__ init
 
 // ------------------------------------------------------------------------------------------------
 // Log-mel spectrogram (LogMelSpectrogramExtractorImpl::Extract, lyra/log_mel_spectrogram_extractor_impl.cc:96-126).
-// One block per stream: periodic-Hann window over [previous hop, current hop], zero-padded radix-2
-// FFT in double (same butterfly order and host-computed twiddles as the oracle), |X|, triangular mel
-// weights accumulated in bin order, float cast, log(max(x, 500)) / 10.
+// One block of 128 threads per stream: periodic-Hann window over [previous hop, current hop], zero-padded 1024-point
+// radix-2 decimation-in-time FFT in double — the same butterflies, operand order and host-computed twiddles as the
+// oracle, so the spectrum is bit-identical to it — |X|, triangular mel weights accumulated in bin order, float cast,
+// log(max(x, 500)) / 10 with the logarithm taken in double and rounded once (equal to a correctly rounded logf).
+// The ten stages run as 3 + 3 + 3 + 1: a thread keeps 8 points in registers across three consecutive stages (points
+// base + j * STRIDE, the closed set of three stages whose half-lengths are STRIDE, 2 STRIDE, 4 STRIDE), so the block
+// synchronises four times instead of ten.
 // prev: [max_streams][window - hop] int16 carried samples (zero after reset).
-__global__ void __launch_bounds__(256)
+constexpr int kLogMelThreads = 128;
+constexpr int kLogMelFft = 1024;
+
+// butterfly of stage `len` on (a, b = a + len/2) with twiddle w = tw[k * (fft / len)]:  x = b * w;  b = a - x;  a = a + x
+__device__ __forceinline__ void FftButterfly(double& ar, double& ai, double& br, double& bi, double wr, double wi) {
+  const double xr = __dsub_rn(__dmul_rn(br, wr), __dmul_rn(bi, wi));
+  const double xi = __dadd_rn(__dmul_rn(br, wi), __dmul_rn(bi, wr));
+  br = __dsub_rn(ar, xr); bi = __dsub_rn(ai, xi);
+  ar = __dadd_rn(ar, xr); ai = __dadd_rn(ai, xi);
+}
+
+// shared-memory index of FFT point i: one pad element per 8 keeps the stride-8 and stride-64 register-blocked passes
+// (nearly) free of bank conflicts
+__device__ __forceinline__ int FftIdx(int i) { return i + (i >> 3); }
+constexpr int kLogMelFftPadded = kLogMelFft + kLogMelFft / 8;
+
+// three consecutive stages (half-lengths STRIDE, 2 STRIDE, 4 STRIDE) on the 8 points base + j * STRIDE; r = base mod STRIDE.
+// tw: per-stage twiddle tables, the stage of half-length h starts at complex entry h - 1.
+template <int STRIDE>
+__device__ __forceinline__ void FftStages3(double* re, double* im, int base, int r, const double2* __restrict__ tw) {
+  double xr[8], xi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { xr[j] = re[FftIdx(base + j * STRIDE)]; xi[j] = im[FftIdx(base + j * STRIDE)]; }
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const int half = STRIDE << s;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(j & (1 << s))) {
+        const int k = r + (j & ((1 << s) - 1)) * STRIDE;
+        const double2 w = tw[half - 1 + k];
+        FftButterfly(xr[j], xi[j], xr[j + (1 << s)], xi[j + (1 << s)], w.x, w.y);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { re[FftIdx(base + j * STRIDE)] = xr[j]; im[FftIdx(base + j * STRIDE)] = xi[j]; }
+}
+
+__global__ void __launch_bounds__(kLogMelThreads)
 LogMelKernel(const uint8_t* __restrict__ blob, LogMelParams P, const int* __restrict__ stream_ids, int n,
-             const int16_t* __restrict__ pcm, int16_t* __restrict__ prev, float* __restrict__ out) {
+             const int16_t* __restrict__ pcm, int16_t* __restrict__ prev, float* __restrict__ out,
+             const uint8_t* __restrict__ mask, int slot_base) {
   unsigned char* smem = LYRA_DYN_SMEM();
   double* re = reinterpret_cast<double*>(smem);
-  double* im = re + P.fft;
-  double* mag = im + P.fft;            // [fft/2 + 1]
-  const int slot = (int)blockIdx.x;
+  double* im = re + kLogMelFftPadded;
+  double* mag = im + kLogMelFftPadded;       // [fft/2 + 1]
+  const int slot = slot_base + (int)blockIdx.x;     // I/O arrays are indexed by slot; a sub-batch starts at slot_base
   if (slot >= n) return;
+  if (mask && !mask[slot]) return;     // this stream's extractor is not fed this hop (its carried samples stay)
   const int stream = stream_ids ? stream_ids[slot] : slot;
-  const int tid = (int)threadIdx.x, NT = (int)blockDim.x;
+  const int tid = (int)threadIdx.x;
+  constexpr int NT = kLogMelThreads;
   const int carry = P.window_len - P.hop;
   const double* win = BlobPtr<double>(blob, P.window);
-  const double* tw = BlobPtr<double>(blob, P.twiddle);
+  const double2* tw = BlobPtr<double2>(blob, P.twiddle);
   int16_t* pv = prev + (size_t)stream * carry;
   const int16_t* cur = pcm + (size_t)slot * P.hop;
-  int bits = 0;
-  while ((1 << bits) < P.fft) ++bits;
-  // windowed, zero-padded frame written in bit-reversed order
-  for (int i = tid; i < P.fft; i += NT) {
+  // windowed, zero-padded frame written in bit-reversed order (10 bits)
+  for (int i = tid; i < kLogMelFft; i += NT) {
     double v = 0.0;
     if (i < P.window_len) {
       const int16_t smp = i < carry ? pv[i] : cur[i - carry];
       v = __dmul_rn((double)smp, win[i]);
     }
-    unsigned rev = 0;
-    for (int b = 0; b < bits; ++b) rev |= ((unsigned)(i >> b) & 1u) << (bits - 1 - b);
+    const int rev = FftIdx((int)(__brev((unsigned)i) >> 22));
     re[rev] = v;
     im[rev] = 0.0;
   }
@@ -171,40 +213,135 @@ LogMelKernel(const uint8_t* __restrict__ blob, LogMelParams P, const int* __rest
     }
     __syncthreads();
     for (int i = tid; i < carry; i += NT) pv[i] = stage[i];
-    __syncthreads();
   }
-  for (int len = 2; len <= P.fft; len <<= 1) {
-    const int half = len >> 1, step = P.fft / len;
-    for (int i = tid; i < P.fft / 2; i += NT) {
-      const int blk = i / half, k = i % half;
-      const int a = blk * len + k, b = a + half;
-      const double wr = tw[2 * (k * step)], wi = tw[2 * (k * step) + 1];
-      const double xr = __dsub_rn(__dmul_rn(re[b], wr), __dmul_rn(im[b], wi));
-      const double xi = __dadd_rn(__dmul_rn(re[b], wi), __dmul_rn(im[b], wr));
-      const double ar = re[a], ai = im[a];
-      re[b] = __dsub_rn(ar, xr); im[b] = __dsub_rn(ai, xi);
-      re[a] = __dadd_rn(ar, xr); im[a] = __dadd_rn(ai, xi);
-    }
-    __syncthreads();
+  FftStages3<1>(re, im, 8 * tid, 0, tw);                                       // stages 2, 4, 8
+  __syncthreads();
+  FftStages3<8>(re, im, 64 * (tid / 8) + tid % 8, tid % 8, tw);                // stages 16, 32, 64
+  __syncthreads();
+  FftStages3<64>(re, im, 512 * (tid / 64) + tid % 64, tid % 64, tw);           // stages 128, 256, 512
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {                                                // stage 1024
+    const int a = tid + NT * m, ia = FftIdx(a), ib = FftIdx(a + 512);
+    const double2 w = tw[511 + a];
+    FftButterfly(re[ia], im[ia], re[ib], im[ib], w.x, w.y);
   }
-  const int bins = P.fft / 2 + 1;
+  __syncthreads();
+  const int bins = kLogMelFft / 2 + 1;
   for (int i = tid; i < bins; i += NT)
-    mag[i] = __dsqrt_rn(__dadd_rn(__dmul_rn(re[i], re[i]), __dmul_rn(im[i], im[i])));
+    mag[i] = __dsqrt_rn(__dadd_rn(__dmul_rn(re[FftIdx(i)], re[FftIdx(i)]), __dmul_rn(im[FftIdx(i)], im[FftIdx(i)])));
   __syncthreads();
   // each mel channel: bins of band ch-1 contribute (v - v*w), bins of band ch contribute v*w, in bin order
   const double* wts = BlobPtr<double>(blob, P.weights);
   const int* band = BlobPtr<int>(blob, P.band);
+  const int* range = BlobPtr<int>(blob, P.range);
   for (int ch = tid; ch < P.num_mel; ch += NT) {
     double acc = 0.0;
-    for (int i = P.start_index; i <= P.end_index; ++i) {
-      const int bd = band[i];
-      if (bd == ch) acc = __dadd_rn(acc, __dmul_rn(mag[i], wts[i]));
-      else if (bd == ch - 1) acc = __dadd_rn(acc, __dsub_rn(mag[i], __dmul_rn(mag[i], wts[i])));
+    const int lo = range[2 * ch], hi = range[2 * ch + 1];
+    for (int i = lo; i <= hi; ++i) {
+      if (band[i] == ch) acc = __dadd_rn(acc, __dmul_rn(mag[i], wts[i]));
+      else acc = __dadd_rn(acc, __dsub_rn(mag[i], __dmul_rn(mag[i], wts[i])));
     }
     float v = (float)acc;
     v = v > 500.0f ? v : 500.0f;
-    out[(size_t)slot * P.num_mel + ch] = __fdiv_rn(logf(v), 10.0f);
+    out[(size_t)slot * P.num_mel + ch] = __fdiv_rn((float)log((double)v), 10.0f);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Minimum-statistics noise estimator on the decoder output:
+// NoiseEstimator::ReceiveSamples for whole hops, after the log-mel kernel has produced this hop's
+// 160-bin spectrum (lyra/noise_estimator.cc:144-245; SmoothingFactor / UpdateMinAndTemp :37-95).
+// One block per stream, one thread per mel bin.  Per-stream state: est | bound | smoothed | squared-smoothed |
+// tmp-min (nf floats each) followed by 4 ints {has_smoothed, hops_received, last_hop_was_not_noise, -} — all-zero
+// is the reference's freshly constructed object (noise estimate and bound 0, is_noise() true).
+// Arithmetic follows the C++ expression types: float ops rounded one by one, the bound in double
+// (std::log of an integer is double), std::exp(float) as (float)exp((double)x) like the oracle.
+// Streams whose mask byte is 0 are left untouched (LyraDecoder only feeds hops decoded from a received
+// packet, lyra/lyra_decoder.cc:306-311) but still report their current is_noise / noise_estimate.
+struct NoiseParams { int nf, hops_per_update; float max_smoothing, bound_decay; double log_nf; };
+constexpr int kNoiseThreads = 192;
+__host__ __device__ constexpr int NoiseStateUnits(int nf) { return 5 * nf + 4; }
+
+__global__ void __launch_bounds__(kNoiseThreads)
+NoiseEstimatorKernel(NoiseParams P, const int* __restrict__ stream_ids, int n, const float* __restrict__ mel,
+                     const uint8_t* __restrict__ mask, float* __restrict__ state, uint8_t* __restrict__ is_noise_out,
+                     float* __restrict__ estimate_out, int slot_base) {
+  unsigned char* smem = LYRA_DYN_SMEM();
+  float* cur = reinterpret_cast<float*>(smem);       // [nf]
+  float* sm = cur + P.nf;                             // [nf] smoothed power before this update
+  float* red = sm + P.nf;                             // [0] smoothing correction
+  int* flag = reinterpret_cast<int*>(red + 1);
+  const int slot = slot_base + (int)blockIdx.x;
+  if (slot >= n) return;
+  const int stream = stream_ids ? stream_ids[slot] : slot;
+  const int i = (int)threadIdx.x, nf = P.nf;
+  float* st = state + (size_t)stream * NoiseStateUnits(nf);
+  float* est = st;
+  float* bound = st + nf;
+  float* smoothed = st + 2 * nf;
+  float* sq = st + 3 * nf;
+  float* tmp_min = st + 4 * nf;
+  int* meta = reinterpret_cast<int*>(st + 5 * nf);
+  const bool feed = mask == nullptr || mask[slot] != 0;
+  if (!feed) {
+    if (is_noise_out && i == 0) is_noise_out[slot] = meta[2] ? 0 : 1;
+    if (estimate_out && i < nf) estimate_out[(size_t)slot * nf + i] = est[i];
+    return;
+  }
+  const int has = meta[0], hops = meta[1];
+  if (i == 0) *flag = 0;
+  __syncthreads();
+  float c = 0.0f, e = 0.0f, b = 0.0f;
+  if (i < nf) {
+    c = mel[(size_t)slot * nf + i];
+    e = est[i];
+    b = bound[i];
+    cur[i] = c;
+    if (fabsf(__fsub_rn(c, e)) > b) *flag = 1;       // ComputeIsNoise: any bin outside estimate +- bound
+  }
+  __syncthreads();
+  const bool not_noise = *flag != 0;
+  if (!not_noise) {
+    if (i < nf) bound[i] = __fmul_rn(b, P.bound_decay);         // DecayBounds
+  } else {
+    float s = 0.0f, q = 0.0f, tm = 0.0f;
+    if (i < nf) {
+      s = has ? smoothed[i] : c;
+      q = has ? sq[i] : __fmul_rn(c, c);
+      tm = has ? tmp_min[i] : c;
+      sm[i] = s;
+    }
+    __syncthreads();
+    if (i == 0) {
+      float a0 = 0.0f, a1 = 0.0f;                      // Average(): std::accumulate in index order, then / size
+      for (int k = 0; k < nf; ++k) { a0 = __fadd_rn(a0, sm[k]); a1 = __fadd_rn(a1, cur[k]); }
+      const float d = __fdiv_rn(__fsub_rn(__fdiv_rn(a0, (float)nf), __fdiv_rn(a1, (float)nf)), 0.3f);
+      red[0] = (float)exp((double)(-__fmul_rn(d, d)));
+    }
+    __syncthreads();
+    if (i < nf) {
+      const float r = __fdiv_rn(__fsub_rn(s, e), 0.3f);
+      const float sf = __fmul_rn(__fmul_rn(P.max_smoothing, red[0]), (float)exp((double)(-__fmul_rn(r, r))));
+      const float om = __fsub_rn(1.0f, sf);
+      const float ns = __fadd_rn(__fmul_rn(sf, s), __fmul_rn(om, c));
+      const float nq = __fadd_rn(__fmul_rn(sf, q), __fmul_rn(om, __fmul_rn(c, c)));
+      float ne, nt;
+      if (hops == 0) { ne = ns < tm ? ns : tm; nt = ns; }          // UpdateMinAndTemp
+      else { ne = ns < e ? ns : e; nt = ns < tm ? ns : tm; }
+      const float t = __fsub_rn(nq, __fmul_rn(ns, ns));
+      const float var = t > 0.0f ? t : 0.0f;
+      const float nb = (float)__dmul_rn((double)0.9f, __dsqrt_rn(__dmul_rn((double)var, P.log_nf)));   // ComputeBounds
+      smoothed[i] = ns; sq[i] = nq; tmp_min[i] = nt; est[i] = ne; bound[i] = nb;
+      e = ne;
+    }
+    if (i == 0) { meta[0] = 1; meta[1] = (hops + 1) % P.hops_per_update; }
+  }
+  if (i == 0) {
+    meta[2] = not_noise ? 1 : 0;
+    if (is_noise_out) is_noise_out[slot] = not_noise ? 0 : 1;
+  }
+  if (estimate_out && i < nf) estimate_out[(size_t)slot * nf + i] = e;
 }
 
 }  // namespace lyra_b200

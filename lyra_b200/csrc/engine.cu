@@ -1,5 +1,6 @@
 // Context + launch logic + the C ABI of include/lyra_b200.h.
 // Compiled by nvcc for sm_100a (product) and, for the CPU test tier only, by g++ with -DLYRA_EMU.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -40,7 +41,11 @@ struct lyra_b200_ctx {
   int units[4] = {EncStateA::kUnits, EncStateB::kUnits, DecStateC::kUnits, DecStateD::kUnits};
   float* d_mid_enc = nullptr;
   float* d_mid_dec = nullptr;
-  int16_t* d_logmel_prev[2] = {nullptr, nullptr};
+  int16_t* d_logmel_prev[3] = {nullptr, nullptr, nullptr};   // banks 0/1: lyra_b200_logmel; bank 2: the noise estimator's extractor
+  float* d_noise = nullptr;          // [max_streams][NoiseStateUnits(160)] noise-estimator state
+  float* d_noise_est = nullptr;      // staging for the host-buffer API
+  uint8_t* d_is_noise = nullptr;
+  NoiseParams noise_params{};
   // device staging for the host-buffer API
   int16_t* d_pcm = nullptr;
   uint8_t* d_packets = nullptr;
@@ -66,9 +71,9 @@ struct lyra_b200_ctx {
   // diagnostics: CUDA-event timing of every kernel launch
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[LYRA_B200_NUM_KERNELS];
-  size_t prof_used[LYRA_B200_NUM_KERNELS] = {0, 0, 0, 0, 0, 0, 0};
-  double prof_ms[LYRA_B200_NUM_KERNELS] = {0, 0, 0, 0, 0, 0, 0};
-  uint64_t prof_n[LYRA_B200_NUM_KERNELS] = {0, 0, 0, 0, 0, 0, 0};
+  size_t prof_used[LYRA_B200_NUM_KERNELS] = {};
+  double prof_ms[LYRA_B200_NUM_KERNELS] = {};
+  uint64_t prof_n[LYRA_B200_NUM_KERNELS] = {};
 };
 
 namespace {
@@ -237,6 +242,23 @@ int Join(lyra_b200_ctx* ctx, int nparts) {
   return LYRA_B200_OK;
 }
 
+// log-mel of this hop (the estimator's own extractor, bank 2) + the estimator recurrences for slots
+// [slot0, slot0 + count) on stream `st`; all arrays are indexed by slot, n = total slots of the call
+int LaunchNoiseUpdate(lyra_b200_ctx* ctx, cudaStream_t st, const int* d_ids, int slot0, int count, int n, const int16_t* d_pcm,
+                      const uint8_t* d_mask, uint8_t* d_is_noise, float* d_estimate) {
+  const LogMelParams& P = ctx->spec.logmel160;
+  const size_t smem = sizeof(double) * (size_t)(2 * kLogMelFftPadded + P.fft / 2 + 1);
+  { ProfScope ps(ctx, 6, st);
+  LYRA_LAUNCH(LogMelKernel, dim3((unsigned)count), dim3(kLogMelThreads), smem, st,
+              ctx->d_blob, P, d_ids, n, d_pcm, ctx->d_logmel_prev[2], ctx->d_melout, d_mask, slot0); }
+  { ProfScope ps(ctx, 7, st);
+  LYRA_LAUNCH(NoiseEstimatorKernel, dim3((unsigned)count), dim3(kNoiseThreads), sizeof(float) * (size_t)(2 * 160 + 2), st,
+              ctx->noise_params, d_ids, n, ctx->d_melout, d_mask, ctx->d_noise, d_is_noise, d_estimate, slot0); }
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  return LYRA_B200_OK;
+}
+
 // h_pcm / h_packets (host-buffer API): each part copies its own slice in on its own stream before its kernels and
 // its result out right after them, so the copies of one part overlap the kernels of the others.
 int RunEncode(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets,
@@ -258,8 +280,11 @@ int RunEncode(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uin
   return rc ? rc : Join(ctx, np);
 }
 
+// track_noise: every sub-batch also feeds its decoded hops to the per-stream noise estimators (received streams only),
+// as LyraDecoder::DecodeSamplesInternal does (lyra/lyra_decoder.cc:306-311); d_ids = the call's stream ids (sparse calls)
 int RunDecode(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits, int16_t* d_pcm,
-              const uint8_t* h_packets = nullptr, const uint8_t* h_received = nullptr, int16_t* h_pcm = nullptr) {
+              const uint8_t* h_packets = nullptr, const uint8_t* h_received = nullptr, int16_t* h_pcm = nullptr,
+              bool track_noise = false, const int* d_ids = nullptr, uint8_t* d_is_noise = nullptr, uint8_t* h_is_noise = nullptr) {
   Part parts[lyra_b200_ctx::kMaxSplit];
   const int np = SplitParts(ctx, n, parts);
   const size_t pb = (size_t)PacketBytes(num_bits);
@@ -272,6 +297,10 @@ int RunDecode(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t
       CU(cudaMemcpyAsync(ctx->d_received + p.slot0, h_received + p.slot0, (size_t)p.nslots, cudaMemcpyHostToDevice, p.st));
     if ((rc = LaunchDequantize(ctx, p, d_packets, d_received, num_bits, ctx->d_features))) break;
     if ((rc = LaunchDecoderNets(ctx, p, ctx->d_features, d_pcm))) break;
+    if (track_noise) {
+      if ((rc = LaunchNoiseUpdate(ctx, p.st, d_ids, p.slot0, p.nslots, n, d_pcm, d_received, d_is_noise, nullptr))) break;
+      if (h_is_noise) CU(cudaMemcpyAsync(h_is_noise + p.slot0, d_is_noise + p.slot0, (size_t)p.nslots, cudaMemcpyDeviceToHost, p.st));
+    }
     if (h_pcm)
       CU(cudaMemcpyAsync(h_pcm + (size_t)p.slot0 * 320, d_pcm + (size_t)p.slot0 * 320, sizeof(int16_t) * 320 * (size_t)p.nslots,
                          cudaMemcpyDeviceToHost, p.st));
@@ -327,13 +356,20 @@ int ResetImpl(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
   }
   CU(cudaGetLastError());
   // log-mel carried samples
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < 3; ++b) {
     if (!ids) {
       CU(cudaMemsetAsync(ctx->d_logmel_prev[b], 0, sizeof(int16_t) * 320 * (size_t)n, ctx->stream));
     } else {
       for (int k = 0; k < n; ++k)
         CU(cudaMemsetAsync(ctx->d_logmel_prev[b] + (size_t)ids[k] * 320, 0, sizeof(int16_t) * 320, ctx->stream));
     }
+  }
+  // noise estimator: all-zero is the freshly constructed object
+  const size_t nu = (size_t)NoiseStateUnits(ctx->noise_params.nf);
+  if (!ids) {
+    CU(cudaMemsetAsync(ctx->d_noise, 0, sizeof(float) * nu * (size_t)n, ctx->stream));
+  } else {
+    for (int k = 0; k < n; ++k) CU(cudaMemsetAsync(ctx->d_noise + (size_t)ids[k] * nu, 0, sizeof(float) * nu, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
   return LYRA_B200_OK;
@@ -419,6 +455,19 @@ int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b2
   ok = ok && DevAlloc(&ctx->d_mid_dec, (size_t)ctx->ntiles * 128 * 4 * kS) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_logmel_prev[0], P * 320) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_logmel_prev[1], P * 320) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_logmel_prev[2], P * 320) == cudaSuccess;
+  {
+    // NoiseEstimator::Create (lyra/noise_estimator.cc:99-120) for (16 kHz, hop 320, 160 features)
+    const float secs_per_hop = static_cast<float>(320) / 16000;
+    ctx->noise_params.nf = 160;
+    ctx->noise_params.hops_per_update = (int)std::round(1.f / secs_per_hop);
+    ctx->noise_params.max_smoothing = std::pow(0.5f, secs_per_hop / 0.7f);
+    ctx->noise_params.bound_decay = std::pow(0.5f, secs_per_hop / 1.f);
+    ctx->noise_params.log_nf = std::log((double)160);
+  }
+  ok = ok && DevAlloc(&ctx->d_noise, P * (size_t)NoiseStateUnits(160)) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_noise_est, P * 160) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_is_noise, P) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_pcm, P * 320) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_packets, P * 24) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_received, P) == cudaSuccess;
@@ -448,7 +497,8 @@ void lyra_b200_destroy(lyra_b200_ctx* ctx) {
   cudaFree(ctx->d_blob);
   for (int w = 0; w < 4; ++w) { cudaFree(ctx->d_state[w]); cudaFree(ctx->d_init[w]); cudaFree(ctx->d_n18[w]); }
   cudaFree(ctx->d_mid_enc); cudaFree(ctx->d_mid_dec);
-  cudaFree(ctx->d_logmel_prev[0]); cudaFree(ctx->d_logmel_prev[1]);
+  cudaFree(ctx->d_logmel_prev[0]); cudaFree(ctx->d_logmel_prev[1]); cudaFree(ctx->d_logmel_prev[2]);
+  cudaFree(ctx->d_noise); cudaFree(ctx->d_noise_est); cudaFree(ctx->d_is_noise);
   cudaFree(ctx->d_pcm); cudaFree(ctx->d_packets); cudaFree(ctx->d_received); cudaFree(ctx->d_features);
   cudaFree(ctx->d_melout); cudaFree(ctx->d_indices); cudaFree(ctx->d_ids); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_slot_of);
   for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k)
@@ -619,15 +669,74 @@ int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* ids, int n, co
   }
   const LogMelParams& P = num_mel_bins == 160 ? ctx->spec.logmel160 : ctx->spec.logmel64;
   CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  const size_t smem = sizeof(double) * (size_t)(2 * P.fft + P.fft / 2 + 1);
+  const size_t smem = sizeof(double) * (size_t)(2 * kLogMelFftPadded + P.fft / 2 + 1);
   { ProfScope ps(ctx, 6, ctx->stream);
-  LYRA_LAUNCH(LogMelKernel, dim3((unsigned)n), dim3(256), smem, ctx->stream,
-              ctx->d_blob, P, d_ids, n, ctx->d_pcm, ctx->d_logmel_prev[bank], ctx->d_melout); }
+  LYRA_LAUNCH(LogMelKernel, dim3((unsigned)n), dim3(kLogMelThreads), smem, ctx->stream,
+              ctx->d_blob, P, d_ids, n, ctx->d_pcm, ctx->d_logmel_prev[bank], ctx->d_melout, (const uint8_t*)nullptr, 0); }
   ctx->launches += 1;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, ctx->d_melout, sizeof(float) * (size_t)num_mel_bins * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return LYRA_B200_OK;
+}
+
+int lyra_b200_noise_update(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, const uint8_t* update_mask,
+                           uint8_t* is_noise, float* noise_estimate) {
+  if (!ctx || !pcm) return LYRA_B200_EINVAL;
+  if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
+  const int* d_ids = nullptr;
+  if (ids) {
+    std::vector<char> seen((size_t)ctx->max_streams, 0);
+    for (int k = 0; k < n; ++k) {
+      if (ids[k] < 0 || ids[k] >= ctx->max_streams || seen[(size_t)ids[k]]) { ctx->err = "bad or duplicate stream id"; return LYRA_B200_EINVAL; }
+      seen[(size_t)ids[k]] = 1;
+    }
+    CU(cudaMemcpyAsync(ctx->d_ids, ids, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    d_ids = ctx->d_ids;
+  }
+  CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if (update_mask) CU(cudaMemcpyAsync(ctx->d_received, update_mask, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = LaunchNoiseUpdate(ctx, ctx->stream, d_ids, 0, n, n, ctx->d_pcm, update_mask ? ctx->d_received : nullptr,
+                             is_noise ? ctx->d_is_noise : nullptr, noise_estimate ? ctx->d_noise_est : nullptr);
+  if (rc) return rc;
+  if (is_noise) CU(cudaMemcpyAsync(is_noise, ctx->d_is_noise, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (noise_estimate) CU(cudaMemcpyAsync(noise_estimate, ctx->d_noise_est, sizeof(float) * 160 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_noise_update_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, const uint8_t* d_update_mask,
+                                  uint8_t* d_is_noise, float* d_noise_estimate) {
+  if (!ctx || !d_pcm) return LYRA_B200_EINVAL;
+  if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
+  return LaunchNoiseUpdate(ctx, ctx->stream, nullptr, 0, n, n, d_pcm, d_update_mask, d_is_noise, d_noise_estimate);
+}
+
+int lyra_b200_decode_track_noise(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_t* packets, const uint8_t* received,
+                                 int num_bits, int16_t* pcm, uint8_t* is_noise) {
+  if (!ctx || !packets || !pcm) return LYRA_B200_EINVAL;
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, ids, n);
+  if (rc) return rc;
+  const int* d_ids = nullptr;
+  if (ids) {
+    CU(cudaMemcpyAsync(ctx->d_ids, ids, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    d_ids = ctx->d_ids;
+  }
+  if ((rc = RunDecode(ctx, n, ctx->d_packets, received ? ctx->d_received : nullptr, num_bits, ctx->d_pcm, packets, received, pcm,
+                      true, d_ids, ctx->d_is_noise, is_noise))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_decode_track_noise_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits,
+                                        int16_t* d_pcm, uint8_t* d_is_noise) {
+  if (!ctx || !d_packets || !d_pcm) return LYRA_B200_EINVAL;
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, nullptr, n);
+  if (rc) return rc;
+  return RunDecode(ctx, n, d_packets, d_received, num_bits, d_pcm, nullptr, nullptr, nullptr, true, nullptr,
+                   d_is_noise ? d_is_noise : ctx->d_is_noise, nullptr);
 }
 
 }  // extern "C"

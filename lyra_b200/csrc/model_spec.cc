@@ -1,6 +1,7 @@
 // See model_spec.h.
 #include "model_spec.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -528,6 +529,7 @@ LogMelParams BuildLogMelParams(std::vector<uint8_t>* blob, int sample_rate_hz, i
   std::memset(&p, 0, sizeof(p));
   int fft = 1;
   while (fft < window) fft <<= 1;
+  SPEC_CHECK(fft == 1024, "log-mel: the FFT kernel is specialised for 1024 points (window 513..1024)");
   const int bins = fft / 2 + 1;
   std::vector<double> win((size_t)window), tw((size_t)fft), weights((size_t)bins, 0.0);
   std::vector<int32_t> band((size_t)bins, -2);
@@ -557,9 +559,27 @@ LogMelParams BuildLogMelParams(std::vector<uint8_t>* blob, int sample_rate_hz, i
     else weights[(size_t)i] = (center[0] - melf) / (center[0] - mel_low);
   }
   p.window = Append(blob, win);
-  p.twiddle = Append(blob, tw);
+  // per-stage copies of the same table (stage with half-length h reads tw[k * (fft/2/h)], k < h, stored contiguously
+  // at entry h - 1) so that neighbouring butterflies read neighbouring twiddles
+  std::vector<double> tws;
+  for (int h = 1; h < fft; h <<= 1)
+    for (int k = 0; k < h; ++k) {
+      tws.push_back(tw[(size_t)2 * (k * (fft / 2 / h))]);
+      tws.push_back(tw[(size_t)2 * (k * (fft / 2 / h)) + 1]);
+    }
+  p.twiddle = Append(blob, tws);
   p.weights = Append(blob, weights);
   p.band = Append(blob, band);
+  // channel ch sums the bins of bands ch-1 and ch; the band index never decreases with the bin, so they are one range
+  std::vector<int32_t> range((size_t)num_mel * 2);
+  for (int ch = 0; ch < num_mel; ++ch) {
+    int lo = bins, hi = -1;
+    for (int i = p.start_index; i <= p.end_index; ++i)
+      if (band[(size_t)i] == ch || band[(size_t)i] == ch - 1) { lo = std::min(lo, i); hi = std::max(hi, i); }
+    range[(size_t)2 * ch] = lo;
+    range[(size_t)2 * ch + 1] = hi;
+  }
+  p.range = Append(blob, range);
   p.num_mel = num_mel; p.fft = fft; p.window_len = window; p.hop = hop;
   return p;
 }

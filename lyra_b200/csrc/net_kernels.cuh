@@ -800,7 +800,7 @@ struct DecD {
   static_assert(128 * LDX <= 64 * LDD, "X must fit in d");
   static_assert(S * 320 * 2 <= 64 * LDD * 4, "PCM staging must fit in d");
   // tensor-core warp tiles: decoder_2 res-units RWM x RWN (one per warp), decoder_2/simple UWM x 2, last_layer 1 x 1
-  static constexpr int RWM = S >= 16 ? 4 : 2, RWN = 4;
+  static constexpr int RWM = S >= 16 ? 4 : 2, RWN = NT >= 320 ? 4 : 8;
   static constexpr int UWM = (5 * S + 15) / 16;
   static_assert(!TC || ((20 * S / 16 + RWM - 1) / RWM) * (8 / RWN) <= NT / 32, "decoder_2: one warp tile per warp");
 };

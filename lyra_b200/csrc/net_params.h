@@ -86,9 +86,10 @@ struct RvqParams {
 
 struct LogMelParams {
   uint32_t window;          // f64 [640]
-  uint32_t twiddle;         // f64 [512][2]  cos, sin of -2*pi*k/1024
+  uint32_t twiddle;         // f64 [1023][2] per-stage tables, stage of half-length h at entry h-1: cos, sin of -2*pi*k/(2h), k < h
   uint32_t weights;         // f64 [513]
   uint32_t band;            // i32 [513]
+  uint32_t range;           // i32 [num_mel][2]: first / last spectrum bin that contributes to the channel (bands ch-1 and ch)
   int32_t start_index, end_index, num_mel, fft, window_len, hop;
 };
 

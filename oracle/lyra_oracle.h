@@ -84,6 +84,18 @@ lo_logmel* lo_logmel_create(int sample_rate_hz, int hop, int window, int num_mel
 void lo_logmel_free(lo_logmel* m);
 int lo_logmel_extract(lo_logmel* m, const int16_t* audio, int n, float* out);
 
+/* NoiseEstimator (lyra/noise_estimator.{h,cc}); see noise_estimator.c */
+typedef struct lo_noise lo_noise;
+lo_noise* lo_noise_create(int sample_rate_hz, int hop, int window, int num_features);
+void lo_noise_free(lo_noise* e);
+void lo_noise_set_constants(lo_noise* e, int hops_per_update, float max_smoothing, float bound_decay);   /* test peer ctor */
+int lo_noise_receive_samples(lo_noise* e, const int16_t* hop, float* logmel_out /* may be NULL */);
+void lo_noise_update(lo_noise* e, const float* current_power_db);          /* UpdateNoiseEstimate */
+int lo_noise_compute_is_noise(const lo_noise* e, const float* current_power_db);
+int lo_noise_is_noise(const lo_noise* e);
+void lo_noise_estimate(const lo_noise* e, float* out);
+void lo_noise_bound(const lo_noise* e, float* out);
+
 /* ---- whole codec, one stream (LyraEncoder::Encode / LyraDecoder::{SetEncodedPacket,DecodeSamples}
  *      restricted to 16 kHz, no DTX, packets always received or concealed with zero features) ---- */
 typedef struct lo_codec lo_codec;

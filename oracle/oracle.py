@@ -47,6 +47,11 @@ def lib():
             "lo_log_spectral_distance": (cf, [vp, vp, ci]),
             "lo_logmel_create": (vp, [ci, ci, ci, ci]), "lo_logmel_free": (None, [vp]),
             "lo_logmel_extract": (ci, [vp, vp, ci, vp]),
+            "lo_noise_create": (vp, [ci, ci, ci, ci]), "lo_noise_free": (None, [vp]),
+            "lo_noise_set_constants": (None, [vp, ci, cf, cf]),
+            "lo_noise_receive_samples": (ci, [vp, vp, vp]), "lo_noise_update": (None, [vp, vp]),
+            "lo_noise_compute_is_noise": (ci, [vp, vp]), "lo_noise_is_noise": (ci, [vp]),
+            "lo_noise_estimate": (None, [vp, vp]), "lo_noise_bound": (None, [vp, vp]),
             "lo_codec_create": (vp, [C.c_char_p]), "lo_codec_free": (None, [vp]), "lo_codec_reset": (ci, [vp]),
             "lo_codec_encode": (ci, [vp, vp, ci, vp, vp, vp]), "lo_codec_decode": (ci, [vp, vp, ci, vp, vp, vp]),
             "lo_codec_encoder_net": (vp, [vp]), "lo_codec_decoder_net": (vp, [vp]),
@@ -210,6 +215,51 @@ class LogMel:
         out = np.empty(self.nmel, dtype=np.float32)
         rc = lib().lo_logmel_extract(self.h, _p(a), a.size, _p(out))
         return out if rc == 0 else None
+
+
+class NoiseEstimator:
+    """NoiseEstimator (lyra/noise_estimator.h): one decoded stream's minimum-statistics noise tracker."""
+
+    def __init__(self, sample_rate_hz=16000, hop=320, window=640, num_features=160):
+        self.h = lib().lo_noise_create(sample_rate_hz, hop, window, num_features)
+        self.nf = num_features
+        if not self.h:
+            raise ValueError("oracle noise estimator: bad parameters")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lo_noise_free(self.h)
+            self.h = None
+
+    def set_constants(self, hops_per_update, max_smoothing, bound_decay):
+        lib().lo_noise_set_constants(self.h, hops_per_update, max_smoothing, bound_decay)
+
+    def receive_samples(self, hop):
+        a = np.ascontiguousarray(hop, dtype=np.int16)
+        mel = np.empty(self.nf, dtype=np.float32)
+        if lib().lo_noise_receive_samples(self.h, _p(a), _p(mel)):
+            raise RuntimeError("oracle noise estimator failed")
+        return mel
+
+    def update(self, current_power_db):
+        lib().lo_noise_update(self.h, _p(np.ascontiguousarray(current_power_db, dtype=np.float32)))
+
+    def compute_is_noise(self, current_power_db):
+        return bool(lib().lo_noise_compute_is_noise(self.h, _p(np.ascontiguousarray(current_power_db, dtype=np.float32))))
+
+    @property
+    def is_noise(self):
+        return bool(lib().lo_noise_is_noise(self.h))
+
+    def noise_estimate(self):
+        out = np.empty(self.nf, dtype=np.float32)
+        lib().lo_noise_estimate(self.h, _p(out))
+        return out
+
+    def noise_bound(self):
+        out = np.empty(self.nf, dtype=np.float32)
+        lib().lo_noise_bound(self.h, _p(out))
+        return out
 
 
 class Codec:

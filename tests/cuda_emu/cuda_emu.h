@@ -132,6 +132,11 @@ static inline int __dp4a(int a, int b, int c) {
   return c;
 }
 static inline int __float2int_rz(float v) { return (int)v; }
+static inline unsigned __brev(unsigned v) {
+  unsigned r = 0;
+  for (int b = 0; b < 32; ++b) r |= ((v >> b) & 1u) << (31 - b);
+  return r;
+}
 static inline uint32_t __float_as_uint(float v) { uint32_t b; std::memcpy(&b, &v, 4); return b; }
 static inline float __uint_as_float(uint32_t b) { float v; std::memcpy(&v, &b, 4); return v; }
 template <typename T>

@@ -1,6 +1,7 @@
 """Parity cases shared by the CPU tier (emulated kernels) and the GPU tier (real kernels): every case drives
 the C ABI and compares with the oracle on the same seeded inputs.  Bar: bit-exact packets, RVQ indices,
-features and int16 PCM; log-mel within 2e-6 absolute (float log).
+features, int16 PCM, log-mel spectra and noise-estimator state (the one libm call on each of those paths, log / exp,
+is taken in double and rounded once on both sides).
 
 The decoder's opt-in tensor-core mode (lyra_b200_set_decoder_mode, split-precision TF32) is the one floating-point
 path that is compared with a tolerance: decoded int16 PCM within TENSOR_PCM_TOL_LSB of the oracle (the drop-in
@@ -130,7 +131,7 @@ def run_error_paths(Context, api, LyraB200Error):
     ctx.close()
 
 
-def run_logmel_parity(Context, api, O, wav, *, n=4, frames=4, tol=2e-6):
+def run_logmel_parity(Context, api, O, wav, *, n=4, frames=4, tol=0.0):
     ctx = Context(n, capi=api)
     for nmel, bank in ((160, 0), (64, 1)):
         refs = [O.LogMel(16000, 320, 640, nmel) for _ in range(n)]
@@ -140,4 +141,70 @@ def run_logmel_parity(Context, api, O, wav, *, n=4, frames=4, tol=2e-6):
             for k in range(n):
                 want = refs[k].extract(pcm[k])
                 assert np.abs(out[k] - want).max() <= tol, (nmel, f, k, np.abs(out[k] - want).max())
+    ctx.close()
+
+
+def run_noise_estimator_parity(Context, api, O, wav, *, n=3, frames=30, seed=4):
+    """lyra_b200_noise_update against one oracle NoiseEstimator per stream: speech with silent stretches (so both the
+    update and the decay branch run), some hops withheld (update_mask 0, as after a lost packet), sparse stream ids.
+    Bar: is_noise identical; noise_estimate bit-identical (the kernel evaluates the C++ expressions operation by operation)."""
+    ctx = Context(4 * n, capi=api)
+    ids = np.arange(n, dtype=np.int32) * 3 + 1
+    est = [O.NoiseEstimator() for _ in range(n)]
+    rng = np.random.default_rng(seed)
+    seen_noise, seen_speech = False, False
+    for f in range(frames):
+        hop = np.stack([wav[(320 * (f + 11 * k)) % (len(wav) - 320):][:320] for k in range(n)]).copy()
+        quiet = rng.random(n) < 0.4                   # silence / faint noise: exercises the is-noise branch
+        for k in range(n):
+            if quiet[k]:
+                hop[k] = rng.integers(-2, 3, size=320, dtype=np.int16) if f % 2 else 0
+        mask = (rng.random(n) < 0.85).astype(np.uint8)
+        flags, got = ctx.noise_update(hop, stream_ids=ids, update_mask=mask)
+        for k in range(n):
+            if mask[k]:
+                est[k].receive_samples(hop[k])
+            assert bool(flags[k]) == est[k].is_noise, "is_noise mismatch frame %d stream %d" % (f, k)
+            want = est[k].noise_estimate()
+            assert np.array_equal(got[k], want), "noise estimate mismatch frame %d stream %d (max |d| %g)" % (
+                f, k, np.abs(got[k] - want).max())
+            seen_noise |= bool(flags[k]) and f > 0
+            seen_speech |= not bool(flags[k])
+    assert seen_noise and seen_speech, "the case must exercise both branches"
+    # reset restores the freshly constructed estimator for the listed streams only
+    ctx.reset(stream_ids=ids[:1])
+    flags, got = ctx.noise_update(np.zeros((n, 320), dtype=np.int16), stream_ids=ids, update_mask=np.zeros(n, dtype=np.uint8))
+    assert flags[0] and not got[0].any()
+    assert np.array_equal(got[1], est[1].noise_estimate())
+    ctx.close()
+
+
+def run_decode_track_noise_parity(Context, api, O, wav, *, n=3, frames=12, max_streams=None, stream_ids=None, loss_every=4,
+                                  check=None):
+    """lyra_b200_decode_track_noise = decode + NoiseEstimator::ReceiveSamples for the received streams
+    (LyraDecoder::DecodeSamplesInternal, lyra/lyra_decoder.cc:306-311): PCM, is_noise and the estimate bit-exact."""
+    ids = np.arange(n, dtype=np.int32) if stream_ids is None else np.asarray(stream_ids, dtype=np.int32)
+    n = len(ids)
+    ctx = Context(max_streams or int(ids.max()) + 1, capi=api)
+    dense = stream_ids is None and (max_streams is None or max_streams == n)
+    check = list(range(n)) if check is None else check
+    codecs = {k: O.Codec(MODEL_DIR) for k in check}
+    est = {k: O.NoiseEstimator() for k in check}
+    for f in range(frames):
+        pcm = np.stack([wav[(320 * (f + 5 * k)) % (len(wav) - 320):][:320] for k in range(n)]).copy()
+        if f % 3 == 2:
+            pcm[:] = 0                                  # silent hops: the decoder output becomes noise-like
+        packets = ctx.encode(pcm, 64, stream_ids=None if dense else ids)
+        received = np.array([0 if (f + k) % loss_every == 0 else 1 for k in range(n)], dtype=np.uint8)
+        out, flags = ctx.decode_track_noise(packets, 64, stream_ids=None if dense else ids, received=received)
+        for k in check:
+            opkt, _, _ = codecs[k].encode(pcm[k], 64)
+            opcm, _, _ = codecs[k].decode(opkt if received[k] else None, 64)
+            assert np.array_equal(out[k], opcm), "PCM mismatch frame %d stream %d" % (f, k)
+            if received[k]:
+                est[k].receive_samples(opcm)
+            assert bool(flags[k]) == est[k].is_noise, "is_noise mismatch frame %d stream %d" % (f, k)
+    _, got = ctx.noise_update(np.zeros((n, 320), dtype=np.int16), stream_ids=None if dense else ids, update_mask=np.zeros(n, dtype=np.uint8))
+    for k in check:
+        assert np.array_equal(got[k], est[k].noise_estimate()), "noise estimate mismatch stream %d" % k
     ctx.close()

@@ -45,3 +45,11 @@ def test_emu_error_paths(emu_api):
 
 def test_emu_logmel(emu_api, oracle, sample1):
     pc.run_logmel_parity(_capi.Context, emu_api, oracle, sample1, n=2, frames=3)
+
+
+def test_emu_noise_estimator(emu_api, oracle, sample1):
+    pc.run_noise_estimator_parity(_capi.Context, emu_api, oracle, sample1, n=2, frames=14)
+
+
+def test_emu_decode_track_noise(emu_api, oracle, sample1):
+    pc.run_decode_track_noise_parity(_capi.Context, emu_api, oracle, sample1, stream_ids=[1, 10], max_streams=16, frames=5, loss_every=3)

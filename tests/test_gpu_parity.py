@@ -80,6 +80,16 @@ def test_logmel(gpu_api, oracle, sample1):
     pc.run_logmel_parity(_capi.Context, gpu_api, oracle, sample1, n=6, frames=8)
 
 
+def test_noise_estimator(gpu_api, oracle, sample1):
+    pc.run_noise_estimator_parity(_capi.Context, gpu_api, oracle, sample1, n=9, frames=120)
+
+
+def test_decode_track_noise_sparse_and_dense(gpu_api, oracle, sample1):
+    pc.run_decode_track_noise_parity(_capi.Context, gpu_api, oracle, sample1, stream_ids=[0, 3, 8, 30], max_streams=32, frames=40)
+    # dense call over 1024 streams: cut into two concurrent sub-batches, each followed by its own estimator update
+    pc.run_decode_track_noise_parity(_capi.Context, gpu_api, oracle, sample1, n=1024, frames=8, check=[0, 7, 511, 512, 777, 1023])
+
+
 def test_golden_fixture_packets(gpu_api, sample1):
     """Committed fixtures (tests/golden/oracle_sample1.json): the GPU path reproduces them without the oracle present."""
     with open(os.path.join(GOLDEN_DIR, "oracle_sample1.json")) as f:

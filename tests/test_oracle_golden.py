@@ -202,3 +202,33 @@ def test_golden_regression_vectors(oracle, sample1):
             assert pkt.hex() == want, (bits, h)
             pcm, _, _ = c.decode(pkt, bits)
             assert int(np.int64(pcm.astype(np.int64) * np.arange(1, 321)).sum()) == g["pcm_checksum_%d" % bits][h]
+
+
+# ---- NoiseEstimator: the reference's own tests are statistical; their properties are
+#      re-run here against the restatement (lyra/noise_estimator_test.cc:131-197)
+def _silence_value():
+    return np.float32(np.log(np.float32(500.0)) / np.float32(10.0))      # GetSilenceValue, log_mel_..._impl.cc:138-140
+
+
+def test_noise_estimator_noise_identification(oracle):
+    ne = oracle.NoiseEstimator()
+    ne.set_constants(10, np.float32(0.5) ** np.float32(1.0 / 20), np.float32(0.5) ** np.float32(1.0 / 50))
+    sil = _silence_value()
+    base = (sil / np.float32(160) * np.arange(160, dtype=np.float32) + sil).astype(np.float32)
+    periodic = np.full(160, sil, dtype=np.float32)
+    periodic[::20] = 1.0
+    rng = np.random.default_rng(7)
+    for _ in range(250):
+        ne.update(base + rng.uniform(-0.1, 0.1, size=160).astype(np.float32))
+    assert ne.compute_is_noise(base)
+    assert not ne.compute_is_noise(periodic)
+
+
+def test_noise_estimator_five_seconds_silence(oracle):
+    ne = oracle.NoiseEstimator()
+    sil = np.full(160, _silence_value(), dtype=np.float32)
+    for i in range(250):
+        mel = ne.receive_samples(np.zeros(320, dtype=np.int16))
+        assert np.array_equal(mel, sil)
+        assert oracle.log_spectral_distance(sil, ne.noise_estimate()) < 0.2, "frame %d" % i
+    assert ne.is_noise     # after the first hop silence is classified as noise and only the bounds decay
