@@ -7,6 +7,7 @@
 //   ResidualVectorQuantizer     residual_vector_quantizer.{h,cc} lyra_b200::ResidualVectorQuantizerB200
 //   LyraGanModel                lyra_gan_model.{h,cc}            lyra_b200::LyraGanModelB200 (: GenerativeModel)
 //   LogMelSpectrogramExtractorImpl  log_mel_spectrogram_extractor_impl.{h,cc}   lyra_b200::LogMelSpectrogramExtractorB200
+//   NoiseEstimator              noise_estimator.{h,cc}           lyra_b200::NoiseEstimatorB200 (: NoiseEstimatorInterface)
 //   Packet<184>                 packet.h                         lyra_b200::Packet184
 //   LyraEncoder / LyraDecoder   lyra_encoder.{h,cc} / lyra_decoder.{h,cc}       lyra_b200::LyraEncoderB200 / LyraDecoderB200
 //                                                                (16 kHz, no DTX; lost packets are concealed with zero
@@ -269,6 +270,60 @@ class LogMelSpectrogramExtractorB200 : public FeatureExtractorInterface {
       : session_(std::move(s)), id_(id), num_mel_(nmel), bank_(bank) {}
   std::shared_ptr<Session> session_;
   int id_, num_mel_, bank_;
+};
+
+// ---- lyra/noise_estimator_interface.h:28-38, implemented by lyra/noise_estimator.{h,cc} ---------------------------------
+class NoiseEstimatorInterface {
+ public:
+  virtual ~NoiseEstimatorInterface() {}
+  virtual bool ReceiveSamples(const std::vector<int16_t>& samples) = 0;
+  virtual std::vector<float> noise_estimate() const = 0;
+  virtual bool is_noise() const = 0;
+};
+
+class NoiseEstimatorB200 : public NoiseEstimatorInterface {
+ public:
+  // NoiseEstimator::Create(sample_rate_hz, num_samples_per_hop, num_samples_per_window, num_features), lyra/noise_estimator.cc:99-120
+  static std::unique_ptr<NoiseEstimatorB200> Create(const std::string& model_path, int sample_rate_hz, int num_samples_per_hop,
+                                                    int num_samples_per_window, int num_features) {
+    if (sample_rate_hz != 16000 || num_samples_per_hop != 320 || num_samples_per_window != 640 || num_features != 160) return nullptr;
+    auto s = Session::Get(model_path);
+    if (!s) return nullptr;
+    const int id = s->Acquire();
+    if (id < 0) return nullptr;
+    return std::unique_ptr<NoiseEstimatorB200>(new NoiseEstimatorB200(std::move(s), id));
+  }
+  ~NoiseEstimatorB200() override { session_->Release(id_); }
+  // Samples are buffered until a hop is complete (their total may never straddle a hop boundary,
+  // lyra/noise_estimator.cc:144-156); a full hop runs the log-mel + estimator kernels.
+  bool ReceiveSamples(const std::vector<int16_t>& samples) override {
+    if (samples.size() + hop_.size() > (size_t)LYRA_B200_HOP) return false;
+    hop_.insert(hop_.end(), samples.begin(), samples.end());
+    if ((int)hop_.size() < LYRA_B200_HOP) return true;
+    uint8_t flag = 1;
+    std::lock_guard<std::mutex> lock(session_->mutex());
+    const int rc = lyra_b200_noise_update(session_->ctx(), &id_, 1, hop_.data(), nullptr, &flag, nullptr);
+    hop_.clear();
+    if (rc != LYRA_B200_OK) return false;
+    is_noise_ = flag != 0;
+    return true;
+  }
+  std::vector<float> noise_estimate() const override {
+    std::vector<float> out(160, 0.0f);
+    const std::vector<int16_t> none((size_t)LYRA_B200_HOP, 0);
+    const uint8_t mask = 0;                                      // report only, the estimator is not fed
+    std::lock_guard<std::mutex> lock(session_->mutex());
+    lyra_b200_noise_update(session_->ctx(), &id_, 1, none.data(), &mask, nullptr, out.data());
+    return out;
+  }
+  bool is_noise() const override { return is_noise_; }
+
+ private:
+  NoiseEstimatorB200(std::shared_ptr<Session> s, int id) : session_(std::move(s)), id_(id) {}
+  std::shared_ptr<Session> session_;
+  int id_;
+  bool is_noise_ = true;
+  std::vector<int16_t> hop_;
 };
 
 // ---- factories with the reference's names (lyra/lyra_components.cc:42-60) ------------------------------------------

@@ -102,6 +102,28 @@ int main(int argc, char** argv) {
     CHECK(e->set_bitrate(9200) && e->bitrate() == 9200 && !e->set_bitrate(1234));
     lo_codec_free(r);
   }
+  // NoiseEstimator counterpart: samples in two pieces per hop, against the oracle's estimator
+  {
+    CHECK(NoiseEstimatorB200::Create(model, 16000, 320, 640, 64) == nullptr);   // only the decoder's configuration
+    auto ne = NoiseEstimatorB200::Create(model, 16000, 320, 640, 160);
+    CHECK(ne != nullptr);
+    lo_noise* r = lo_noise_create(16000, 320, 640, 160);
+    CHECK(ne->is_noise());
+    for (int f = 0; f < 12; ++f) {
+      std::vector<int16_t> pcm(320);
+      for (auto& v : pcm) v = f % 4 == 3 ? 0 : (int16_t)(d(rng) >> (f % 3 == 0 ? 0 : 6));
+      CHECK(ne->ReceiveSamples(std::vector<int16_t>(pcm.begin(), pcm.begin() + 100)));
+      CHECK(!ne->ReceiveSamples(std::vector<int16_t>(221)));                      // would straddle the hop boundary
+      CHECK(ne->ReceiveSamples(std::vector<int16_t>(pcm.begin() + 100, pcm.end())));
+      CHECK(lo_noise_receive_samples(r, pcm.data(), nullptr) == 0);
+      float want[160];
+      lo_noise_estimate(r, want);
+      const std::vector<float> got = ne->noise_estimate();
+      CHECK(ne->is_noise() == (lo_noise_is_noise(r) != 0));
+      CHECK(got.size() == 160 && std::memcmp(got.data(), want, sizeof(want)) == 0);
+    }
+    lo_noise_free(r);
+  }
   std::printf(g_fail ? "FAILED (%d)\n" : "ALL OK\n", g_fail);
   return g_fail ? 1 : 0;
 }

@@ -53,3 +53,20 @@ def test_emu_noise_estimator(emu_api, oracle, sample1):
 
 def test_emu_decode_track_noise(emu_api, oracle, sample1):
     pc.run_decode_track_noise_parity(_capi.Context, emu_api, oracle, sample1, stream_ids=[1, 10], max_streams=16, frames=5, loss_every=3)
+
+
+def test_emu_cpp_components(emu_api, oracle, tmp_path):
+    """The C++ adapters (include/lyra_b200/lyra_b200_components.h: SoundStreamEncoder / ResidualVectorQuantizer /
+    LyraGanModel / NoiseEstimator / LyraEncoder / LyraDecoder counterparts) over the emulated library, vs the oracle."""
+    import os
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    shutil.copy(emu_api.path, str(tmp_path / "liblyra_b200.so"))
+    exe = str(tmp_path / "test_components")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                           os.path.join(ROOT, "tests", "cpp", "test_components.cc"), "-o", exe,
+                           "-L" + str(tmp_path), "-llyra_b200", "-L" + os.path.join(ROOT, "oracle", "_build"), "-llyra_oracle",
+                           "-Wl,-rpath," + str(tmp_path), "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build"), "-lpthread"])
+    out = subprocess.run([exe, _capi.MODEL_DIR], capture_output=True, text=True, env=dict(os.environ, LYRA_B200_MAX_STREAMS="16"))
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
