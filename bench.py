@@ -200,8 +200,8 @@ def main():
                     help="codec: encode+decode (the headline metric). decode_plc: BASELINE configs[3], decoder only with a received "
                          "mask (lost packets are concealed from zero features) + log-mel and noise-estimator update of the decoded hop")
     ap.add_argument("--loss", type=float, default=0.1, help="decode_plc: packet loss probability (Bernoulli, seed 1234); 1.0 = all lost")
-    ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
-    ap.add_argument("--e2e-split", type=int, default=2, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
+    ap.add_argument("--split", type=int, default=3, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
+    ap.add_argument("--e2e-split", type=int, default=3, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
     ap.add_argument("--decoder-mode", default="exact", choices=["exact", "tensor"],
                     help="exact: decoded PCM bit-identical to the oracle (default); tensor: split-precision TF32 tensor-core decoder")
     args = ap.parse_args()
@@ -353,6 +353,13 @@ def main():
                                    "achieved_gbs": total_algo * n * args.steps / (elapsed_ms / 1e3) / 1e9 if world == 1 else None,
                                    "frac": (total_algo * n * args.steps / (elapsed_ms / 1e3) / 1e9) / peak if world == 1 else None},
                     "kernels": kern}
+        if world == 1 and args.decoder_mode == "exact":
+            # the roofline that actually binds the bit-exact mode: ordered FFMA chains on the CUDA cores
+            fp32_macs = 1236736 if plc else 1475840 + 1236736          # SURVEY.md section 8d, fp32 MACs per stream-frame
+            pipe_peak = 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12
+            roofline["fp32_pipe"] = {"achieved": value * 2 * fp32_macs / 1e12, "peak": pipe_peak, "unit": "TFLOP/s",
+                                     "frac": value * 2 * fp32_macs / 1e12 / pipe_peak,
+                                     "peak_source": "148 SMs x 128 FP32 lanes x 2 x SM clock sampled during the run"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = host_cores()

@@ -121,7 +121,7 @@ int lyra_b200_decode_track_noise_device(lyra_b200_ctx* ctx, int n, const uint8_t
 int lyra_b200_noise_update_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, const uint8_t* d_update_mask,
                                   uint8_t* d_is_noise, float* d_noise_estimate);
 int lyra_b200_synchronize(lyra_b200_ctx* ctx);
-/* Dense calls (stream_ids == NULL / *_device) over many tiles are cut into `parts` (1..4, default 2) sub-batches that
+/* Dense calls (stream_ids == NULL / *_device) over many tiles are cut into `parts` (1..4, default 3) sub-batches that
  * run concurrently on internal CUDA streams so partial waves of one kernel are filled by another's blocks.
  * parts = 1 serialises the kernels (used by bench.py's per-kernel roofline pass). */
 int lyra_b200_set_split(lyra_b200_ctx* ctx, int parts);

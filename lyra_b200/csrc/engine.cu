@@ -64,7 +64,7 @@ struct lyra_b200_ctx {
   static constexpr int kMaxSplit = 4;
   cudaStream_t aux_stream[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
-  int nsplit = 2;
+  int nsplit = 3;
   int decoder_mode = LYRA_B200_DECODER_EXACT;   // lyra_b200_set_decoder_mode
   uint64_t launches = 0;
   std::string err;
@@ -214,9 +214,10 @@ int LaunchDecoderNets(lyra_b200_ctx* ctx, const Part& p, const float* d_features
   return tc ? LaunchDecoderNetsT<8, true>(ctx, p, d_features, d_pcm) : LaunchDecoderNetsT<8, false>(ctx, p, d_features, d_pcm);
 }
 
-// Dense calls over many tiles are cut into two halves that run on two CUDA streams: the block scheduler then
-// fills the partial last wave of one half's kernel with blocks of the other half (independent streams, so no
-// ordering between them), which removes most of the wave-quantisation loss of 512 tiles on 2 x 148 block slots.
+// Dense calls over many tiles are cut into sub-batches (default 3) that run on their own CUDA streams: the block
+// scheduler then fills the partial last wave of one sub-batch's kernel with blocks of another's (independent
+// streams, so no ordering between them) and co-schedules blocks of different kernels on an SM, which removes most
+// of the wave-quantisation loss of 512 tiles on 2-3 x 148 block slots and mixes FMA-bound with latency-bound phases.
 int SplitParts(lyra_b200_ctx* ctx, int n, Part* parts) {
   int np = ctx->nsplit < 1 ? 1 : (ctx->nsplit > lyra_b200_ctx::kMaxSplit ? lyra_b200_ctx::kMaxSplit : ctx->nsplit);
   if (!(ctx->map_dense_n == n && ctx->active_tiles >= 64 * np)) np = 1;

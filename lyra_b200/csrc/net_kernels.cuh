@@ -314,7 +314,7 @@ struct EncB {
 #else
   static constexpr int NT = 256;
 #endif
-#ifdef LYRA_BC_2BLOCKS
+#ifdef LYRA_B_2BLOCKS
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
 #else
   static constexpr int kMinBlocks = S <= 8 ? 3 : 1;
@@ -527,7 +527,7 @@ struct DecC {
 #else
   static constexpr int NT = 256;
 #endif
-#ifdef LYRA_BC_2BLOCKS
+#ifdef LYRA_C_2BLOCKS
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
 #else
   static constexpr int kMinBlocks = S <= 8 ? 3 : 1;
