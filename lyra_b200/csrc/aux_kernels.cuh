@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(kRvqThreads)
 RvqEncodeKernel(const uint8_t* __restrict__ blob, RvqParams P, const float* __restrict__ features, int n, int nq,
                 uint8_t* __restrict__ packets, int packet_bytes, int* __restrict__ indices_out) {
   unsigned char* smem = LYRA_DYN_SMEM();
-  float* cbs = reinterpret_cast<float*>(smem);                                  // [2][64][16] stage codebooks (double buffer)
+  float* cbs = reinterpret_cast<float*>(smem);                                  // [2][64][16] stage codebooks (double buffer, 16-byte aligned)
   float* rs = cbs + 2 * 1024;                                                   // [slots][64] residuals
   int* idxs = reinterpret_cast<int*>(rs + kRvqSlotsPerBlock * 64);              // [slots][48]
   const int tid = (int)threadIdx.x, grp = tid / 16, c = tid % 16;
@@ -29,19 +29,19 @@ RvqEncodeKernel(const uint8_t* __restrict__ blob, RvqParams P, const float* __re
   float* r = rs + grp * 64;
   int* idx = idxs + grp * 48;
   const float* cbt = BlobPtr<float>(blob, P.codebooks_t);
-  // stage 0 codebook -> buffer 0 (4 KB = 256 x 16 B, two packets per thread)
-  for (int i = tid; i < 256; i += kRvqThreads) lyra_cp_async16(cbs + 4 * i, cbt + 4 * i);
-  lyra_cp_async_commit();
+  // per-stage codebooks (4 KB each) arrive by bulk asynchronous copy (TMA) into a double buffer; one mbarrier per buffer
+  LYRA_STATIC_SMEM(LyraMbar, full, 2);
+  if (tid == 0) {
+    lyra_mbar_init(&full[0], 1);
+    lyra_mbar_init(&full[1], 1);
+    lyra_mbar_fence_init();
+    lyra_bulk_g2s(cbs, cbt, 4096u, &full[0]);
+  }
   for (int jj = 0; jj < 4; ++jj) r[c + 16 * jj] = valid ? features[(size_t)slot * 64 + c + 16 * jj] : 0.0f;
   for (int s = 0; s < nq; ++s) {
-    lyra_cp_async_wait<0>();
-    __syncthreads();                       // codebook s landed; everyone finished stage s-1 (its buffer is free again)
-    if (s + 1 < nq) {
-      float* dst = cbs + ((s + 1) & 1) * 1024;
-      const float* src = cbt + (size_t)(s + 1) * 1024;
-      for (int i = tid; i < 256; i += kRvqThreads) lyra_cp_async16(dst + 4 * i, src + 4 * i);
-    }
-    lyra_cp_async_commit();
+    __syncthreads();                       // everyone finished stage s-1: its buffer is free again (and the barriers are initialised)
+    if (tid == 0 && s + 1 < nq) lyra_bulk_g2s(cbs + ((s + 1) & 1) * 1024, cbt + (size_t)(s + 1) * 1024, 4096u, &full[(s + 1) & 1]);
+    lyra_mbar_wait(&full[s & 1], (unsigned)((s >> 1) & 1));     // codebook s has landed
     const float* cs = cbs + (s & 1) * 1024 + c;
     float d = 0.0f;
 #pragma unroll 16

@@ -42,6 +42,66 @@ template <int N>
 __device__ __forceinline__ void lyra_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif
 
+// ---- mbarrier + bulk asynchronous copy (TMA, cp.async.bulk): the weight pipeline of the fp32 GEMMs.
+//      One elected thread arms a "full" barrier with the byte count and issues one bulk copy per weight chunk; consumer
+//      warps wait on its phase parity, and release the stage through an "empty" barrier (one arrival per warp).
+//      lyra_mbar_wait(bar, parity) returns once the phase with that parity has completed.
+struct alignas(8) LyraMbar { unsigned long long v; };
+#if defined(LYRA_EMU)
+struct LyraMbarEmu { uint16_t expected, arrived, phase, pad; };
+static inline LyraMbarEmu* lyra_mbar_emu(LyraMbar* b) { return reinterpret_cast<LyraMbarEmu*>(b); }
+static inline void lyra_mbar_init(LyraMbar* b, unsigned count) { LyraMbarEmu* e = lyra_mbar_emu(b); e->expected = (uint16_t)count; e->arrived = 0; e->phase = 0; e->pad = 0; }
+static inline void lyra_mbar_fence_init() {}
+static inline void lyra_fence_proxy_async() {}
+static inline void lyra_mbar_arrive(LyraMbar* b) {
+  LyraMbarEmu* e = lyra_mbar_emu(b);
+  if (++e->arrived == e->expected) { e->arrived = 0; e->phase ^= 1; }
+}
+// the emulated bulk copy is synchronous and fibers are cooperative, so arming + copying is one atomic step:
+// the arrival is counted after the data has been written
+static inline void lyra_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, LyraMbar* b) {
+  std::memcpy(smem_dst, gmem_src, bytes);
+  lyra_mbar_arrive(b);
+}
+static inline void lyra_mbar_wait(LyraMbar* b, unsigned parity) {
+  while (lyra_mbar_emu(b)->phase == parity) cuda_emu::yield();
+}
+#define LYRA_STATIC_SMEM(type, name, count) type* name = reinterpret_cast<type*>(cuda_emu::g_blk->static_smem)
+#elif defined(__CUDACC__)
+__device__ __forceinline__ unsigned lyra_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lyra_mbar_init(LyraMbar* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(lyra_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lyra_mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later asynchronous-proxy (bulk copy) ones
+__device__ __forceinline__ void lyra_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void lyra_mbar_arrive(LyraMbar* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(lyra_smem_u32(b)) : "memory");
+}
+// arm the barrier with the byte count and issue the bulk copy that completes it
+__device__ __forceinline__ void lyra_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, LyraMbar* b) {
+  const unsigned bar = lyra_smem_u32(b);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(lyra_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void lyra_mbar_wait(LyraMbar* b, unsigned parity) {
+  const unsigned bar = lyra_smem_u32(b);
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "LYRA_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra LYRA_DONE;\n"
+               "bra LYRA_WAIT;\n"
+               "LYRA_DONE:\n"
+               "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+#define LYRA_STATIC_SMEM(type, name, count) __shared__ type name##_storage[count]; type* name = name##_storage
+#endif
+
 // ---- warp-level int8 tensor-core MMA: D(16x8,s32) += A(16x32,s8,row) * B(32x8,s8,col), fragments as in the PTX ISA
 //      (mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32).  Integer accumulation is exact, so results are
 //      bit-identical to the dp4a / scalar formulation whatever the internal order.

@@ -67,14 +67,42 @@ __device__ __forceinline__ void BatchedLoop(int n, LoadFn ld, StoreFn st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Weight chunk copy: `n16` 16-byte packets, contiguous in global memory, by all NT threads.
-template <int NT>
-__device__ __forceinline__ void StageChunk(void* smem_dst, const void* gsrc, int n16) {
-  for (int i = (int)threadIdx.x; i < n16; i += NT)
-    lyra_cp_async16(reinterpret_cast<char*>(smem_dst) + 16 * i, reinterpret_cast<const char*>(gsrc) + 16 * i);
+// Weight pipeline of the fp32 GEMMs: a ring of kStages chunk buffers in shared memory filled by bulk asynchronous
+// copies (TMA, cp.async.bulk) that one elected thread issues, with a full / empty mbarrier pair per stage.  Consumer
+// warps wait on `full`, compute, and release the stage with one arrival per warp on `empty`; the producer refills a
+// stage once every warp has released it.  No block-wide barrier inside the K loop: warps drift up to kStages - 1
+// chunks apart instead of meeting at every chunk.
+// Two barrier sets alternate between consecutive GEMMs so that the first chunks of the NEXT GEMM can be issued
+// (into the other set) before the current GEMM's epilogue; each GEMM re-initialises the set its successor will use.
+constexpr int kStages = 3;
+
+struct WeightPipe {
+  LyraMbar full[2][kStages];
+  LyraMbar empty[2][kStages];
+  int cur;          // barrier set of the next GEMM to run (or of the prologue issued for it)
+};
+
+__device__ __forceinline__ WeightPipe* GetWeightPipe() {
+  LYRA_STATIC_SMEM(WeightPipe, pipe, 1);
+  return pipe;
 }
 
-constexpr int kStages = 3;   // cp.async ring depth of the weight stream (one block barrier per chunk)
+__device__ __forceinline__ void InitPipeSet(WeightPipe* pipe, int set, int nwarps) {
+#pragma unroll
+  for (int s = 0; s < kStages; ++s) { lyra_mbar_init(&pipe->full[set][s], 1); lyra_mbar_init(&pipe->empty[set][s], (unsigned)nwarps); }
+  lyra_mbar_fence_init();
+}
+
+// Once per kernel, by every thread, before the first block barrier of the kernel.
+template <int NT>
+__device__ __forceinline__ void InitWeightPipe() {
+  WeightPipe* pipe = GetWeightPipe();
+  if (threadIdx.x == 0) {
+    InitPipeSet(pipe, 0, NT / 32);
+    InitPipeSet(pipe, 1, NT / 32);
+    pipe->cur = 0;
+  }
+}
 
 // Description of a GEMM's weight stream, used to issue its first kStages-1 chunks EARLY (right after the previous
 // GEMM's K loop, before that GEMM's epilogue and any element-wise pass in between) so the L2 latency of the
@@ -88,16 +116,26 @@ struct WNext {
 __device__ __forceinline__ WNext NoNext() { return WNext{nullptr, 0, 0, nullptr}; }
 __device__ __forceinline__ WNext NextF32(const float* w, int KC, int N, int Ktot, void* ring = nullptr) { return WNext{w, KC * N, Ktot / KC, ring}; }
 
+// Thread 0: chunks 0 .. kStages-2 of a GEMM into barrier set `set` (whose buffers and barriers are idle).
+__device__ __forceinline__ void IssuePrologueSet(WeightPipe* pipe, int set, void* wbuf, const void* w, int chunk_words, int nchunks) {
+#pragma unroll
+  for (int p = 0; p < kStages - 1; ++p)
+    if (p < nchunks)
+      lyra_bulk_g2s(reinterpret_cast<uint32_t*>(wbuf) + (size_t)p * chunk_words,
+                    reinterpret_cast<const uint32_t*>(w) + (size_t)p * chunk_words, (unsigned)chunk_words * 4u, &pipe->full[set][p]);
+}
+
+// Start the weight stream of the GEMM that runs next (kernel prologue, or after a phase without fp32 GEMMs).
+// Called by every thread: the ring may alias buffers that were written with ordinary stores, so every thread fences
+// its stores against the asynchronous proxy and the block synchronises before the elected thread issues the copies.
 template <int NT>
 __device__ __forceinline__ void IssuePrologue(void* wbuf_default, const WNext& nx) {
   if (nx.w == nullptr) return;
-  void* wbuf = nx.ring ? nx.ring : wbuf_default;
-#pragma unroll
-  for (int p = 0; p < kStages - 1; ++p) {
-    if (p < nx.nchunks)
-      StageChunk<NT>(reinterpret_cast<uint32_t*>(wbuf) + (size_t)p * nx.chunk_words,
-                     reinterpret_cast<const uint32_t*>(nx.w) + (size_t)p * nx.chunk_words, nx.chunk_words / 4);
-    lyra_cp_async_commit();
+  lyra_fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    WeightPipe* pipe = GetWeightPipe();
+    IssuePrologueSet(pipe, pipe->cur, nx.ring ? nx.ring : wbuf_default, nx.w, nx.chunk_words, nx.nchunks);
   }
 }
 
@@ -136,9 +174,19 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
   const int MG = T_out * MGS, NG = N / TN;
   const TileMap<WM> map(MG, NG);
   const int Ktot = ntaps * CinG, nchunks = Ktot / KC;
-  const int chunk16 = KC * N / 4;
   const int CoutG = N / groups;
-  const int warp = (int)threadIdx.x >> 5;
+  const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+  WeightPipe* pipe = GetWeightPipe();
+  const int set = pipe->cur;                                 // stable: written only between block barriers
+  const int npass = (map.nwt + NT / 32 - 1) / (NT / 32);
+  const int total = npass * nchunks;                         // chunk sequence of the whole call: every pass re-streams W
+  const unsigned chunk_bytes = (unsigned)(KC * N) * 4u;
+  if (nchunks < kStages - 1) LYRA_TRAP();
+  if (threadIdx.x == 0) {
+    InitPipeSet(pipe, set ^ 1, NT / 32);                     // the set of the GEMM after this one (idle since the previous GEMM ended)
+    if (!pre) IssuePrologueSet(pipe, set, wbuf, Wg, KC * N, nchunks);
+  }
+  int cg = 0;                                                // chunk index within the call
   for (int wt0 = 0; wt0 < map.nwt; wt0 += NT / 32) {
     int mg, ng;
     const bool active = map.Locate(wt0 + warp, MG, NG, mg, ng);
@@ -151,24 +199,20 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
-    // prologue: chunks 0 .. kStages-2 in flight (already issued by the previous GEMM when `pre`)
-    if (!(pre && wt0 == 0)) {
-#pragma unroll
-      for (int p = 0; p < kStages - 1; ++p) {
-        if (p < nchunks) StageChunk<NT>(wbuf + p * (KC * N), Wg + (size_t)p * KC * N, chunk16);
-        lyra_cp_async_commit();
+    for (int c = 0; c < nchunks; ++c, ++cg) {
+      if (threadIdx.x == 0) {
+        // producer: chunk cg + kStages - 1 goes into the stage that chunk cg - 1 occupied, once every warp has released it
+        const int ci = cg + kStages - 1;
+        if (ci < total) {
+          const int si = ci % kStages;
+          if (ci >= kStages) lyra_mbar_wait(&pipe->empty[set][si], (unsigned)((ci / kStages - 1) & 1));
+          lyra_bulk_g2s(wbuf + (size_t)si * (KC * N), Wg + (size_t)(ci % nchunks) * KC * N, chunk_bytes, &pipe->full[set][si]);
+        }
       }
-    }
-    for (int c = 0; c < nchunks; ++c) {
-      lyra_cp_async_wait<kStages - 2>();     // chunk c has landed (for this thread's copies)
-      __syncthreads();                       // ... for everyone's; and everyone is done with chunk c-1
-      {
-        const int nc = c + kStages - 1;
-        if (nc < nchunks) StageChunk<NT>(wbuf + (nc % kStages) * (KC * N), Wg + (size_t)nc * KC * N, chunk16);
-        lyra_cp_async_commit();
-      }
+      const int st = cg % kStages;
+      lyra_mbar_wait(&pipe->full[set][st], (unsigned)((cg / kStages) & 1));      // chunk cg has landed
       if (active) {
-        const float* wcur = wbuf + (c % kStages) * (KC * N);
+        const float* wcur = wbuf + (size_t)st * (KC * N);
         const int kk0 = c * KC;
         const float* Ap;
         int astep;
@@ -207,9 +251,16 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
           wp += N;
         }
       }
+      __syncwarp();
+      if (lane == 0) lyra_mbar_arrive(&pipe->empty[set][st]);                    // this warp is done with the stage
     }
+    lyra_fence_proxy_async();   // this thread's earlier stores to buffers the next ring may alias, before the bulk copies below
     __syncthreads();   // every thread is past the K loop: A may be overwritten, the weight ring reused
-    if (wt0 + NT / 32 >= map.nwt) IssuePrologue<NT>(wbuf, nxt);   // last pass: start the next GEMM's weight stream
+    if (wt0 + NT / 32 >= map.nwt && threadIdx.x == 0) {
+      // last pass: start the next GEMM's weight stream (other barrier set) and hand the pipe over to it
+      if (nxt.w != nullptr) IssuePrologueSet(pipe, set ^ 1, nxt.ring ? nxt.ring : wbuf, nxt.w, nxt.chunk_words, nxt.nchunks);
+      pipe->cur = set ^ 1;
+    }
     if (active) epi(t_out, s0, n0, acc);
   }
   __syncthreads();

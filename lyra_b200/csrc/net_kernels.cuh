@@ -232,6 +232,7 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   int* active = slot + S;
   int* n18 = active + S;
   int tile;
+  InitWeightPipe<NT>();
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
   float* st = state + (size_t)tile * EncStateA::kUnits * S;
   const int tid = (int)threadIdx.x;
@@ -369,6 +370,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   int* active = slot + S;
   int* n18 = active + S;
   int tile;
+  InitWeightPipe<NT>();
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
   uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * EncStateB::kUnits * S;
   float* st = reinterpret_cast<float*>(stw);
@@ -584,6 +586,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   int* active = slot + S;
   int* n18 = active + S;
   int tile;
+  InitWeightPipe<NT>();
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
   uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * DecStateC::kUnits * S;
   float* st = reinterpret_cast<float*>(stw);
@@ -821,6 +824,7 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   int* active = slot + S;
   int* n18 = active + S;
   int tile;
+  InitWeightPipe<NT>();
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const int tid = (int)threadIdx.x;

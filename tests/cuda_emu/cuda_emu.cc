@@ -38,6 +38,8 @@ void warp_barrier() {
   yield_to_sched();
 }
 
+void yield() { yield_to_sched(); }
+
 uint64_t warp_exchange(uint64_t v, int src_lane) {
   BlockState* b = g_blk;
   const unsigned w = b->cur / 32, lane = b->cur % 32;
@@ -79,6 +81,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         g_blockIdx = uint3_emu{bx, by, bz};
         std::memset(b.smem, 0xCD, smem_bytes);   // poison: uninitialised shared memory shows up as garbage
+        std::memset(b.static_smem, 0, sizeof(b.static_smem));
         b.arrived = 0;
         b.done = 0;
         for (unsigned w = 0; w < nwarps; ++w) {

@@ -63,6 +63,7 @@ struct BlockState {
   uint64_t warp_xchg[64][32];
   uint32_t warp_scratch[64][32][8];
   char* smem = nullptr;
+  alignas(16) char static_smem[512];   // storage for the product's function-local __shared__ objects (zeroed per block)
   std::function<void()> body;
 };
 
@@ -73,6 +74,7 @@ extern thread_local dim3 g_blockDim, g_gridDim;
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
 void block_barrier();
 void warp_barrier();
+void yield();   // cooperative spin-wait: let the other fibers of the block run (used by the mbarrier emulation)
 uint64_t warp_exchange(uint64_t v, int src_lane);
 // every lane deposits n (<= 8) words; after the call `all` points at the warp's [32][8] table (valid until the next barrier)
 const uint32_t (*warp_gather(const uint32_t* vals, int n))[8];
