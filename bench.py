@@ -222,6 +222,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not land in front of the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, bits = args.streams, args.bits
     P = (bits + 7) // 8
