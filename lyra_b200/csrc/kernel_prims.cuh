@@ -281,11 +281,7 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 template <int S, int NT, int NTW, typename Epi>
 __device__ __forceinline__ void GemmI8Mma(const uint32_t* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
                                           int groups, int T_out, int N, const uint2* __restrict__ Wf, Epi epi) {
-#ifdef LYRA_MMA_PD
-  constexpr int PD = LYRA_MMA_PD;
-#else
   constexpr int PD = 2;      // register prefetch depth of the B fragments (k-steps); deeper spills at 3 blocks/SM
-#endif
   const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
   const int M = T_out * S, MT = (M + 15) / 16, NTILES = N / 8, NWT = MT * (NTILES / NTW);
   const int CinG4 = CinG / 4, KS = ntaps * CinG4 / 8, CoutG = N / groups;

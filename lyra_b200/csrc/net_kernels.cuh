@@ -201,13 +201,8 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
 // ================================================================================================
 template <int S>
 struct EncA {
-#ifndef LYRA_TILE_8x8
   static constexpr int NT = 320;
   static constexpr int TN = S >= 16 ? 8 : 4;
-#else
-  static constexpr int NT = S >= 16 ? 320 : 160;          // 8 x 8 thread tiles: 20*S tiles of the T = 20 layers
-  static constexpr int TN = 8;                            // 1x1 / first-layer thread tile: 8 streams x 8 channels
-#endif
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;       // S = 8 tiles fit two blocks per SM
   static constexpr int LDU = 25 * S, LDD = 20 * S;
   static constexpr int kSmemU = 0;
@@ -310,21 +305,9 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 // ================================================================================================
 template <int S>
 struct EncB {
-#ifdef LYRA_BC_NT128
-  static constexpr int NT = 128;
-#else
   static constexpr int NT = 256;
-#endif
-#ifdef LYRA_B_2BLOCKS
-  static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
-#else
   static constexpr int kMinBlocks = S <= 8 ? 3 : 1;
-#endif
-#ifdef LYRA_BC_TM4
-  static constexpr int TM = S >= 16 ? 8 : 4;              // streams per thread tile
-#else
   static constexpr int TM = 8;                            // streams per fp32 thread tile (8 x 4 tiles: fewer smem wavefronts per FMA)
-#endif
   static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
   static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;
   static constexpr int WM1 = 1 * S / TM >= 4 ? 4 : 1 * S / TM;
@@ -524,21 +507,9 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 // ================================================================================================
 template <int S, bool TC = false>
 struct DecC {
-#ifdef LYRA_BC_NT128
-  static constexpr int NT = 128;
-#else
   static constexpr int NT = 256;
-#endif
-#ifdef LYRA_C_2BLOCKS
-  static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
-#else
   static constexpr int kMinBlocks = S <= 8 ? 3 : 1;
-#endif
-#ifdef LYRA_BC_TM4
-  static constexpr int TM = S >= 16 ? 8 : 4;              // streams per thread tile
-#else
   static constexpr int TM = 8;                            // streams per fp32 thread tile (8 x 4 tiles: fewer smem wavefronts per FMA)
-#endif
   static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
   static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;
   static constexpr int WM1 = 1 * S / TM >= 4 ? 4 : 1 * S / TM;
@@ -770,23 +741,12 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
 // ================================================================================================
 template <int S, bool TC = false>
 struct DecD {
-#ifndef LYRA_TILE_8x8
   static constexpr int NT = 320;
   static constexpr int TN = S >= 16 ? 8 : 4;
-#else
-  static constexpr int NT = S >= 16 ? 320 : 160;
-  static constexpr int TN = 8;                            // 1x1 thread tile: 8 streams x 8 channels
-#endif
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;
-#ifndef LYRA_TILE_8x8
   static constexpr int TNU = S >= 16 ? 10 : 5;            // decoder_2/simple column tile (320 columns)
   static constexpr int TNL = S >= 16 ? 4 : 2;             // last_layer column tile (16 columns)
   static constexpr int WML = S >= 16 ? 8 : 4;
-#else
-  static constexpr int TNU = 10;
-  static constexpr int TNL = 4;
-  static constexpr int WML = 8;
-#endif
   static constexpr int WMU = S >= 16 ? 2 : 1;
   static constexpr int KCU = 8;                           // its ring starts right behind X inside d and runs into the regular ring
   // u: 3 zero rows + 20 + 3 zero rows.  Tensor-core mode pads the strides of the MMA A operands (u, d, X) and

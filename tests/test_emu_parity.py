@@ -70,3 +70,9 @@ def test_emu_cpp_components(emu_api, oracle, tmp_path):
                            "-Wl,-rpath," + str(tmp_path), "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build"), "-lpthread"])
     out = subprocess.run([exe, _capi.MODEL_DIR], capture_output=True, text=True, env=dict(os.environ, LYRA_B200_MAX_STREAMS="16"))
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_emu_sixteen_stream_tiles(emu_api, oracle, monkeypatch):
+    monkeypatch.setenv("LYRA_B200_TILE_STREAMS", "16")
+    pc.run_codec_parity(_capi.Context, emu_api, oracle, max_streams=32, stream_ids=[3, 17], frames=3, bits=64)
+    pc.run_codec_parity(_capi.Context, emu_api, oracle, max_streams=16, stream_ids=[5], frames=2, bits=64, decoder_mode="tensor")

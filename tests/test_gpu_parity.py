@@ -58,6 +58,35 @@ def test_tensor_decoder_mode_full_size_matches_exact_mode(gpu_api):
     assert worst <= pc.TENSOR_PCM_TOL_LSB
 
 
+@pytest.mark.parametrize("mode", ["exact", "tensor"])
+def test_sixteen_stream_tiles(gpu_api, oracle, sample1, monkeypatch, mode):
+    # the alternative tile size (LYRA_B200_TILE_STREAMS=16, one block per SM) runs the same kernels with other tile shapes
+    monkeypatch.setenv("LYRA_B200_TILE_STREAMS", "16")
+    ctx = _capi.Context(16, capi=gpu_api)
+    assert ctx.tile_streams == 16
+    ctx.close()
+    pc.run_codec_parity(_capi.Context, gpu_api, oracle, max_streams=40, stream_ids=[0, 15, 16, 33, 39], frames=24, bits=120,
+                        wav=sample1, loss_every=5, decoder_mode=mode)
+
+
+def test_bitrate_switch_mid_stream(gpu_api, oracle):
+    # LyraEncoder::set_bitrate (lyra/lyra_encoder.cc:158-167): the number of quantized bits may change from hop to hop
+    n, ids = 3, np.array([1, 8, 9], dtype=np.int32)
+    ctx = _capi.Context(16, capi=gpu_api)
+    from conftest import MODEL_DIR
+    codecs = [oracle.Codec(MODEL_DIR) for _ in range(n)]
+    rng = np.random.default_rng(3)
+    for f, bits in enumerate([64, 184, 120, 64, 120, 184, 64, 64]):
+        pcm = pc.synth_pcm(rng, n)
+        pk = ctx.encode(pcm, bits, stream_ids=ids)
+        out = ctx.decode(pk, bits, stream_ids=ids)
+        for k in range(n):
+            opkt, _, _ = codecs[k].encode(pcm[k], bits)
+            opcm, _, _ = codecs[k].decode(opkt, bits)
+            assert bytes(pk[k]) == opkt and np.array_equal(out[k], opcm), (f, bits, k)
+    ctx.close()
+
+
 def test_non_standard_bit_counts(gpu_api, oracle):
     # any multiple of 4 up to 184 is accepted by Quantize (residual_vector_quantizer.cc:79-89)
     for bits in (4, 60, 100, 180):
