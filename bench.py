@@ -200,8 +200,12 @@ def main():
                     help="codec: encode+decode (the headline metric). decode_plc: BASELINE configs[3], decoder only with a received "
                          "mask (lost packets are concealed from zero features) + log-mel and noise-estimator update of the decoded hop")
     ap.add_argument("--loss", type=float, default=0.1, help="decode_plc: packet loss probability (Bernoulli, seed 1234); 1.0 = all lost")
-    ap.add_argument("--split", type=int, default=3, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
-    ap.add_argument("--e2e-split", type=int, default=3, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
+    ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
+    ap.add_argument("--e2e-split", type=int, default=2, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
+    ap.add_argument("--groups", type=int, default=2,
+                    help="worker groups: the streams are divided among this many encoder/decoder context pairs, each pair with its own "
+                         "CUDA streams and, in the host-buffer pass, its own two host threads (a server's worker threads); calls on "
+                         "one context stay serialised")
     ap.add_argument("--decoder-mode", default="exact", choices=["exact", "tensor"],
                     help="exact: decoded PCM bit-identical to the oracle (default); tensor: split-precision TF32 tensor-core decoder")
     args = ap.parse_args()
@@ -226,11 +230,42 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, bits = args.streams, args.bits
     P = (bits + 7) // 8
-    ctx = _capi.Context(n, device=local_rank)
-    ctx.set_decoder_mode(args.decoder_mode)
-    ctx.set_split(args.split)
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
+    plc = args.workload == "decode_plc"
+    # LyraEncoder and LyraDecoder are separate objects in the reference; here they are an encoder-only and a decoder-only
+    # context with their own CUDA streams (and, in the host-buffer pass, their own host threads), so the encode of step
+    # i + 1 overlaps the decode of step i on the GPU.  Every step's decode consumes that step's packets.
+    enc = None if plc else _capi.Context(n, device=local_rank, roles="encoder")
+    dec = _capi.Context(n, device=local_rank, roles="decoder")
+    dec.set_decoder_mode(args.decoder_mode)
+    ctxs = [c for c in (enc, dec) if c is not None]
+    for c in ctxs:
+        c.set_split(args.split)
+    sx, sy = torch.cuda.Stream(), torch.cuda.Stream()
+    if enc:
+        enc.set_stream(sx.cuda_stream)
+    dec.set_stream(sy.cuda_stream)
+    # worker groups: G context pairs of n / G streams each, used by the two timed passes; the full-size pair above serves the
+    # per-kernel pass (one launch per kernel over all n streams)
+    G = max(1, args.groups)
+    while n % G:
+        G -= 1
+    ng = n // G
+    if G == 1:
+        groups = [(enc, dec, sx, sy)]
+    else:
+        groups = []
+        for _ in range(G):
+            e_ = None if plc else _capi.Context(ng, device=local_rank, roles="encoder")
+            d_ = _capi.Context(ng, device=local_rank, roles="decoder")
+            d_.set_decoder_mode(args.decoder_mode)
+            gx, gy = torch.cuda.Stream(), torch.cuda.Stream()
+            if e_:
+                e_.set_stream(gx.cuda_stream)
+                e_.set_split(args.split)
+            d_.set_stream(gy.cuda_stream)
+            d_.set_split(args.split)
+            groups.append((e_, d_, gx, gy))
+    group_ctxs = [c for grp in groups for c in grp[:2] if c is not None]
 
     def barrier():
         if world > 1:
@@ -240,56 +275,89 @@ def main():
     NBUF = 8
     host = synth_pcm_np(n, NBUF, SEED + rank)
     d_pcm = [torch.from_numpy(host[i]).cuda() for i in range(NBUF)]
-    d_pk = torch.zeros((n, P), dtype=torch.uint8, device="cuda")
+    d_pks = [torch.zeros((n, P), dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
     d_out = torch.zeros((n, 320), dtype=torch.int16, device="cuda")
-
-    plc = args.workload == "decode_plc"
+    ev_pk = [[torch.cuda.Event() for _ in range(NBUF)] for _ in range(max(G, 1) + 1)]      # [group][slot] packets written by the encoder
+    ev_free = [[torch.cuda.Event() for _ in range(NBUF)] for _ in range(max(G, 1) + 1)]    # ... consumed by the decoder
     if plc:
         # packets of NBUF encoded hops + Bernoulli received masks
-        d_pks = [torch.zeros((n, P), dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
+        tmp = _capi.Context(n, device=local_rank, roles="encoder")
         for i in range(NBUF):
-            ctx.encode_device(n, d_pcm[i].data_ptr(), bits, d_pks[i].data_ptr())
-        ctx.synchronize()
+            tmp.encode_device(n, d_pcm[i].data_ptr(), bits, d_pks[i].data_ptr())
+        tmp.synchronize()
+        tmp.close()
         mrng = np.random.default_rng(1234 + rank)
         h_masks = [(mrng.random(n) >= args.loss).astype(np.uint8) for _ in range(NBUF)]
         d_masks = [torch.from_numpy(m).cuda() for m in h_masks]
         d_flags = torch.zeros(n, dtype=torch.uint8, device="cuda")
 
-    def step_device(i):
-        if plc:
-            ctx.decode_track_noise_device(n, d_pks[i % NBUF].data_ptr(), d_masks[i % NBUF].data_ptr(), bits, d_out.data_ptr(), d_flags.data_ptr())
-            return
-        ctx.encode_device(n, d_pcm[i % NBUF].data_ptr(), bits, d_pk.data_ptr())
-        ctx.decode_device(n, d_pk.data_ptr(), 0, bits, d_out.data_ptr())
+    def run_device(first, count, grps, serial=False):
+        """steps first .. first+count-1 over the given context groups (each group owns a contiguous slice of the streams);
+        serial: step i+1's encode waits for step i's decode (per-kernel timing pass)"""
+        m = n // len(grps)
+        for i in range(first, first + count):
+            b = i % NBUF
+            for g, (e_, d_, gx, gy) in enumerate(grps):
+                k = g if len(grps) > 1 else G        # event row: the full-size pair has its own
+                off = g * m
+                if plc:
+                    d_.decode_track_noise_device(m, d_pks[b].data_ptr() + off * P, d_masks[b].data_ptr() + off, bits,
+                                                 d_out.data_ptr() + off * 640, d_flags.data_ptr() + off)
+                    continue
+                if serial and i > first:
+                    gx.wait_event(ev_free[k][(i - 1) % NBUF])
+                elif i - first >= NBUF:
+                    gx.wait_event(ev_free[k][b])                   # the ring slot's previous packets have been decoded
+                e_.encode_device(m, d_pcm[b].data_ptr() + off * 640, bits, d_pks[b].data_ptr() + off * P)
+                ev_pk[k][b].record(gx)
+                gy.wait_event(ev_pk[k][b])
+                d_.decode_device(m, d_pks[b].data_ptr() + off * P, 0, bits, d_out.data_ptr() + off * 640)
+                ev_free[k][b].record(gy)
+
+    def drain(grps, onto):
+        for _, _, gx, gy in grps:
+            onto.wait_stream(gx)
+            onto.wait_stream(gy)
 
     # ---------------- device-resident throughput (`value`) ----------------
-    for i in range(max(3, args.warmup)):
-        step_device(i)
+    timer = torch.cuda.Stream()
+    run_device(0, max(3, args.warmup), groups)
     barrier()
-    launches0 = ctx.launch_count
+    launches0 = sum(c.launch_count for c in group_ctxs)
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        step_device(i)
-    e1.record(stream)
+    e0.record(timer)
+    for _, _, gx, gy in groups:          # nothing of the timed region starts before e0
+        gx.wait_stream(timer)
+        gy.wait_stream(timer)
+    run_device(0, args.steps, groups)
+    drain(groups, timer)
+    e1.record(timer)
     torch.cuda.synchronize()
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    gpu_launches = ctx.launch_count - launches0
+    gpu_launches = sum(c.launch_count for c in group_ctxs) - launches0
     barrier()
-    # per-kernel roofline pass: the same steps with the kernels serialised (one launch per kernel and step over all
-    # streams, no concurrent sub-batches) and CUDA events around every launch on the launching stream
-    ctx.set_split(1)
-    for i in range(3):
-        step_device(i)
-    ctx.profile_enable(True)
-    for i in range(args.steps):
-        step_device(i)
-    prof = ctx.profile_read()
-    ctx.profile_enable(False)
-    ctx.set_split(args.e2e_split)
+    # per-kernel roofline pass on the full-size context pair: the same steps with the kernels serialised (one launch per kernel
+    # and step over all n streams, no concurrent sub-batches, no encode/decode overlap), CUDA events around every launch
+    full = [(enc, dec, sx, sy)]
+    for c in ctxs:
+        c.set_split(1)
+    run_device(0, 3, full, serial=True)
+    torch.cuda.synchronize()
+    for c in ctxs:
+        c.profile_enable(True)
+    run_device(0, args.steps, full, serial=True)
+    torch.cuda.synchronize()
+    prof = {}
+    for c in ctxs:
+        for k, v in c.profile_read().items():
+            if v[1]:
+                prof[k] = v
+        c.profile_enable(False)
+    for c in group_ctxs:
+        c.set_split(args.e2e_split)
     barrier()
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -298,35 +366,64 @@ def main():
     value = world * n * args.steps / (elapsed_ms / 1e3)
 
     # ---------------- end to end through the host-buffer C ABI (`e2e`) ----------------
-    pin_in = [torch.from_numpy(host[i]).pin_memory() for i in range(NBUF)]
-    pin_pk = torch.zeros((n, P), dtype=torch.uint8).pin_memory()
-    pin_out = torch.zeros((n, 320), dtype=torch.int16).pin_memory()
-    lib, h = ctx.api.lib, ctx.h
+    # pinned host buffers in, pinned host buffers out, every call synchronous (H2D, kernels, D2H inside it); the encoder and
+    # the decoder are driven by one host thread each, the way a full-duplex server runs its uplink and downlink
     import ctypes as C
-
+    import threading
+    pin_in = [torch.from_numpy(host[i]).pin_memory() for i in range(NBUF)]
+    pin_pks = [d_pks[i].cpu().pin_memory() for i in range(NBUF)]
+    pin_out = torch.zeros((n, 320), dtype=torch.int16).pin_memory()
+    lib = dec.api.lib
+    errors = []
     if plc:
-        pin_pks = [d_pks[i].cpu().pin_memory() for i in range(NBUF)]
         pin_masks = [torch.from_numpy(h_masks[i]).pin_memory() for i in range(NBUF)]
         pin_flags = torch.zeros(n, dtype=torch.uint8).pin_memory()
 
-    def step_host(i):
-        if plc:
-            rc = lib.lyra_b200_decode_track_noise(h, None, n, C.c_void_p(pin_pks[i % NBUF].data_ptr()), C.c_void_p(pin_masks[i % NBUF].data_ptr()),
-                                                  bits, C.c_void_p(pin_out.data_ptr()), C.c_void_p(pin_flags.data_ptr()))
-            if rc:
-                raise RuntimeError("host API failed: %s" % lib.lyra_b200_last_error(h))
-            return
-        rc = lib.lyra_b200_encode(h, None, n, C.c_void_p(pin_in[i % NBUF].data_ptr()), bits, C.c_void_p(pin_pk.data_ptr()))
-        rc |= lib.lyra_b200_decode(h, None, n, C.c_void_p(pin_pk.data_ptr()), None, bits, C.c_void_p(pin_out.data_ptr()))
-        if rc:
-            raise RuntimeError("host API failed: %s" % lib.lyra_b200_last_error(h))
+    def ptr(t, g, row_bytes):
+        return C.c_void_p(t.data_ptr() + g * ng * row_bytes)
 
-    for i in range(3):
-        step_host(i)
+    def run_host(count):
+        threads = []
+        for g, (e_, d_, _gx, _gy) in enumerate(groups):
+            if plc:
+                def downlink_only(g=g, d_=d_):
+                    for i in range(count):
+                        b = i % NBUF
+                        if lib.lyra_b200_decode_track_noise(d_.h, None, ng, ptr(pin_pks[b], g, P), ptr(pin_masks[b], g, 1), bits,
+                                                            ptr(pin_out, g, 640), ptr(pin_flags, g, 1)):
+                            errors.append("decode: %s" % lib.lyra_b200_last_error(d_.h))
+                threads.append(threading.Thread(target=downlink_only))
+                continue
+            ready, free = threading.Semaphore(0), threading.Semaphore(NBUF)
+
+            def uplink(g=g, e_=e_, ready=ready, free=free):
+                for i in range(count):
+                    b = i % NBUF
+                    free.acquire()
+                    if lib.lyra_b200_encode(e_.h, None, ng, ptr(pin_in[b], g, 640), bits, ptr(pin_pks[b], g, P)):
+                        errors.append("encode: %s" % lib.lyra_b200_last_error(e_.h))
+                    ready.release()
+
+            def downlink(g=g, d_=d_, ready=ready, free=free):
+                for i in range(count):
+                    b = i % NBUF
+                    ready.acquire()
+                    if lib.lyra_b200_decode(d_.h, None, ng, ptr(pin_pks[b], g, P), None, bits, ptr(pin_out, g, 640)):
+                        errors.append("decode: %s" % lib.lyra_b200_last_error(d_.h))
+                    free.release()
+
+            threads += [threading.Thread(target=uplink), threading.Thread(target=downlink)]
+        for x in threads:
+            x.start()
+        for x in threads:
+            x.join()
+        if errors:
+            raise RuntimeError("host API failed: %s" % errors[0])
+
+    run_host(3)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_host(i)
+    run_host(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -380,12 +477,16 @@ def main():
                                     % (n, bits * 50 / 1000.0, 1.0 - args.loss)) if plc else
                                    "%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode "
                                    "(BASELINE configs[2] at %.1f kbps; the north_star target size)" % (n, bits * 50 / 1000.0, bits * 50 / 1000.0),
-                       "streams_per_gpu": n, "bits_per_frame": bits, "tile_streams": ctx.tile_streams,
-                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split},
+                       "streams_per_gpu": n, "bits_per_frame": bits, "tile_streams": dec.tile_streams,
+                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G,
                        "real_time_factor": value / (50.0 * n * world),
                        "l2": "no flush needed: per-step state working set %d x %.0f KB = %.0f MB exceeds the 126 MB L2; PCM inputs rotate over %d buffers"
                              % (n, (EncDecStateBytes()) / 1024.0, n * EncDecStateBytes() / 1e6, NBUF),
                        "parallelism": "streams sharded by rank, no data-path collective",
+                       "execution": ("decoder context only" if plc else
+                                     "full duplex: encoder-only and decoder-only context on their own CUDA streams (host-buffer pass: "
+                                     "their own host threads); the encode of step i+1 overlaps the decode of step i, and every "
+                                     "step's decode consumes that step's packets"),
                        "output_checksum": checksum},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (P + 1) if plc else n * (640 + P),
                     "d2h_bytes_per_step": n * (640 + 1) if plc else n * (P + 640)},
@@ -395,7 +496,8 @@ def main():
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for c in ctxs + (group_ctxs if G > 1 else []):
+        c.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -39,6 +39,15 @@ typedef struct lyra_b200_ctx lyra_b200_ctx;
  * .tflite files + lyra_config.binarypb from `model_dir`, uploads weights, allocates the state of
  * `max_streams` streams on CUDA device `device`.  *out is NULL on failure. */
 int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b200_ctx** out);
+/* The same with a choice of roles.  LyraEncoder and LyraDecoder are separate objects in the reference
+ * (lyra/lyra_encoder.h:112-120, lyra/lyra_decoder.h:130-160) and a full-duplex server drives them independently: an
+ * encoder-only and a decoder-only context hold only their half of the streaming state and may be called concurrently
+ * (one host thread / one CUDA stream each), so the uplink's encode kernels overlap the downlink's decode kernels on the
+ * GPU.  Calls that need a role the context lacks return LYRA_B200_EINVAL; quantize / dequantize / logmel are stateless
+ * or self-contained and work in any context. */
+#define LYRA_B200_ROLE_ENCODER 1
+#define LYRA_B200_ROLE_DECODER 2
+int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int roles, lyra_b200_ctx** out);
 void lyra_b200_destroy(lyra_b200_ctx* ctx);
 /* Human-readable reason of the last failure on this context (or of the last failed create when ctx is NULL). */
 const char* lyra_b200_last_error(const lyra_b200_ctx* ctx);

@@ -35,6 +35,7 @@ class CApi:
         vp, ci = C.c_void_p, C.c_int
         sig = {
             "lyra_b200_create": (ci, [C.c_char_p, ci, ci, C.POINTER(vp)]),
+            "lyra_b200_create_ex": (ci, [C.c_char_p, ci, ci, ci, C.POINTER(vp)]),
             "lyra_b200_destroy": (None, [vp]),
             "lyra_b200_last_error": (C.c_char_p, [vp]),
             "lyra_b200_max_streams": (ci, [vp]),
@@ -69,7 +70,7 @@ class CApi:
         self.lib = L
         self.path = so_path
 
-    EXPORTS = ["lyra_b200_create", "lyra_b200_destroy", "lyra_b200_last_error", "lyra_b200_max_streams",
+    EXPORTS = ["lyra_b200_create", "lyra_b200_create_ex", "lyra_b200_destroy", "lyra_b200_last_error", "lyra_b200_max_streams",
                "lyra_b200_tile_streams", "lyra_b200_reset", "lyra_b200_encode", "lyra_b200_decode",
                "lyra_b200_extract_features", "lyra_b200_quantize", "lyra_b200_dequantize", "lyra_b200_generate",
                "lyra_b200_logmel", "lyra_b200_set_stream", "lyra_b200_encode_device", "lyra_b200_decode_device",
@@ -109,10 +110,12 @@ def packet_bytes(num_bits):
 class Context:
     """One GPU context: weights + the streaming state of ``max_streams`` independent 16 kHz streams."""
 
-    def __init__(self, max_streams, model_dir=MODEL_DIR, device=0, capi=None):
+    ROLES = {"both": 3, "encoder": 1, "decoder": 2}
+
+    def __init__(self, max_streams, model_dir=MODEL_DIR, device=0, capi=None, roles="both"):
         self.api = capi or load()
         h = C.c_void_p()
-        rc = self.api.lib.lyra_b200_create(str(model_dir).encode(), int(device), int(max_streams), C.byref(h))
+        rc = self.api.lib.lyra_b200_create_ex(str(model_dir).encode(), int(device), int(max_streams), self.ROLES[roles], C.byref(h))
         if rc != OK:
             raise LyraB200Error(rc, (self.api.lib.lyra_b200_last_error(None) or b"").decode())
         self.h = h

@@ -33,6 +33,7 @@ struct lyra_b200_ctx {
   ModelSpec spec;
   int device = 0, max_streams = 0, ntiles = 0, padded = 0;
   int S = 8;                // streams per tile (8: two blocks per SM; 16: one)
+  int roles = LYRA_B200_ROLE_ENCODER | LYRA_B200_ROLE_DECODER;   // which halves of the streaming state this context holds
   uint8_t* d_blob = nullptr;
   // streaming state, one block per kernel
   uint32_t* d_state[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -113,6 +114,12 @@ void ProfDrain(lyra_b200_ctx* ctx) {
     }
     ctx->prof_used[k] = 0;
   }
+}
+
+bool RoleOk(lyra_b200_ctx* ctx, int role) {
+  if (ctx->roles & role) return true;
+  ctx->err = role == LYRA_B200_ROLE_ENCODER ? "this context was created without the encoder role" : "this context was created without the decoder role";
+  return false;
 }
 
 bool BitsOk(lyra_b200_ctx* ctx, int num_bits) {
@@ -351,6 +358,7 @@ int ResetImpl(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
     d_ids = ctx->d_ids;
   }
   for (int w = 0; w < 4; ++w) {
+    if (!ctx->d_state[w]) continue;
     LYRA_LAUNCH(ResetStateKernel, dim3((unsigned)n), dim3(256), (size_t)0, ctx->stream,
                 ctx->d_state[w], ctx->d_init[w], ctx->units[w], ctx->S, d_ids, n, ctx->d_n18[w]);
     ctx->launches += 1;
@@ -405,8 +413,12 @@ extern "C" int lyra_b200_debug_phases(lyra_b200_ctx* ctx, long long* out) {
 extern "C" {
 
 int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b200_ctx** out) {
+  return lyra_b200_create_ex(model_dir, device, max_streams, LYRA_B200_ROLE_ENCODER | LYRA_B200_ROLE_DECODER, out);
+}
+
+int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int roles, lyra_b200_ctx** out) {
   if (out) *out = nullptr;
-  if (!out || !model_dir || max_streams <= 0) { g_create_error = "bad argument"; return LYRA_B200_EINVAL; }
+  if (!out || !model_dir || max_streams <= 0 || (roles & ~3) || roles == 0) { g_create_error = "bad argument"; return LYRA_B200_EINVAL; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     g_create_error = "no CUDA device available (lyra_b200 has no CPU fallback)";
@@ -423,6 +435,7 @@ int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b2
   }
   ctx->device = device;
   ctx->max_streams = max_streams;
+  ctx->roles = roles;
   {
     // streams per tile: 8 (default, two blocks per SM) or 16; LYRA_B200_TILE_STREAMS overrides for experiments
     const char* e = std::getenv("LYRA_B200_TILE_STREAMS");
@@ -446,14 +459,15 @@ int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b2
   ok = ok && DevAlloc(&ctx->d_blob, ctx->spec.blob.size()) == cudaSuccess;
   ok = ok && cudaMemcpy(ctx->d_blob, ctx->spec.blob.data(), ctx->spec.blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
   for (int w = 0; w < 4 && ok; ++w) {
+    if (!(roles & (w < 2 ? LYRA_B200_ROLE_ENCODER : LYRA_B200_ROLE_DECODER))) continue;   // an encoder-only / decoder-only context
     const std::vector<uint32_t> img = InitImage(ctx->spec, w);
     ok = ok && DevAlloc(&ctx->d_state[w], (size_t)ctx->units[w] * P) == cudaSuccess;
     ok = ok && DevAlloc(&ctx->d_init[w], img.size()) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_init[w], img.data(), img.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && DevAlloc(&ctx->d_n18[w], P) == cudaSuccess;
   }
-  ok = ok && DevAlloc(&ctx->d_mid_enc, (size_t)ctx->ntiles * 128 * 4 * kS) == cudaSuccess;
-  ok = ok && DevAlloc(&ctx->d_mid_dec, (size_t)ctx->ntiles * 128 * 4 * kS) == cudaSuccess;
+  if (roles & LYRA_B200_ROLE_ENCODER) ok = ok && DevAlloc(&ctx->d_mid_enc, (size_t)ctx->ntiles * 128 * 4 * kS) == cudaSuccess;
+  if (roles & LYRA_B200_ROLE_DECODER) ok = ok && DevAlloc(&ctx->d_mid_dec, (size_t)ctx->ntiles * 128 * 4 * kS) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_logmel_prev[0], P * 320) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_logmel_prev[1], P * 320) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_logmel_prev[2], P * 320) == cudaSuccess;
@@ -568,6 +582,7 @@ int lyra_b200_synchronize(lyra_b200_ctx* ctx) {
 
 int lyra_b200_encode_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets) {
   if (!ctx || !d_pcm || !d_packets) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_ENCODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, nullptr, n);
   if (rc) return rc;
@@ -577,6 +592,7 @@ int lyra_b200_encode_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int
 int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits,
                             int16_t* d_pcm) {
   if (!ctx || !d_packets || !d_pcm) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, nullptr, n);
   if (rc) return rc;
@@ -585,6 +601,7 @@ int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets,
 
 int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, int num_bits, uint8_t* packets) {
   if (!ctx || !pcm || !packets) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_ENCODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
@@ -596,6 +613,7 @@ int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_
 int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_t* packets, const uint8_t* received,
                      int num_bits, int16_t* pcm) {
   if (!ctx || !packets || !pcm) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
@@ -606,6 +624,7 @@ int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_
 
 int lyra_b200_extract_features(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, float* features) {
   if (!ctx || !pcm || !features) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_ENCODER)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -644,6 +663,7 @@ int lyra_b200_dequantize(lyra_b200_ctx* ctx, int n, const uint8_t* packets, int 
 
 int lyra_b200_generate(lyra_b200_ctx* ctx, const int32_t* ids, int n, const float* features, int16_t* pcm) {
   if (!ctx || !features || !pcm) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->d_features, features, sizeof(float) * 64 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -684,6 +704,7 @@ int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* ids, int n, co
 int lyra_b200_noise_update(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, const uint8_t* update_mask,
                            uint8_t* is_noise, float* noise_estimate) {
   if (!ctx || !pcm) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
   const int* d_ids = nullptr;
   if (ids) {
@@ -709,6 +730,7 @@ int lyra_b200_noise_update(lyra_b200_ctx* ctx, const int32_t* ids, int n, const 
 int lyra_b200_noise_update_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, const uint8_t* d_update_mask,
                                   uint8_t* d_is_noise, float* d_noise_estimate) {
   if (!ctx || !d_pcm) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
   return LaunchNoiseUpdate(ctx, ctx->stream, nullptr, 0, n, n, d_pcm, d_update_mask, d_is_noise, d_noise_estimate);
 }
@@ -716,6 +738,7 @@ int lyra_b200_noise_update_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pc
 int lyra_b200_decode_track_noise(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_t* packets, const uint8_t* received,
                                  int num_bits, int16_t* pcm, uint8_t* is_noise) {
   if (!ctx || !packets || !pcm) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
@@ -733,6 +756,7 @@ int lyra_b200_decode_track_noise(lyra_b200_ctx* ctx, const int32_t* ids, int n, 
 int lyra_b200_decode_track_noise_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits,
                                         int16_t* d_pcm, uint8_t* d_is_noise) {
   if (!ctx || !d_packets || !d_pcm) return LYRA_B200_EINVAL;
+  if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, nullptr, n);
   if (rc) return rc;

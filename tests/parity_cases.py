@@ -208,3 +208,33 @@ def run_decode_track_noise_parity(Context, api, O, wav, *, n=3, frames=12, max_s
     for k in check:
         assert np.array_equal(got[k], est[k].noise_estimate()), "noise estimate mismatch stream %d" % k
     ctx.close()
+
+
+def run_role_contexts(Context, api, O, LyraB200Error, *, frames=4, seed=9):
+    """lyra_b200_create_ex: an encoder-only and a decoder-only context together reproduce the oracle; calls of the missing
+    role are refused with EINVAL (the mirror of LyraEncoder / LyraDecoder being separate objects)."""
+    n = 3
+    enc = Context(8, capi=api, roles="encoder")
+    dec = Context(8, capi=api, roles="decoder")
+    codecs = [O.Codec(MODEL_DIR) for _ in range(n)]
+    rng = np.random.default_rng(seed)
+    for f in range(frames):
+        pcm = synth_pcm(rng, n)
+        pk = enc.encode(pcm, 120)
+        out = dec.decode(pk, 120)
+        for k in range(n):
+            opkt, _, _ = codecs[k].encode(pcm[k], 120)
+            opcm, _, _ = codecs[k].decode(opkt, 120)
+            assert bytes(pk[k]) == opkt and np.array_equal(out[k], opcm), (f, k)
+    for bad in (lambda: enc.decode(pk, 120), lambda: dec.encode(pcm, 120), lambda: enc.noise_update(pcm),
+                lambda: dec.extract_features(pcm)):
+        try:
+            bad()
+            raise AssertionError("a call of the missing role must fail")
+        except LyraB200Error as e:
+            assert e.code == -1
+    assert enc.quantize(np.zeros((1, 64), dtype=np.float32), 64).shape == (1, 8)      # stateless calls work in any context
+    enc.reset()
+    dec.reset()
+    enc.close()
+    dec.close()

@@ -119,6 +119,10 @@ def test_decode_track_noise_sparse_and_dense(gpu_api, oracle, sample1):
     pc.run_decode_track_noise_parity(_capi.Context, gpu_api, oracle, sample1, n=1024, frames=8, check=[0, 7, 511, 512, 777, 1023])
 
 
+def test_role_contexts(gpu_api, oracle):
+    pc.run_role_contexts(_capi.Context, gpu_api, oracle, _capi.LyraB200Error, frames=20)
+
+
 def test_golden_fixture_packets(gpu_api, sample1):
     """Committed fixtures (tests/golden/oracle_sample1.json): the GPU path reproduces them without the oracle present."""
     with open(os.path.join(GOLDEN_DIR, "oracle_sample1.json")) as f:
