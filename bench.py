@@ -266,6 +266,10 @@ def main():
             d_.set_split(args.split)
             groups.append((e_, d_, gx, gy))
     group_ctxs = [c for grp in groups for c in grp[:2] if c is not None]
+    # the host-buffer pass runs 2 G waiting threads per rank: let them sleep instead of spin when the box has fewer cores than that
+    oversubscribed = world * 2 * G > host_cores()
+    for c in group_ctxs:
+        c.set_blocking_sync(oversubscribed)
 
     def barrier():
         if world > 1:
@@ -478,7 +482,7 @@ def main():
                                    "%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode "
                                    "(BASELINE configs[2] at %.1f kbps; the north_star target size)" % (n, bits * 50 / 1000.0, bits * 50 / 1000.0),
                        "streams_per_gpu": n, "bits_per_frame": bits, "tile_streams": dec.tile_streams,
-                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G,
+                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G, "host_threads_wait": "sleep (blocking-sync event)" if oversubscribed else "spin",
                        "real_time_factor": value / (50.0 * n * world),
                        "l2": "no flush needed: per-step state working set %d x %.0f KB = %.0f MB exceeds the 126 MB L2; PCM inputs rotate over %d buffers"
                              % (n, (EncDecStateBytes()) / 1024.0, n * EncDecStateBytes() / 1e6, NBUF),

@@ -147,6 +147,9 @@ int lyra_b200_set_split(lyra_b200_ctx* ctx, int parts);
 #define LYRA_B200_DECODER_TENSOR 1
 int lyra_b200_set_decoder_mode(lyra_b200_ctx* ctx, int mode);
 int lyra_b200_decoder_mode(const lyra_b200_ctx* ctx);
+/* How the synchronous host-buffer calls wait for the GPU: 0 (default) spins (lowest latency), 1 sleeps on a blocking-sync
+ * CUDA event — for servers that run more waiting worker threads than they have cores. */
+int lyra_b200_set_blocking_sync(lyra_b200_ctx* ctx, int enable);
 /* number of CUDA kernels this context has launched so far */
 uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx);
 

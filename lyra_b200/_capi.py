@@ -57,6 +57,7 @@ class CApi:
             "lyra_b200_decode_track_noise_device": (ci, [vp, ci, vp, vp, ci, vp, vp]),
             "lyra_b200_noise_update_device": (ci, [vp, ci, vp, vp, vp, vp]),
             "lyra_b200_set_split": (ci, [vp, ci]),
+            "lyra_b200_set_blocking_sync": (ci, [vp, ci]),
             "lyra_b200_set_decoder_mode": (ci, [vp, ci]),
             "lyra_b200_decoder_mode": (ci, [vp]),
             "lyra_b200_launch_count": (C.c_uint64, [vp]),
@@ -75,7 +76,7 @@ class CApi:
                "lyra_b200_extract_features", "lyra_b200_quantize", "lyra_b200_dequantize", "lyra_b200_generate",
                "lyra_b200_logmel", "lyra_b200_set_stream", "lyra_b200_encode_device", "lyra_b200_decode_device",
                "lyra_b200_synchronize", "lyra_b200_noise_update", "lyra_b200_noise_update_device", "lyra_b200_decode_track_noise",
-               "lyra_b200_decode_track_noise_device", "lyra_b200_set_split", "lyra_b200_set_decoder_mode", "lyra_b200_decoder_mode", "lyra_b200_launch_count", "lyra_b200_profile_enable",
+               "lyra_b200_decode_track_noise_device", "lyra_b200_set_split", "lyra_b200_set_blocking_sync", "lyra_b200_set_decoder_mode", "lyra_b200_decoder_mode", "lyra_b200_launch_count", "lyra_b200_profile_enable",
                "lyra_b200_profile_read"]
 
 
@@ -86,7 +87,7 @@ def load():
     """Bind the product library (nvcc build). Fails loudly if it is missing."""
     global _product
     if _product is None:
-        _product = CApi(PRODUCT_SO)
+        _product = CApi(os.environ.get("LYRA_B200_LIB", PRODUCT_SO))   # the override is for kernel-variant experiments (tools/)
     return _product
 
 
@@ -251,6 +252,9 @@ class Context:
     def set_decoder_mode(self, mode):
         """mode: "exact" (bit-identical PCM, default) or "tensor" (split-precision TF32 tensor-core decoder)."""
         self._check(self.api.lib.lyra_b200_set_decoder_mode(self.h, {"exact": 0, "tensor": 1}[mode]))
+
+    def set_blocking_sync(self, enable):
+        self._check(self.api.lib.lyra_b200_set_blocking_sync(self.h, 1 if enable else 0))
 
     def set_split(self, parts):
         self._check(self.api.lib.lyra_b200_set_split(self.h, int(parts)))

@@ -66,6 +66,8 @@ struct lyra_b200_ctx {
   cudaStream_t aux_stream[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   int nsplit = 3;
+  bool blocking_sync = false;        // host-buffer calls sleep on an event instead of spinning (lyra_b200_set_blocking_sync)
+  cudaEvent_t ev_sync = nullptr;
   int decoder_mode = LYRA_B200_DECODER_EXACT;   // lyra_b200_set_decoder_mode
   uint64_t launches = 0;
   std::string err;
@@ -116,6 +118,14 @@ void ProfDrain(lyra_b200_ctx* ctx) {
   }
 }
 
+// End of a synchronous host-buffer call.  Spinning (cudaStreamSynchronize) has the lowest wake-up latency; when more host
+// threads wait than there are cores, sleeping on a blocking-sync event keeps them from starving the launching threads.
+cudaError_t SyncStream(lyra_b200_ctx* ctx) {
+  if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_sync);
+}
+
 bool RoleOk(lyra_b200_ctx* ctx, int role) {
   if (ctx->roles & role) return true;
   ctx->err = role == LYRA_B200_ROLE_ENCODER ? "this context was created without the encoder role" : "this context was created without the decoder role";
@@ -146,7 +156,7 @@ int PrepareMap(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
   ctx->active_tiles = (int)ctx->h_tile_list.size();
   CU(cudaMemcpyAsync(ctx->d_slot_of, ctx->h_slot_of.data(), sizeof(int) * (size_t)ctx->padded, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_tile_list, ctx->h_tile_list.data(), sizeof(int) * (size_t)ctx->active_tiles, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));   // the host vectors are reused by the next call
+  CU(SyncStream(ctx));   // the host vectors are reused by the next call
   ctx->map_dense_n = ids ? -1 : n;
   return LYRA_B200_OK;
 }
@@ -380,7 +390,7 @@ int ResetImpl(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
   } else {
     for (int k = 0; k < n; ++k) CU(cudaMemsetAsync(ctx->d_noise + (size_t)ids[k] * nu, 0, sizeof(float) * nu, ctx->stream));
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -453,6 +463,8 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
   }
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
+  if (const char* e = std::getenv("LYRA_B200_BLOCKING_SYNC")) ctx->blocking_sync = std::atoi(e) != 0;
   if (const char* e = std::getenv("LYRA_B200_SPLIT")) ctx->nsplit = std::atoi(e);
   if (const char* e = std::getenv("LYRA_B200_DECODER_MODE")) ctx->decoder_mode = std::strcmp(e, "tensor") == 0 ? LYRA_B200_DECODER_TENSOR : LYRA_B200_DECODER_EXACT;
   ctx->stream = ctx->own_stream;
@@ -519,6 +531,7 @@ void lyra_b200_destroy(lyra_b200_ctx* ctx) {
   for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k)
     for (auto& ev : ctx->prof_events[k]) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
   for (int i = 0; i < lyra_b200_ctx::kMaxSplit - 1; ++i) {
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
@@ -534,7 +547,7 @@ uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx) { return ctx ? ctx->la
 
 int lyra_b200_profile_enable(lyra_b200_ctx* ctx, int enable) {
   if (!ctx) return LYRA_B200_EINVAL;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   ProfDrain(ctx);
   ctx->profiling = enable != 0;
   if (enable) for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
@@ -543,7 +556,7 @@ int lyra_b200_profile_enable(lyra_b200_ctx* ctx, int enable) {
 
 int lyra_b200_profile_read(lyra_b200_ctx* ctx, double* ms_sum, uint64_t* launches) {
   if (!ctx || !ms_sum || !launches) return LYRA_B200_EINVAL;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   ProfDrain(ctx);
   for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k) { ms_sum[k] = ctx->prof_ms[k]; launches[k] = ctx->prof_n[k]; }
   return LYRA_B200_OK;
@@ -566,6 +579,12 @@ int lyra_b200_set_split(lyra_b200_ctx* ctx, int parts) {
   return LYRA_B200_OK;
 }
 
+int lyra_b200_set_blocking_sync(lyra_b200_ctx* ctx, int enable) {
+  if (!ctx) return LYRA_B200_EINVAL;
+  ctx->blocking_sync = enable != 0;
+  return LYRA_B200_OK;
+}
+
 int lyra_b200_set_decoder_mode(lyra_b200_ctx* ctx, int mode) {
   if (!ctx || (mode != LYRA_B200_DECODER_EXACT && mode != LYRA_B200_DECODER_TENSOR)) return LYRA_B200_EINVAL;
   ctx->decoder_mode = mode;
@@ -576,7 +595,7 @@ int lyra_b200_decoder_mode(const lyra_b200_ctx* ctx) { return ctx ? ctx->decoder
 
 int lyra_b200_synchronize(lyra_b200_ctx* ctx) {
   if (!ctx) return LYRA_B200_EINVAL;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -606,7 +625,7 @@ int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
   if ((rc = RunEncode(ctx, n, ctx->d_pcm, num_bits, ctx->d_packets, pcm, packets))) return rc;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -618,7 +637,7 @@ int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
   if ((rc = RunDecode(ctx, n, ctx->d_packets, received ? ctx->d_received : nullptr, num_bits, ctx->d_pcm, packets, received, pcm))) return rc;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -630,7 +649,7 @@ int lyra_b200_extract_features(lyra_b200_ctx* ctx, const int32_t* ids, int n, co
   CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = LaunchEncoderNets(ctx, WholeCall(ctx, n), ctx->d_pcm, ctx->d_features))) return rc;
   CU(cudaMemcpyAsync(features, ctx->d_features, sizeof(float) * 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -644,7 +663,7 @@ int lyra_b200_quantize(lyra_b200_ctx* ctx, int n, const float* features, int num
   if (rc) return rc;
   CU(cudaMemcpyAsync(packets, ctx->d_packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   if (indices) CU(cudaMemcpyAsync(indices, ctx->d_indices, sizeof(int) * 46 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -657,7 +676,7 @@ int lyra_b200_dequantize(lyra_b200_ctx* ctx, int n, const uint8_t* packets, int 
   int rc = LaunchDequantize(ctx, whole, ctx->d_packets, nullptr, num_bits, ctx->d_features);
   if (rc) return rc;
   CU(cudaMemcpyAsync(features, ctx->d_features, sizeof(float) * 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -669,7 +688,7 @@ int lyra_b200_generate(lyra_b200_ctx* ctx, const int32_t* ids, int n, const floa
   CU(cudaMemcpyAsync(ctx->d_features, features, sizeof(float) * 64 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = LaunchDecoderNets(ctx, WholeCall(ctx, n), ctx->d_features, ctx->d_pcm))) return rc;
   CU(cudaMemcpyAsync(pcm, ctx->d_pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -697,7 +716,7 @@ int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* ids, int n, co
   ctx->launches += 1;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, ctx->d_melout, sizeof(float) * (size_t)num_mel_bins * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -723,7 +742,7 @@ int lyra_b200_noise_update(lyra_b200_ctx* ctx, const int32_t* ids, int n, const 
   if (rc) return rc;
   if (is_noise) CU(cudaMemcpyAsync(is_noise, ctx->d_is_noise, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   if (noise_estimate) CU(cudaMemcpyAsync(noise_estimate, ctx->d_noise_est, sizeof(float) * 160 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
@@ -749,7 +768,7 @@ int lyra_b200_decode_track_noise(lyra_b200_ctx* ctx, const int32_t* ids, int n, 
   }
   if ((rc = RunDecode(ctx, n, ctx->d_packets, received ? ctx->d_received : nullptr, num_bits, ctx->d_pcm, packets, received, pcm,
                       true, d_ids, ctx->d_is_noise, is_noise))) return rc;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 

@@ -13,6 +13,11 @@
 
 #include "kernel_prims.cuh"
 
+// resident blocks per SM the small-M kernels (B, C) are compiled for at S = 8 (their 59-72 KB of shared memory allow 3)
+#ifndef LYRA_BC_MIN_BLOCKS
+#define LYRA_BC_MIN_BLOCKS 3
+#endif
+
 namespace lyra_b200 {
 
 // Development aid (-DLYRA_PHASE_PROF): thread 0 of every block stamps clock64() at phase boundaries.
@@ -306,7 +311,7 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 template <int S>
 struct EncB {
   static constexpr int NT = 256;
-  static constexpr int kMinBlocks = S <= 8 ? 3 : 1;
+  static constexpr int kMinBlocks = S <= 8 ? LYRA_BC_MIN_BLOCKS : 1;
   static constexpr int TM = 8;                            // streams per fp32 thread tile (8 x 4 tiles: fewer smem wavefronts per FMA)
   static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
   static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;
@@ -508,7 +513,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 template <int S, bool TC = false>
 struct DecC {
   static constexpr int NT = 256;
-  static constexpr int kMinBlocks = S <= 8 ? 3 : 1;
+  static constexpr int kMinBlocks = S <= 8 ? LYRA_BC_MIN_BLOCKS : 1;
   static constexpr int TM = 8;                            // streams per fp32 thread tile (8 x 4 tiles: fewer smem wavefronts per FMA)
   static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
   static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;

@@ -13,9 +13,9 @@ python bench.py --decoder-mode tensor --no-cpu-baseline > gpurun_out/${tag}_benc
 # launch list of the bench command (cold-cache, serialised launches: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
-# one full capture of each hot kernel (skip the warm-up launches: 3 warm-up steps x 6 kernels + resets)
+# one full capture of each hot kernel, serialised (one worker group, no sub-batches); skip the warm-up launches: 3 steps x 6 kernels
 ncu --set full --clock-control none --import-source on -k regex:'EncoderKernel|DecoderKernel|Rvq' -s 24 -c 6 \
-    -o gpurun_out/${tag}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
+    -o gpurun_out/${tag}_full python bench.py --groups 1 --split 1 --e2e-split 1 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'DecoderKernel|LogMel|NoiseEst' -s 12 -c 4 \
-    -o gpurun_out/${tag}_full_plc_tensor python bench.py --workload decode_plc --decoder-mode tensor --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full2.log 2>&1
+    -o gpurun_out/${tag}_full_plc_tensor python bench.py --workload decode_plc --decoder-mode tensor --groups 1 --split 1 --e2e-split 1 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full2.log 2>&1
 ls -la gpurun_out | tail -20
