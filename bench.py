@@ -69,14 +69,44 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and clock-event (throttle) reasons while the timed region runs: NVML in-process every 20 ms
+    (nvidia-ml-py), falling back to an `nvidia-smi -lms` subprocess when NVML cannot be loaded."""
 
-    def __init__(self, gpu_index):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index, uuid=None):
         self.gpu = gpu_index
+        self.uuid = uuid
         self.proc = None
         self.lines = []
+        self.samples = []          # (sm_mhz, reasons bitmask)
+        self.smax = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid.encode() if isinstance(self.uuid, str) else self.uuid) if self.uuid \
+                else pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.02)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -91,6 +121,15 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            sm = [x[0] for x in self.samples]
+            bits = 0
+            for x in self.samples:
+                bits |= x[1]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted(v for k, v in self.REASONS.items() if bits & k), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -110,7 +149,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def host_cores():
@@ -328,7 +367,11 @@ def main():
     run_device(0, max(3, args.warmup), groups)
     barrier()
     launches0 = sum(c.launch_count for c in group_ctxs)
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(timer)
