@@ -37,7 +37,9 @@ typedef struct lyra_b200_ctx lyra_b200_ctx;
  * (lyra/soundstream_encoder.cc:36-46, lyra/residual_vector_quantizer.cc:36-67, lyra/lyra_gan_model.cc:36-46)
  * and the asset/version gate of AreParamsSupported (lyra/lyra_config.h:119-168): loads the three
  * .tflite files + lyra_config.binarypb from `model_dir`, uploads weights, allocates the state of
- * `max_streams` streams on CUDA device `device`.  *out is NULL on failure. */
+ * `max_streams` streams on CUDA device `device`.  *out is NULL on failure.
+ * Every call that takes a context makes that context's device the calling thread's current CUDA device (the current
+ * device is per host thread; worker threads need not set it themselves). */
 int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b200_ctx** out);
 /* The same with a choice of roles.  LyraEncoder and LyraDecoder are separate objects in the reference
  * (lyra/lyra_encoder.h:112-120, lyra/lyra_decoder.h:130-160) and a full-duplex server drives them independently: an

@@ -521,6 +521,7 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
 
 void lyra_b200_destroy(lyra_b200_ctx* ctx) {
   if (!ctx) return;
+  cudaSetDevice(ctx->device);
   cudaFree(ctx->d_blob);
   for (int w = 0; w < 4; ++w) { cudaFree(ctx->d_state[w]); cudaFree(ctx->d_init[w]); cudaFree(ctx->d_n18[w]); }
   cudaFree(ctx->d_mid_enc); cudaFree(ctx->d_mid_dec);
@@ -547,6 +548,7 @@ uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx) { return ctx ? ctx->la
 
 int lyra_b200_profile_enable(lyra_b200_ctx* ctx, int enable) {
   if (!ctx) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   CU(SyncStream(ctx));
   ProfDrain(ctx);
   ctx->profiling = enable != 0;
@@ -556,6 +558,7 @@ int lyra_b200_profile_enable(lyra_b200_ctx* ctx, int enable) {
 
 int lyra_b200_profile_read(lyra_b200_ctx* ctx, double* ms_sum, uint64_t* launches) {
   if (!ctx || !ms_sum || !launches) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   CU(SyncStream(ctx));
   ProfDrain(ctx);
   for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k) { ms_sum[k] = ctx->prof_ms[k]; launches[k] = ctx->prof_n[k]; }
@@ -564,29 +567,34 @@ int lyra_b200_profile_read(lyra_b200_ctx* ctx, double* ms_sum, uint64_t* launche
 
 int lyra_b200_reset(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n) {
   if (!ctx) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   return ResetImpl(ctx, stream_ids, n);
 }
 
 int lyra_b200_set_stream(lyra_b200_ctx* ctx, void* cuda_stream) {
   if (!ctx) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
   return LYRA_B200_OK;
 }
 
 int lyra_b200_set_split(lyra_b200_ctx* ctx, int parts) {
   if (!ctx || parts < 1 || parts > lyra_b200_ctx::kMaxSplit) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   ctx->nsplit = parts;
   return LYRA_B200_OK;
 }
 
 int lyra_b200_set_blocking_sync(lyra_b200_ctx* ctx, int enable) {
   if (!ctx) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   ctx->blocking_sync = enable != 0;
   return LYRA_B200_OK;
 }
 
 int lyra_b200_set_decoder_mode(lyra_b200_ctx* ctx, int mode) {
   if (!ctx || (mode != LYRA_B200_DECODER_EXACT && mode != LYRA_B200_DECODER_TENSOR)) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   ctx->decoder_mode = mode;
   return LYRA_B200_OK;
 }
@@ -595,12 +603,14 @@ int lyra_b200_decoder_mode(const lyra_b200_ctx* ctx) { return ctx ? ctx->decoder
 
 int lyra_b200_synchronize(lyra_b200_ctx* ctx) {
   if (!ctx) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
 
 int lyra_b200_encode_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets) {
   if (!ctx || !d_pcm || !d_packets) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_ENCODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, nullptr, n);
@@ -611,6 +621,7 @@ int lyra_b200_encode_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int
 int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits,
                             int16_t* d_pcm) {
   if (!ctx || !d_packets || !d_pcm) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, nullptr, n);
@@ -620,6 +631,7 @@ int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets,
 
 int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, int num_bits, uint8_t* packets) {
   if (!ctx || !pcm || !packets) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_ENCODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
@@ -632,6 +644,7 @@ int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_
 int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_t* packets, const uint8_t* received,
                      int num_bits, int16_t* pcm) {
   if (!ctx || !packets || !pcm) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
@@ -643,6 +656,7 @@ int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_
 
 int lyra_b200_extract_features(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, float* features) {
   if (!ctx || !pcm || !features) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_ENCODER)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
@@ -655,6 +669,7 @@ int lyra_b200_extract_features(lyra_b200_ctx* ctx, const int32_t* ids, int n, co
 
 int lyra_b200_quantize(lyra_b200_ctx* ctx, int n, const float* features, int num_bits, uint8_t* packets, int32_t* indices) {
   if (!ctx || !features || !packets) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "count out of range"; return LYRA_B200_EINVAL; }
   CU(cudaMemcpyAsync(ctx->d_features, features, sizeof(float) * 64 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -669,6 +684,7 @@ int lyra_b200_quantize(lyra_b200_ctx* ctx, int n, const float* features, int num
 
 int lyra_b200_dequantize(lyra_b200_ctx* ctx, int n, const uint8_t* packets, int num_bits, float* features) {
   if (!ctx || !features || !packets) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "count out of range"; return LYRA_B200_EINVAL; }
   CU(cudaMemcpyAsync(ctx->d_packets, packets, (size_t)PacketBytes(num_bits) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -682,6 +698,7 @@ int lyra_b200_dequantize(lyra_b200_ctx* ctx, int n, const uint8_t* packets, int 
 
 int lyra_b200_generate(lyra_b200_ctx* ctx, const int32_t* ids, int n, const float* features, int16_t* pcm) {
   if (!ctx || !features || !pcm) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
@@ -694,6 +711,7 @@ int lyra_b200_generate(lyra_b200_ctx* ctx, const int32_t* ids, int n, const floa
 
 int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* ids, int n, const int16_t* pcm, int num_mel_bins, float* out) {
   if (!ctx || !pcm || !out) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (bank < 0 || bank > 1) { ctx->err = "log-mel bank must be 0 or 1"; return LYRA_B200_EINVAL; }
   if (num_mel_bins != 160 && num_mel_bins != 64) { ctx->err = "log-mel supports 160 or 64 mel bins"; return LYRA_B200_EINVAL; }
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
@@ -723,6 +741,7 @@ int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* ids, int n, co
 int lyra_b200_noise_update(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, const uint8_t* update_mask,
                            uint8_t* is_noise, float* noise_estimate) {
   if (!ctx || !pcm) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
   const int* d_ids = nullptr;
@@ -749,6 +768,7 @@ int lyra_b200_noise_update(lyra_b200_ctx* ctx, const int32_t* ids, int n, const 
 int lyra_b200_noise_update_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, const uint8_t* d_update_mask,
                                   uint8_t* d_is_noise, float* d_noise_estimate) {
   if (!ctx || !d_pcm) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
   return LaunchNoiseUpdate(ctx, ctx->stream, nullptr, 0, n, n, d_pcm, d_update_mask, d_is_noise, d_noise_estimate);
@@ -757,6 +777,7 @@ int lyra_b200_noise_update_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pc
 int lyra_b200_decode_track_noise(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_t* packets, const uint8_t* received,
                                  int num_bits, int16_t* pcm, uint8_t* is_noise) {
   if (!ctx || !packets || !pcm) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
@@ -775,6 +796,7 @@ int lyra_b200_decode_track_noise(lyra_b200_ctx* ctx, const int32_t* ids, int n, 
 int lyra_b200_decode_track_noise_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits,
                                         int16_t* d_pcm, uint8_t* d_is_noise) {
   if (!ctx || !d_packets || !d_pcm) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, nullptr, n);
