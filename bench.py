@@ -268,6 +268,8 @@ def main():
                     help="worker groups: the streams are divided among this many encoder/decoder context pairs, each pair with its own "
                          "CUDA streams and, in the host-buffer pass, its own two host threads (a server's worker threads); calls on "
                          "one context stay serialised")
+    ap.add_argument("--host-wait", default="auto", choices=["auto", "spin", "sleep"],
+                    help="how the worker threads of the host-buffer pass wait for the GPU (auto: sleep only when threads outnumber cores)")
     ap.add_argument("--decoder-mode", default="exact", choices=["exact", "tensor"],
                     help="exact: decoded PCM bit-identical to the oracle (default); tensor: split-precision TF32 tensor-core decoder")
     args = ap.parse_args()
@@ -329,7 +331,7 @@ def main():
             groups.append((e_, d_, gx, gy))
     group_ctxs = [c for grp in groups for c in grp[:2] if c is not None]
     # the host-buffer pass runs 2 G waiting threads per rank: let them sleep instead of spin when the box has fewer cores than that
-    oversubscribed = world * 2 * G > host_cores()
+    oversubscribed = args.host_wait == "sleep" or (args.host_wait == "auto" and world * 2 * G > host_cores())
     for c in group_ctxs:
         c.set_blocking_sync(oversubscribed)
 
@@ -440,6 +442,7 @@ def main():
     # the decoder are driven by one host thread each, the way a full-duplex server runs its uplink and downlink
     import ctypes as C
     import threading
+    sys.setswitchinterval(5e-5)      # worker threads hand the GIL over quickly between their (GIL-free) C-ABI calls
     pin_in = [torch.from_numpy(host[i]).pin_memory() for i in range(NBUF)]
     pin_pks = [d_pks[i].cpu().pin_memory() for i in range(NBUF)]
     pin_out = torch.zeros((n, 320), dtype=torch.int16).pin_memory()
