@@ -123,6 +123,36 @@ def test_role_contexts(gpu_api, oracle):
     pc.run_role_contexts(_capi.Context, gpu_api, oracle, _capi.LyraB200Error, frames=20)
 
 
+@pytest.mark.parametrize("mode", ["exact", "tensor"])
+def test_schedule_independence_full_size(gpu_api, mode):
+    # 4096 streams x 24 frames: the result may not depend on how the call is cut into concurrent sub-batches, on the number
+    # of resident blocks the scheduler mixes, or on encoder and decoder living in separate contexts
+    n = 4096
+    rng = np.random.default_rng(21)
+    ref = _capi.Context(n, capi=gpu_api)
+    ref.set_split(1)
+    ref.set_decoder_mode(mode)
+    alt = _capi.Context(n, capi=gpu_api)
+    alt.set_split(3)
+    alt.set_decoder_mode(mode)
+    enc = _capi.Context(n, capi=gpu_api, roles="encoder")
+    dec = _capi.Context(n, capi=gpu_api, roles="decoder")
+    dec.set_decoder_mode(mode)
+    enc.set_split(2)
+    dec.set_split(4)
+    for f in range(24):
+        pcm = pc.synth_pcm(rng, n, "noise" if f % 5 else "loud")
+        bits = (64, 120, 184)[f % 3]
+        received = (rng.random(n) < 0.9).astype(np.uint8)
+        pk = ref.encode(pcm, bits)
+        out = ref.decode(pk, bits, received=received)
+        assert np.array_equal(pk, alt.encode(pcm, bits)) and np.array_equal(pk, enc.encode(pcm, bits)), f
+        assert np.array_equal(out, alt.decode(pk, bits, received=received)), f
+        assert np.array_equal(out, dec.decode(pk, bits, received=received)), f
+    for c in (ref, alt, enc, dec):
+        c.close()
+
+
 def test_golden_fixture_packets(gpu_api, sample1):
     """Committed fixtures (tests/golden/oracle_sample1.json): the GPU path reproduces them without the oracle present."""
     with open(os.path.join(GOLDEN_DIR, "oracle_sample1.json")) as f:
