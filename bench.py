@@ -553,7 +553,10 @@ def main():
                        "streams_per_gpu": n, "bits_per_frame": bits, "tile_streams": dec.tile_streams,
                        "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G, "host_threads_wait": "sleep (blocking-sync event)" if oversubscribed else "spin",
                        "real_time_factor": value / (50.0 * n * world),
-                       "l2": "no flush needed: per-step state working set %d x %.0f KB = %.0f MB exceeds the 126 MB L2; PCM inputs rotate over %d buffers"
+                       "l2": ("no flush needed: per-step state working set %d x %.0f KB = %.0f MB exceeds the 126 MB L2; PCM inputs rotate over %d buffers"
+                              if n * EncDecStateBytes() > 126e6 else
+                              "NOT flushed: the state working set %d x %.0f KB = %.0f MB fits in the 126 MB L2 at this stream count (as it would "
+                              "in steady-state serving); PCM inputs rotate over %d buffers; the headline configuration (4096 streams) exceeds L2")
                              % (n, (EncDecStateBytes()) / 1024.0, n * EncDecStateBytes() / 1e6, NBUF),
                        "parallelism": "streams sharded by rank, no data-path collective",
                        "execution": ("decoder context only" if plc else
