@@ -168,10 +168,21 @@ def host_cores():
     return n
 
 
-def synth_pcm_np(n, nbuf, seed):
-    """Seeded synthetic input: uniform noise at 0.25 full scale (the reference benchmark feeds uniform random audio,
-    lyra/lyra_benchmark_lib.cc:233-239); `nbuf` distinct hops are rotated through the steps."""
+def synth_pcm_np(n, nbuf, seed, kind="noise"):
+    """Seeded synthetic input, `nbuf` distinct hops rotated through the steps:
+    noise  — uniform noise at 0.25 full scale (the reference benchmark feeds uniform random audio, lyra/lyra_benchmark_lib.cc:233-239);
+    speech — the reference's test clips tests/data/sample{1,2}_16kHz.wav tiled, stream i starting at offset (i * 7919) mod len."""
     import numpy as np
+    if kind == "speech":
+        import wave
+        clips = []
+        for name in ("sample1_16kHz.wav", "sample2_16kHz.wav"):
+            with wave.open(os.path.join(ROOT, "tests", "data", name)) as w:
+                clips.append(np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16))
+        clip = np.concatenate(clips)
+        start = (np.arange(n, dtype=np.int64) * 7919 + seed) % (len(clip) - 320 * nbuf)
+        idx = start[None, :, None] + (np.arange(nbuf, dtype=np.int64) * 320)[:, None, None] + np.arange(320, dtype=np.int64)[None, None, :]
+        return np.ascontiguousarray(clip[idx])
     rng = np.random.default_rng(seed)
     return rng.integers(-8192, 8192, size=(nbuf, n, 320), dtype=np.int16)
 
@@ -268,6 +279,8 @@ def main():
                     help="worker groups: the streams are divided among this many encoder/decoder context pairs, each pair with its own "
                          "CUDA streams and, in the host-buffer pass, its own two host threads (a server's worker threads); calls on "
                          "one context stay serialised")
+    ap.add_argument("--input", default="noise", choices=["noise", "speech"],
+                    help="synthetic input: uniform noise at 0.25 full scale (default) or the tiled reference speech clips")
     ap.add_argument("--host-wait", default="auto", choices=["auto", "spin", "sleep"],
                     help="how the worker threads of the host-buffer pass wait for the GPU (auto: sleep only when threads outnumber cores)")
     ap.add_argument("--decoder-mode", default="exact", choices=["exact", "tensor"],
@@ -341,7 +354,7 @@ def main():
         torch.cuda.synchronize()
 
     NBUF = 8
-    host = synth_pcm_np(n, NBUF, SEED + rank)
+    host = synth_pcm_np(n, NBUF, SEED + rank, args.input)
     d_pcm = [torch.from_numpy(host[i]).cuda() for i in range(NBUF)]
     d_pks = [torch.zeros((n, P), dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
     d_out = torch.zeros((n, 320), dtype=torch.int16, device="cuda")
@@ -544,7 +557,7 @@ def main():
         line = {
             "metric": METRIC_PLC if plc else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+i8", "data": "synthetic",
+            "dtype": "f32+i8", "data": "synthetic" if args.input == "noise" else "synthetic (reference speech clips tiled over the streams)",
             "config": {"workload": ("%d concurrent 16kHz streams per GPU, %.1f kbps, decoder only with packet-loss concealment "
                                     "(BASELINE configs[3]): received mask Bernoulli(%.2f, seed 1234), log-mel + noise estimator on the decoded hop"
                                     % (n, bits * 50 / 1000.0, 1.0 - args.loss)) if plc else
