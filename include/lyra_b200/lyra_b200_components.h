@@ -101,19 +101,25 @@ class Session {
  public:
   // nullptr when the context cannot be created (no GPU, bad model directory): factories then return nullptr,
   // like the reference's Create() functions (e.g. lyra/soundstream_encoder.cc:36-46).
-  static std::shared_ptr<Session> Get(const std::string& model_path, int device = 0) {
+  // One session per role: encoder-side objects (SoundStreamEncoder) share an encoder-only context, decoder-side objects
+  // (LyraGanModel, NoiseEstimator) a decoder-only one, stateless ones (quantizer, log-mel) use the encoder's.  The two
+  // contexts hold only their half of the streaming state and have their own mutex, so a LyraEncoder thread and a
+  // LyraDecoder thread never wait for each other.
+  static std::shared_ptr<Session> Get(const std::string& model_path, int role = LYRA_B200_ROLE_ENCODER, int device = 0) {
     static std::mutex mu;
-    static std::weak_ptr<Session> cached;
-    static std::string cached_path;
+    static std::weak_ptr<Session> cached[2];
+    static std::string cached_path[2];
+    const int k = role == LYRA_B200_ROLE_DECODER ? 1 : 0;
     std::lock_guard<std::mutex> lock(mu);
-    if (auto s = cached.lock()) if (cached_path == model_path) return s;
+    if (auto s = cached[k].lock()) if (cached_path[k] == model_path) return s;
     int max_streams = 4096;
     if (const char* e = std::getenv("LYRA_B200_MAX_STREAMS")) max_streams = std::atoi(e) > 0 ? std::atoi(e) : max_streams;
     lyra_b200_ctx* ctx = nullptr;
-    if (lyra_b200_create(model_path.c_str(), device, max_streams, &ctx) != LYRA_B200_OK) return nullptr;
+    if (lyra_b200_create_ex(model_path.c_str(), device, max_streams, k ? LYRA_B200_ROLE_DECODER : LYRA_B200_ROLE_ENCODER, &ctx) != LYRA_B200_OK)
+      return nullptr;
     std::shared_ptr<Session> s(new Session(ctx, max_streams));
-    cached = s;
-    cached_path = model_path;
+    cached[k] = s;
+    cached_path[k] = model_path;
     return s;
   }
   ~Session() { lyra_b200_destroy(ctx_); }
@@ -217,7 +223,7 @@ class LyraGanModelB200 : public GenerativeModel {
  public:
   static std::unique_ptr<LyraGanModelB200> Create(const std::string& model_path, int num_features) {
     if (num_features != LYRA_B200_NUM_FEATURES) return nullptr;
-    auto s = Session::Get(model_path);
+    auto s = Session::Get(model_path, LYRA_B200_ROLE_DECODER);
     if (!s) return nullptr;
     const int id = s->Acquire();
     if (id < 0) return nullptr;
@@ -287,7 +293,7 @@ class NoiseEstimatorB200 : public NoiseEstimatorInterface {
   static std::unique_ptr<NoiseEstimatorB200> Create(const std::string& model_path, int sample_rate_hz, int num_samples_per_hop,
                                                     int num_samples_per_window, int num_features) {
     if (sample_rate_hz != 16000 || num_samples_per_hop != 320 || num_samples_per_window != 640 || num_features != 160) return nullptr;
-    auto s = Session::Get(model_path);
+    auto s = Session::Get(model_path, LYRA_B200_ROLE_DECODER);
     if (!s) return nullptr;
     const int id = s->Acquire();
     if (id < 0) return nullptr;
