@@ -154,10 +154,7 @@ constexpr int kLogMelFftPadded = kLogMelFft + kLogMelFft / 8;
 // three consecutive stages (half-lengths STRIDE, 2 STRIDE, 4 STRIDE) on the 8 points base + j * STRIDE; r = base mod STRIDE.
 // tw: per-stage twiddle tables, the stage of half-length h starts at complex entry h - 1.
 template <int STRIDE>
-__device__ __forceinline__ void FftStages3(double* re, double* im, int base, int r, const double2* __restrict__ tw) {
-  double xr[8], xi[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { xr[j] = re[FftIdx(base + j * STRIDE)]; xi[j] = im[FftIdx(base + j * STRIDE)]; }
+__device__ __forceinline__ void FftButterflies3(double (&xr)[8], double (&xi)[8], int r, const double2* __restrict__ tw) {
 #pragma unroll
   for (int s = 0; s < 3; ++s) {
     const int half = STRIDE << s;
@@ -169,6 +166,14 @@ __device__ __forceinline__ void FftStages3(double* re, double* im, int base, int
         FftButterfly(xr[j], xi[j], xr[j + (1 << s)], xi[j + (1 << s)], w.x, w.y);
       }
   }
+}
+
+template <int STRIDE>
+__device__ __forceinline__ void FftStages3(double* re, double* im, int base, int r, const double2* __restrict__ tw) {
+  double xr[8], xi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { xr[j] = re[FftIdx(base + j * STRIDE)]; xi[j] = im[FftIdx(base + j * STRIDE)]; }
+  FftButterflies3<STRIDE>(xr, xi, r, tw);
 #pragma unroll
   for (int j = 0; j < 8; ++j) { re[FftIdx(base + j * STRIDE)] = xr[j]; im[FftIdx(base + j * STRIDE)] = xi[j]; }
 }
@@ -181,6 +186,7 @@ LogMelKernel(const uint8_t* __restrict__ blob, LogMelParams P, const int* __rest
   double* re = reinterpret_cast<double*>(smem);
   double* im = re + kLogMelFftPadded;
   double* mag = im + kLogMelFftPadded;       // [fft/2 + 1]
+  double* xw = mag + kLogMelFft / 2 + 1;     // [window_len, padded like the FFT buffers] windowed samples in natural order
   const int slot = slot_base + (int)blockIdx.x;     // I/O arrays are indexed by slot; a sub-batch starts at slot_base
   if (slot >= n) return;
   if (mask && !mask[slot]) return;     // this stream's extractor is not fed this hop (its carried samples stay)
@@ -192,16 +198,10 @@ LogMelKernel(const uint8_t* __restrict__ blob, LogMelParams P, const int* __rest
   const double2* tw = BlobPtr<double2>(blob, P.twiddle);
   int16_t* pv = prev + (size_t)stream * carry;
   const int16_t* cur = pcm + (size_t)slot * P.hop;
-  // windowed, zero-padded frame written in bit-reversed order (10 bits)
-  for (int i = tid; i < kLogMelFft; i += NT) {
-    double v = 0.0;
-    if (i < P.window_len) {
-      const int16_t smp = i < carry ? pv[i] : cur[i - carry];
-      v = __dmul_rn((double)smp, win[i]);
-    }
-    const int rev = FftIdx((int)(__brev((unsigned)i) >> 22));
-    re[rev] = v;
-    im[rev] = 0.0;
+  // windowed samples in natural order (the zero padding up to 1024 points is implicit)
+  for (int i = tid; i < P.window_len; i += NT) {
+    const int16_t smp = i < carry ? pv[i] : cur[i - carry];
+    xw[FftIdx(i)] = __dmul_rn((double)smp, win[i]);
   }
   __syncthreads();
   // the carried samples become the tail of (previous carry, current hop); staged through `mag`
@@ -214,7 +214,20 @@ LogMelKernel(const uint8_t* __restrict__ blob, LogMelParams P, const int* __rest
     __syncthreads();
     for (int i = tid; i < carry; i += NT) pv[i] = stage[i];
   }
-  FftStages3<1>(re, im, 8 * tid, 0, tw);                                       // stages 2, 4, 8
+  {                                                                            // stages 2, 4, 8 on points 8 tid .. 8 tid + 7
+    double xr[8], xi[8];
+    const int b7 = (int)(__brev((unsigned)tid) >> 25);                         // bit-reversed position 8t + j <-> natural index brev7(t) + 128 brev3(j)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int j3 = ((j & 1) << 2) | (j & 2) | ((j & 4) >> 2);
+      const int i = b7 + 128 * j3;
+      xr[j] = i < P.window_len ? xw[FftIdx(i)] : 0.0;
+      xi[j] = 0.0;
+    }
+    FftButterflies3<1>(xr, xi, 0, tw);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { re[FftIdx(8 * tid + j)] = xr[j]; im[FftIdx(8 * tid + j)] = xi[j]; }
+  }
   __syncthreads();
   FftStages3<8>(re, im, 64 * (tid / 8) + tid % 8, tid % 8, tw);                // stages 16, 32, 64
   __syncthreads();

@@ -265,7 +265,7 @@ int Join(lyra_b200_ctx* ctx, int nparts) {
 int LaunchNoiseUpdate(lyra_b200_ctx* ctx, cudaStream_t st, const int* d_ids, int slot0, int count, int n, const int16_t* d_pcm,
                       const uint8_t* d_mask, uint8_t* d_is_noise, float* d_estimate) {
   const LogMelParams& P = ctx->spec.logmel160;
-  const size_t smem = sizeof(double) * (size_t)(2 * kLogMelFftPadded + P.fft / 2 + 1);
+  const size_t smem = sizeof(double) * (size_t)(2 * kLogMelFftPadded + P.fft / 2 + 1 + P.window_len + P.window_len / 8 + 1);
   { ProfScope ps(ctx, 6, st);
   LYRA_LAUNCH(LogMelKernel, dim3((unsigned)count), dim3(kLogMelThreads), smem, st,
               ctx->d_blob, P, d_ids, n, d_pcm, ctx->d_logmel_prev[2], ctx->d_melout, d_mask, slot0); }
@@ -727,7 +727,7 @@ int lyra_b200_logmel(lyra_b200_ctx* ctx, int bank, const int32_t* ids, int n, co
   }
   const LogMelParams& P = num_mel_bins == 160 ? ctx->spec.logmel160 : ctx->spec.logmel64;
   CU(cudaMemcpyAsync(ctx->d_pcm, pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  const size_t smem = sizeof(double) * (size_t)(2 * kLogMelFftPadded + P.fft / 2 + 1);
+  const size_t smem = sizeof(double) * (size_t)(2 * kLogMelFftPadded + P.fft / 2 + 1 + P.window_len + P.window_len / 8 + 1);
   { ProfScope ps(ctx, 6, ctx->stream);
   LYRA_LAUNCH(LogMelKernel, dim3((unsigned)n), dim3(kLogMelThreads), smem, ctx->stream,
               ctx->d_blob, P, d_ids, n, ctx->d_pcm, ctx->d_logmel_prev[bank], ctx->d_melout, (const uint8_t*)nullptr, 0); }
