@@ -344,7 +344,8 @@ def main():
             groups.append((e_, d_, gx, gy))
     group_ctxs = [c for grp in groups for c in grp[:2] if c is not None]
     # the host-buffer pass runs 2 G waiting threads per rank: let them sleep instead of spin when the box has fewer cores than that
-    oversubscribed = args.host_wait == "sleep" or (args.host_wait == "auto" and world * 2 * G > host_cores())
+    # spinning waiters must leave cores for the ranks' launching threads: 2 G workers + 1 main thread per rank vs 3/4 of the cores
+    oversubscribed = args.host_wait == "sleep" or (args.host_wait == "auto" and world * (2 * G + 1) > host_cores() * 3 // 4)
     for c in group_ctxs:
         c.set_blocking_sync(oversubscribed)
 
