@@ -66,7 +66,10 @@ static inline void lyra_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned 
 static inline void lyra_mbar_wait(LyraMbar* b, unsigned parity) {
   while (lyra_mbar_emu(b)->phase == parity) cuda_emu::yield();
 }
-#define LYRA_STATIC_SMEM(type, name, count) type* name = reinterpret_cast<type*>(cuda_emu::g_blk->static_smem)
+// one function-local shared object per kernel (the emulator backs them all with the same per-block scratch area)
+#define LYRA_STATIC_SMEM(type, name, count) \
+  static_assert(sizeof(type) * (count) <= 512, "emulated static shared memory is 512 bytes"); \
+  type* name = reinterpret_cast<type*>(cuda_emu::g_blk->static_smem)
 #elif defined(__CUDACC__)
 __device__ __forceinline__ unsigned lyra_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void lyra_mbar_init(LyraMbar* b, unsigned count) {
