@@ -80,3 +80,51 @@ def test_emu_sixteen_stream_tiles(emu_api, oracle, monkeypatch):
 
 def test_emu_role_contexts(emu_api, oracle):
     pc.run_role_contexts(_capi.Context, emu_api, oracle, _capi.LyraB200Error, frames=2)
+
+
+def test_emu_full_duplex_threads(emu_api, oracle):
+    """An encoder-only and a decoder-only context driven concurrently by two host threads (the benchmark's host-buffer pass,
+    INTEGRATION.md section 3): packets and PCM still equal the oracle's."""
+    import queue
+    import threading
+    from conftest import MODEL_DIR
+    n, frames = 2, 4
+    enc = _capi.Context(8, capi=emu_api, roles="encoder")
+    dec = _capi.Context(8, capi=emu_api, roles="decoder")
+    rng = np.random.default_rng(12)
+    pcm = [pc.synth_pcm(rng, n) for _ in range(frames)]
+    q, packets, outs, errors = queue.Queue(), [None] * frames, [None] * frames, []
+
+    def uplink():
+        try:
+            for f in range(frames):
+                packets[f] = enc.encode(pcm[f], 64)
+                q.put(f)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+            q.put(None)
+
+    def downlink():
+        try:
+            for _ in range(frames):
+                f = q.get()
+                if f is None:
+                    return
+                outs[f] = dec.decode(packets[f], 64)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+
+    th = [threading.Thread(target=uplink), threading.Thread(target=downlink)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    codecs = [oracle.Codec(MODEL_DIR) for _ in range(n)]
+    for f in range(frames):
+        for k in range(n):
+            opkt, _, _ = codecs[k].encode(pcm[f][k], 64)
+            opcm, _, _ = codecs[k].decode(opkt, 64)
+            assert bytes(packets[f][k]) == opkt and np.array_equal(outs[f][k], opcm), (f, k)
+    enc.close()
+    dec.close()
