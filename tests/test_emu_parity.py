@@ -128,3 +128,36 @@ def test_emu_full_duplex_threads(emu_api, oracle):
             assert bytes(packets[f][k]) == opkt and np.array_equal(outs[f][k], opcm), (f, k)
     enc.close()
     dec.close()
+
+
+def test_emu_cpp_duplex_server_example(emu_api, oracle, tmp_path):
+    """examples/duplex_server.cc (C++ worker threads over encoder-only / decoder-only contexts) against the oracle."""
+    import os
+    import shutil
+    import subprocess
+    from conftest import MODEL_DIR, ROOT
+    shutil.copy(emu_api.path, str(tmp_path / "liblyra_b200.so"))
+    exe = str(tmp_path / "duplex_server")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "duplex_server.cc"),
+                           "-o", exe, "-L" + str(tmp_path), "-llyra_b200", "-Wl,-rpath," + str(tmp_path), "-lpthread"])
+    streams, steps = 4, 3
+
+    def hop(stream, step):          # FillHop of the example
+        x = (2463534242 ^ (stream * 7919 + step * 104729)) & 0xFFFFFFFF
+        out = np.empty(320, dtype=np.int16)
+        for i in range(320):
+            x = (x * 1664525 + 1013904223) & 0xFFFFFFFF
+            out[i] = ((x >> 16) & 16383) - 8192
+        return out
+
+    want = 0
+    for s in range(streams):
+        c = oracle.Codec(MODEL_DIR)
+        for i in range(steps):
+            pkt, _, _ = c.encode(hop(s, i), 64)
+            pcm, _, _ = c.decode(pkt, 64)
+        want += int(pcm.astype(np.int64).sum())
+    for groups in (1, 2):
+        out = subprocess.run([exe, MODEL_DIR, str(streams), str(steps), str(groups), "64"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert int(out.stdout.strip().rsplit("checksum", 1)[1]) == want, out.stdout
