@@ -250,3 +250,35 @@ def test_cpp_components_against_oracle(gpu_api, oracle, tmp_path):
     env = dict(os.environ, LYRA_B200_MAX_STREAMS="64")
     out = subprocess.run([exe, _capi.MODEL_DIR], capture_output=True, text=True, env=env)
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_cpp_duplex_server_example(gpu_api, oracle, tmp_path):
+    """examples/duplex_server.cc on the GPU: checksum of the decoded audio against the oracle (small), then a full-size run."""
+    import subprocess
+    from conftest import MODEL_DIR, ROOT
+    exe = str(tmp_path / "duplex_server")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "duplex_server.cc"),
+                           "-o", exe, "-L" + os.path.join(ROOT, "lyra_b200"), "-llyra_b200", "-Wl,-rpath," + os.path.join(ROOT, "lyra_b200"), "-lpthread"])
+    streams, steps = 16, 5
+
+    def hop(stream, step):          # FillHop of the example
+        x = (2463534242 ^ (stream * 7919 + step * 104729)) & 0xFFFFFFFF
+        out = np.empty(320, dtype=np.int16)
+        for i in range(320):
+            x = (x * 1664525 + 1013904223) & 0xFFFFFFFF
+            out[i] = ((x >> 16) & 16383) - 8192
+        return out
+
+    want = 0
+    for s in range(streams):
+        c = oracle.Codec(MODEL_DIR)
+        for i in range(steps):
+            pkt, _, _ = c.encode(hop(s, i), 120)
+            pcm, _, _ = c.decode(pkt, 120)
+        want += int(pcm.astype(np.int64).sum())
+    out = subprocess.run([exe, MODEL_DIR, str(streams), str(steps), "2", "120"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert int(out.stdout.strip().rsplit("checksum", 1)[1]) == want, out.stdout
+    big = subprocess.run([exe, MODEL_DIR, "4096", "60", "2", "64"], capture_output=True, text=True, timeout=300)
+    assert big.returncode == 0, big.stdout + big.stderr
+    print(big.stdout.strip())
