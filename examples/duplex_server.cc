@@ -10,6 +10,8 @@
 //
 //   duplex_server <model_dir> <streams> <steps> [groups=2] [bits=64]
 // prints frames/s and a checksum of the decoded audio of the last step (tests compare it with the oracle's).
+// It is an illustration, not the benchmark: the input is synthesised inside the uplink thread and the host buffers are
+// ordinary pageable vectors (bench.py measures the same loop with pinned buffers and precomputed input).
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
