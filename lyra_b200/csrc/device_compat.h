@@ -175,3 +175,97 @@ __device__ __forceinline__ void lyra_mma_tf32_16x8x8(float (&c)[4], const uint32
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 #endif
+
+// ---- 5th-generation tensor cores (tcgen05 / UMMA) with accumulators in tensor memory (TMEM).
+//      Not used by the shipped kernels yet: these wrappers carry the instruction sequences that
+//      tools/tcgen05_probe.cu verified on a B200, plus an emulator model so the CPU test tier can run UMMA kernels.
+//      Shared-memory matrix descriptor (no swizzle, K-major): element (row, k) of an operand lives at
+//        start + (k / 4) * LBO + (row / 8) * SBO + (row % 8) * 16 + (k % 4) * 4   bytes
+//      i.e. 8-row x 16-byte core matrices, LBO = byte distance of the two 4-element k-halves of one MMA (K = 8),
+//      SBO = byte distance of consecutive 8-row groups.  kind::tf32 reads the top 19 bits of every operand.
+//      TMEM address = (lane << 16) | column; an M = 128 accumulator puts row r in lane r, column n in column n.
+__host__ __device__ inline uint32_t lyra_umma_idesc_tf32(int M, int N) {
+  // D = f32 (bits 4-5 = 1), A = B = tf32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+#if defined(LYRA_EMU)
+static inline uint32_t lyra_emu_smem_addr(const void* p) { return (uint32_t)(reinterpret_cast<const char*>(p) - cuda_emu::g_blk->smem); }
+static inline uint64_t lyra_umma_desc(const void* smem, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((lyra_emu_smem_addr(smem) >> 4) & 0x3FFF) | (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16 |
+         (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32 | (uint64_t)1 << 46;
+}
+static inline float* lyra_emu_tmem(uint32_t taddr, int lane_add, int col_add) {
+  cuda_emu::BlockState* b = cuda_emu::g_blk;
+  if (b->tmem.empty()) b->tmem.assign(128 * 512, 0.0f);
+  const unsigned lane = (taddr >> 16) + (unsigned)lane_add, col = (taddr & 0xffffu) + (unsigned)col_add;
+  if (lane >= 128 || col >= 512) { std::fprintf(stderr, "cuda_emu: TMEM access out of range (lane %u, column %u)\n", lane, col); std::abort(); }
+  return &b->tmem[(size_t)lane * 512 + col];
+}
+// warp-collective in hardware; here every lane of the calling warp runs it and lane 0 does the work
+static inline void lyra_tmem_alloc(uint32_t* smem_slot, int ncols) {
+  if ((threadIdx.x & 31) == 0) {
+    cuda_emu::BlockState* b = cuda_emu::g_blk;
+    if (ncols < 32 || (ncols & (ncols - 1)) || b->tmem_used + (unsigned)ncols > 512) { std::fprintf(stderr, "cuda_emu: bad TMEM allocation\n"); std::abort(); }
+    *smem_slot = b->tmem_used;
+    b->tmem_used += (unsigned)ncols;
+  }
+  __syncwarp();
+}
+static inline void lyra_tmem_dealloc(uint32_t, int) { __syncwarp(); }
+static inline void lyra_tc_fence_before_sync() {}
+static inline void lyra_tc_fence_after_sync() {}
+// D[M x N] (+)= A[M x 8] * B[N x 8]^T, one thread issues it; the emulator executes it on the spot
+static inline void lyra_umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+  const char* base = cuda_emu::g_blk->smem;
+  auto elem = [&](uint64_t d, int row, int k) {
+    const uint32_t start = (uint32_t)(d & 0x3FFF) << 4, lbo = (uint32_t)((d >> 16) & 0x3FFF) << 4, sbo = (uint32_t)((d >> 32) & 0x3FFF) << 4;
+    uint32_t bits;
+    std::memcpy(&bits, base + start + (uint32_t)(k / 4) * lbo + (uint32_t)(row / 8) * sbo + (uint32_t)(row % 8) * 16 + (uint32_t)(k % 4) * 4, 4);
+    return (double)lyra_emu_tf32(bits);
+  };
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double acc = accumulate ? (double)*lyra_emu_tmem(tmem_d, m, n) : 0.0;
+      for (int k = 0; k < 8; ++k) acc += elem(desc_a, m, k) * elem(desc_b, n, k);
+      *lyra_emu_tmem(tmem_d, m, n) = (float)acc;
+    }
+}
+// all MMAs issued so far by this thread are complete when the barrier's phase completes
+static inline void lyra_umma_commit(LyraMbar* b) { lyra_mbar_arrive(b); }
+// 32x32b shape: lane i of the warp reads TMEM lane (address lane) + i, 8 consecutive columns
+static inline void lyra_tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  const int lane = (int)(threadIdx.x & 31);
+  for (int j = 0; j < 8; ++j) v[j] = *lyra_emu_tmem(taddr, lane, j);
+}
+#elif defined(__CUDACC__)
+__device__ __forceinline__ uint64_t lyra_umma_desc(const void* smem, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((lyra_smem_u32(smem) >> 4) & 0x3FFF) | (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16 |
+         (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32 | (uint64_t)1 << 46;     // descriptor version 1, no swizzle
+}
+// one whole warp; ncols a power of two >= 32; the TMEM base address is written to *smem_slot (shared memory)
+__device__ __forceinline__ void lyra_tmem_alloc(uint32_t* smem_slot, int ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(lyra_smem_u32(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void lyra_tmem_dealloc(uint32_t taddr, int ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void lyra_tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void lyra_tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void lyra_umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void lyra_umma_commit(LyraMbar* b) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(lyra_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void lyra_tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+#endif

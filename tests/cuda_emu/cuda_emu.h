@@ -64,6 +64,8 @@ struct BlockState {
   uint32_t warp_scratch[64][32][8];
   char* smem = nullptr;
   alignas(16) char static_smem[512];   // storage for the product's function-local __shared__ objects (zeroed per block)
+  std::vector<float> tmem;             // tensor memory: 128 lanes x 512 columns of 32-bit cells (allocated on first use)
+  unsigned tmem_used = 0;              // columns handed out by the emulated tcgen05.alloc
   std::function<void()> body;
 };
 

@@ -161,3 +161,16 @@ def test_emu_cpp_duplex_server_example(emu_api, oracle, tmp_path):
         out = subprocess.run([exe, MODEL_DIR, str(streams), str(steps), str(groups), "64"], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stdout + out.stderr
         assert int(out.stdout.strip().rsplit("checksum", 1)[1]) == want, out.stdout
+
+
+def test_emu_umma_probe(tmp_path):
+    """tests/cpp/umma_probe.cu on the emulator's tcgen05 / TMEM model (device_compat.h): the UMMA groundwork for the decoder's
+    tensor-core mode — descriptors, split-precision MMAs, overlapping 128-row blocks, in-place operand rewrite."""
+    import os
+    import subprocess
+    from conftest import EMU_DIR, ROOT
+    exe = str(tmp_path / "umma_probe")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-DLYRA_EMU", "-x", "c++", "-I" + EMU_DIR, "-I" + os.path.join(ROOT, "lyra_b200", "csrc"),
+                           "-Wno-unknown-pragmas", os.path.join(ROOT, "tests", "cpp", "umma_probe.cu"), os.path.join(EMU_DIR, "cuda_emu.cc"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.count("MATCH") == 2 and "MISMATCH" not in out.stdout, out.stdout + out.stderr
