@@ -235,7 +235,11 @@ static inline void lyra_umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t des
 static inline void lyra_umma_commit(LyraMbar* b) { lyra_mbar_arrive(b); }
 // 32x32b shape: lane i of the warp reads TMEM lane (address lane) + i, 8 consecutive columns
 static inline void lyra_tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  const int lane = (int)(threadIdx.x & 31);
+  const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+  if ((taddr >> 16) != (uint32_t)(32 * (warp % 4))) {      // hardware rule: warp w of a warpgroup reaches TMEM lanes 32 (w % 4) .. + 31 only
+    std::fprintf(stderr, "cuda_emu: warp %d may not read TMEM lanes starting at %u\n", warp, taddr >> 16);
+    std::abort();
+  }
   for (int j = 0; j < 8; ++j) v[j] = *lyra_emu_tmem(taddr, lane, j);
 }
 #elif defined(__CUDACC__)
