@@ -68,7 +68,7 @@ static inline void lyra_mbar_wait(LyraMbar* b, unsigned parity) {
 }
 // one function-local shared object per kernel (the emulator backs them all with the same per-block scratch area)
 #define LYRA_STATIC_SMEM(type, name, count) \
-  static_assert(sizeof(type) * (count) <= 512, "emulated static shared memory is 512 bytes"); \
+  static_assert(sizeof(type) * (count) <= 448, "emulated static shared memory: 448 bytes for objects + 64 for named barriers"); \
   type* name = reinterpret_cast<type*>(cuda_emu::g_blk->static_smem)
 #elif defined(__CUDACC__)
 __device__ __forceinline__ unsigned lyra_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -242,6 +242,78 @@ static inline void lyra_tmem_ld8(uint32_t taddr, float (&v)[8]) {
   }
   for (int j = 0; j < 8; ++j) v[j] = *lyra_emu_tmem(taddr, lane, j);
 }
+
+// ---- additions for the product's UMMA kernels: A operand in TMEM, kind::i8, tcgen05.st, wide tcgen05.ld ----
+static inline uint32_t* lyra_emu_tmem_u32(uint32_t taddr, int lane_add, int col_add) { return reinterpret_cast<uint32_t*>(lyra_emu_tmem(taddr, lane_add, col_add)); }
+static inline void lyra_emu_check_lane_window(uint32_t taddr) {
+  const int warp = (int)(threadIdx.x >> 5);
+  if ((taddr >> 16) != (uint32_t)(32 * (warp % 4))) {
+    std::fprintf(stderr, "cuda_emu: warp %d may not access TMEM lanes starting at %u\n", warp, taddr >> 16);
+    std::abort();
+  }
+}
+// D[M x N] (+)= A[M x 8] * B[N x 8]^T with A in TMEM: row r of A is TMEM lane r, element k is column (address column) + k
+static inline void lyra_umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+  const char* base = cuda_emu::g_blk->smem;
+  auto belem = [&](int row, int k) {
+    const uint32_t start = (uint32_t)(desc_b & 0x3FFF) << 4, lbo = (uint32_t)((desc_b >> 16) & 0x3FFF) << 4, sbo = (uint32_t)((desc_b >> 32) & 0x3FFF) << 4;
+    uint32_t bits;
+    std::memcpy(&bits, base + start + (uint32_t)(k / 4) * lbo + (uint32_t)(row / 8) * sbo + (uint32_t)(row % 8) * 16 + (uint32_t)(k % 4) * 4, 4);
+    return (double)lyra_emu_tf32(bits);
+  };
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double acc = accumulate ? (double)*lyra_emu_tmem(tmem_d, m, n) : 0.0;
+      for (int k = 0; k < 8; ++k) acc += (double)lyra_emu_tf32(*lyra_emu_tmem_u32(tmem_a, m, k)) * belem(n, k);
+      *lyra_emu_tmem(tmem_d, m, n) = (float)acc;
+    }
+}
+// kind::i8: D (s32) [M x N] (+)= A (s8) [M x 32] * B (s8) [N x 32]^T; K-major no-swizzle operands are 8-row x 16-byte core
+// matrices: element (row, k) at start + (k / 16) * LBO + (row / 8) * SBO + (row % 8) * 16 + k % 16 bytes
+__host__ __device__ inline uint32_t lyra_umma_idesc_i8(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D = s32, A = B = s8
+}
+static inline int lyra_emu_i8_elem(uint64_t d, int row, int k) {
+  const char* base = cuda_emu::g_blk->smem;
+  const uint32_t start = (uint32_t)(d & 0x3FFF) << 4, lbo = (uint32_t)((d >> 16) & 0x3FFF) << 4, sbo = (uint32_t)((d >> 32) & 0x3FFF) << 4;
+  return (int)*reinterpret_cast<const int8_t*>(base + start + (uint32_t)(k / 16) * lbo + (uint32_t)(row / 8) * sbo + (uint32_t)(row % 8) * 16 + (uint32_t)(k % 16));
+}
+static inline void lyra_umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      int32_t* d = reinterpret_cast<int32_t*>(lyra_emu_tmem(tmem_d, m, n));
+      int acc = accumulate ? *d : 0;
+      for (int k = 0; k < 32; ++k) acc += lyra_emu_i8_elem(desc_a, m, k) * lyra_emu_i8_elem(desc_b, n, k);
+      *d = acc;
+    }
+}
+// A (s8) in TMEM: row r is lane r, 4 consecutive k per 32-bit column (little endian), 8 columns per MMA
+static inline void lyra_umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      int32_t* d = reinterpret_cast<int32_t*>(lyra_emu_tmem(tmem_d, m, n));
+      int acc = accumulate ? *d : 0;
+      for (int k = 0; k < 32; ++k) acc += (int)(int8_t)((*lyra_emu_tmem_u32(tmem_a, m, k / 4) >> (8 * (k % 4))) & 0xff) * lyra_emu_i8_elem(desc_b, n, k);
+      *d = acc;
+    }
+}
+template <int NC>
+static inline void lyra_tmem_ld(uint32_t taddr, uint32_t (&v)[NC]) {
+  lyra_emu_check_lane_window(taddr);
+  const int lane = (int)(threadIdx.x & 31);
+  for (int j = 0; j < NC; ++j) v[j] = *lyra_emu_tmem_u32(taddr, lane, j);
+}
+template <int NC>
+static inline void lyra_tmem_st(uint32_t taddr, const uint32_t (&v)[NC]) {
+  lyra_emu_check_lane_window(taddr);
+  const int lane = (int)(threadIdx.x & 31);
+  for (int j = 0; j < NC; ++j) *lyra_emu_tmem_u32(taddr, lane, j) = v[j];
+}
+static inline void lyra_tmem_wait_ld() {}
+static inline void lyra_tmem_wait_st() {}
 #elif defined(__CUDACC__)
 __device__ __forceinline__ uint64_t lyra_umma_desc(const void* smem, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((lyra_smem_u32(smem) >> 4) & 0x3FFF) | (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16 |
@@ -272,4 +344,70 @@ __device__ __forceinline__ void lyra_tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
 }
+
+__host__ __device__ inline uint32_t lyra_umma_idesc_i8(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D = s32, A = B = s8
+}
+__device__ __forceinline__ void lyra_umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void lyra_umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void lyra_umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+// 32x32b shape, NC consecutive columns: lane i of the warp accesses TMEM lane (address lane) + i.  The loaded registers are valid
+// after lyra_tmem_wait_ld(); stored data is visible to later MMAs after lyra_tmem_wait_st() (+ the usual fences).
+template <int NC> __device__ __forceinline__ void lyra_tmem_ld(uint32_t taddr, uint32_t (&v)[NC]);
+template <> __device__ __forceinline__ void lyra_tmem_ld<8>(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void lyra_tmem_ld<16>(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
+}
+template <int NC> __device__ __forceinline__ void lyra_tmem_st(uint32_t taddr, const uint32_t (&v)[NC]);
+template <> __device__ __forceinline__ void lyra_tmem_st<8>(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+template <> __device__ __forceinline__ void lyra_tmem_st<16>(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void lyra_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void lyra_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+#endif
+
+// ---- bulk asynchronous store shared -> global (TMA, cp.async.bulk.global.shared::cta) and named barriers for warp subsets.
+//      Stores are grouped with lyra_bulk_commit(); lyra_bulk_wait_read() returns once the shared-memory source of every committed
+//      group may be overwritten, lyra_bulk_wait_all() once the writes themselves are complete.  One thread issues and waits.
+#if defined(LYRA_EMU)
+static inline void lyra_bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) { std::memcpy(gmem_dst, smem_src, bytes); }
+static inline void lyra_bulk_commit() {}
+static inline void lyra_bulk_wait_read() {}
+static inline void lyra_bulk_wait_all() {}
+// barrier `id` (1..15) over `nthreads` threads (a multiple of 32): every participating thread calls it
+static inline void lyra_named_bar_sync(int id, int nthreads) {
+  cuda_emu::BlockState* b = cuda_emu::g_blk;
+  unsigned* st = reinterpret_cast<unsigned*>(b->static_smem + 448) + 2 * (id & 7);     // {arrived, generation}; ids are used modulo 8 here
+  const unsigned gen = st[1];
+  if (++st[0] == (unsigned)nthreads) { st[0] = 0; st[1] = gen + 1; }
+  while (st[1] == gen) cuda_emu::yield();
+}
+#elif defined(__CUDACC__)
+__device__ __forceinline__ void lyra_bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(lyra_smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lyra_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void lyra_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void lyra_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void lyra_named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory"); }
 #endif

@@ -27,6 +27,17 @@ std::string g_create_error;
     }                                                                                   \
   } while (0)
 
+// inside a loop of a forked region: record the error and leave the loop (the region is joined afterwards)
+#define CUB(call)                                                                       \
+  {                                                                                     \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+      rc = LYRA_B200_ENODEV;                                                            \
+      break;                                                                            \
+    }                                                                                   \
+  }
+
 }  // namespace
 
 struct lyra_b200_ctx {
@@ -58,7 +69,16 @@ struct lyra_b200_ctx {
   // tile map
   int* d_tile_list = nullptr;
   int* d_slot_of = nullptr;
-  std::vector<int> h_tile_list, h_slot_of;
+  // host images of the map, pinned and double-buffered: a sparse call fills the buffer the previous call did not use and
+  // copies it asynchronously (no host synchronisation on the call path); ev_map[b] marks "the copy out of buffer b is done"
+  int* h_tile_list[2] = {nullptr, nullptr};
+  int* h_slot_of[2] = {nullptr, nullptr};
+  cudaEvent_t ev_map[2] = {nullptr, nullptr};
+  bool map_pending[2] = {false, false};
+  int map_buf = 0;
+  std::vector<uint32_t> tile_gen;       // tile_gen[t] == map_gen: tile t is already in this call's tile list
+  uint32_t map_gen = 0;
+  std::vector<int> touched[2];          // slots of h_slot_of[b] that are not -1 (cleared lazily instead of an O(max_streams) fill)
   int map_dense_n = -1;     // >= 0: the device map currently describes streams 0..n-1
   int active_tiles = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -139,24 +159,40 @@ bool BitsOk(lyra_b200_ctx* ctx, int num_bits) {
   return true;
 }
 
-// Build / upload the (tile list, slot-of-stream) map for this call.
+// Build / upload the (tile list, slot-of-stream) map for this call.  The copies are stream-ordered behind the previous call's
+// kernels (sub-batch streams are joined into ctx->stream at the end of every call), and the pinned host image is
+// double-buffered, so a server whose active set changes every tick never waits for the GPU here.
 int PrepareMap(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
   if (ids == nullptr && ctx->map_dense_n == n) return LYRA_B200_OK;
-  std::fill(ctx->h_slot_of.begin(), ctx->h_slot_of.end(), -1);
-  ctx->h_tile_list.clear();
-  std::vector<char> tile_used((size_t)ctx->ntiles, 0);
+  const int b = ctx->map_buf;
+  if (ctx->map_pending[b]) { CU(cudaEventSynchronize(ctx->ev_map[b])); ctx->map_pending[b] = false; }   // two calls ago: long done
+  int* slot_of = ctx->h_slot_of[b];
+  int* tile_list = ctx->h_tile_list[b];
+  for (int id : ctx->touched[b]) slot_of[id] = -1;
+  ctx->touched[b].clear();
+  int ntl = 0;
+  int rc = LYRA_B200_OK;
   for (int k = 0; k < n; ++k) {
     const int id = ids ? ids[k] : k;
-    if (id < 0 || id >= ctx->max_streams) { ctx->err = "stream id out of range"; ctx->map_dense_n = -1; return LYRA_B200_EINVAL; }
-    if (ctx->h_slot_of[(size_t)id] != -1) { ctx->err = "duplicate stream id in one call"; ctx->map_dense_n = -1; return LYRA_B200_EINVAL; }
-    ctx->h_slot_of[(size_t)id] = k;
-    if (!tile_used[(size_t)(id / ctx->S)]) { tile_used[(size_t)(id / ctx->S)] = 1; ctx->h_tile_list.push_back(id / ctx->S); }
+    if (id < 0 || id >= ctx->max_streams) { ctx->err = "stream id out of range"; rc = LYRA_B200_EINVAL; break; }
+    if (slot_of[id] != -1) { ctx->err = "duplicate stream id in one call"; rc = LYRA_B200_EINVAL; break; }
+    slot_of[id] = k;
+    ctx->touched[b].push_back(id);
   }
-  ctx->active_tiles = (int)ctx->h_tile_list.size();
-  CU(cudaMemcpyAsync(ctx->d_slot_of, ctx->h_slot_of.data(), sizeof(int) * (size_t)ctx->padded, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_tile_list, ctx->h_tile_list.data(), sizeof(int) * (size_t)ctx->active_tiles, cudaMemcpyHostToDevice, ctx->stream));
-  CU(SyncStream(ctx));   // the host vectors are reused by the next call
+  if (rc) { ctx->map_dense_n = -1; return rc; }
+  // tiles in order of first appearance
+  if (++ctx->map_gen == 0) { std::fill(ctx->tile_gen.begin(), ctx->tile_gen.end(), 0u); ctx->map_gen = 1; }
+  for (int k = 0; k < n; ++k) {
+    const int t = (ids ? ids[k] : k) / ctx->S;
+    if (ctx->tile_gen[(size_t)t] != ctx->map_gen) { ctx->tile_gen[(size_t)t] = ctx->map_gen; tile_list[ntl++] = t; }
+  }
+  ctx->active_tiles = ntl;
+  CU(cudaMemcpyAsync(ctx->d_slot_of, slot_of, sizeof(int) * (size_t)ctx->padded, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_tile_list, tile_list, sizeof(int) * (size_t)ntl, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaEventRecord(ctx->ev_map[b], ctx->stream));
+  ctx->map_pending[b] = true;
+  ctx->map_buf = b ^ 1;
   ctx->map_dense_n = ids ? -1 : n;
   return LYRA_B200_OK;
 }
@@ -259,6 +295,17 @@ int Join(lyra_b200_ctx* ctx, int nparts) {
   }
   return LYRA_B200_OK;
 }
+// End of a forked region: the sub-batch streams are ALWAYS joined back, also when a copy or launch inside the region failed
+// (`rc` != 0) - otherwise the next call would race leftover work on them.  After a failure the stream is drained as well and
+// the caller gets the first error; per-stream state of the sub-batches that did run has advanced (the call is not atomic).
+int JoinAfter(lyra_b200_ctx* ctx, int nparts, int rc) {
+  if (!rc) return Join(ctx, nparts);
+  const std::string first = ctx->err;
+  Join(ctx, nparts);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->err = first;
+  return rc;
+}
 
 // log-mel of this hop (the estimator's own extractor, bank 2) + the estimator recurrences for slots
 // [slot0, slot0 + count) on stream `st`; all arrays are indexed by slot, n = total slots of the call
@@ -285,17 +332,18 @@ int RunEncode(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uin
   const int np = SplitParts(ctx, n, parts);
   const size_t pb = (size_t)PacketBytes(num_bits);
   int rc = Fork(ctx, np);
+  if (rc) return rc;
   for (int i = 0; i < np && !rc; ++i) {
     const Part& p = parts[i];
     if (h_pcm)
-      CU(cudaMemcpyAsync(ctx->d_pcm + (size_t)p.slot0 * 320, h_pcm + (size_t)p.slot0 * 320, sizeof(int16_t) * 320 * (size_t)p.nslots,
-                         cudaMemcpyHostToDevice, p.st));
+      CUB(cudaMemcpyAsync(ctx->d_pcm + (size_t)p.slot0 * 320, h_pcm + (size_t)p.slot0 * 320, sizeof(int16_t) * 320 * (size_t)p.nslots,
+                          cudaMemcpyHostToDevice, p.st));
     if ((rc = LaunchEncoderNets(ctx, p, d_pcm, ctx->d_features))) break;
     if ((rc = LaunchQuantize(ctx, p, ctx->d_features, num_bits, d_packets, nullptr))) break;
     if (h_packets)
-      CU(cudaMemcpyAsync(h_packets + (size_t)p.slot0 * pb, d_packets + (size_t)p.slot0 * pb, pb * (size_t)p.nslots, cudaMemcpyDeviceToHost, p.st));
+      CUB(cudaMemcpyAsync(h_packets + (size_t)p.slot0 * pb, d_packets + (size_t)p.slot0 * pb, pb * (size_t)p.nslots, cudaMemcpyDeviceToHost, p.st));
   }
-  return rc ? rc : Join(ctx, np);
+  return JoinAfter(ctx, np, rc);
 }
 
 // track_noise: every sub-batch also feeds its decoded hops to the per-stream noise estimators (received streams only),
@@ -307,23 +355,24 @@ int RunDecode(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t
   const int np = SplitParts(ctx, n, parts);
   const size_t pb = (size_t)PacketBytes(num_bits);
   int rc = Fork(ctx, np);
+  if (rc) return rc;
   for (int i = 0; i < np && !rc; ++i) {
     const Part& p = parts[i];
     if (h_packets)
-      CU(cudaMemcpyAsync(ctx->d_packets + (size_t)p.slot0 * pb, h_packets + (size_t)p.slot0 * pb, pb * (size_t)p.nslots, cudaMemcpyHostToDevice, p.st));
+      CUB(cudaMemcpyAsync(ctx->d_packets + (size_t)p.slot0 * pb, h_packets + (size_t)p.slot0 * pb, pb * (size_t)p.nslots, cudaMemcpyHostToDevice, p.st));
     if (h_received)
-      CU(cudaMemcpyAsync(ctx->d_received + p.slot0, h_received + p.slot0, (size_t)p.nslots, cudaMemcpyHostToDevice, p.st));
+      CUB(cudaMemcpyAsync(ctx->d_received + p.slot0, h_received + p.slot0, (size_t)p.nslots, cudaMemcpyHostToDevice, p.st));
     if ((rc = LaunchDequantize(ctx, p, d_packets, d_received, num_bits, ctx->d_features))) break;
     if ((rc = LaunchDecoderNets(ctx, p, ctx->d_features, d_pcm))) break;
     if (track_noise) {
       if ((rc = LaunchNoiseUpdate(ctx, p.st, d_ids, p.slot0, p.nslots, n, d_pcm, d_received, d_is_noise, nullptr))) break;
-      if (h_is_noise) CU(cudaMemcpyAsync(h_is_noise + p.slot0, d_is_noise + p.slot0, (size_t)p.nslots, cudaMemcpyDeviceToHost, p.st));
+      if (h_is_noise) CUB(cudaMemcpyAsync(h_is_noise + p.slot0, d_is_noise + p.slot0, (size_t)p.nslots, cudaMemcpyDeviceToHost, p.st));
     }
     if (h_pcm)
-      CU(cudaMemcpyAsync(h_pcm + (size_t)p.slot0 * 320, d_pcm + (size_t)p.slot0 * 320, sizeof(int16_t) * 320 * (size_t)p.nslots,
-                         cudaMemcpyDeviceToHost, p.st));
+      CUB(cudaMemcpyAsync(h_pcm + (size_t)p.slot0 * 320, d_pcm + (size_t)p.slot0 * 320, sizeof(int16_t) * 320 * (size_t)p.nslots,
+                          cudaMemcpyDeviceToHost, p.st));
   }
-  return rc ? rc : Join(ctx, np);
+  return JoinAfter(ctx, np, rc);
 }
 
 template <int kS>
@@ -454,7 +503,7 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
   const int kS = ctx->S;
   ctx->ntiles = (max_streams + kS - 1) / kS;
   ctx->padded = ctx->ntiles * kS;
-  ctx->h_slot_of.assign((size_t)ctx->padded, -1);
+  ctx->tile_gen.assign((size_t)ctx->ntiles, 0u);
   const size_t P = (size_t)ctx->padded;
   bool ok = cudaSetDevice(device) == cudaSuccess;
   ok = ok && cudaStreamCreate(&ctx->own_stream) == cudaSuccess;
@@ -504,6 +553,12 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
   ok = ok && DevAlloc(&ctx->d_ids, P) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_tile_list, (size_t)ctx->ntiles) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_slot_of, P) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b) {
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_slot_of[b]), sizeof(int) * P) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_tile_list[b]), sizeof(int) * (size_t)ctx->ntiles) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_map[b], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) for (size_t i = 0; i < P; ++i) ctx->h_slot_of[b][i] = -1;
+  }
   if (ok) ok = kS == 16 ? SetSmemLimits<16>() : SetSmemLimits<8>();
   if (!ok) {
     g_create_error = std::string("CUDA allocation / setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -529,6 +584,11 @@ void lyra_b200_destroy(lyra_b200_ctx* ctx) {
   cudaFree(ctx->d_noise); cudaFree(ctx->d_noise_est); cudaFree(ctx->d_is_noise);
   cudaFree(ctx->d_pcm); cudaFree(ctx->d_packets); cudaFree(ctx->d_received); cudaFree(ctx->d_features);
   cudaFree(ctx->d_melout); cudaFree(ctx->d_indices); cudaFree(ctx->d_ids); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_slot_of);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->h_slot_of[b]) cudaFreeHost(ctx->h_slot_of[b]);
+    if (ctx->h_tile_list[b]) cudaFreeHost(ctx->h_tile_list[b]);
+    if (ctx->ev_map[b]) cudaEventDestroy(ctx->ev_map[b]);
+  }
   for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k)
     for (auto& ev : ctx->prof_events[k]) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);

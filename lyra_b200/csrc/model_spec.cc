@@ -110,17 +110,19 @@ struct Net {
       if (c == kConv2D || c == kDepthwiseConv2D || c == kTransposeConv) convs.push_back((int)i);
     }
   }
-  const TflOp& op(int i) const { return g.ops[i]; }
-  const TflTensor& T(int i) const { return g.tensors[i]; }
-  const TflOp& conv(int i) const { return g.ops[convs.at(i)]; }
+  const TflOp& op(int i) const { SPEC_CHECK(i >= 0 && (size_t)i < g.ops.size(), "operator index out of range"); return g.ops[(size_t)i]; }
+  const TflTensor& T(int i) const { SPEC_CHECK(i >= 0 && (size_t)i < g.tensors.size(), "tensor index out of range"); return g.tensors[(size_t)i]; }
+  const TflOp& conv(int i) const { return op(convs.at((size_t)i)); }
+  static int In(const TflOp& o, size_t i) { SPEC_CHECK(i < o.inputs.size(), "operator has too few inputs"); return o.inputs[i]; }
+  static int Out(const TflOp& o, size_t i) { SPEC_CHECK(i < o.outputs.size(), "operator has too few outputs"); return o.outputs[i]; }
 
   // tensor roles of a conv-like op
-  int in_tensor(const TflOp& o) const { return o.code == kTransposeConv ? o.inputs[2] : o.inputs[0]; }
-  int w_tensor(const TflOp& o) const { return o.inputs[1]; }
-  int b_tensor(const TflOp& o) const { return o.code == kTransposeConv ? o.inputs[3] : o.inputs[2]; }
+  int in_tensor(const TflOp& o) const { return o.code == kTransposeConv ? In(o, 2) : In(o, 0); }
+  int w_tensor(const TflOp& o) const { return In(o, 1); }
+  int b_tensor(const TflOp& o) const { return o.code == kTransposeConv ? In(o, 3) : In(o, 2); }
 
   int next(int tensor, int code) const { return g.sole_consumer(tensor, code); }
-  int out0(int opi) const { return g.ops[opi].outputs[0]; }
+  int out0(int opi) const { return Out(op(opi), 0); }
 
   void expect_conv(const TflOp& o, int code, DType wt, int cout, int k, int cing, int stride, int dil = 1) const {
     const TflTensor& w = T(w_tensor(o));
@@ -143,15 +145,17 @@ struct Net {
   GemmF32 PackConvF32(const TflOp& o) const {
     const TflTensor& w = T(w_tensor(o));
     const TflTensor& b = T(b_tensor(o));
+    SPEC_CHECK(w.shape.size() == 4 && w.type == DType::F32 && b.type == DType::F32, "conv: filter rank / type");
     const int Cout = w.shape[0], K = w.shape[1], CinG = w.shape[3];
+    SPEC_CHECK(Cout > 0 && K > 0 && CinG > 0 && w.shape[2] == 1, "conv: filter shape");
     std::vector<float> wt((size_t)K * CinG * Cout);
     const float* src = w.as<float>();
     for (int co = 0; co < Cout; ++co)
       for (int k = 0; k < K; ++k)
         for (int ci = 0; ci < CinG; ++ci)
           wt[((size_t)k * CinG + ci) * Cout + co] = src[((size_t)co * K + k) * CinG + ci];
-    SPEC_CHECK((int)b.count() == Cout && b.data, "conv bias");
-    std::vector<float> bias(b.as<float>(), b.as<float>() + Cout);
+    SPEC_CHECK((int)b.count() == Cout, "conv bias");
+    std::vector<float> bias(b.as<float>((size_t)Cout), b.as<float>((size_t)Cout) + Cout);
     const uint32_t wf = pack_tc && (K * CinG) % 8 == 0 && Cout % 8 == 0 ? Append(blob, PackMmaBTf32(wt, K * CinG, Cout)) : 0u;
     return GemmF32{Append(blob, wt), Append(blob, bias), wf};
   }
@@ -160,8 +164,9 @@ struct Net {
   GemmF32 PackTconvF32(const TflOp& o, int stride) const {
     const TflTensor& w = T(w_tensor(o));
     const TflTensor& b = T(b_tensor(o));
+    SPEC_CHECK(w.shape.size() == 4 && w.type == DType::F32 && b.type == DType::F32, "transposed conv: filter rank / type");
     const int Cout = w.shape[0], K = w.shape[1], Cin = w.shape[3];
-    SPEC_CHECK(K % stride == 0, "transposed conv: K must be a multiple of the stride");
+    SPEC_CHECK(Cout > 0 && K > 0 && Cin > 0 && w.shape[2] == 1 && K % stride == 0, "transposed conv: K must be a multiple of the stride");
     const int J = K / stride, N = stride * Cout;
     std::vector<float> wt((size_t)J * Cin * N);
     const float* src = w.as<float>();
@@ -170,7 +175,7 @@ struct Net {
         for (int r = 0; r < stride; ++r)
           for (int co = 0; co < Cout; ++co)
             wt[((size_t)j * Cin + ci) * N + (size_t)r * Cout + co] = src[((size_t)co * K + (r + stride * (J - 1 - j))) * Cin + ci];
-    std::vector<float> bias(b.as<float>(), b.as<float>() + Cout);
+    std::vector<float> bias(b.as<float>((size_t)Cout), b.as<float>((size_t)Cout) + Cout);
     const uint32_t wf = pack_tc && (J * Cin) % 8 == 0 && N % 8 == 0 ? Append(blob, PackMmaBTf32(wt, J * Cin, N)) : 0u;
     return GemmF32{Append(blob, wt), Append(blob, bias), wf};
   }
@@ -193,14 +198,16 @@ struct Net {
     const TflTensor& w = T(w_tensor(o));
     const TflTensor& b = T(b_tensor(o));
     const TflTensor& x = T(in_tensor(o));
-    const TflTensor& y = T(o.outputs[0]);
+    const TflTensor& y = T(Out(o, 0));
+    SPEC_CHECK(w.shape.size() == 4 && w.type == DType::I8 && b.type == DType::I32, "int8 conv: filter rank / type");
     const int Cout = w.shape[0], K = w.shape[1], CinG = w.shape[3];
-    SPEC_CHECK(CinG % 32 == 0, "int8 conv: CinG must be a multiple of 32");
+    SPEC_CHECK(Cout > 0 && K > 0 && w.shape[2] == 1 && CinG > 0 && CinG % 32 == 0, "int8 conv: CinG must be a multiple of 32");
     std::vector<int8_t> dense((size_t)K * CinG * Cout);
     std::vector<int32_t> bias(Cout), mult, shift;
     const int8_t* src = w.as<int8_t>();
-    const int32_t* bsrc = b.as<int32_t>();
+    const int32_t* bsrc = b.as<int32_t>((size_t)Cout);
     const int in_zp = x.zp0();
+    SPEC_CHECK(w.scale.size() == 1 || w.scale.size() == (size_t)Cout, "int8 conv: per-channel scale count");
     for (int co = 0; co < Cout; ++co) {
       int64_t wsum = 0;
       for (int k = 0; k < K; ++k)
@@ -218,6 +225,7 @@ struct Net {
   DwF32 PackDwF32(const TflOp& o) const {
     const TflTensor& w = T(w_tensor(o));
     const TflTensor& b = T(b_tensor(o));
+    SPEC_CHECK(w.shape.size() == 4 && w.type == DType::F32 && b.type == DType::F32 && (int)b.count() == w.shape[3], "depthwise: filter rank / type / bias");
     std::vector<float> wt(w.as<float>(), w.as<float>() + w.count());
     std::vector<float> bias(b.as<float>(), b.as<float>() + b.count());
     return DwF32{Append(blob, wt), Append(blob, bias)};
@@ -227,14 +235,19 @@ struct Net {
     const TflTensor& w = T(w_tensor(o));
     const TflTensor& b = T(b_tensor(o));
     const TflTensor& x = T(in_tensor(o));
-    const TflTensor& y = T(o.outputs[0]);
+    const TflTensor& y = T(Out(o, 0));
+    SPEC_CHECK(w.shape.size() == 4 && w.type == DType::I8 && b.type == DType::I32, "int8 depthwise: filter rank / type");
     const int K = w.shape[1], C = w.shape[3];
+    SPEC_CHECK(K > 0 && C > 0 && w.shape[0] == 1 && w.shape[2] == 1, "int8 depthwise: filter shape");
+    SPEC_CHECK(w.scale.size() == 1 || w.scale.size() == (size_t)C, "int8 depthwise: per-channel scale count");
     std::vector<int32_t> wt((size_t)K * C), bias(C), mult, shift;
     const int in_zp = x.zp0();
+    const int8_t* wsrc = w.as<int8_t>((size_t)K * C);
+    const int32_t* bsrc = b.as<int32_t>((size_t)C);
     for (int c = 0; c < C; ++c) {
       int64_t wsum = 0;
-      for (int k = 0; k < K; ++k) { wt[(size_t)k * C + c] = w.as<int8_t>()[(size_t)k * C + c]; wsum += wt[(size_t)k * C + c]; }
-      bias[c] = (int32_t)(b.as<int32_t>()[c] - (int64_t)in_zp * wsum);
+      for (int k = 0; k < K; ++k) { wt[(size_t)k * C + c] = wsrc[(size_t)k * C + c]; wsum += wt[(size_t)k * C + c]; }
+      bias[c] = (int32_t)(bsrc[c] - (int64_t)in_zp * wsum);
     }
     RequantArrays(x, w, y, C, 1, &mult, &shift);
     return DwI8{Append(blob, wt), Append(blob, bias), Append(blob, mult), Append(blob, shift), y.zp0(), in_zp};
@@ -244,10 +257,10 @@ struct Net {
 
   // int8 LEAKY_RELU as a 256-entry table (kernels/activations.cc LeakyReluPrepare + QuantizeLeakyRelu)
   LReluQ PackLRelu(int opi) const {
-    const TflOp& o = g.ops[opi];
+    const TflOp& o = op(opi);
     SPEC_CHECK(o.code == kLeakyRelu, "expected LEAKY_RELU");
-    const TflTensor& x = T(o.inputs[0]);
-    const TflTensor& y = T(o.outputs[0]);
+    const TflTensor& x = T(In(o, 0));
+    const TflTensor& y = T(Out(o, 0));
     SPEC_CHECK(x.type == DType::I8 && y.type == DType::I8, "expected int8 LEAKY_RELU");
     const float alpha = m.OptF32(o, 0, 0.0f);
     const double alpha_mult = (double)(x.scale0() * alpha / y.scale0());   // float expression, widened
@@ -266,11 +279,11 @@ struct Net {
 
   // int8 ADD: per-input scaled terms as tables, final rescale on device (kernels/add.cc + integer_ops/add.h)
   AddQ PackAdd(int opi) const {
-    const TflOp& o = g.ops[opi];
+    const TflOp& o = op(opi);
     SPEC_CHECK(o.code == kAdd && m.OptI8(o, 0, 0) == 0, "expected ADD without activation");
-    const TflTensor& a = T(o.inputs[0]);
-    const TflTensor& b = T(o.inputs[1]);
-    const TflTensor& y = T(o.outputs[0]);
+    const TflTensor& a = T(In(o, 0));
+    const TflTensor& b = T(In(o, 1));
+    const TflTensor& y = T(Out(o, 0));
     SPEC_CHECK(a.type == DType::I8 && b.type == DType::I8, "expected int8 ADD");
     const int left_shift = 20;
     const float maxs = a.scale0() > b.scale0() ? a.scale0() : b.scale0();
@@ -303,12 +316,12 @@ struct Net {
     ResI8 r;
     r.dw = PackDwI8(conv(first_conv));
     r.pw1 = PackConvI8(conv(first_conv + 1));
-    const int lr1 = next(conv(first_conv + 1).outputs[0], kLeakyRelu);
+    const int lr1 = next(Out(conv(first_conv + 1), 0), kLeakyRelu);
     r.lr1 = PackLRelu(lr1);
     SPEC_CHECK(in_tensor(conv(first_conv + 2)) == out0(lr1), "res-unit wiring (pw2 input)");
     r.pw2 = PackConvI8(conv(first_conv + 2));
-    const int add = next(conv(first_conv + 2).outputs[0], kAdd);
-    SPEC_CHECK(g.ops[add].inputs[0] == conv(first_conv + 2).outputs[0], "res-unit ADD operand order");
+    const int add = next(Out(conv(first_conv + 2), 0), kAdd);
+    SPEC_CHECK(In(op(add), 0) == Out(conv(first_conv + 2), 0), "res-unit ADD operand order");
     r.add = PackAdd(add);
     r.lr2 = PackLRelu(next(out0(add), kLeakyRelu));
     return r;
@@ -337,16 +350,16 @@ EncoderParams BuildEncoder(const TflModel& m, std::vector<uint8_t>* blob) {
   n.expect_conv(n.conv(23), kConv2D, DType::I8, 256, 1, 64, 1);
   p.m_dw = n.PackDwF32(n.conv(21));
   p.m_pw1 = n.PackConvF32(n.conv(22));
-  const int q1 = n.next(n.conv(22).outputs[0], kQuantize);
+  const int q1 = n.next(Net::Out(n.conv(22), 0), kQuantize);
   p.m_q1 = n.QP(n.out0(q1));
   const int lr1 = n.next(n.out0(q1), kLeakyRelu);
   p.m_lr1 = n.PackLRelu(lr1);
   SPEC_CHECK(n.in_tensor(n.conv(23)) == n.out0(lr1), "encoder mixed unit wiring");
   p.m_pw2 = n.PackConvI8(n.conv(23));
-  const int dq = n.next(n.conv(23).outputs[0], kDequantize);
-  p.m_dq = n.QP(n.conv(23).outputs[0]);
+  const int dq = n.next(Net::Out(n.conv(23), 0), kDequantize);
+  p.m_dq = n.QP(Net::Out(n.conv(23), 0));
   const int addf = n.next(n.out0(dq), kAdd);
-  SPEC_CHECK(n.g.ops[addf].inputs[1] == n.conv(20).outputs[0], "encoder mixed unit residual");
+  SPEC_CHECK(Net::In(n.op(addf), 1) == Net::Out(n.conv(20), 0), "encoder mixed unit residual");
   const int q2 = n.next(n.out0(addf), kQuantize);
   p.m_q2 = n.QP(n.out0(q2));
   // the quantised sum feeds both the next unit's ADD and a LEAKY_RELU
@@ -355,11 +368,11 @@ EncoderParams BuildEncoder(const TflModel& m, std::vector<uint8_t>* blob) {
   p.q[1] = n.PackResI8(27, 256, 9);
   n.expect_conv(n.conv(30), kConv2D, DType::I8, 512, 4, 64, 2);
   p.down2 = n.PackConvI8(n.conv(30));
-  p.down2_lr = n.PackLRelu(n.next(n.conv(30).outputs[0], kLeakyRelu));
+  p.down2_lr = n.PackLRelu(n.next(Net::Out(n.conv(30), 0), kLeakyRelu));
   n.expect_conv(n.conv(31), kConv2D, DType::I8, 64, 3, 128, 1);
   p.bott = n.PackConvI8(n.conv(31));
-  p.out_dq = n.QP(n.conv(31).outputs[0]);
-  SPEC_CHECK(n.T(n.g.outputs[0]).count() == 64, "encoder output size");
+  p.out_dq = n.QP(Net::Out(n.conv(31), 0));
+  SPEC_CHECK(!n.g.outputs.empty() && n.T(n.g.outputs[0]).count() == 64, "encoder output size");
   p.zp_state[0] = p.q[0].dw.in_zp;
   p.zp_state[1] = p.q[1].dw.in_zp;
   p.zp_state[2] = p.down2.in_zp;
@@ -378,7 +391,7 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
   n.expect_conv(n.conv(0), kConv2D, DType::F32, 512, 3, 16, 1);
   p.bott = n.PackConvF32(n.conv(0));
   {
-    const int lr = n.next(n.conv(0).outputs[0], kLeakyRelu);
+    const int lr = n.next(Net::Out(n.conv(0), 0), kLeakyRelu);
     const int q = n.next(n.out0(lr), kQuantize);
     p.bott_q = n.QP(n.out0(q));
   }
@@ -397,10 +410,12 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
       const TflTensor& w = n.T(n.w_tensor(o));
       const TflTensor& b = n.T(n.b_tensor(o));
       const TflTensor& x = n.T(n.in_tensor(o));
-      const TflTensor& y = n.T(o.outputs[0]);
+      const TflTensor& y = n.T(Net::Out(o, 0));
       if (gi == 0) in_zp = x.zp0();
       SPEC_CHECK(x.zp0() == in_zp, "transposed conv bank: inputs must share quantisation");
-      const int8_t* src = w.as<int8_t>();
+      const int8_t* src = w.as<int8_t>((size_t)Cout * K * Cin);
+      const int32_t* bsrc = b.as<int32_t>((size_t)Cout);
+      SPEC_CHECK(w.scale.size() == 1 || w.scale.size() == (size_t)Cout, "transposed conv bank: per-channel scale count");
       for (int r = 0; r < stride; ++r)
         for (int co = 0; co < Cout; ++co) {
           const size_t col = (size_t)gi * NG + (size_t)r * Cout + co;
@@ -412,27 +427,27 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
               dense[((size_t)j * Cin + ci) * N + col] = v;
             }
           // rows outside the input are padded with the zero point, so the fold uses all J taps
-          bias[col] = (int32_t)(b.as<int32_t>()[co] - (int64_t)in_zp * wsum);
+          bias[col] = (int32_t)(bsrc[co] - (int64_t)in_zp * wsum);
           const double eff = (double)x.scale0() * (double)w.scale[w.scale.size() > 1 ? (size_t)co : 0] / (double)y.scale0();
           int32_t qm; int sh;
           QuantizeMultiplier(eff, &qm, &sh);
           mult[col] = qm;
           shift[col] = sh;
         }
-      const int dq = n.next(o.outputs[0], kDequantize);
-      up.dq[gi] = n.QP(o.outputs[0]);
+      const int dq = n.next(Net::Out(o, 0), kDequantize);
+      up.dq[gi] = n.QP(Net::Out(o, 0));
       up.out_zp[gi] = y.zp0();
       const int add = n.next(n.out0(dq), kAdd);
       // the tail slice of the sum has the f32 bias subtracted before it becomes the next overlap state
       int sub = -1;
       for (int c : n.g.consumers(n.out0(add)))
-        if (n.g.ops[c].code == kStridedSlice)
+        if (n.op(c).code == kStridedSlice)
           for (int c2 : n.g.consumers(n.out0(c)))
-            if (n.g.ops[c2].code == kSub) sub = c2;
+            if (n.op(c2).code == kSub) sub = c2;
       SPEC_CHECK(sub >= 0, "transposed conv: overlap SUB not found");
-      const TflTensor& bf = n.T(n.g.ops[sub].inputs[1]);
-      SPEC_CHECK(bf.data && bf.count() == 64 && bf.type == DType::F32, "transposed conv: f32 bias constant");
-      up.bias_f32[gi] = Append(blob, std::vector<float>(bf.as<float>(), bf.as<float>() + 64));
+      const TflTensor& bf = n.T(Net::In(n.op(sub), 1));
+      SPEC_CHECK(bf.count() == 64 && bf.type == DType::F32, "transposed conv: f32 bias constant");
+      up.bias_f32[gi] = Append(blob, std::vector<float>(bf.as<float>(64), bf.as<float>(64) + 64));
     }
     up.g = GemmI8{Append(blob, PackMmaB(dense, J * Cin, N)), Append(blob, bias), Append(blob, mult), Append(blob, shift), 0, in_zp};
     return up;
@@ -445,11 +460,11 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
   p.up0_q = n.QP(n.in_tensor(n.conv(5)));
   p.m_dw = n.PackDwI8(n.conv(5));
   p.m_pw1 = n.PackConvI8(n.conv(6));
-  p.m_lr1 = n.PackLRelu(n.next(n.conv(6).outputs[0], kLeakyRelu));
+  p.m_lr1 = n.PackLRelu(n.next(Net::Out(n.conv(6), 0), kLeakyRelu));
   p.m_pw2 = n.PackConvI8(n.conv(7));
   {
-    const int dq = n.next(n.conv(7).outputs[0], kDequantize);
-    p.m_dq = n.QP(n.conv(7).outputs[0]);
+    const int dq = n.next(Net::Out(n.conv(7), 0), kDequantize);
+    p.m_dq = n.QP(Net::Out(n.conv(7), 0));
     const int addf = n.next(n.out0(dq), kAdd);
     const int q2 = n.next(n.out0(addf), kQuantize);
     p.m_q2 = n.QP(n.out0(q2));
@@ -474,32 +489,41 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
 RvqParams BuildRvq(const TflModel& m, std::vector<uint8_t>* blob, int* bits_per_stage) {
   const int se = m.SignatureSubgraph("encode"), sd = m.SignatureSubgraph("decode");
   SPEC_CHECK(se >= 0 && sd >= 0, "quantizer: missing encode/decode signatures");
-  const TflSubgraph& ge = m.subgraphs()[se];
+  SPEC_CHECK((size_t)se < m.subgraphs().size() && (size_t)sd < m.subgraphs().size(), "quantizer: signature subgraph index");
+  const TflSubgraph& ge = m.subgraphs()[(size_t)se];
+  auto tensor_of = [](const TflSubgraph& g, int i) -> const TflTensor& {
+    SPEC_CHECK(i >= 0 && (size_t)i < g.tensors.size(), "quantizer: tensor index out of range");
+    return g.tensors[(size_t)i];
+  };
   std::vector<const float*> stage_cb;
   for (const TflOp& o : ge.ops)
     if (o.code == kSquaredDifference) {
-      const TflTensor& cb = ge.tensors[o.inputs[1]];
-      SPEC_CHECK(cb.data && cb.count() == 16 * 64 && cb.type == DType::F32, "quantizer: codebook shape");
-      stage_cb.push_back(cb.as<float>());
+      SPEC_CHECK(o.inputs.size() >= 2, "quantizer: SQUARED_DIFFERENCE operands");
+      const TflTensor& cb = tensor_of(ge, o.inputs[1]);
+      SPEC_CHECK(cb.count() == 16 * 64 && cb.type == DType::F32, "quantizer: codebook shape");
+      stage_cb.push_back(cb.as<float>(16 * 64));
     }
   SPEC_CHECK(stage_cb.size() == 46, "quantizer: expected 46 stages");
   *bits_per_stage = 0;
-  for (int o : ge.outputs)
-    if (ge.tensors[o].data && ge.tensors[o].count() == 1) *bits_per_stage = ge.tensors[o].as<int32_t>()[0];
+  for (int o : ge.outputs) {
+    const TflTensor& t = tensor_of(ge, o);
+    if (t.data && t.count() == 1 && t.type == DType::I32) *bits_per_stage = t.as<int32_t>(1)[0];
+  }
   SPEC_CHECK(*bits_per_stage == 4, "quantizer: expected 4 bits per stage");
   // the decode signature must use the same codebook for the same index slot
-  const TflSubgraph& gd = m.subgraphs()[sd];
+  const TflSubgraph& gd = m.subgraphs()[(size_t)sd];
   int checked = 0;
   for (const TflOp& o : gd.ops)
     if (o.code == kGather) {
+      SPEC_CHECK(o.inputs.size() >= 2, "quantizer: GATHER operands");
       const int sl = gd.producer(o.inputs[1]);
-      SPEC_CHECK(sl >= 0 && gd.ops[sl].code == kStridedSlice, "quantizer: decode GATHER index is not a slice");
-      const TflTensor& bg = gd.tensors[gd.ops[sl].inputs[1]];
-      SPEC_CHECK(bg.data, "quantizer: decode slice begin");
-      const int stage = bg.as<int32_t>()[0];
+      SPEC_CHECK(sl >= 0 && gd.ops[(size_t)sl].code == kStridedSlice && gd.ops[(size_t)sl].inputs.size() >= 2, "quantizer: decode GATHER index is not a slice");
+      const TflTensor& bg = tensor_of(gd, gd.ops[(size_t)sl].inputs[1]);
+      SPEC_CHECK(bg.type == DType::I32 && bg.count() >= 1, "quantizer: decode slice begin");
+      const int stage = bg.as<int32_t>(1)[0];
       SPEC_CHECK(stage >= 0 && stage < 46, "quantizer: decode stage index");
-      const TflTensor& cb = gd.tensors[o.inputs[0]];
-      SPEC_CHECK(cb.data && cb.count() == 16 * 64 && std::memcmp(cb.data, stage_cb[(size_t)stage], 16 * 64 * 4) == 0,
+      const TflTensor& cb = tensor_of(gd, o.inputs[0]);
+      SPEC_CHECK(cb.count() == 16 * 64 && cb.type == DType::F32 && std::memcmp(cb.as<float>(16 * 64), stage_cb[(size_t)stage], 16 * 64 * 4) == 0,
                  "quantizer: decode codebook differs from encode codebook");
       ++checked;
     }

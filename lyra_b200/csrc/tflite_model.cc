@@ -13,13 +13,15 @@ class Cursor {
  public:
   Cursor(const std::vector<uint8_t>& img) : p_(img.data()), n_(img.size()) {}
   template <typename T> T Read(size_t off) const {
-    if (off + sizeof(T) > n_) throw std::runtime_error("tflite: read past end of file");
+    if (off > n_ || sizeof(T) > n_ - off) throw std::runtime_error("tflite: read past end of file");
     T v; std::memcpy(&v, p_ + off, sizeof(T)); return v;
   }
   size_t Deref(size_t off) const { return off + Read<uint32_t>(off); }
   // absolute position of a table field, 0 if the field is absent (default value)
   size_t Field(size_t table, int id) const {
-    const size_t vt = table - (size_t)(int64_t)Read<int32_t>(table);
+    const int64_t vts = (int64_t)table - (int64_t)Read<int32_t>(table);
+    if (vts < 0 || (uint64_t)vts >= n_) throw std::runtime_error("tflite: vtable offset out of range");
+    const size_t vt = (size_t)vts;
     const uint16_t vt_bytes = Read<uint16_t>(vt);
     const size_t slot = 4 + 2 * (size_t)id;
     if (slot + 2 > vt_bytes) return 0;
@@ -36,17 +38,19 @@ class Cursor {
   }
   template <typename T> std::vector<T> Scalars(size_t table, int id) const {
     const Vec v = Vector(table, id);
+    if (v.begin > n_ || (uint64_t)v.size * sizeof(T) > n_ - v.begin) throw std::runtime_error("tflite: vector past end of file");
     std::vector<T> out(v.size);
     for (uint32_t i = 0; i < v.size; ++i) out[i] = Read<T>(v.begin + sizeof(T) * i);
     return out;
   }
   std::string String(size_t table, int id) const {
     const Vec v = Vector(table, id);
-    if (v.begin + v.size > n_) throw std::runtime_error("tflite: string past end of file");
+    if (v.begin > n_ || v.size > n_ - v.begin) throw std::runtime_error("tflite: string past end of file");
     return std::string(reinterpret_cast<const char*>(p_ + v.begin), v.size);
   }
   std::vector<size_t> Tables(size_t table, int id) const {
     const Vec v = Vector(table, id);
+    if (v.begin > n_ || (uint64_t)v.size * 4 > n_ - v.begin) throw std::runtime_error("tflite: table vector past end of file");
     std::vector<size_t> out(v.size);
     for (uint32_t i = 0; i < v.size; ++i) out[i] = Deref(v.begin + 4 * (size_t)i);
     return out;
@@ -126,7 +130,7 @@ TflModel TflModel::Load(const std::string& path) {
       if (bi < buffers.size()) {
         const Cursor::Vec d = c.Vector(buffers[bi], 0);   // Buffer { 0: data }
         if (d.size) {
-          if (d.begin + d.size > c.size()) throw std::runtime_error("tflite: buffer past end of file");
+          if (d.begin > c.size() || d.size > c.size() - d.begin) throw std::runtime_error("tflite: buffer past end of file");
           t.data = c.base() + d.begin;
           t.nbytes = d.size;
         }

@@ -33,7 +33,13 @@ struct TflTensor {
   size_t count() const { size_t c = 1; for (int d : shape) c *= (size_t)d; return c; }
   float scale0() const { if (scale.empty()) throw std::runtime_error("tensor " + name + " has no scale"); return scale[0]; }
   int zp0() const { if (zero_point.empty()) throw std::runtime_error("tensor " + name + " has no zero point"); return (int)zero_point[0]; }
-  template <typename T> const T* as() const { return reinterpret_cast<const T*>(data); }
+  // constant payload as `n` elements of T; throws unless the file really holds that many bytes for this tensor
+  template <typename T> const T* as(size_t n) const {
+    if (data == nullptr || nbytes / sizeof(T) < n) throw std::runtime_error("tensor " + name + ": constant data missing or too short");
+    return reinterpret_cast<const T*>(data);
+  }
+  // the whole declared shape (count() elements)
+  template <typename T> const T* as() const { return as<T>(count()); }
 };
 
 struct TflOp {

@@ -62,3 +62,59 @@ def test_damaged_models_are_rejected_not_crashing(emu_api, tmp_path):
     os.remove(d / "quantizer.tflite")
     r = subprocess.run([sys.executable, "-c", CHILD, emu_api.path, str(d)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == "rc -3", r.stdout + r.stderr
+
+
+# Targeted metadata fuzzing: overwrite single 32-bit words that look like flatbuffer metadata (buffer indices,
+# vtable offsets, shape entries, vector lengths - anything currently holding a small integer) and require the loader to answer
+# OK or EMODEL for every one of them.  Many mutations run inside one child process; a crash kills the child.
+CHILD_WORDS = r'''
+import sys, os, shutil, struct, ctypes as C
+lib = C.CDLL(sys.argv[1])
+lib.lyra_b200_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+lib.lyra_b200_destroy.argtypes = [C.c_void_p]
+src, work = sys.argv[2], sys.argv[3]
+counts = {0: 0, -3: 0}
+for line in open(sys.argv[4]):
+    name, off, val = line.split()
+    off, val = int(off), int(val)
+    path = os.path.join(work, name)
+    orig = open(os.path.join(src, name), "rb").read()
+    with open(path, "wb") as f:
+        f.write(orig[:off] + struct.pack("<I", val) + orig[off + 4:])
+    h = C.c_void_p()
+    rc = lib.lyra_b200_create(work.encode(), 0, 8, C.byref(h))
+    assert rc in (0, -3), (name, off, val, rc)
+    assert (rc == 0) == bool(h.value)
+    if h.value:
+        lib.lyra_b200_destroy(h)
+    counts[rc] += 1
+    with open(path, "wb") as f:
+        f.write(orig)
+    print("done", name, off, val, rc, flush=True)
+print("ok", counts[0], counts[-3])
+'''
+
+
+def test_metadata_word_mutations_never_crash(emu_api, tmp_path):
+    import struct
+    rng = random.Random(11)
+    work = tmp_path / "work"
+    shutil.copytree(MODEL_DIR, work)
+    lines = []
+    for name in ("soundstream_encoder.tflite", "lyragan.tflite", "quantizer.tflite"):
+        data = (work / name).read_bytes()
+        words = struct.unpack("<%dI" % (len(data) // 4), data[:len(data) // 4 * 4])
+        cand = [i for i, w in enumerate(words) if w < 4096 or w >= 0xFFFFF000]       # small ints / small negative offsets
+        for i in rng.sample(cand, 70):
+            val = rng.choice([0, 1, 2, 3, words[i] + 1, words[i] ^ 1, 0x7FFFFFFF, 0xFFFFFFFF, 0x80000000, len(data), len(data) - 2])
+            lines.append("%s %d %d" % (name, 4 * i, val & 0xFFFFFFFF))
+    # the reproducer from the advisor's report
+    lines.append("lyragan.tflite 1446900 2")
+    plan = tmp_path / "plan.txt"
+    plan.write_text("\n".join(lines) + "\n")
+    r = subprocess.run([sys.executable, "-c", CHILD_WORDS, emu_api.path, MODEL_DIR, str(work), str(plan)],
+                       capture_output=True, text=True, timeout=900)
+    last = [ln for ln in r.stdout.splitlines() if ln.startswith("done")][-1:] or ["(none)"]
+    assert r.returncode == 0, "loader crashed after %s: %s" % (last[0], r.stderr[-400:])
+    ok, refused = map(int, r.stdout.strip().splitlines()[-1].split()[1:])
+    assert ok + refused == len(lines) and refused > 0
