@@ -66,6 +66,11 @@ static inline void lyra_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned 
 static inline void lyra_mbar_wait(LyraMbar* b, unsigned parity) {
   while (lyra_mbar_emu(b)->phase == parity) cuda_emu::yield();
 }
+// several bulk copies completing ONE barrier phase: begin(total bytes), copy ..., end (the emulated copies are synchronous, so
+// the single arrival is counted by end; on the GPU begin arms the barrier and end is a no-op)
+static inline void lyra_bulk_multi_begin(LyraMbar*, unsigned) {}
+static inline void lyra_bulk_multi_copy(void* smem_dst, const void* gmem_src, unsigned bytes, LyraMbar*) { std::memcpy(smem_dst, gmem_src, bytes); }
+static inline void lyra_bulk_multi_end(LyraMbar* b) { lyra_mbar_arrive(b); }
 // one function-local shared object per kernel (the emulator backs them all with the same per-block scratch area)
 #define LYRA_STATIC_SMEM(type, name, count) \
   static_assert(sizeof(type) * (count) <= 448, "emulated static shared memory: 448 bytes for objects + 64 for named barriers"); \
@@ -91,6 +96,14 @@ __device__ __forceinline__ void lyra_bulk_g2s(void* smem_dst, const void* gmem_s
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                ::"r"(lyra_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void lyra_bulk_multi_begin(LyraMbar* b, unsigned total_bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(lyra_smem_u32(b)), "r"(total_bytes) : "memory");
+}
+__device__ __forceinline__ void lyra_bulk_multi_copy(void* smem_dst, const void* gmem_src, unsigned bytes, LyraMbar* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(lyra_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(lyra_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void lyra_bulk_multi_end(LyraMbar*) {}
 __device__ __forceinline__ void lyra_mbar_wait(LyraMbar* b, unsigned parity) {
   const unsigned bar = lyra_smem_u32(b);
   asm volatile("{\n"

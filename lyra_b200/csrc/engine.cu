@@ -11,6 +11,7 @@
 #include "aux_kernels.cuh"
 #include "model_spec.h"
 #include "net_kernels.cuh"
+#include "net_kernels_umma.cuh"
 
 using namespace lyra_b200;
 
@@ -261,8 +262,24 @@ int LaunchDecoderNetsT(lyra_b200_ctx* ctx, const Part& p, const float* d_feature
   CU(cudaGetLastError());
   return LYRA_B200_OK;
 }
+// Tensor mode at 8-stream tiles (the default tile): kernel C with its fp32 residual units on mma.sync TF32, kernel D on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators and A operands in tensor memory; net_kernels_umma.cuh).
+int LaunchDecoderNetsUmma(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int16_t* d_pcm) {
+  const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of};
+  using LC = DecC<8, true>;
+  { ProfScope ps(ctx, 4, p.st);
+  LYRA_LAUNCH((DecoderKernelC<8, true>), dim3((unsigned)p.ntiles), dim3(LC::NT), (size_t)LC::kSmemBytes, p.st,
+              ctx->d_blob, ctx->spec.dec, io, d_features, reinterpret_cast<float*>(ctx->d_state[2]), ctx->d_n18[2], ctx->d_mid_dec); }
+  { ProfScope ps(ctx, 5, p.st);
+  LYRA_LAUNCH(DecoderKernelDU, dim3((unsigned)p.ntiles), dim3(DecDU::NT), (size_t)DecDU::kSmemBytes, p.st,
+              ctx->d_blob, ctx->spec.dec, io, ctx->d_mid_dec, reinterpret_cast<float*>(ctx->d_state[3]), ctx->d_n18[3], d_pcm); }
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  return LYRA_B200_OK;
+}
 int LaunchDecoderNets(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int16_t* d_pcm) {
   const bool tc = ctx->decoder_mode == LYRA_B200_DECODER_TENSOR;
+  if (tc && ctx->S == 8) return LaunchDecoderNetsUmma(ctx, p, d_features, d_pcm);
   if (ctx->S == 16) return tc ? LaunchDecoderNetsT<16, true>(ctx, p, d_features, d_pcm) : LaunchDecoderNetsT<16, false>(ctx, p, d_features, d_pcm);
   return tc ? LaunchDecoderNetsT<8, true>(ctx, p, d_features, d_pcm) : LaunchDecoderNetsT<8, false>(ctx, p, d_features, d_pcm);
 }
@@ -560,6 +577,7 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
     if (ok) for (size_t i = 0; i < P; ++i) ctx->h_slot_of[b][i] = -1;
   }
   if (ok) ok = kS == 16 ? SetSmemLimits<16>() : SetSmemLimits<8>();
+  if (ok) ok = LYRA_SET_MAX_SMEM(DecoderKernelDU, DecDU::kSmemBytes) == 0;
   if (!ok) {
     g_create_error = std::string("CUDA allocation / setup failed: ") + cudaGetErrorString(cudaGetLastError());
     lyra_b200_destroy(ctx);

@@ -60,6 +60,21 @@ struct UpI8 {
   uint32_t bias_f32[4];     // the f32 constants subtracted from the overlap tails (SUB ops), [64] each
 };
 
+// Kernel D's GEMM weights for the tcgen05 (UMMA) decoder: kDuNumChunks chunks of kDuChunkBytes.  A chunk is a [rows x kc]
+// slice of one layer's weight operand, split into hi + lo (hi = the 19 bits a TF32 operand keeps, lo = x - hi) and stored as
+// [hi part][lo part], each part in the K-major no-swizzle core-matrix layout [kc/4][rows/8][8 rows][4 k] that a UMMA
+// shared-memory descriptor addresses with LBO = (rows/8) * 128 bytes and SBO = 128 bytes.  One chunk = one bulk copy = one
+// stage of the kernel's weight ring.
+//   chunks  0..39  decoder_2/simple, as the A operand (the GEMM is computed transposed: weights are the rows, the 32
+//                  (input row, stream) pairs the columns): row m = (tap j, phase r, cout) = j * 320 + r * 64 + co (rows 640..
+//                  are zero padding), k = cin; 128-row block major (5 blocks), 16 k per chunk
+//   chunks 40..51  decoder_2/resnet_{0,1,2}: pw1 (2 chunks of 32 k), pw2 (2 chunks), B operand, row = cout
+//   chunks 52..53  last_layer as ONE 64 x 64 GEMM: B row = tap * 16 + n (n = output sample within the stride), k = cin;
+//                  the four taps are summed across time rows in the epilogue
+constexpr int kDuChunkBytes = 16384;
+constexpr int kDuNumChunks = 54;
+constexpr int kDuUp2Chunks = 40, kDuUnitChunk0 = 40, kDuLastChunk0 = 52;
+
 struct DecoderParams {
   // ---- kernel C: T = 1 / 2 / 4
   GemmF32 bott;             // bottleneck_2/simpleconv: K=3, 64 -> 512, g = 4
@@ -75,6 +90,7 @@ struct DecoderParams {
   GemmF32 up2;              // decoder_2/simple: transposed K=10 s=5, 128 -> 64; weights [(j,ci)][(r,co)], bias [64]
   ResF32 r2[3];             // decoder_2/resnet_*: 64 ch
   GemmF32 last;             // last_layer: transposed K=64 s=16, 64 -> 1; weights [(j,ci)][r], bias [1]
+  uint32_t du_chunks;       // the UMMA decoder's weight chunks (see kDuChunkBytes)
   int32_t zp_state[3];      // int8 ring zero points: m_dw ring, q[0], q[1]
 };
 

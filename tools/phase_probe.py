@@ -37,8 +37,15 @@ def main():
         ctx.decode(pk, 64)
     api.lib.lyra_b200_debug_phases(ctx.h, buf.ctypes.data_as(C.c_void_p))
     nblk = min(1024, n // ctx.tile_streams)
+    du = os.environ.get("LYRA_B200_DECODER_MODE") == "tensor"
+    if du:
+        NAMES[3] = ["loads+X", "up2 mma", "up2 epi"] + sum([["u%d ring wait" % i, "u%d dw" % i, "u%d ring upd" % i, "u%d pw1 mma" % i, "u%d epi1" % i,
+                                                          "u%d pw2 mma" % i, "u%d epi2" % i] for i in range(3)], []) + ["last (4 taps)", "last epi+store"]
     for k in range(4):
         t = buf[k, :nblk]
+        t = t[t[:, 0] != 0]                     # blocks that really stamped (sub-batches launch fewer blocks than the buffer holds)
+        if not len(t):
+            continue
         nph = int((t[0] != 0).sum())
         d = np.diff(t[:, :nph], axis=1).astype(np.float64)
         tot = d.sum(axis=1).mean()
