@@ -96,6 +96,57 @@ int lo_noise_is_noise(const lo_noise* e);
 void lo_noise_estimate(const lo_noise* e, float* out);
 void lo_noise_bound(const lo_noise* e, float* out);
 
+int lo_noise_receive_partial(lo_noise* e, const int16_t* samples, int n);   /* ReceiveSamples with partial-hop buffering */
+
+/* ---- GenerativeModel base: FIFO of feature vectors + partial-hop bookkeeping (lyra/generative_model_interface.h:45-134);
+ *      run_conditioning(self, features, hop_out) produces one whole hop, generate slices it.  comfort_noise.c ---- */
+typedef int (*lo_gen_conditioning_fn)(void* self, const float* features, int16_t* hop_out);
+typedef struct lo_gen {
+  int hop, nf, next_sample_in_hop;
+  int head, count, cap;
+  float* queue;
+  int16_t* hop_samples;
+  lo_gen_conditioning_fn run_conditioning;
+  void* self;
+  int calls_add, calls_generate, last_generate;      /* counters for the mock-style tests */
+} lo_gen;
+void lo_gen_init(lo_gen* g, int num_samples_per_hop, int num_features, lo_gen_conditioning_fn fn, void* self);
+void lo_gen_free(lo_gen* g);
+int lo_gen_add_features(lo_gen* g, const float* features, int n);           /* 0, or -1 for a wrong feature count */
+int lo_gen_num_samples_available(const lo_gen* g);
+int lo_gen_generate_samples(lo_gen* g, int num_samples, int16_t* out);      /* count, or -1 (reference: nullopt) */
+
+/* ---- ComfortNoiseGenerator (lyra/comfort_noise_generator.{h,cc}); see comfort_noise.c for the restated audio_dsp pieces,
+ *      the seeded phase policy and what pins it ---- */
+typedef struct lo_cng lo_cng;
+lo_cng* lo_cng_create(int sample_rate_hz, int hop, int window, int num_mel_bins, uint64_t seed);
+void lo_cng_free(lo_cng* c);
+lo_gen* lo_cng_gen(lo_cng* c);                                              /* AddFeatures / GenerateSamples / num_samples_available */
+int lo_cng_condition(lo_cng* c, const float* log_mel_features, const uint32_t* phase /* [bins] or NULL */, int16_t* hop_out);
+uint32_t lo_cng_phase_index(uint64_t seed, uint64_t hop, int bin);          /* 0..1023 */
+double lo_cng_synthesis_gain(const lo_cng* c);
+const double* lo_cng_norm(const lo_cng* c);
+const double* lo_cng_synth(const lo_cng* c);
+
+/* ---- LyraDecoder at 16 kHz: packet-loss concealment / comfort-noise / fade state machine (lyra/lyra_decoder.cc:172-383)
+ *      and LyraEncoder::Encode with DTX (lyra/lyra_encoder.cc:113-156); lyra_decoder.c ---- */
+typedef struct lo_decoder lo_decoder;
+lo_decoder* lo_decoder_create(const char* model_dir, uint64_t cng_seed);                 /* real components */
+lo_decoder* lo_decoder_create_fake(int16_t model_value, int16_t cng_value);               /* the reference tests' fakes */
+void lo_decoder_free(lo_decoder* d);
+int lo_decoder_set_encoded_packet(lo_decoder* d, const uint8_t* encoded, int nbytes);     /* 0 / -1 (reference: true / false) */
+int lo_decoder_decode_samples(lo_decoder* d, int num_samples, int16_t* out);              /* count / -1 */
+int lo_decoder_is_comfort_noise(const lo_decoder* d);
+void lo_decoder_get_state(const lo_decoder* d, int* s3);   /* concealment_progress, fade_progress, fade_direction (-1 from / +1 to CNG) */
+void lo_decoder_set_state(lo_decoder* d, const int* s3);   /* LyraDecoderPeer of lyra_decoder_test.cc:56-90 */
+void lo_decoder_counters(const lo_decoder* d, int* c9);
+lo_noise* lo_decoder_noise(lo_decoder* d);
+lo_cng* lo_decoder_cng(lo_decoder* d);
+typedef struct lo_encoder lo_encoder;
+lo_encoder* lo_encoder_create(const char* model_dir, int enable_dtx);
+void lo_encoder_free(lo_encoder* e);
+int lo_encoder_encode(lo_encoder* e, const int16_t* pcm, int n, int num_bits, uint8_t* packet);   /* packet bytes (0 = DTX), < 0 error */
+
 /* ---- whole codec, one stream (LyraEncoder::Encode / LyraDecoder::{SetEncodedPacket,DecodeSamples}
  *      restricted to 16 kHz, no DTX, packets always received or concealed with zero features) ---- */
 typedef struct lo_codec lo_codec;

@@ -23,6 +23,8 @@
 #include "lyra_oracle.h"
 
 struct lo_noise {
+  int16_t past[2048];       /* past_samples_hop_ (noise_estimator.cc:144-160), hop <= 2048 */
+  int next_sample_in_hop;
   int nf, hop, hops_per_update;
   float max_smoothing, bound_decay;
   float *smoothed, *sq_smoothed, *tmp_min, *est, *bound;
@@ -132,6 +134,19 @@ int lo_noise_receive_samples(lo_noise* e, const int16_t* hop, float* logmel_out)
   }
   if (logmel_out) memcpy(logmel_out, cur, sizeof(float) * (size_t)e->nf);
   free(cur);
+  return 0;
+}
+
+/* noise_estimator.cc:144-172 with the partial-hop buffering: samples accumulate until a hop is complete; a call may
+ * not straddle a hop boundary */
+int lo_noise_receive_partial(lo_noise* e, const int16_t* samples, int n) {
+  if (n < 0 || e->hop > 2048 || n + e->next_sample_in_hop > e->hop) return -1;
+  memcpy(e->past + e->next_sample_in_hop, samples, sizeof(int16_t) * (size_t)n);
+  e->next_sample_in_hop += n;
+  if (e->next_sample_in_hop == e->hop) {
+    e->next_sample_in_hop = 0;
+    return lo_noise_receive_samples(e, e->past, NULL);
+  }
   return 0;
 }
 

@@ -52,6 +52,19 @@ def lib():
             "lo_noise_receive_samples": (ci, [vp, vp, vp]), "lo_noise_update": (None, [vp, vp]),
             "lo_noise_compute_is_noise": (ci, [vp, vp]), "lo_noise_is_noise": (ci, [vp]),
             "lo_noise_estimate": (None, [vp, vp]), "lo_noise_bound": (None, [vp, vp]),
+            "lo_noise_receive_partial": (ci, [vp, vp, ci]),
+            "lo_gen_add_features": (ci, [vp, vp, ci]), "lo_gen_num_samples_available": (ci, [vp]),
+            "lo_gen_generate_samples": (ci, [vp, ci, vp]),
+            "lo_cng_create": (vp, [ci, ci, ci, ci, C.c_uint64]), "lo_cng_free": (None, [vp]), "lo_cng_gen": (vp, [vp]),
+            "lo_cng_condition": (ci, [vp, vp, vp, vp]), "lo_cng_phase_index": (C.c_uint32, [C.c_uint64, C.c_uint64, ci]),
+            "lo_cng_synthesis_gain": (C.c_double, [vp]),
+            "lo_decoder_create": (vp, [C.c_char_p, C.c_uint64]), "lo_decoder_create_fake": (vp, [C.c_int16, C.c_int16]),
+            "lo_decoder_free": (None, [vp]), "lo_decoder_set_encoded_packet": (ci, [vp, vp, ci]),
+            "lo_decoder_decode_samples": (ci, [vp, ci, vp]), "lo_decoder_is_comfort_noise": (ci, [vp]),
+            "lo_decoder_get_state": (None, [vp, vp]), "lo_decoder_set_state": (None, [vp, vp]),
+            "lo_decoder_counters": (None, [vp, vp]), "lo_decoder_noise": (vp, [vp]), "lo_decoder_cng": (vp, [vp]),
+            "lo_encoder_create": (vp, [C.c_char_p, ci]), "lo_encoder_free": (None, [vp]),
+            "lo_encoder_encode": (ci, [vp, vp, ci, ci, vp]),
             "lo_codec_create": (vp, [C.c_char_p]), "lo_codec_free": (None, [vp]), "lo_codec_reset": (ci, [vp]),
             "lo_codec_encode": (ci, [vp, vp, ci, vp, vp, vp]), "lo_codec_decode": (ci, [vp, vp, ci, vp, vp, vp]),
             "lo_codec_encoder_net": (vp, [vp]), "lo_codec_decoder_net": (vp, [vp]),
@@ -260,6 +273,121 @@ class NoiseEstimator:
         out = np.empty(self.nf, dtype=np.float32)
         lib().lo_noise_bound(self.h, _p(out))
         return out
+
+
+class ComfortNoiseGenerator:
+    """ComfortNoiseGenerator (lyra/comfort_noise_generator.{h,cc}) with the GenerativeModel FIFO; seeded phases."""
+
+    def __init__(self, sample_rate_hz=16000, hop=320, window=640, num_mel_bins=160, seed=0):
+        self.h = lib().lo_cng_create(sample_rate_hz, hop, window, num_mel_bins, seed)
+        if not self.h:
+            raise ValueError("lo_cng_create failed")
+        self.hop, self.nmel, self.bins = hop, num_mel_bins, 513
+        self.gen = lib().lo_cng_gen(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lo_cng_free(self.h)
+            self.h = None
+
+    def add_features(self, features):
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        return lib().lo_gen_add_features(self.gen, _p(f), int(f.size)) == 0
+
+    def num_samples_available(self):
+        return lib().lo_gen_num_samples_available(self.gen)
+
+    def generate_samples(self, n):
+        out = np.zeros(max(n, 0) + 1, dtype=np.int16)
+        r = lib().lo_gen_generate_samples(self.gen, n, _p(out))
+        return None if r < 0 else out[:r].copy()
+
+    def condition(self, features, phase=None):
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        out = np.zeros(self.hop, dtype=np.int16)
+        ph = None if phase is None else np.ascontiguousarray(phase, dtype=np.uint32)
+        assert lib().lo_cng_condition(self.h, _p(f), None if ph is None else _p(ph), _p(out)) == 0
+        return out
+
+    @property
+    def synthesis_gain(self):
+        return lib().lo_cng_synthesis_gain(self.h)
+
+
+def cng_phase_index(seed, hop, bin_):
+    return int(lib().lo_cng_phase_index(seed, hop, bin_))
+
+
+class Decoder:
+    """LyraDecoder at 16 kHz with the packet-loss / comfort-noise / fade state machine (oracle/lyra_decoder.c)."""
+    COUNTERS = ["vq_decode", "model_add", "model_generate", "model_last_request", "cng_add", "cng_generate", "cng_last_request",
+                "noise_receive", "noise_estimate"]
+
+    def __init__(self, model_dir=None, cng_seed=0, fake=None):
+        if fake is not None:
+            self.h = lib().lo_decoder_create_fake(int(fake[0]), int(fake[1]))
+        else:
+            self.h = lib().lo_decoder_create(model_dir.encode(), cng_seed)
+        if not self.h:
+            raise ValueError("lo_decoder_create failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lo_decoder_free(self.h)
+            self.h = None
+
+    def set_encoded_packet(self, packet):
+        b = np.frombuffer(bytes(packet), dtype=np.uint8).copy() if len(packet) else np.zeros(1, np.uint8)
+        return lib().lo_decoder_set_encoded_packet(self.h, _p(b), len(packet)) == 0
+
+    def decode_samples(self, n):
+        out = np.zeros(max(n, 0) + 1, dtype=np.int16)
+        r = lib().lo_decoder_decode_samples(self.h, n, _p(out))
+        return None if r < 0 else out[:r].copy()
+
+    def is_comfort_noise(self):
+        return bool(lib().lo_decoder_is_comfort_noise(self.h))
+
+    @property
+    def state(self):
+        s = np.zeros(3, dtype=np.int32)
+        lib().lo_decoder_get_state(self.h, _p(s))
+        return tuple(int(x) for x in s)
+
+    @state.setter
+    def state(self, v):
+        s = np.asarray(v, dtype=np.int32)
+        lib().lo_decoder_set_state(self.h, _p(s))
+
+    def counters(self):
+        c = np.zeros(9, dtype=np.int32)
+        lib().lo_decoder_counters(self.h, _p(c))
+        return dict(zip(self.COUNTERS, (int(x) for x in c)))
+
+    def noise_estimate(self):
+        out = np.zeros(160, dtype=np.float32)
+        lib().lo_noise_estimate(lib().lo_decoder_noise(self.h), _p(out))
+        return out
+
+
+class Encoder:
+    """LyraEncoder::Encode at 16 kHz, optionally with DTX (lyra/lyra_encoder.cc:113-156)."""
+
+    def __init__(self, model_dir, enable_dtx=False):
+        self.h = lib().lo_encoder_create(model_dir.encode(), 1 if enable_dtx else 0)
+        if not self.h:
+            raise ValueError("lo_encoder_create failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lo_encoder_free(self.h)
+            self.h = None
+
+    def encode(self, pcm, num_bits):
+        a = np.ascontiguousarray(pcm, dtype=np.int16)
+        out = np.zeros(32, dtype=np.uint8)
+        r = lib().lo_encoder_encode(self.h, _p(a), int(a.size), num_bits, _p(out))
+        return None if r < 0 else bytes(out[:r])
 
 
 class Codec:
