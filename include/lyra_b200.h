@@ -45,8 +45,8 @@ int lyra_b200_create(const char* model_dir, int device, int max_streams, lyra_b2
  * (lyra/lyra_encoder.h:112-120, lyra/lyra_decoder.h:130-160) and a full-duplex server drives them independently: an
  * encoder-only and a decoder-only context hold only their half of the streaming state and may be called concurrently
  * (one host thread / one CUDA stream each), so the uplink's encode kernels overlap the downlink's decode kernels on the
- * GPU.  Calls that need a role the context lacks return LYRA_B200_EINVAL; quantize / dequantize / logmel are stateless
- * or self-contained and work in any context. */
+ * GPU.  Calls that need a role the context lacks return LYRA_B200_EINVAL; quantize / dequantize / logmel / noise_update /
+ * cng_generate are stateless or self-contained and work in any context. */
 #define LYRA_B200_ROLE_ENCODER 1
 #define LYRA_B200_ROLE_DECODER 2
 int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int roles, lyra_b200_ctx** out);
@@ -120,6 +120,41 @@ int lyra_b200_noise_update(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n,
 int lyra_b200_decode_track_noise(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const uint8_t* packets,
                                  const uint8_t* received, int num_bits, int16_t* pcm, uint8_t* is_noise);
 
+/* NoiseEstimator::noise_estimate() / is_noise() of the decoder-side estimators without feeding them (read-only;
+ * lyra/noise_estimator.h:55-62).  Either output may be NULL. */
+int lyra_b200_noise_estimate(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, float* noise_estimate, uint8_t* is_noise);
+
+/* ---- packet-loss concealment, comfort noise and DTX ------------------------------ */
+
+/* LyraDecoder::SetEncodedPacket (for streams with received[i] != 0) + DecodeSamples(320) with the reference's full behaviour
+ * (lyra/lyra_decoder.cc:172-315, 342-383): up to 80 ms of a lost stream are concealed by the generative model on zero
+ * features, then the output cross-fades (raised cosine, 40 ms) into comfort noise synthesised from the stream's noise
+ * estimate, and fades back when packets return; the noise estimator is fed by hops decoded from received packets only.
+ * Per-stream control state (concealment progress, fade progress, fade direction) lives on the device; one call = one 20 ms
+ * tick of every listed stream.  is_comfort_noise[n] (may be NULL) = LyraDecoder::is_comfort_noise() after the tick.
+ * Requests that are not whole hops are served by the C++ adapter LyraDecoderB200 (include/lyra_b200/lyra_b200_components.h),
+ * which runs the same state machine on the host over lyra_b200_generate / lyra_b200_cng_generate. */
+int lyra_b200_decode_plc(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const uint8_t* packets, const uint8_t* received,
+                         int num_bits, int16_t* pcm, uint8_t* is_comfort_noise);
+/* The control state of the listed streams, state[n][3] = {concealment_progress, fade_progress, fade_direction (-1 = from, +1 =
+ * to comfort noise)} - what the reference's test peer exposes (lyra/lyra_decoder_test.cc:56-90).  set accepts hop-aligned
+ * values only. */
+int lyra_b200_plc_get_state(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, int32_t* state);
+int lyra_b200_plc_set_state(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const int32_t* state);
+
+/* ComfortNoiseGenerator::RunConditioning + RunModel(320) (lyra/comfort_noise_generator.cc:74-119) for n streams:
+ * features[n][160] (log-mel, e.g. a noise estimate) -> pcm[n][320].  Every stream owns an overlap-add buffer and a hop
+ * counter (cleared by lyra_b200_reset).  The reference draws random phases from an unseeded generator (:103); here the phase
+ * of bin i of hop h of stream s is a pure function of (seed + s, h, i) - reproducible, see oracle/comfort_noise.c. */
+int lyra_b200_cng_generate(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const float* features, int16_t* pcm);
+int lyra_b200_set_cng_seed(lyra_b200_ctx* ctx, uint64_t seed);   /* default 0 */
+
+/* LyraEncoder::Encode with enable_dtx (lyra/lyra_encoder.cc:113-156): every hop first updates the stream's encoder-side noise
+ * estimator; a hop classified as noise is not encoded (the stream's encoder state does not advance) and yields an EMPTY packet:
+ * packet_bytes[i] = 0 (its bytes in `packets` are zero), otherwise ceil(num_bits / 8). */
+int lyra_b200_encode_dtx(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const int16_t* pcm, int num_bits, uint8_t* packets,
+                         int32_t* packet_bytes);
+
 /* ---- device-resident variants (pointers are CUDA device pointers; asynchronous on the context's
  *      stream; streams 0..n-1).  Used by bench.py for the HBM-resident `value` measurement and by
  *      callers that keep audio on the GPU. ---------------------------------------------------------- */
@@ -131,6 +166,10 @@ int lyra_b200_decode_track_noise_device(lyra_b200_ctx* ctx, int n, const uint8_t
                                         int num_bits, int16_t* d_pcm, uint8_t* d_is_noise);
 int lyra_b200_noise_update_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, const uint8_t* d_update_mask,
                                   uint8_t* d_is_noise, float* d_noise_estimate);
+int lyra_b200_decode_plc_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits,
+                                int16_t* d_pcm, uint8_t* d_is_comfort_noise /* may be NULL */);
+int lyra_b200_encode_dtx_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets,
+                                uint8_t* d_is_noise /* [n], 1 = empty packet */);
 int lyra_b200_synchronize(lyra_b200_ctx* ctx);
 /* Dense calls (stream_ids == NULL / *_device) over many tiles are cut into `parts` (1..4, default 3) sub-batches that
  * run concurrently on internal CUDA streams so partial waves of one kernel are filled by another's blocks.

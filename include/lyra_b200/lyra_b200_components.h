@@ -9,9 +9,10 @@
 //   LogMelSpectrogramExtractorImpl  log_mel_spectrogram_extractor_impl.{h,cc}   lyra_b200::LogMelSpectrogramExtractorB200
 //   NoiseEstimator              noise_estimator.{h,cc}           lyra_b200::NoiseEstimatorB200 (: NoiseEstimatorInterface)
 //   Packet<184>                 packet.h                         lyra_b200::Packet184
+//   ComfortNoiseGenerator       comfort_noise_generator.{h,cc}   lyra_b200::ComfortNoiseGeneratorB200 (: GenerativeModel)
 //   LyraEncoder / LyraDecoder   lyra_encoder.{h,cc} / lyra_decoder.{h,cc}       lyra_b200::LyraEncoderB200 / LyraDecoderB200
-//                                                                (16 kHz, no DTX; lost packets are concealed with zero
-//                                                                 features; comfort noise / fades are out of scope)
+//                                                                (16 kHz; DTX; packet-loss concealment, comfort noise and
+//                                                                 the cross-fades between them, arbitrary request sizes)
 //
 // The reference's interface headers need abseil, which is not available in this build environment, so the
 // three interfaces are restated below with std:: types (absl::Span<const T> -> pointer + size overloads on
@@ -23,6 +24,7 @@
 // API-compatible but latency-bound; throughput users call the batched C ABI directly (include/lyra_b200.h).
 #pragma once
 
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <memory>
@@ -109,9 +111,10 @@ class Session {
     static std::mutex mu;
     static std::weak_ptr<Session> cached[2];
     static std::string cached_path[2];
+    static int cached_device[2] = {-1, -1};
     const int k = role == LYRA_B200_ROLE_DECODER ? 1 : 0;
     std::lock_guard<std::mutex> lock(mu);
-    if (auto s = cached[k].lock()) if (cached_path[k] == model_path) return s;
+    if (auto s = cached[k].lock()) if (cached_path[k] == model_path && cached_device[k] == device) return s;
     int max_streams = 4096;
     if (const char* e = std::getenv("LYRA_B200_MAX_STREAMS")) max_streams = std::atoi(e) > 0 ? std::atoi(e) : max_streams;
     lyra_b200_ctx* ctx = nullptr;
@@ -120,6 +123,7 @@ class Session {
     std::shared_ptr<Session> s(new Session(ctx, max_streams));
     cached[k] = s;
     cached_path[k] = model_path;
+    cached_device[k] = device;
     return s;
   }
   ~Session() { lyra_b200_destroy(ctx_); }
@@ -131,7 +135,7 @@ class Session {
     if (!free_.empty()) { id = free_.back(); free_.pop_back(); }
     else if (next_ < max_streams_) id = next_++;
     else return -1;
-    lyra_b200_reset(ctx_, &id, 1);
+    if (lyra_b200_reset(ctx_, &id, 1) != LYRA_B200_OK) { free_.push_back(id); return -1; }
     return id;
   }
   void Release(int id) { std::lock_guard<std::mutex> lock(mu_); free_.push_back(id); }
@@ -188,8 +192,10 @@ struct Packet184 {
 // ---- ResidualVectorQuantizer (lyra/residual_vector_quantizer.cc:36-168) --------------------------------------------
 class ResidualVectorQuantizerB200 : public VectorQuantizerInterface {
  public:
-  static std::unique_ptr<ResidualVectorQuantizerB200> Create(const std::string& model_path) {
-    auto s = Session::Get(model_path);
+  // role: which process-wide context serves the (stateless) calls - a decoder's quantizer shares the decoder context, so a
+  // decoder-only process never allocates encoder state and encoder / decoder threads never share a mutex
+  static std::unique_ptr<ResidualVectorQuantizerB200> Create(const std::string& model_path, int role = LYRA_B200_ROLE_ENCODER) {
+    auto s = Session::Get(model_path, role);
     if (!s) return nullptr;
     return std::unique_ptr<ResidualVectorQuantizerB200>(new ResidualVectorQuantizerB200(std::move(s)));
   }
@@ -316,10 +322,8 @@ class NoiseEstimatorB200 : public NoiseEstimatorInterface {
   }
   std::vector<float> noise_estimate() const override {
     std::vector<float> out(160, 0.0f);
-    const std::vector<int16_t> none((size_t)LYRA_B200_HOP, 0);
-    const uint8_t mask = 0;                                      // report only, the estimator is not fed
     std::lock_guard<std::mutex> lock(session_->mutex());
-    lyra_b200_noise_update(session_->ctx(), &id_, 1, none.data(), &mask, nullptr, out.data());
+    lyra_b200_noise_estimate(session_->ctx(), &id_, 1, out.data(), nullptr);
     return out;
   }
   bool is_noise() const override { return is_noise_; }
@@ -332,8 +336,40 @@ class NoiseEstimatorB200 : public NoiseEstimatorInterface {
   std::vector<int16_t> hop_;
 };
 
+// ---- ComfortNoiseGenerator (lyra/comfort_noise_generator.{h,cc}) ---------------------------------------------------
+class ComfortNoiseGeneratorB200 : public GenerativeModel {
+ public:
+  static std::unique_ptr<ComfortNoiseGeneratorB200> Create(const std::string& model_path, int sample_rate_hz, int num_samples_per_hop,
+                                                           int window_length_samples, int num_mel_bins) {
+    if (sample_rate_hz != 16000 || num_samples_per_hop != 320 || window_length_samples != 640 || num_mel_bins != 160) return nullptr;
+    auto s = Session::Get(model_path, LYRA_B200_ROLE_DECODER);
+    if (!s) return nullptr;
+    const int id = s->Acquire();
+    if (id < 0) return nullptr;
+    return std::unique_ptr<ComfortNoiseGeneratorB200>(new ComfortNoiseGeneratorB200(std::move(s), id));
+  }
+  ~ComfortNoiseGeneratorB200() override { session_->Release(id_); }
+
+ protected:
+  bool RunConditioning(const std::vector<float>& features) override {       // FftFromFeatures + InvertFft, .cc:74-77
+    std::lock_guard<std::mutex> lock(session_->mutex());
+    return lyra_b200_cng_generate(session_->ctx(), &id_, 1, features.data(), hop_) == LYRA_B200_OK;
+  }
+  std::optional<std::vector<int16_t>> RunModel(int num_samples) override {   // .cc:79-84
+    return std::vector<int16_t>(hop_ + next_sample_in_hop(), hop_ + next_sample_in_hop() + num_samples);
+  }
+
+ private:
+  ComfortNoiseGeneratorB200(std::shared_ptr<Session> s, int id) : GenerativeModel(LYRA_B200_HOP, 160), session_(std::move(s)), id_(id) {}
+  std::shared_ptr<Session> session_;
+  int id_;
+  int16_t hop_[LYRA_B200_HOP] = {0};
+};
+
 // ---- factories with the reference's names (lyra/lyra_components.cc:42-60) ------------------------------------------
-inline std::unique_ptr<VectorQuantizerInterface> CreateQuantizer(const std::string& model_path) { return ResidualVectorQuantizerB200::Create(model_path); }
+inline std::unique_ptr<VectorQuantizerInterface> CreateQuantizer(const std::string& model_path, int role = LYRA_B200_ROLE_ENCODER) {
+  return ResidualVectorQuantizerB200::Create(model_path, role);
+}
 inline std::unique_ptr<GenerativeModelInterface> CreateGenerativeModel(int num_output_features, const std::string& model_path) {
   return LyraGanModelB200::Create(model_path, num_output_features);
 }
@@ -344,20 +380,29 @@ inline int GetPacketSize(int num_quantized_bits) { return (num_quantized_bits + 
 inline int BitrateToNumQuantizedBits(int bitrate) { return bitrate == 3200 ? 64 : bitrate == 6000 ? 120 : bitrate == 9200 ? 184 : -1; }
 inline int PacketSizeToNumQuantizedBits(int packet_size) { return packet_size == 8 ? 64 : packet_size == 15 ? 120 : packet_size == 23 ? 184 : -1; }
 
-// ---- LyraEncoder at 16 kHz, mono, no DTX (lyra/lyra_encoder.h:44-122, lyra/lyra_encoder.cc:43-156) --------------------
+// ---- LyraEncoder at 16 kHz, mono (lyra/lyra_encoder.h:44-122, lyra/lyra_encoder.cc:43-156), DTX included ------------------
 class LyraEncoderB200 {
  public:
   static std::unique_ptr<LyraEncoderB200> Create(int sample_rate_hz, int num_channels, int bitrate, bool enable_dtx, const std::string& model_path) {
-    if (sample_rate_hz != 16000 || num_channels != 1 || enable_dtx) return nullptr;   // resamplers / DTX are out of scope here
+    if (sample_rate_hz != 16000 || num_channels != 1) return nullptr;   // other rates need the resampler (lyra_encoder.cc:58-66): not on this path
     const int bits = BitrateToNumQuantizedBits(bitrate);
     if (bits < 0) return nullptr;
     auto fe = CreateFeatureExtractor(model_path);
     auto vq = CreateQuantizer(model_path);
     if (!fe || !vq) return nullptr;
-    return std::unique_ptr<LyraEncoderB200>(new LyraEncoderB200(std::move(fe), std::move(vq), bits));
+    std::unique_ptr<NoiseEstimatorInterface> ne;
+    if (enable_dtx) {                                                    // lyra_encoder.cc:80-89
+      ne = NoiseEstimatorB200::Create(model_path, 16000, LYRA_B200_HOP, 640, 160);
+      if (!ne) return nullptr;
+    }
+    return std::unique_ptr<LyraEncoderB200>(new LyraEncoderB200(std::move(fe), std::move(vq), std::move(ne), bits));
   }
   std::optional<std::vector<uint8_t>> Encode(const std::vector<int16_t>& audio) {
     if ((int)audio.size() != LYRA_B200_HOP) return std::nullopt;                      // lyra_encoder.cc:124-129
+    if (noise_estimator_) {                                                           // :131-141
+      if (!noise_estimator_->ReceiveSamples(audio)) return std::nullopt;
+      if (noise_estimator_->is_noise()) return std::vector<uint8_t>();               // the empty packet
+    }
     auto features = feature_extractor_->Extract(audio);
     if (!features.has_value()) return std::nullopt;
     auto quantized = vector_quantizer_->Quantize(features.value(), num_quantized_bits_);
@@ -376,55 +421,111 @@ class LyraEncoderB200 {
   int frame_rate() const { return 50; }
 
  private:
-  LyraEncoderB200(std::unique_ptr<FeatureExtractorInterface> fe, std::unique_ptr<VectorQuantizerInterface> vq, int bits)
-      : feature_extractor_(std::move(fe)), vector_quantizer_(std::move(vq)), num_quantized_bits_(bits) {}
+  LyraEncoderB200(std::unique_ptr<FeatureExtractorInterface> fe, std::unique_ptr<VectorQuantizerInterface> vq,
+                  std::unique_ptr<NoiseEstimatorInterface> ne, int bits)
+      : feature_extractor_(std::move(fe)), vector_quantizer_(std::move(vq)), noise_estimator_(std::move(ne)), num_quantized_bits_(bits) {}
   std::unique_ptr<FeatureExtractorInterface> feature_extractor_;
   std::unique_ptr<VectorQuantizerInterface> vector_quantizer_;
+  std::unique_ptr<NoiseEstimatorInterface> noise_estimator_;
   int num_quantized_bits_;
 };
 
-// ---- LyraDecoder at 16 kHz (lyra/lyra_decoder.h:41-163): SetEncodedPacket + DecodeSamples.  A hop requested
-//      without a packet is concealed by feeding 64 zero features (ZeroFeatureEstimator, lyra_decoder.cc:317-326);
-//      the comfort-noise / fade state machine (lyra_decoder.cc:228-373) is out of scope. -----------
+// ---- LyraDecoder at 16 kHz (lyra/lyra_decoder.h:41-163, lyra/lyra_decoder.cc:95-383): packet-loss concealment, comfort noise and
+//      the fades between them, for any number of requested samples.  The components are interfaces, as in the reference's
+//      constructor (lyra_decoder.cc:148-170), so tests can plug fakes like lyra/lyra_decoder_test.cc does. -----------------------
 class LyraDecoderB200 {
  public:
+  enum FadeDirection { kFadeFromCNG = -1, kFadeToCNG = 1 };                          // lyra_decoder.h:105-108
+
   static std::unique_ptr<LyraDecoderB200> Create(int sample_rate_hz, int num_channels, const std::string& model_path) {
-    if (sample_rate_hz != 16000 || num_channels != 1) return nullptr;
+    if (sample_rate_hz != 16000 || num_channels != 1) return nullptr;   // other rates need the buffered resampler (lyra_decoder.cc:108-114)
     auto gm = CreateGenerativeModel(LYRA_B200_NUM_FEATURES, model_path);
-    auto vq = CreateQuantizer(model_path);
-    if (!gm || !vq) return nullptr;
-    return std::unique_ptr<LyraDecoderB200>(new LyraDecoderB200(std::move(gm), std::move(vq)));
+    auto cng = ComfortNoiseGeneratorB200::Create(model_path, 16000, LYRA_B200_HOP, 640, 160);
+    auto ne = NoiseEstimatorB200::Create(model_path, 16000, LYRA_B200_HOP, 640, 160);
+    auto vq = CreateQuantizer(model_path, LYRA_B200_ROLE_DECODER);
+    if (!gm || !cng || !ne || !vq) return nullptr;
+    return std::unique_ptr<LyraDecoderB200>(new LyraDecoderB200(std::move(gm), std::move(cng), std::move(vq), std::move(ne)));
   }
-  bool SetEncodedPacket(const std::vector<uint8_t>& encoded) {
+  LyraDecoderB200(std::unique_ptr<GenerativeModelInterface> generative_model, std::unique_ptr<GenerativeModelInterface> comfort_noise_generator,
+                  std::unique_ptr<VectorQuantizerInterface> vector_quantizer, std::unique_ptr<NoiseEstimatorInterface> noise_estimator)
+      : generative_model_(std::move(generative_model)), comfort_noise_generator_(std::move(comfort_noise_generator)),
+        vector_quantizer_(std::move(vector_quantizer)), noise_estimator_(std::move(noise_estimator)) {}
+
+  bool SetEncodedPacket(const std::vector<uint8_t>& encoded) {                       // lyra_decoder.cc:172-209
     const int bits = PacketSizeToNumQuantizedBits((int)encoded.size());
-    if (bits < 0) return false;                                                         // lyra_decoder.cc:173-178
+    if (bits < 0) return false;
     const auto unpacked = Packet184::UnpackPacket(encoded, bits);
     if (!unpacked.has_value()) return false;
+    if (concealment_progress_ == kConcealmentSamples) concealment_progress_ = -comfort_noise_generator_->num_samples_available();
+    else if (concealment_progress_ > 0) concealment_progress_ = -generative_model_->num_samples_available();
     auto features = vector_quantizer_->DecodeToLossyFeatures(unpacked.value());
     if (!features.has_value()) return false;
-    return generative_model_->AddFeatures(features.value());
+    return generative_model_->AddFeatures(features.value());                        // ZeroFeatureEstimator::Update is a no-op
   }
-  std::optional<std::vector<int16_t>> DecodeSamples(int num_samples) {
+
+  std::optional<std::vector<int16_t>> DecodeSamples(int num_samples) {               // lyra_decoder.cc:211-315 at the internal rate
     if (num_samples < 0) return std::nullopt;
     std::vector<int16_t> result;
+    result.reserve((size_t)num_samples);
     while ((int)result.size() < num_samples) {
-      if (generative_model_->num_samples_available() == 0)
-        generative_model_->AddFeatures(std::vector<float>(LYRA_B200_NUM_FEATURES, 0.0f));   // packet-loss concealment
-      const int want = num_samples - (int)result.size();
-      const int in_hop = (generative_model_->num_samples_available() - 1) % LYRA_B200_HOP + 1;   // left in the current hop
-      const int take = want < in_hop ? want : in_hop;
-      auto s = generative_model_->GenerateSamples(take);
-      if (!s.has_value()) return std::nullopt;
-      result.insert(result.end(), s->begin(), s->end());
+      const int n = NumSamplesToGenerate(num_samples, (int)result.size());
+      const bool is_packet_received = generative_model_->num_samples_available() > 0 && concealment_progress_ == 0;
+      if (is_packet_received) fade_direction_ = kFadeFromCNG;
+      else if (concealment_progress_ == kConcealmentSamples) fade_direction_ = kFadeToCNG;
+      else concealment_progress_ += n;
+      int cng_n = n, gen_n = n;
+      int next_fade = fade_progress_ + fade_direction_ * n;
+      if (fade_direction_ == kFadeToCNG && fade_progress_ == kFadeSamples) { next_fade = kFadeSamples; gen_n = 0; }
+      else if (fade_direction_ == kFadeFromCNG && fade_progress_ == 0) { next_fade = 0; cng_n = 0; }
+      if (gen_n > 0 && generative_model_->num_samples_available() == 0 &&                                      // RunGenerativeModel :317-326
+          !generative_model_->AddFeatures(std::vector<float>(LYRA_B200_NUM_FEATURES, 0.0f))) return std::nullopt;
+      auto audio = generative_model_->GenerateSamples(gen_n);
+      if (!audio.has_value()) return std::nullopt;
+      if (cng_n > 0 && comfort_noise_generator_->num_samples_available() == 0 &&                              // RunComfortNoiseGenerator :328-340
+          !comfort_noise_generator_->AddFeatures(noise_estimator_->noise_estimate())) return std::nullopt;
+      auto noise = comfort_noise_generator_->GenerateSamples(cng_n);
+      if (!noise.has_value()) return std::nullopt;
+      if (noise->empty()) result.insert(result.end(), audio->begin(), audio->end());                          // MaybeOverlapAndInsert :342-373
+      else if (audio->empty()) result.insert(result.end(), noise->begin(), noise->end());
+      else {
+        if (audio->size() != noise->size()) return std::nullopt;
+        int fp = fade_progress_;
+        for (size_t i = 0; i < audio->size(); ++i) {
+          const float w = (1.f + std::cos(fp * M_PI / kFadeSamples)) / 2.f;
+          result.push_back((int16_t)((*audio)[i] * w + (*noise)[i] * (1.f - w)));
+          fp += fade_direction_;
+        }
+      }
+      fade_progress_ = next_fade;
+      if (is_packet_received && !noise_estimator_->ReceiveSamples(audio.value())) return std::nullopt;
     }
     return result;
   }
+  int sample_rate_hz() const { return 16000; }
+  int num_channels() const { return 1; }
+  int frame_rate() const { return 50; }
+  bool is_comfort_noise() const { return fade_progress_ == kFadeSamples; }           // lyra_decoder.cc:381-383
+
+  // test peer (lyra_decoder_test.cc:56-90)
+  void SetStateForTest(int concealment_progress, int fade_progress, FadeDirection d) { concealment_progress_ = concealment_progress; fade_progress_ = fade_progress; fade_direction_ = d; }
+  int concealment_progress() const { return concealment_progress_; }
+  int fade_progress() const { return fade_progress_; }
 
  private:
-  LyraDecoderB200(std::unique_ptr<GenerativeModelInterface> gm, std::unique_ptr<VectorQuantizerInterface> vq)
-      : generative_model_(std::move(gm)), vector_quantizer_(std::move(vq)) {}
-  std::unique_ptr<GenerativeModelInterface> generative_model_;
+  static constexpr int kConcealmentSamples = 1280, kFadeSamples = 640;               // 0.08 s, 0.04 s (lyra_decoder.cc:42-63)
+  int NumSamplesToGenerate(int requested, int so_far) const {                        // lyra_decoder.cc:65-93
+    int remaining;
+    if (concealment_progress_ < 0) remaining = -concealment_progress_;
+    else if (concealment_progress_ < kConcealmentSamples) remaining = generative_model_->num_samples_available() % LYRA_B200_HOP;
+    else remaining = comfort_noise_generator_->num_samples_available();
+    if (remaining == 0) remaining = LYRA_B200_HOP;
+    return requested - so_far < remaining ? requested - so_far : remaining;
+  }
+  std::unique_ptr<GenerativeModelInterface> generative_model_, comfort_noise_generator_;
   std::unique_ptr<VectorQuantizerInterface> vector_quantizer_;
+  std::unique_ptr<NoiseEstimatorInterface> noise_estimator_;
+  int concealment_progress_ = 0, fade_progress_ = 0;
+  FadeDirection fade_direction_ = kFadeFromCNG;
 };
 
 }  // namespace lyra_b200

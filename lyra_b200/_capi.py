@@ -63,6 +63,15 @@ class CApi:
             "lyra_b200_launch_count": (C.c_uint64, [vp]),
             "lyra_b200_profile_enable": (ci, [vp, ci]),
             "lyra_b200_profile_read": (ci, [vp, vp, vp]),
+            "lyra_b200_noise_estimate": (ci, [vp, vp, ci, vp, vp]),
+            "lyra_b200_decode_plc": (ci, [vp, vp, ci, vp, vp, ci, vp, vp]),
+            "lyra_b200_decode_plc_device": (ci, [vp, ci, vp, vp, ci, vp, vp]),
+            "lyra_b200_plc_get_state": (ci, [vp, vp, ci, vp]),
+            "lyra_b200_plc_set_state": (ci, [vp, vp, ci, vp]),
+            "lyra_b200_cng_generate": (ci, [vp, vp, ci, vp, vp]),
+            "lyra_b200_set_cng_seed": (ci, [vp, C.c_uint64]),
+            "lyra_b200_encode_dtx": (ci, [vp, vp, ci, vp, ci, vp, vp]),
+            "lyra_b200_encode_dtx_device": (ci, [vp, ci, vp, ci, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)   # AttributeError here = the library does not export the declared ABI
@@ -77,7 +86,9 @@ class CApi:
                "lyra_b200_logmel", "lyra_b200_set_stream", "lyra_b200_encode_device", "lyra_b200_decode_device",
                "lyra_b200_synchronize", "lyra_b200_noise_update", "lyra_b200_noise_update_device", "lyra_b200_decode_track_noise",
                "lyra_b200_decode_track_noise_device", "lyra_b200_set_split", "lyra_b200_set_blocking_sync", "lyra_b200_set_decoder_mode", "lyra_b200_decoder_mode", "lyra_b200_launch_count", "lyra_b200_profile_enable",
-               "lyra_b200_profile_read"]
+               "lyra_b200_profile_read", "lyra_b200_noise_estimate", "lyra_b200_decode_plc", "lyra_b200_decode_plc_device",
+               "lyra_b200_plc_get_state", "lyra_b200_plc_set_state", "lyra_b200_cng_generate", "lyra_b200_set_cng_seed",
+               "lyra_b200_encode_dtx", "lyra_b200_encode_dtx_device"]
 
 
 _product = None
@@ -101,6 +112,15 @@ def _ids(stream_ids, n):
     a = np.ascontiguousarray(stream_ids, dtype=np.int32)
     if a.size != n:
         raise ValueError("stream_ids must have one id per row")
+    return a
+
+
+def _mask(mask, n, what):
+    if mask is None:
+        return None
+    a = np.ascontiguousarray(mask, dtype=np.uint8)
+    if a.size != n:
+        raise ValueError("%s must have one entry per row" % what)
     return a
 
 
@@ -162,7 +182,7 @@ class Context:
         packets = np.ascontiguousarray(packets, dtype=np.uint8).reshape(-1, packet_bytes(num_bits))
         n = packets.shape[0]
         ids = _ids(stream_ids, n)
-        rec = None if received is None else np.ascontiguousarray(received, dtype=np.uint8)
+        rec = _mask(received, n, "received")
         out = np.empty((n, HOP), dtype=np.int16)
         self._check(self.api.lib.lyra_b200_decode(self.h, _ptr(ids), n, _ptr(packets), _ptr(rec), num_bits, _ptr(out)))
         return out
@@ -214,7 +234,7 @@ class Context:
         packets = np.ascontiguousarray(packets, dtype=np.uint8).reshape(-1, packet_bytes(num_bits))
         n = packets.shape[0]
         ids = _ids(stream_ids, n)
-        rec = None if received is None else np.ascontiguousarray(received, dtype=np.uint8)
+        rec = _mask(received, n, "received")
         out = np.empty((n, HOP), dtype=np.int16)
         flags = np.empty(n, dtype=np.uint8)
         self._check(self.api.lib.lyra_b200_decode_track_noise(self.h, _ptr(ids), n, _ptr(packets), _ptr(rec), num_bits, _ptr(out), _ptr(flags)))
@@ -229,11 +249,72 @@ class Context:
         pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, HOP)
         n = pcm.shape[0]
         ids = _ids(stream_ids, n)
-        mask = None if update_mask is None else np.ascontiguousarray(update_mask, dtype=np.uint8)
+        mask = _mask(update_mask, n, "update_mask")
         flags = np.empty(n, dtype=np.uint8)
         est = np.empty((n, 160), dtype=np.float32)
         self._check(self.api.lib.lyra_b200_noise_update(self.h, _ptr(ids), n, _ptr(pcm), _ptr(mask), _ptr(flags), _ptr(est)))
         return flags.astype(bool), est
+
+    def noise_estimate(self, n=None, stream_ids=None):
+        """Read-only: (noise_estimate[n][160], is_noise[n] bool) of the decoder-side estimators."""
+        ids = None if stream_ids is None else np.ascontiguousarray(stream_ids, dtype=np.int32)
+        n = ids.size if ids is not None else (self.max_streams if n is None else n)
+        est = np.empty((n, 160), dtype=np.float32)
+        flags = np.empty(n, dtype=np.uint8)
+        self._check(self.api.lib.lyra_b200_noise_estimate(self.h, _ptr(ids), n, _ptr(est), _ptr(flags)))
+        return est, flags.astype(bool)
+
+    # ---- packet-loss concealment / comfort noise / DTX ----
+    def decode_plc(self, packets, num_bits, stream_ids=None, received=None):
+        """One tick of LyraDecoder with the full concealment / comfort-noise / fade behaviour -> (pcm[n][320], is_comfort_noise[n])."""
+        packets = np.ascontiguousarray(packets, dtype=np.uint8).reshape(-1, packet_bytes(num_bits))
+        n = packets.shape[0]
+        ids = _ids(stream_ids, n)
+        rec = _mask(received, n, "received")
+        out = np.empty((n, HOP), dtype=np.int16)
+        cn = np.empty(n, dtype=np.uint8)
+        self._check(self.api.lib.lyra_b200_decode_plc(self.h, _ptr(ids), n, _ptr(packets), _ptr(rec), num_bits, _ptr(out), _ptr(cn)))
+        return out, cn.astype(bool)
+
+    def decode_plc_device(self, n, d_packets, d_received, num_bits, d_pcm, d_is_cn=0):
+        self._check(self.api.lib.lyra_b200_decode_plc_device(self.h, n, C.c_void_p(d_packets), C.c_void_p(d_received or 0), num_bits,
+                                                             C.c_void_p(d_pcm), C.c_void_p(d_is_cn or 0)))
+
+    def plc_state(self, n=None, stream_ids=None):
+        ids = None if stream_ids is None else np.ascontiguousarray(stream_ids, dtype=np.int32)
+        n = ids.size if ids is not None else (self.max_streams if n is None else n)
+        st = np.empty((n, 3), dtype=np.int32)
+        self._check(self.api.lib.lyra_b200_plc_get_state(self.h, _ptr(ids), n, _ptr(st)))
+        return st
+
+    def set_plc_state(self, state, stream_ids=None):
+        st = np.ascontiguousarray(state, dtype=np.int32).reshape(-1, 3)
+        ids = _ids(stream_ids, st.shape[0])
+        self._check(self.api.lib.lyra_b200_plc_set_state(self.h, _ptr(ids), st.shape[0], _ptr(st)))
+
+    def cng_generate(self, features, stream_ids=None):
+        f = np.ascontiguousarray(features, dtype=np.float32).reshape(-1, 160)
+        n = f.shape[0]
+        ids = _ids(stream_ids, n)
+        out = np.empty((n, HOP), dtype=np.int16)
+        self._check(self.api.lib.lyra_b200_cng_generate(self.h, _ptr(ids), n, _ptr(f), _ptr(out)))
+        return out
+
+    def set_cng_seed(self, seed):
+        self._check(self.api.lib.lyra_b200_set_cng_seed(self.h, int(seed)))
+
+    def encode_dtx(self, pcm, num_bits, stream_ids=None):
+        """LyraEncoder::Encode with DTX -> (packets[n][P], packet_bytes[n]: P, or 0 for an empty (noise) packet)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, HOP)
+        n = pcm.shape[0]
+        ids = _ids(stream_ids, n)
+        out = np.empty((n, packet_bytes(num_bits)), dtype=np.uint8)
+        sizes = np.empty(n, dtype=np.int32)
+        self._check(self.api.lib.lyra_b200_encode_dtx(self.h, _ptr(ids), n, _ptr(pcm), num_bits, _ptr(out), _ptr(sizes)))
+        return out, sizes
+
+    def encode_dtx_device(self, n, d_pcm, num_bits, d_packets, d_is_noise):
+        self._check(self.api.lib.lyra_b200_encode_dtx_device(self.h, n, C.c_void_p(d_pcm), num_bits, C.c_void_p(d_packets), C.c_void_p(d_is_noise)))
 
     def noise_update_device(self, n, d_pcm, d_mask, d_is_noise, d_estimate):
         self._check(self.api.lib.lyra_b200_noise_update_device(self.h, n, C.c_void_p(d_pcm), C.c_void_p(d_mask or 0),

@@ -18,7 +18,7 @@ constexpr int kRvqSlotsPerBlock = kRvqThreads / 16;
 
 __global__ void __launch_bounds__(kRvqThreads)
 RvqEncodeKernel(const uint8_t* __restrict__ blob, RvqParams P, const float* __restrict__ features, int n, int nq,
-                uint8_t* __restrict__ packets, int packet_bytes, int* __restrict__ indices_out) {
+                uint8_t* __restrict__ packets, int packet_bytes, int* __restrict__ indices_out, const uint8_t* __restrict__ skip) {
   unsigned char* smem = LYRA_DYN_SMEM();
   float* cbs = reinterpret_cast<float*>(smem);                                  // [2][64][16] stage codebooks (double buffer, 16-byte aligned)
   float* rs = cbs + 2 * 1024;                                                   // [slots][64] residuals
@@ -26,6 +26,7 @@ RvqEncodeKernel(const uint8_t* __restrict__ blob, RvqParams P, const float* __re
   const int tid = (int)threadIdx.x, grp = tid / 16, c = tid % 16;
   const int slot = (int)blockIdx.x * kRvqSlotsPerBlock + grp;
   const bool valid = slot < n;
+  const bool skipped = valid && skip != nullptr && skip[slot];     // DTX: the hop was noise, its packet is empty (bytes zeroed)
   float* r = rs + grp * 64;
   int* idx = idxs + grp * 48;
   const float* cbt = BlobPtr<float>(blob, P.codebooks_t);
@@ -73,7 +74,7 @@ RvqEncodeKernel(const uint8_t* __restrict__ blob, RvqParams P, const float* __re
     // first quantizer in the most significant bits (residual_vector_quantizer.cc:101-109), bytes MSB-first
     for (int b = c; b < packet_bytes; b += 16) {
       const int hi = idx[2 * b], lo = 2 * b + 1 < nq ? idx[2 * b + 1] : 0;
-      packets[(size_t)slot * packet_bytes + b] = (uint8_t)((hi << 4) | lo);
+      packets[(size_t)slot * packet_bytes + b] = skipped ? (uint8_t)0 : (uint8_t)((hi << 4) | lo);
     }
     if (indices_out)
       for (int s = c; s < P.num_stages; s += 16) indices_out[(size_t)slot * P.num_stages + s] = s < nq ? idx[s] : -1;

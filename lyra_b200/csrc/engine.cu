@@ -12,6 +12,7 @@
 #include "model_spec.h"
 #include "net_kernels.cuh"
 #include "net_kernels_umma.cuh"
+#include "plc_kernels.cuh"
 
 using namespace lyra_b200;
 
@@ -58,7 +59,24 @@ struct lyra_b200_ctx {
   float* d_noise = nullptr;          // [max_streams][NoiseStateUnits(160)] noise-estimator state
   float* d_noise_est = nullptr;      // staging for the host-buffer API
   uint8_t* d_is_noise = nullptr;
+  float* d_noise_enc = nullptr;      // the encoder side's own estimators (DTX, lyra/lyra_encoder.cc:80-89)
+  int16_t* d_logmel_prev_enc = nullptr;
   NoiseParams noise_params{};
+  // decoder packet-loss path (PlcPlanKernel / ComfortNoiseKernel / PlcMixKernel)
+  int* d_plc = nullptr;                      // [max_streams][4] concealment_progress, fade_progress, fade_direction, -
+  double* d_cng_work = nullptr;              // [max_streams][1024] overlap-add buffers of the comfort-noise generators
+  unsigned long long* d_cng_hops = nullptr;  // [max_streams]
+  unsigned long long cng_seed = 0;
+  uint8_t* d_plan = nullptr;                 // by slot
+  uint8_t* d_skip = nullptr;
+  uint8_t* d_feed = nullptr;
+  uint8_t* d_is_cn = nullptr;
+  int* d_fade0 = nullptr;
+  int* d_dir = nullptr;
+  int16_t* d_model_pcm = nullptr;
+  int16_t* d_cng_pcm = nullptr;
+  float* d_cng_feat = nullptr;
+  const uint8_t* cur_skip = nullptr;         // skip mask of the call in flight (TileIo::skip)
   // device staging for the host-buffer API
   int16_t* d_pcm = nullptr;
   uint8_t* d_packets = nullptr;
@@ -208,7 +226,7 @@ Part WholeCall(lyra_b200_ctx* ctx, int n) { return Part{0, ctx->active_tiles, 0,
 
 template <int kS>
 int LaunchEncoderNetsT(lyra_b200_ctx* ctx, const Part& p, const int16_t* d_pcm, float* d_features) {
-  const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of};
+  const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of, ctx->cur_skip};
   { ProfScope ps(ctx, 0, p.st);
   LYRA_LAUNCH(EncoderKernelA<kS>, dim3((unsigned)p.ntiles), dim3(EncA<kS>::NT), (size_t)EncA<kS>::kSmemBytes, p.st,
               ctx->d_blob, ctx->spec.enc, io, d_pcm, reinterpret_cast<float*>(ctx->d_state[0]), ctx->d_n18[0], ctx->d_mid_enc); }
@@ -223,13 +241,14 @@ int LaunchEncoderNets(lyra_b200_ctx* ctx, const Part& p, const int16_t* d_pcm, f
   return ctx->S == 16 ? LaunchEncoderNetsT<16>(ctx, p, d_pcm, d_features) : LaunchEncoderNetsT<8>(ctx, p, d_pcm, d_features);
 }
 
-int LaunchQuantize(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int num_bits, uint8_t* d_packets, int* d_indices) {
+int LaunchQuantize(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int num_bits, uint8_t* d_packets, int* d_indices,
+                   const uint8_t* d_skip = nullptr) {
   const int nq = num_bits / ctx->spec.bits_per_stage, pb = PacketBytes(num_bits);
   const int blocks = (p.nslots + kRvqSlotsPerBlock - 1) / kRvqSlotsPerBlock;
   { ProfScope ps(ctx, 2, p.st);
   LYRA_LAUNCH(RvqEncodeKernel, dim3((unsigned)blocks), dim3(kRvqThreads), (size_t)(2 * 1024 * 4 + kRvqSlotsPerBlock * (64 * 4 + 48 * 4)), p.st,
               ctx->d_blob, ctx->spec.rvq, d_features + (size_t)p.slot0 * 64, p.nslots, nq, d_packets + (size_t)p.slot0 * pb, pb,
-              d_indices ? d_indices + (size_t)p.slot0 * 46 : nullptr); }
+              d_indices ? d_indices + (size_t)p.slot0 * 46 : nullptr, d_skip ? d_skip + p.slot0 : nullptr); }
   ctx->launches += 1;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
@@ -249,7 +268,7 @@ int LaunchDequantize(lyra_b200_ctx* ctx, const Part& p, const uint8_t* d_packets
 
 template <int kS, bool kTC>
 int LaunchDecoderNetsT(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int16_t* d_pcm) {
-  const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of};
+  const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of, ctx->cur_skip};
   using LC = DecC<kS, kTC>;
   using LD = DecD<kS, kTC>;
   { ProfScope ps(ctx, 4, p.st);
@@ -265,7 +284,7 @@ int LaunchDecoderNetsT(lyra_b200_ctx* ctx, const Part& p, const float* d_feature
 // Tensor mode at 8-stream tiles (the default tile): kernel C with its fp32 residual units on mma.sync TF32, kernel D on the
 // 5th-generation tensor cores (tcgen05.mma, accumulators and A operands in tensor memory; net_kernels_umma.cuh).
 int LaunchDecoderNetsUmma(lyra_b200_ctx* ctx, const Part& p, const float* d_features, int16_t* d_pcm) {
-  const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of};
+  const TileIo io{ctx->d_tile_list + p.tile0, ctx->d_slot_of, ctx->cur_skip};
   using LC = DecC<8, true>;
   { ProfScope ps(ctx, 4, p.st);
   LYRA_LAUNCH((DecoderKernelC<8, true>), dim3((unsigned)p.ntiles), dim3(LC::NT), (size_t)LC::kSmemBytes, p.st,
@@ -327,15 +346,17 @@ int JoinAfter(lyra_b200_ctx* ctx, int nparts, int rc) {
 // log-mel of this hop (the estimator's own extractor, bank 2) + the estimator recurrences for slots
 // [slot0, slot0 + count) on stream `st`; all arrays are indexed by slot, n = total slots of the call
 int LaunchNoiseUpdate(lyra_b200_ctx* ctx, cudaStream_t st, const int* d_ids, int slot0, int count, int n, const int16_t* d_pcm,
-                      const uint8_t* d_mask, uint8_t* d_is_noise, float* d_estimate) {
+                      const uint8_t* d_mask, uint8_t* d_is_noise, float* d_estimate, bool encoder_side = false) {
+  float* noise_state = encoder_side ? ctx->d_noise_enc : ctx->d_noise;
+  int16_t* carried = encoder_side ? ctx->d_logmel_prev_enc : ctx->d_logmel_prev[2];
   const LogMelParams& P = ctx->spec.logmel160;
   const size_t smem = sizeof(double) * (size_t)(2 * kLogMelFftPadded + P.fft / 2 + 1 + P.window_len + P.window_len / 8 + 1);
   { ProfScope ps(ctx, 6, st);
   LYRA_LAUNCH(LogMelKernel, dim3((unsigned)count), dim3(kLogMelThreads), smem, st,
-              ctx->d_blob, P, d_ids, n, d_pcm, ctx->d_logmel_prev[2], ctx->d_melout, d_mask, slot0); }
+              ctx->d_blob, P, d_ids, n, d_pcm, carried, ctx->d_melout, d_mask, slot0); }
   { ProfScope ps(ctx, 7, st);
   LYRA_LAUNCH(NoiseEstimatorKernel, dim3((unsigned)count), dim3(kNoiseThreads), sizeof(float) * (size_t)(2 * 160 + 2), st,
-              ctx->noise_params, d_ids, n, ctx->d_melout, d_mask, ctx->d_noise, d_is_noise, d_estimate, slot0); }
+              ctx->noise_params, d_ids, n, ctx->d_melout, d_mask, noise_state, d_is_noise, d_estimate, slot0); }
   ctx->launches += 2;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
@@ -343,8 +364,11 @@ int LaunchNoiseUpdate(lyra_b200_ctx* ctx, cudaStream_t st, const int* d_ids, int
 
 // h_pcm / h_packets (host-buffer API): each part copies its own slice in on its own stream before its kernels and
 // its result out right after them, so the copies of one part overlap the kernels of the others.
+// dtx: every sub-batch first feeds its hops to the encoder-side noise estimators; hops classified as noise skip the encoder
+// (their streams' state does not advance) and get an empty packet (lyra/lyra_encoder.cc:131-141); d_is_noise[slot] = 1 marks them
 int RunEncode(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets,
-              const int16_t* h_pcm = nullptr, uint8_t* h_packets = nullptr) {
+              const int16_t* h_pcm = nullptr, uint8_t* h_packets = nullptr, bool dtx = false, const int* d_ids = nullptr,
+              uint8_t* d_is_noise = nullptr, uint8_t* h_is_noise = nullptr) {
   Part parts[lyra_b200_ctx::kMaxSplit];
   const int np = SplitParts(ctx, n, parts);
   const size_t pb = (size_t)PacketBytes(num_bits);
@@ -355,8 +379,15 @@ int RunEncode(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uin
     if (h_pcm)
       CUB(cudaMemcpyAsync(ctx->d_pcm + (size_t)p.slot0 * 320, h_pcm + (size_t)p.slot0 * 320, sizeof(int16_t) * 320 * (size_t)p.nslots,
                           cudaMemcpyHostToDevice, p.st));
-    if ((rc = LaunchEncoderNets(ctx, p, d_pcm, ctx->d_features))) break;
-    if ((rc = LaunchQuantize(ctx, p, ctx->d_features, num_bits, d_packets, nullptr))) break;
+    if (dtx) {
+      if ((rc = LaunchNoiseUpdate(ctx, p.st, d_ids, p.slot0, p.nslots, n, d_pcm, nullptr, d_is_noise, nullptr, true))) break;
+      if (h_is_noise) CUB(cudaMemcpyAsync(h_is_noise + p.slot0, d_is_noise + p.slot0, (size_t)p.nslots, cudaMemcpyDeviceToHost, p.st));
+    }
+    ctx->cur_skip = dtx ? d_is_noise : nullptr;
+    rc = LaunchEncoderNets(ctx, p, d_pcm, ctx->d_features);
+    ctx->cur_skip = nullptr;
+    if (rc) break;
+    if ((rc = LaunchQuantize(ctx, p, ctx->d_features, num_bits, d_packets, nullptr, dtx ? d_is_noise : nullptr))) break;
     if (h_packets)
       CUB(cudaMemcpyAsync(h_packets + (size_t)p.slot0 * pb, d_packets + (size_t)p.slot0 * pb, pb * (size_t)p.nslots, cudaMemcpyDeviceToHost, p.st));
   }
@@ -390,6 +421,65 @@ int RunDecode(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t
                           cudaMemcpyDeviceToHost, p.st));
   }
   return JoinAfter(ctx, np, rc);
+}
+
+// LyraDecoder::{SetEncodedPacket, DecodeSamples(320)} with the reference's concealment / comfort-noise / fade behaviour for n
+// streams (lyra/lyra_decoder.cc:172-315): plan (per-stream state machine) -> RVQ decode -> LyraGAN for the streams that need
+// model audio -> comfort noise from the current noise estimates for the streams that need it -> cross-fade -> noise-estimator
+// update of the streams that decoded a received packet.  One whole hop per stream and call.
+int RunDecodePlc(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits, int16_t* d_pcm,
+                 const int* d_ids, uint8_t* d_is_cn, const uint8_t* h_packets, const uint8_t* h_received, int16_t* h_pcm, uint8_t* h_is_cn) {
+  const size_t pb = (size_t)PacketBytes(num_bits);
+  if (h_received) CU(cudaMemcpyAsync(ctx->d_received, h_received, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  LYRA_LAUNCH(PlcPlanKernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, ctx->stream,
+              d_ids, n, d_received, ctx->d_plc, ctx->d_plan, ctx->d_fade0, ctx->d_dir, ctx->d_skip, ctx->d_feed, d_is_cn);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  Part parts[lyra_b200_ctx::kMaxSplit];
+  const int np = SplitParts(ctx, n, parts);
+  int rc = Fork(ctx, np);
+  if (rc) return rc;
+  const size_t cng_smem = sizeof(double) * (size_t)(4 * kLogMelFftPadded + 160);
+  for (int i = 0; i < np && !rc; ++i) {
+    const Part& p = parts[i];
+    if (h_packets)
+      CUB(cudaMemcpyAsync(ctx->d_packets + (size_t)p.slot0 * pb, h_packets + (size_t)p.slot0 * pb, pb * (size_t)p.nslots, cudaMemcpyHostToDevice, p.st));
+    if ((rc = LaunchDequantize(ctx, p, d_packets, d_received, num_bits, ctx->d_features))) break;
+    ctx->cur_skip = ctx->d_skip;
+    rc = LaunchDecoderNets(ctx, p, ctx->d_features, ctx->d_model_pcm);
+    ctx->cur_skip = nullptr;
+    if (rc) break;
+    LYRA_LAUNCH(ComfortNoiseKernel, dim3((unsigned)p.nslots), dim3(kCngThreads), cng_smem, p.st,
+                ctx->d_blob, ctx->spec.cng, d_ids, n, (const float*)nullptr, ctx->d_noise, NoiseStateUnits(ctx->noise_params.nf),
+                ctx->d_plan, ctx->d_cng_work, ctx->d_cng_hops, ctx->cng_seed, ctx->d_cng_pcm, p.slot0);
+    LYRA_LAUNCH(PlcMixKernel, dim3((unsigned)p.nslots), dim3(320), (size_t)0, p.st,
+                ctx->d_blob, ctx->spec.cng, p.nslots, ctx->d_plan + p.slot0, ctx->d_fade0 + p.slot0, ctx->d_dir + p.slot0,
+                ctx->d_model_pcm + (size_t)p.slot0 * 320, ctx->d_cng_pcm + (size_t)p.slot0 * 320, d_pcm + (size_t)p.slot0 * 320);
+    ctx->launches += 2;
+    CUB(cudaGetLastError());
+    if ((rc = LaunchNoiseUpdate(ctx, p.st, d_ids, p.slot0, p.nslots, n, ctx->d_model_pcm, ctx->d_feed, nullptr, nullptr))) break;
+    if (h_pcm)
+      CUB(cudaMemcpyAsync(h_pcm + (size_t)p.slot0 * 320, d_pcm + (size_t)p.slot0 * 320, sizeof(int16_t) * 320 * (size_t)p.nslots,
+                          cudaMemcpyDeviceToHost, p.st));
+    if (h_is_cn) CUB(cudaMemcpyAsync(h_is_cn + p.slot0, d_is_cn + p.slot0, (size_t)p.nslots, cudaMemcpyDeviceToHost, p.st));
+  }
+  return JoinAfter(ctx, np, rc);
+}
+
+// stream ids of a sparse call -> device (validated: in range, no duplicates); *d_ids stays nullptr for dense calls
+int UploadIds(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int** d_ids) {
+  *d_ids = nullptr;
+  if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
+  if (!ids) return LYRA_B200_OK;
+  std::vector<char> seen((size_t)ctx->max_streams, 0);
+  for (int k = 0; k < n; ++k) {
+    if (ids[k] < 0 || ids[k] >= ctx->max_streams || seen[(size_t)ids[k]]) { ctx->err = "bad or duplicate stream id"; return LYRA_B200_EINVAL; }
+    seen[(size_t)ids[k]] = 1;
+  }
+  CU(cudaMemcpyAsync(ctx->d_ids, ids, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(SyncStream(ctx));          // `ids` is the caller's (pageable) memory
+  *d_ids = ctx->d_ids;
+  return LYRA_B200_OK;
 }
 
 template <int kS>
@@ -455,6 +545,28 @@ int ResetImpl(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
     CU(cudaMemsetAsync(ctx->d_noise, 0, sizeof(float) * nu * (size_t)n, ctx->stream));
   } else {
     for (int k = 0; k < n; ++k) CU(cudaMemsetAsync(ctx->d_noise + (size_t)ids[k] * nu, 0, sizeof(float) * nu, ctx->stream));
+  }
+  // decoder control state (0, 0, fade from comfort noise: lyra_decoder.cc:164-166), comfort-noise buffers and hop counters,
+  // encoder-side estimators and their carried samples
+  std::vector<int> hs;
+  if (ids) hs.assign(ids, ids + n); else { hs.resize((size_t)n); for (int k = 0; k < n; ++k) hs[(size_t)k] = k; }
+  const int plc0[4] = {0, 0, -1, 0};
+  for (int k = 0; k < n && ids; ++k) {
+    const size_t id = (size_t)hs[(size_t)k];
+    CU(cudaMemcpyAsync(ctx->d_plc + id * 4, plc0, sizeof(plc0), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cng_work + id * 1024, 0, sizeof(double) * 1024, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cng_hops + id, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_noise_enc + id * nu, 0, sizeof(float) * nu, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_logmel_prev_enc + id * 320, 0, sizeof(int16_t) * 320, ctx->stream));
+  }
+  if (!ids) {
+    std::vector<int> img((size_t)n * 4);
+    for (int k = 0; k < n; ++k) { img[(size_t)k * 4] = 0; img[(size_t)k * 4 + 1] = 0; img[(size_t)k * 4 + 2] = -1; img[(size_t)k * 4 + 3] = 0; }
+    CU(cudaMemcpy(ctx->d_plc, img.data(), sizeof(int) * img.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemsetAsync(ctx->d_cng_work, 0, sizeof(double) * 1024 * (size_t)n, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cng_hops, 0, sizeof(unsigned long long) * (size_t)n, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_noise_enc, 0, sizeof(float) * nu * (size_t)n, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_logmel_prev_enc, 0, sizeof(int16_t) * 320 * (size_t)n, ctx->stream));
   }
   CU(SyncStream(ctx));
   return LYRA_B200_OK;
@@ -560,6 +672,20 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
   }
   ok = ok && DevAlloc(&ctx->d_noise, P * (size_t)NoiseStateUnits(160)) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_noise_est, P * 160) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_noise_enc, P * (size_t)NoiseStateUnits(160)) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_logmel_prev_enc, P * 320) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_plc, P * 4) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_cng_work, P * 1024) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_cng_hops, P) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_plan, P) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_skip, P) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_feed, P) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_is_cn, P) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_fade0, P) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_dir, P) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_model_pcm, P * 320) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_cng_pcm, P * 320) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_cng_feat, P * 160) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_is_noise, P) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_pcm, P * 320) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_packets, P * 24) == cudaSuccess;
@@ -600,6 +726,9 @@ void lyra_b200_destroy(lyra_b200_ctx* ctx) {
   cudaFree(ctx->d_mid_enc); cudaFree(ctx->d_mid_dec);
   cudaFree(ctx->d_logmel_prev[0]); cudaFree(ctx->d_logmel_prev[1]); cudaFree(ctx->d_logmel_prev[2]);
   cudaFree(ctx->d_noise); cudaFree(ctx->d_noise_est); cudaFree(ctx->d_is_noise);
+  cudaFree(ctx->d_noise_enc); cudaFree(ctx->d_logmel_prev_enc); cudaFree(ctx->d_plc); cudaFree(ctx->d_cng_work); cudaFree(ctx->d_cng_hops);
+  cudaFree(ctx->d_plan); cudaFree(ctx->d_skip); cudaFree(ctx->d_feed); cudaFree(ctx->d_is_cn); cudaFree(ctx->d_fade0); cudaFree(ctx->d_dir);
+  cudaFree(ctx->d_model_pcm); cudaFree(ctx->d_cng_pcm); cudaFree(ctx->d_cng_feat);
   cudaFree(ctx->d_pcm); cudaFree(ctx->d_packets); cudaFree(ctx->d_received); cudaFree(ctx->d_features);
   cudaFree(ctx->d_melout); cudaFree(ctx->d_indices); cudaFree(ctx->d_ids); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_slot_of);
   for (int b = 0; b < 2; ++b) {
@@ -820,7 +949,6 @@ int lyra_b200_noise_update(lyra_b200_ctx* ctx, const int32_t* ids, int n, const 
                            uint8_t* is_noise, float* noise_estimate) {
   if (!ctx || !pcm) return LYRA_B200_EINVAL;
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
-  if (!RoleOk(ctx, LYRA_B200_ROLE_DECODER)) return LYRA_B200_EINVAL;
   if (n <= 0 || n > ctx->max_streams) { ctx->err = "stream count out of range"; return LYRA_B200_EINVAL; }
   const int* d_ids = nullptr;
   if (ids) {
@@ -881,6 +1009,130 @@ int lyra_b200_decode_track_noise_device(lyra_b200_ctx* ctx, int n, const uint8_t
   if (rc) return rc;
   return RunDecode(ctx, n, d_packets, d_received, num_bits, d_pcm, nullptr, nullptr, nullptr, true, nullptr,
                    d_is_noise ? d_is_noise : ctx->d_is_noise, nullptr);
+}
+
+#define ENTER(role)                                                                                          \
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }    \
+  if ((role) && !RoleOk(ctx, (role))) return LYRA_B200_EINVAL;
+
+int lyra_b200_encode_dtx(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, int num_bits, uint8_t* packets,
+                         int32_t* packet_bytes) {
+  if (!ctx || !pcm || !packets || !packet_bytes) return LYRA_B200_EINVAL;
+  ENTER(LYRA_B200_ROLE_ENCODER);
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  const int* d_ids = nullptr;
+  int rc = UploadIds(ctx, ids, n, &d_ids);
+  if (rc) return rc;
+  if ((rc = PrepareMap(ctx, ids, n))) return rc;
+  std::vector<uint8_t> flags((size_t)n);
+  if ((rc = RunEncode(ctx, n, ctx->d_pcm, num_bits, ctx->d_packets, pcm, packets, true, d_ids, ctx->d_is_noise, flags.data()))) return rc;
+  CU(SyncStream(ctx));
+  for (int k = 0; k < n; ++k) packet_bytes[k] = flags[(size_t)k] ? 0 : PacketBytes(num_bits);
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_encode_dtx_device(lyra_b200_ctx* ctx, int n, const int16_t* d_pcm, int num_bits, uint8_t* d_packets, uint8_t* d_is_noise) {
+  if (!ctx || !d_pcm || !d_packets || !d_is_noise) return LYRA_B200_EINVAL;
+  ENTER(LYRA_B200_ROLE_ENCODER);
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, nullptr, n);
+  if (rc) return rc;
+  return RunEncode(ctx, n, d_pcm, num_bits, d_packets, nullptr, nullptr, true, nullptr, d_is_noise, nullptr);
+}
+
+int lyra_b200_decode_plc(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_t* packets, const uint8_t* received, int num_bits,
+                         int16_t* pcm, uint8_t* is_comfort_noise) {
+  if (!ctx || !packets || !pcm) return LYRA_B200_EINVAL;
+  ENTER(LYRA_B200_ROLE_DECODER);
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  const int* d_ids = nullptr;
+  int rc = UploadIds(ctx, ids, n, &d_ids);
+  if (rc) return rc;
+  if ((rc = PrepareMap(ctx, ids, n))) return rc;
+  if ((rc = RunDecodePlc(ctx, n, ctx->d_packets, received ? ctx->d_received : nullptr, num_bits, ctx->d_pcm, d_ids, ctx->d_is_cn, packets,
+                         received, pcm, is_comfort_noise))) return rc;
+  CU(SyncStream(ctx));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_decode_plc_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets, const uint8_t* d_received, int num_bits,
+                                int16_t* d_pcm, uint8_t* d_is_comfort_noise) {
+  if (!ctx || !d_packets || !d_pcm) return LYRA_B200_EINVAL;
+  ENTER(LYRA_B200_ROLE_DECODER);
+  if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
+  int rc = PrepareMap(ctx, nullptr, n);
+  if (rc) return rc;
+  return RunDecodePlc(ctx, n, d_packets, d_received, num_bits, d_pcm, nullptr, d_is_comfort_noise ? d_is_comfort_noise : ctx->d_is_cn,
+                      nullptr, nullptr, nullptr, nullptr);
+}
+
+int lyra_b200_plc_get_state(lyra_b200_ctx* ctx, const int32_t* ids, int n, int32_t* state) {
+  if (!ctx || !state || n <= 0 || n > ctx->max_streams) return LYRA_B200_EINVAL;
+  ENTER(0);
+  CU(SyncStream(ctx));
+  for (int k = 0; k < n; ++k) {
+    const int id = ids ? ids[k] : k;
+    if (id < 0 || id >= ctx->max_streams) { ctx->err = "stream id out of range"; return LYRA_B200_EINVAL; }
+    CU(cudaMemcpy(state + (size_t)k * 3, ctx->d_plc + (size_t)id * 4, sizeof(int) * 3, cudaMemcpyDeviceToHost));
+  }
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_plc_set_state(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int32_t* state) {
+  if (!ctx || !state || n <= 0 || n > ctx->max_streams) return LYRA_B200_EINVAL;
+  ENTER(0);
+  CU(SyncStream(ctx));
+  for (int k = 0; k < n; ++k) {
+    const int id = ids ? ids[k] : k;
+    if (id < 0 || id >= ctx->max_streams) { ctx->err = "stream id out of range"; return LYRA_B200_EINVAL; }
+    const int32_t* s3 = state + (size_t)k * 3;
+    if (s3[0] < 0 || s3[0] > kPlcConcealSamples || s3[0] % 320 || s3[1] < 0 || s3[1] > kPlcFadeSamples || s3[1] % 320 || (s3[2] != 1 && s3[2] != -1)) {
+      ctx->err = "decoder control state must be hop aligned: concealment 0..1280, fade 0..640, direction +-1";
+      return LYRA_B200_EINVAL;
+    }
+    CU(cudaMemcpy(ctx->d_plc + (size_t)id * 4, s3, sizeof(int) * 3, cudaMemcpyHostToDevice));
+  }
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_set_cng_seed(lyra_b200_ctx* ctx, uint64_t seed) {
+  if (!ctx) return LYRA_B200_EINVAL;
+  ctx->cng_seed = seed;
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_cng_generate(lyra_b200_ctx* ctx, const int32_t* ids, int n, const float* features, int16_t* pcm) {
+  if (!ctx || !features || !pcm) return LYRA_B200_EINVAL;
+  ENTER(0);
+  const int* d_ids = nullptr;
+  int rc = UploadIds(ctx, ids, n, &d_ids);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->d_cng_feat, features, sizeof(float) * 160 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t cng_smem = sizeof(double) * (size_t)(4 * kLogMelFftPadded + 160);
+  LYRA_LAUNCH(ComfortNoiseKernel, dim3((unsigned)n), dim3(kCngThreads), cng_smem, ctx->stream,
+              ctx->d_blob, ctx->spec.cng, d_ids, n, ctx->d_cng_feat, ctx->d_noise, NoiseStateUnits(ctx->noise_params.nf),
+              (const uint8_t*)nullptr, ctx->d_cng_work, ctx->d_cng_hops, ctx->cng_seed, ctx->d_cng_pcm, 0);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(pcm, ctx->d_cng_pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(SyncStream(ctx));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_noise_estimate(lyra_b200_ctx* ctx, const int32_t* ids, int n, float* noise_estimate, uint8_t* is_noise) {
+  if (!ctx || (!noise_estimate && !is_noise)) return LYRA_B200_EINVAL;
+  ENTER(0);
+  const int* d_ids = nullptr;
+  int rc = UploadIds(ctx, ids, n, &d_ids);
+  if (rc) return rc;
+  LYRA_LAUNCH(NoiseReadKernel, dim3((unsigned)n), dim3(192), (size_t)0, ctx->stream,
+              d_ids, n, ctx->d_noise, ctx->noise_params.nf, noise_estimate ? ctx->d_noise_est : nullptr, is_noise ? ctx->d_is_noise : nullptr);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  if (noise_estimate) CU(cudaMemcpyAsync(noise_estimate, ctx->d_noise_est, sizeof(float) * 160 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (is_noise) CU(cudaMemcpyAsync(is_noise, ctx->d_is_noise, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(SyncStream(ctx));
+  return LYRA_B200_OK;
 }
 
 }  // extern "C"

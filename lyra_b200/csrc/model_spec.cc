@@ -658,6 +658,35 @@ LogMelParams BuildLogMelParams(std::vector<uint8_t>* blob, int sample_rate_hz, i
   return p;
 }
 
+// Tables of the comfort-noise generator; `lm` = the 160-bin log-mel tables already in the blob.  Same expressions, in the same
+// order, as oracle/comfort_noise.c lo_cng_create (the sums are order-sensitive in their last bits).
+CngParams BuildCngParams(std::vector<uint8_t>* blob, const LogMelParams& lm, int window) {
+  CngParams p;
+  std::memset(&p, 0, sizeof(p));
+  const int bins = lm.fft / 2 + 1;
+  const double* weights = reinterpret_cast<const double*>(blob->data() + lm.weights);
+  const int32_t* band = reinterpret_cast<const int32_t*>(blob->data() + lm.band);
+  std::vector<double> norm((size_t)lm.num_mel, 0.0), synth((size_t)lm.fft);
+  for (int i = lm.start_index; i <= lm.end_index && i < bins; ++i) {
+    const int ch = band[i];
+    if (ch >= 0) norm[(size_t)ch] += weights[i];
+    if (ch + 1 < lm.num_mel) norm[(size_t)ch + 1] += 1.0 - weights[i];
+  }
+  double swa = 0.0, sws = 0.0;
+  for (int i = 0; i < window; ++i) { const double w = 0.5 - 0.5 * std::cos(2.0 * M_PI * i / (double)window); swa += w * w; }
+  for (int i = 0; i < lm.fft; ++i) { synth[(size_t)i] = 0.5 - 0.5 * std::cos(2.0 * M_PI * i / (double)lm.fft); sws += synth[(size_t)i] * synth[(size_t)i]; }
+  const double gain = std::sqrt((double)lm.fft * (double)lm.hop / (swa * sws));
+  for (int i = 0; i < lm.fft; ++i) synth[(size_t)i] *= gain;
+  std::vector<float> fade(641);
+  for (int fp = 0; fp <= 640; ++fp) fade[(size_t)fp] = (float)((1.0 + std::cos((double)fp * M_PI / (double)640)) / 2.0);
+  p.weights = lm.weights; p.band = lm.band; p.twiddle = lm.twiddle;
+  p.norm = Append(blob, norm);
+  p.synth = Append(blob, synth);
+  p.fade = Append(blob, fade);
+  p.start_index = lm.start_index; p.end_index = lm.end_index; p.num_mel = lm.num_mel; p.fft = lm.fft; p.hop = lm.hop;
+  return p;
+}
+
 ModelSpec BuildModelSpec(const std::string& model_dir) {
   ModelSpec s;
   {
@@ -676,6 +705,7 @@ ModelSpec BuildModelSpec(const std::string& model_dir) {
   s.rvq = BuildRvq(rvq, &s.blob, &s.bits_per_stage);
   s.logmel160 = BuildLogMelParams(&s.blob, 16000, 320, 640, 160);
   s.logmel64 = BuildLogMelParams(&s.blob, 16000, 320, 640, 64);
+  s.cng = BuildCngParams(&s.blob, s.logmel160, 640);
   while (s.blob.size() % 256) s.blob.push_back(0);
   return s;
 }

@@ -109,4 +109,18 @@ struct LogMelParams {
   int32_t start_index, end_index, num_mel, fft, window_len, hop;
 };
 
+// Comfort-noise generator (lyra/comfort_noise_generator.cc:37-119) for (16 kHz, hop 320, window 640, 160 mel bins): the mel
+// tables are those of the 160-bin log-mel extractor; norm = per-channel sum of filter weights (mel inverse), synth = synthesis
+// window incl. the power-preserving constant, fade = the decoder's raised-cosine cross-fade weights
+// (1 + cos(p * pi / 640)) / 2 for fade progress p = 0..640 (lyra/lyra_decoder.cc:364-366), all computed on the host with the
+// oracle's expressions.
+struct CngParams {
+  uint32_t weights, band;   // f64 [513], i32 [513]  (shared with LogMelParams of 160 bins)
+  uint32_t norm;            // f64 [160]
+  uint32_t synth;           // f64 [1024]
+  uint32_t twiddle;         // f64 [1023][2], the FFT's per-stage tables (shared)
+  uint32_t fade;            // f32 [641]
+  int32_t start_index, end_index, num_mel, fft, hop;
+};
+
 }  // namespace lyra_b200

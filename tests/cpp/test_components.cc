@@ -124,6 +124,96 @@ int main(int argc, char** argv) {
     }
     lo_noise_free(r);
   }
+  // LyraDecoder's concealment / comfort-noise / fade state machine with the reference tests' fakes (constant-valued generative
+  // models, fixed lossy features and noise estimate; lyra_decoder_test.cc:143-151, testing/mock_generative_model.h:33-53) against
+  // the oracle's restatement driven by the same random script of packets and arbitrary request sizes
+  {
+    struct FakeModel : GenerativeModel {
+      FakeModel(int16_t v, int nf) : GenerativeModel(320, nf), v_(v) {}
+      bool RunConditioning(const std::vector<float>&) override { return true; }
+      std::optional<std::vector<int16_t>> RunModel(int n) override { return std::vector<int16_t>((size_t)n, v_); }
+      int16_t v_;
+    };
+    struct FakeVq : VectorQuantizerInterface {
+      std::optional<std::string> Quantize(const std::vector<float>&, int) const override { return std::nullopt; }
+      std::optional<std::vector<float>> DecodeToLossyFeatures(const std::string&) const override {
+        std::vector<float> f(64);
+        for (int i = 0; i < 64; ++i) f[(size_t)i] = (float)i;
+        return f;
+      }
+    };
+    struct FakeNoise : NoiseEstimatorInterface {
+      bool ReceiveSamples(const std::vector<int16_t>&) override { return true; }
+      std::vector<float> noise_estimate() const override { std::vector<float> f(160); for (int i = 0; i < 160; ++i) f[(size_t)i] = 10.f + (float)i; return f; }
+      bool is_noise() const override { return false; }
+    };
+    LyraDecoderB200 dec(std::make_unique<FakeModel>((int16_t)-10000, 64), std::make_unique<FakeModel>((int16_t)10000, 160),
+                        std::make_unique<FakeVq>(), std::make_unique<FakeNoise>());
+    lo_decoder* r = lo_decoder_create_fake(-10000, 10000);
+    std::uniform_int_distribution<int> coin(0, 99), len(0, 700);
+    const std::vector<uint8_t> zeros(8, 0);
+    int faded = 0;
+    for (int step = 0; step < 400; ++step) {
+      const int burst = (step / 40) % 2;                       // alternate good and bad stretches so every state is visited
+      if (coin(rng) < (burst ? 10 : 85)) { CHECK(dec.SetEncodedPacket(zeros)); CHECK(lo_decoder_set_encoded_packet(r, zeros.data(), 8) == 0); }
+      const int n = coin(rng) < 50 ? 320 : len(rng);
+      auto out = dec.DecodeSamples(n);
+      std::vector<int16_t> want((size_t)n + 1);
+      CHECK(lo_decoder_decode_samples(r, n, want.data()) == n);
+      CHECK(out.has_value() && (int)out->size() == n && std::memcmp(out->data(), want.data(), sizeof(int16_t) * (size_t)n) == 0);
+      int s3[3];
+      lo_decoder_get_state(r, s3);
+      CHECK(dec.concealment_progress() == s3[0] && dec.fade_progress() == s3[1]);
+      CHECK(dec.is_comfort_noise() == (lo_decoder_is_comfort_noise(r) != 0));
+      for (int16_t v : *out) faded += v != -10000 && v != 10000;
+    }
+    CHECK(faded > 0);                                          // cross-faded samples were produced and matched
+    CHECK(!dec.DecodeSamples(-1).has_value());
+    lo_decoder_free(r);
+  }
+  // the real components behind LyraDecoder::Create: comfort noise generator basics (comfort_noise_generator_test.cc:42-98) and a
+  // long outage that ends in comfort noise, then recovery
+  {
+    CHECK(ComfortNoiseGeneratorB200::Create(model, 16000, 320, 640, 64) == nullptr);
+    auto cng = ComfortNoiseGeneratorB200::Create(model, 16000, 320, 640, 160);
+    CHECK(cng != nullptr);
+    CHECK(!cng->AddFeatures(std::vector<float>(159, 1.0f)) && !cng->GenerateSamples(320).has_value());
+    CHECK(cng->AddFeatures(std::vector<float>(160, 0.0f)));
+    CHECK(!cng->GenerateSamples(321).has_value() && !cng->GenerateSamples(-1).has_value());
+    auto z = cng->GenerateSamples(320);
+    CHECK(z.has_value() && z->size() == 320);
+    if (z.has_value()) for (int16_t v : *z) CHECK(v == 0);     // features without energy give silence
+    auto e = LyraEncoderB200::Create(16000, 1, 3200, false, model);
+    auto dcd = LyraDecoderB200::Create(16000, 1, model);
+    CHECK(e && dcd);
+    bool reached_cn = false, back = false;
+    for (int f = 0; f < 30 && e && dcd; ++f) {
+      std::vector<int16_t> pcm(320);
+      for (auto& v : pcm) v = (int16_t)d(rng);
+      auto pkt = e->Encode(pcm);
+      CHECK(pkt.has_value());
+      if (f < 5 || f >= 18) CHECK(dcd->SetEncodedPacket(*pkt));
+      auto out = dcd->DecodeSamples(f % 2 ? 320 : 123);        // odd request sizes keep working
+      CHECK(out.has_value());
+      if (f % 2 == 0) CHECK(dcd->DecodeSamples(197).has_value());
+      reached_cn |= dcd->is_comfort_noise();
+      back |= reached_cn && !dcd->is_comfort_noise() && dcd->fade_progress() == 0 && dcd->concealment_progress() == 0;
+    }
+    CHECK(reached_cn && back);
+  }
+  // DTX (lyra_encoder.cc:131-141): digital silence becomes empty packets from the second hop on, speech-level input is encoded
+  {
+    auto e = LyraEncoderB200::Create(16000, 1, 3200, true, model);
+    CHECK(e != nullptr);
+    for (int f = 0; f < 6 && e; ++f) {
+      auto pkt = e->Encode(std::vector<int16_t>(320, 0));
+      CHECK(pkt.has_value() && pkt->size() == (f == 0 ? 8u : 0u));
+    }
+    std::vector<int16_t> loud(320);
+    for (auto& v : loud) v = (int16_t)d(rng);
+    auto pkt = e ? e->Encode(loud) : std::nullopt;
+    CHECK(pkt.has_value() && pkt->size() == 8);
+  }
   std::printf(g_fail ? "FAILED (%d)\n" : "ALL OK\n", g_fail);
   return g_fail ? 1 : 0;
 }

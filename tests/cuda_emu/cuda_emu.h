@@ -131,6 +131,7 @@ static inline double __dadd_rn(double a, double b) { volatile double r = a + b; 
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline int __dp4a(int a, int b, int c) {
   for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i));
   return c;

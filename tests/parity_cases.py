@@ -226,15 +226,122 @@ def run_role_contexts(Context, api, O, LyraB200Error, *, frames=4, seed=9):
             opkt, _, _ = codecs[k].encode(pcm[k], 120)
             opcm, _, _ = codecs[k].decode(opkt, 120)
             assert bytes(pk[k]) == opkt and np.array_equal(out[k], opcm), (f, k)
-    for bad in (lambda: enc.decode(pk, 120), lambda: dec.encode(pcm, 120), lambda: enc.noise_update(pcm),
-                lambda: dec.extract_features(pcm)):
+    for bad in (lambda: enc.decode(pk, 120), lambda: dec.encode(pcm, 120), lambda: enc.decode_plc(pk, 120),
+                lambda: dec.encode_dtx(pcm, 120), lambda: dec.extract_features(pcm)):
         try:
             bad()
             raise AssertionError("a call of the missing role must fail")
         except LyraB200Error as e:
             assert e.code == -1
     assert enc.quantize(np.zeros((1, 64), dtype=np.float32), 64).shape == (1, 8)      # stateless calls work in any context
+    assert enc.noise_update(pcm)[1].shape == (n, 160)                                  # ... and so do the self-contained estimators
     enc.reset()
     dec.reset()
     enc.close()
     dec.close()
+
+
+# ---- packet-loss concealment / comfort noise / DTX ----
+
+def run_cng_parity(Context, api, O, *, stream_ids=(0, 5), hops=4, seed=9, cng_seed=77):
+    """lyra_b200_cng_generate vs the oracle's ComfortNoiseGenerator on the same features and the same seeded phases:
+    bit-identical int16 hops (overlap-add state included), several hops in a row."""
+    ids = np.asarray(stream_ids, dtype=np.int32)
+    ctx = Context(int(ids.max()) + 1, capi=api)
+    ctx.set_cng_seed(cng_seed)
+    gens = [O.ComfortNoiseGenerator(seed=cng_seed + int(i)) for i in ids]
+    rng = np.random.default_rng(seed)
+    for h in range(hops):
+        feats = rng.uniform(0.62, 1.2, size=(len(ids), 160)).astype(np.float32)       # log-mel values between the floor and loud noise
+        out = ctx.cng_generate(feats, stream_ids=ids)
+        for k, g in enumerate(gens):
+            want = g.condition(feats[k])
+            assert np.array_equal(out[k], want), "comfort noise mismatch hop %d stream %d (max |d| %d)" % (
+                h, ids[k], int(np.abs(out[k].astype(int) - want.astype(int)).max()))
+    ctx.close()
+
+
+def run_plc_parity(Context, api, O, *, max_streams=16, stream_ids=(1, 6, 9), frames=26, bits=64, wav=None, seed=4, cng_seed=5,
+                   outages=((3, 12), (5, 3), (0, 0)), decoder_mode="exact"):
+    """lyra_b200_decode_plc tick by tick vs one oracle LyraDecoder per stream: stream k loses `outages[k] = (first, count)` hops.
+    PCM (model audio, comfort noise and their cross-fades), the control state and is_comfort_noise must all agree bit for bit
+    (PCM within the stated tolerance in the tensor decoder mode)."""
+    ids = np.asarray(stream_ids, dtype=np.int32)
+    n = len(ids)
+    ctx = Context(max_streams, capi=api)
+    ctx.set_decoder_mode(decoder_mode)
+    ctx.set_cng_seed(cng_seed)
+    tol = TENSOR_PCM_TOL_LSB if decoder_mode == "tensor" else 0
+    encs = [O.Encoder(MODEL_DIR) for _ in range(n)]
+    decs = [O.Decoder(MODEL_DIR, cng_seed=cng_seed + int(i)) for i in ids]
+    rng = np.random.default_rng(seed)
+    seen_cn = False
+    for f in range(frames):
+        if wav is not None:
+            pcm = np.stack([wav[(320 * (f + 11 * k)) % (len(wav) - 320):][:320] for k in range(n)])
+        else:
+            pcm = synth_pcm(rng, n, "noise")
+        pk = np.stack([np.frombuffer(encs[k].encode(pcm[k], bits), dtype=np.uint8) for k in range(n)])
+        rec = np.array([0 if outages[k][0] <= f < outages[k][0] + outages[k][1] else 1 for k in range(n)], dtype=np.uint8)
+        out, cn = ctx.decode_plc(pk, bits, stream_ids=ids, received=rec)
+        st = ctx.plc_state(stream_ids=ids)
+        for k in range(n):
+            if rec[k]:
+                assert decs[k].set_encoded_packet(bytes(pk[k]))
+            want = decs[k].decode_samples(320)
+            d = int(np.abs(out[k].astype(int) - want.astype(int)).max())
+            assert d <= tol, "PLC PCM mismatch frame %d stream %d: max |d| %d (state %s)" % (f, ids[k], d, decs[k].state)
+            assert tuple(int(x) for x in st[k]) == decs[k].state, (f, k, st[k], decs[k].state)
+            assert bool(cn[k]) == decs[k].is_comfort_noise()
+            seen_cn |= bool(cn[k])
+    assert seen_cn, "the case never reached comfort noise"
+    ctx.close()
+
+
+def run_plc_state_peer(Context, api, O):
+    """The reference's test peer (lyra_decoder_test.cc:56-90): forced states produce the same next hop as the oracle, and
+    misaligned states are refused."""
+    ctx = Context(4, capi=api)
+    ctx.set_cng_seed(3)
+    pk = np.zeros((1, 8), dtype=np.uint8)
+    for state, rec in [((1280, 0, 1), 0), ((1280, 640, 1), 0), ((0, 640, -1), 1), ((1280, 320, 1), 1), ((640, 0, -1), 0)]:
+        ctx.reset()
+        ctx.set_plc_state([state], stream_ids=[2])
+        dec = O.Decoder(MODEL_DIR, cng_seed=3 + 2)
+        dec.state = state
+        if rec:
+            assert dec.set_encoded_packet(bytes(pk[0]))
+        want = dec.decode_samples(320)
+        out, cn = ctx.decode_plc(pk, 64, stream_ids=[2], received=[rec])
+        assert np.array_equal(out[0], want), state
+        assert tuple(int(x) for x in ctx.plc_state(stream_ids=[2])[0]) == dec.state
+    try:
+        ctx.set_plc_state([(100, 0, 1)], stream_ids=[0])
+    except Exception:
+        pass
+    else:
+        raise AssertionError("a misaligned control state must be refused")
+    ctx.close()
+
+
+def run_dtx_parity(Context, api, O, *, wav, frames=24, bits=64, stream_ids=(0, 3, 4)):
+    """lyra_b200_encode_dtx vs the oracle's LyraEncoder(enable_dtx): stream 0 speech, stream 1 digital silence, stream 2
+    silence then speech.  Packet sizes (0 = DTX) and bytes agree; encoder state only advances on encoded hops."""
+    ids = np.asarray(stream_ids, dtype=np.int32)
+    n = len(ids)
+    ctx = Context(int(ids.max()) + 1, capi=api)
+    encs = [O.Encoder(MODEL_DIR, enable_dtx=True) for _ in range(n)]
+    sizes_seen = set()
+    for f in range(frames):
+        speech = wav[320 * (f + 20):320 * (f + 21)]
+        pcm = np.stack([speech, np.zeros(320, np.int16), speech if f >= frames // 2 else np.zeros(320, np.int16)])
+        pk, sizes = ctx.encode_dtx(pcm, bits, stream_ids=ids)
+        for k in range(n):
+            want = encs[k].encode(pcm[k], bits)
+            assert sizes[k] == len(want), (f, k, sizes[k], len(want))
+            assert bytes(pk[k][:sizes[k]]) == want
+            if sizes[k] == 0:
+                assert not pk[k].any()
+            sizes_seen.add(int(sizes[k]))
+    assert sizes_seen == {0, (bits + 7) // 8}
+    ctx.close()

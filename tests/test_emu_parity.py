@@ -174,3 +174,17 @@ def test_emu_umma_probe(tmp_path):
                            "-Wno-unknown-pragmas", os.path.join(ROOT, "tests", "cpp", "umma_probe.cu"), os.path.join(EMU_DIR, "cuda_emu.cc"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.count("MATCH") == 2 and "MISMATCH" not in out.stdout, out.stdout + out.stderr
+
+
+def test_emu_comfort_noise_generator(emu_api, oracle):
+    pc.run_cng_parity(_capi.Context, emu_api, oracle, stream_ids=(0, 5), hops=3)
+
+
+def test_emu_plc_state_machine(emu_api, oracle, sample1):
+    # batched LyraDecoder tick (plan -> RVQ -> LyraGAN -> comfort noise -> cross-fade -> noise estimator) vs the oracle decoder
+    pc.run_plc_parity(_capi.Context, emu_api, oracle, max_streams=16, stream_ids=(1, 9), frames=14, wav=sample1, outages=((2, 9), (4, 2)))
+    pc.run_plc_state_peer(_capi.Context, emu_api, oracle)
+
+
+def test_emu_dtx_encoder(emu_api, oracle, sample1):
+    pc.run_dtx_parity(_capi.Context, emu_api, oracle, wav=sample1, frames=8)

@@ -301,3 +301,68 @@ def test_umma_probe_on_hardware(tmp_path):
     # groundwork, not product code: a mismatch (or a time-out of the probe) is reported as an expected failure, never as a red tier
     if out.returncode != 0 or out.stdout.count("MATCH") != 2 or "MISMATCH" in out.stdout:
         pytest.xfail("UMMA probe not matching on this hardware yet: %r" % (out.stdout.strip() or out.stderr.strip())[-300:])
+
+
+# ---- packet-loss concealment, comfort noise, DTX ----
+
+def test_comfort_noise_generator_parity(gpu_api, oracle):
+    pc.run_cng_parity(_capi.Context, gpu_api, oracle, stream_ids=(0, 5, 63, 64), hops=12)
+
+
+def test_comfort_noise_reference_criterion_on_gpu(gpu_api, oracle):
+    """comfort_noise_generator_test.cc:100-138 on the GPU path: log-mel of the generated noise within LSD 0.7 of its conditioning."""
+    ctx = _capi.Context(8, capi=gpu_api)
+    ctx.set_cng_seed(1)
+    rng = np.random.default_rng(1)
+    x = rng.integers(-10000, 10001, size=(8, 320)).astype(np.int16)
+    for _ in range(10):
+        fi = ctx.logmel(x, 160, bank=0)
+        fo = ctx.logmel(ctx.cng_generate(fi), 160, bank=1)
+    lsd = [oracle.log_spectral_distance(fi[k], fo[k]) for k in range(8)]
+    print("CNG log-spectral distance per stream:", ["%.3f" % v for v in lsd])
+    assert max(lsd) < 0.7
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["exact", "tensor"])
+def test_plc_state_machine_parity(gpu_api, oracle, sample1, mode):
+    pc.run_plc_parity(_capi.Context, gpu_api, oracle, max_streams=64, stream_ids=(1, 6, 9, 40, 63), frames=40, wav=sample1,
+                      outages=((3, 12), (5, 3), (0, 0), (10, 25), (20, 7)), decoder_mode=mode)
+    if mode == "exact":
+        pc.run_plc_state_peer(_capi.Context, gpu_api, oracle)
+
+
+def test_plc_full_size_bernoulli_loss(gpu_api, oracle):
+    """BASELINE configs[3] with the reference's real state machine: 4096 streams, burst losses; a few streams are checked against
+    the oracle, all of them against the invariants of the state machine."""
+    n, bits = 4096, 64
+    ctx = _capi.Context(n, capi=gpu_api)
+    ctx.set_cng_seed(21)
+    rng = np.random.default_rng(1234)
+    check = [0, 77, 2048, 4095]
+    decs = {k: oracle.Decoder(_capi.MODEL_DIR, cng_seed=21 + k) for k in check}
+    pk = rng.integers(0, 256, size=(n, 8), dtype=np.uint8)
+    burst = np.zeros(n, dtype=np.int32)
+    cn_hops = 0
+    for f in range(24):
+        start = (rng.random(n) < 0.08) & (burst == 0)
+        burst[start] = rng.integers(1, 12, size=int(start.sum()))
+        rec = (burst == 0).astype(np.uint8)
+        burst = np.maximum(burst - 1, 0)
+        out, cn = ctx.decode_plc(pk, bits, received=rec)
+        st = ctx.plc_state(n)
+        assert ((st[:, 0] % 320 == 0) & (st[:, 0] >= 0) & (st[:, 0] <= 1280)).all()
+        assert np.isin(st[:, 1], [0, 320, 640]).all() and np.isin(st[:, 2], [-1, 1]).all()
+        assert (st[rec == 1, 0] == 0).all()                      # a received packet always ends concealment
+        assert (cn == (st[:, 1] == 640)).all()
+        cn_hops += int(cn.sum())
+        for k in check:
+            if rec[k]:
+                assert decs[k].set_encoded_packet(bytes(pk[k]))
+            assert np.array_equal(out[k], decs[k].decode_samples(320)), (f, k)
+    assert cn_hops > 0
+    ctx.close()
+
+
+def test_dtx_encoder_parity(gpu_api, oracle, sample1):
+    pc.run_dtx_parity(_capi.Context, gpu_api, oracle, wav=sample1, frames=40)
