@@ -4,8 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU arm
 
-One "step" = one 20 ms hop of every stream: PCM -> SoundStream encoder -> RVQ -> packet bytes -> RVQ decode ->
-LyraGAN -> PCM, for `--streams` (default 4096) concurrent 16 kHz streams per GPU.  One process per GPU (torchrun
+One "step" = HOPS_PER_STEP (50) consecutive 20 ms hops = one second of audio of every stream, each hop PCM -> SoundStream
+encoder -> RVQ -> packet bytes -> RVQ decode -> LyraGAN -> PCM, for `--streams` (default 4096) concurrent 16 kHz streams per GPU
+(so `--steps 20` times 1000 hops: about a second of GPU time, enough for the clock sampler and for a stable wall-clock e2e).  One process per GPU (torchrun
 for N > 1); streams are independent, so ranks shard them with no data-path collective (weak scaling); NCCL is
 only used for the barrier and the max-over-ranks of the elapsed time.
 
@@ -29,6 +30,7 @@ METRIC = "20ms-frame encode+decode throughput (frames/s) @16kHz"
 METRIC_PLC = "20ms-frame decode throughput with packet-loss concealment and noise tracking (frames/s) @16kHz"
 UNIT = "frames/s"
 SEED = 0x4C595241
+HOPS_PER_STEP = 50          # one bench step = 50 hops = 1 s of audio per stream
 
 # Algorithmic bytes per stream-frame (SURVEY.md §8d / BASELINE.md §2; fp32 state, read every state element once +
 # write the new rows, + PCM + packet), split by the kernel that owns the state:
@@ -202,6 +204,11 @@ def cpu_calibrated_sample(bits, threads, target_s):
     return threads, frames
 
 
+def codec_workload(n, bits, world):
+    return ("%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode (BASELINE configs[%s]); one step = %d consecutive "
+            "20 ms hops (1 s of audio per stream)" % (n, bits * 50 / 1000.0, "4" if world >= 8 else ("1" if n == 1024 else "2"), HOPS_PER_STEP))
+
+
 def reference_arm(args, rank, world):
     """`--impl reference`: the reference algorithm's CPU implementation (oracle port) on all host cores."""
     if rank != 0:
@@ -223,8 +230,8 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+i8", "data": "synthetic",
-        "config": {"workload": "%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode" % (args.streams, bits * 50 / 1000.0),
-                   "streams_per_gpu": args.streams, "bits_per_frame": bits,
+        "config": {"workload": codec_workload(args.streams, bits, args.gpus),
+                   "streams_per_gpu": args.streams, "bits_per_frame": bits, "hops_per_step": HOPS_PER_STEP,
                    "note": "CPU arm: bounded sample of the same workload; the reference binary cannot be built offline, "
                            "this is the oracle's C restatement of its algorithm (kind=port)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
@@ -259,61 +266,22 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
-def main():
-    protect_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
-    ap.add_argument("--bits", type=int, default=64, help="quantized bits per frame: 64 / 120 / 184 (3.2 / 6.0 / 9.2 kbps)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="codec", choices=["codec", "decode_plc"],
-                    help="codec: encode+decode (the headline metric). decode_plc: BASELINE configs[3], decoder only with a received "
-                         "mask (lost packets are concealed from zero features) + log-mel and noise-estimator update of the decoded hop")
-    ap.add_argument("--loss", type=float, default=0.1, help="decode_plc: packet loss probability (Bernoulli, seed 1234); 1.0 = all lost")
-    ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
-    ap.add_argument("--e2e-split", type=int, default=2, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
-    ap.add_argument("--groups", type=int, default=2,
-                    help="worker groups: the streams are divided among this many encoder/decoder context pairs, each pair with its own "
-                         "CUDA streams and, in the host-buffer pass, its own two host threads (a server's worker threads); calls on "
-                         "one context stay serialised")
-    ap.add_argument("--input", default="noise", choices=["noise", "speech"],
-                    help="synthetic input: uniform noise at 0.25 full scale (default) or the tiled reference speech clips")
-    ap.add_argument("--host-wait", default="auto", choices=["auto", "spin", "sleep"],
-                    help="how the worker threads of the host-buffer pass wait for the GPU (auto: sleep only when threads outnumber cores)")
-    ap.add_argument("--decoder-mode", default="exact", choices=["exact", "tensor"],
-                    help="exact: decoded PCM bit-identical to the oracle (default); tensor: split-precision TF32 tensor-core decoder")
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
-    if args.impl == "reference":
-        return reference_arm(args, rank, world)
-
+def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, world, rank, local_rank, decoder_mode, want_clocks):
+    """One configuration on this rank's GPU: device-resident throughput over `hops` hops, a serialised per-kernel pass, and the
+    end-to-end pass through the host-buffer C ABI.  Returns a dict; multi-rank reductions (max over ranks) are done inside."""
+    import ctypes as C
     import numpy as np
     import torch
     import torch.distributed as dist
     from lyra_b200 import _capi
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not land in front of the JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n, bits = args.streams, args.bits
     P = (bits + 7) // 8
-    plc = args.workload == "decode_plc"
     # LyraEncoder and LyraDecoder are separate objects in the reference; here they are an encoder-only and a decoder-only
-    # context with their own CUDA streams (and, in the host-buffer pass, their own host threads), so the encode of step
-    # i + 1 overlaps the decode of step i on the GPU.  Every step's decode consumes that step's packets.
+    # context with their own CUDA streams (and, in the host-buffer pass, their own host threads), so the encode of hop
+    # i + 1 overlaps the decode of hop i on the GPU.  Every hop's decode consumes that hop's packets.
     enc = None if plc else _capi.Context(n, device=local_rank, roles="encoder")
     dec = _capi.Context(n, device=local_rank, roles="decoder")
-    dec.set_decoder_mode(args.decoder_mode)
+    dec.set_decoder_mode(decoder_mode)
     ctxs = [c for c in (enc, dec) if c is not None]
     for c in ctxs:
         c.set_split(args.split)
@@ -334,7 +302,7 @@ def main():
         for _ in range(G):
             e_ = None if plc else _capi.Context(ng, device=local_rank, roles="encoder")
             d_ = _capi.Context(ng, device=local_rank, roles="decoder")
-            d_.set_decoder_mode(args.decoder_mode)
+            d_.set_decoder_mode(decoder_mode)
             gx, gy = torch.cuda.Stream(), torch.cuda.Stream()
             if e_:
                 e_.set_stream(gx.cuda_stream)
@@ -343,8 +311,7 @@ def main():
             d_.set_split(args.split)
             groups.append((e_, d_, gx, gy))
     group_ctxs = [c for grp in groups for c in grp[:2] if c is not None]
-    # the host-buffer pass runs 2 G waiting threads per rank: let them sleep instead of spin when the box has fewer cores than that
-    # spinning waiters must leave cores for the ranks' launching threads: 2 G workers + 1 main thread per rank vs 3/4 of the cores
+    # the host-buffer pass runs 2 G waiting threads per rank: they sleep instead of spin when the box has fewer cores than that
     oversubscribed = args.host_wait == "sleep" or (args.host_wait == "auto" and world * (2 * G + 1) > host_cores() * 3 // 4)
     for c in group_ctxs:
         c.set_blocking_sync(oversubscribed)
@@ -369,13 +336,13 @@ def main():
         tmp.synchronize()
         tmp.close()
         mrng = np.random.default_rng(1234 + rank)
-        h_masks = [(mrng.random(n) >= args.loss).astype(np.uint8) for _ in range(NBUF)]
+        h_masks = [(mrng.random(n) >= loss).astype(np.uint8) for _ in range(NBUF)]
         d_masks = [torch.from_numpy(m).cuda() for m in h_masks]
         d_flags = torch.zeros(n, dtype=torch.uint8, device="cuda")
 
     def run_device(first, count, grps, serial=False):
-        """steps first .. first+count-1 over the given context groups (each group owns a contiguous slice of the streams);
-        serial: step i+1's encode waits for step i's decode (per-kernel timing pass)"""
+        """hops first .. first+count-1 over the given context groups (each group owns a contiguous slice of the streams);
+        serial: hop i+1's encode waits for hop i's decode (per-kernel timing pass)"""
         m = n // len(grps)
         for i in range(first, first + count):
             b = i % NBUF
@@ -383,8 +350,8 @@ def main():
                 k = g if len(grps) > 1 else G        # event row: the full-size pair has its own
                 off = g * m
                 if plc:
-                    d_.decode_track_noise_device(m, d_pks[b].data_ptr() + off * P, d_masks[b].data_ptr() + off, bits,
-                                                 d_out.data_ptr() + off * 640, d_flags.data_ptr() + off)
+                    d_.decode_plc_device(m, d_pks[b].data_ptr() + off * P, d_masks[b].data_ptr() + off, bits,
+                                         d_out.data_ptr() + off * 640, d_flags.data_ptr() + off)
                     continue
                 if serial and i > first:
                     gx.wait_event(ev_free[k][(i - 1) % NBUF])
@@ -403,30 +370,32 @@ def main():
 
     # ---------------- device-resident throughput (`value`) ----------------
     timer = torch.cuda.Stream()
-    run_device(0, max(3, args.warmup), groups)
+    run_device(0, max(3, warm_hops), groups)
     barrier()
     launches0 = sum(c.launch_count for c in group_ctxs)
-    try:
-        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
-    except Exception:
-        gpu_uuid = None
-    sampler = ClockSampler(local_rank, gpu_uuid)
-    sampler.start()
+    sampler = None
+    if want_clocks:
+        try:
+            gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+        except Exception:
+            gpu_uuid = None
+        sampler = ClockSampler(local_rank, gpu_uuid)
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(timer)
     for _, _, gx, gy in groups:          # nothing of the timed region starts before e0
         gx.wait_stream(timer)
         gy.wait_stream(timer)
-    run_device(0, args.steps, groups)
+    run_device(0, hops, groups)
     drain(groups, timer)
     e1.record(timer)
     torch.cuda.synchronize()
     elapsed_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     gpu_launches = sum(c.launch_count for c in group_ctxs) - launches0
     barrier()
-    # per-kernel roofline pass on the full-size context pair: the same steps with the kernels serialised (one launch per kernel
-    # and step over all n streams, no concurrent sub-batches, no encode/decode overlap), CUDA events around every launch
+    # per-kernel roofline pass on the full-size context pair: the same hops with the kernels serialised (one launch per kernel
+    # and hop over all n streams, no concurrent sub-batches, no encode/decode overlap), CUDA events around every launch
     full = [(enc, dec, sx, sy)]
     for c in ctxs:
         c.set_split(1)
@@ -434,7 +403,7 @@ def main():
     torch.cuda.synchronize()
     for c in ctxs:
         c.profile_enable(True)
-    run_device(0, args.steps, full, serial=True)
+    run_device(0, kernel_hops, full, serial=True)
     torch.cuda.synchronize()
     prof = {}
     for c in ctxs:
@@ -449,13 +418,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
-    value = world * n * args.steps / (elapsed_ms / 1e3)
+    value = world * n * hops / (elapsed_ms / 1e3)
 
     # ---------------- end to end through the host-buffer C ABI (`e2e`) ----------------
     # pinned host buffers in, pinned host buffers out, every call synchronous (H2D, kernels, D2H inside it); the encoder and
     # the decoder are driven by one host thread each, the way a full-duplex server runs its uplink and downlink
-    import ctypes as C
-    import threading
     sys.setswitchinterval(5e-5)      # worker threads hand the GIL over quickly between their (GIL-free) C-ABI calls
     pin_in = [torch.from_numpy(host[i]).pin_memory() for i in range(NBUF)]
     pin_pks = [d_pks[i].cpu().pin_memory() for i in range(NBUF)]
@@ -466,8 +433,8 @@ def main():
         pin_masks = [torch.from_numpy(h_masks[i]).pin_memory() for i in range(NBUF)]
         pin_flags = torch.zeros(n, dtype=torch.uint8).pin_memory()
 
-    def ptr(t, g, row_bytes):
-        return C.c_void_p(t.data_ptr() + g * ng * row_bytes)
+    def ptr(tn, g, row_bytes):
+        return C.c_void_p(tn.data_ptr() + g * ng * row_bytes)
 
     def run_host(count):
         threads = []
@@ -476,8 +443,8 @@ def main():
                 def downlink_only(g=g, d_=d_):
                     for i in range(count):
                         b = i % NBUF
-                        if lib.lyra_b200_decode_track_noise(d_.h, None, ng, ptr(pin_pks[b], g, P), ptr(pin_masks[b], g, 1), bits,
-                                                            ptr(pin_out, g, 640), ptr(pin_flags, g, 1)):
+                        if lib.lyra_b200_decode_plc(d_.h, None, ng, ptr(pin_pks[b], g, P), ptr(pin_masks[b], g, 1), bits,
+                                                    ptr(pin_out, g, 640), ptr(pin_flags, g, 1)):
                             errors.append("decode: %s" % lib.lyra_b200_last_error(d_.h))
                 threads.append(threading.Thread(target=downlink_only))
                 continue
@@ -510,41 +477,134 @@ def main():
     run_host(3)
     barrier()
     t0 = time.perf_counter()
-    run_host(args.steps)
+    run_host(e2e_hops)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.steps / float(t.item())
+    e2e_value = world * n * e2e_hops / float(t.item())
     checksum = int(pin_out.to(torch.int64).sum().item())
+    tile_streams = dec.tile_streams
+    for c in ctxs + (group_ctxs if G > 1 else []):
+        c.close()
+    return {"value": value, "elapsed_ms": elapsed_ms, "e2e_value": e2e_value, "e2e_s": float(t.item()), "prof": prof, "clocks": clocks,
+            "gpu_launches": int(gpu_launches), "checksum": checksum, "G": G, "oversubscribed": oversubscribed, "tile_streams": tile_streams,
+            "P": P}
+
+
+def roofline_of(res, n, bits, plc, world, hops, decoder_mode, clocks):
+    """The `roofline` object of one measured configuration (per-kernel times from the serialised pass)."""
+    peak, peak_src = measured_peaks()
+    P = res["P"]
+    kern = {}
+    for k, (ms, cnt) in res["prof"].items():
+        if cnt:
+            ab = ALGO_BYTES.get(k, 0) + (P if k.startswith("Rvq") else 0)
+            kern[k] = {"ms_per_launch": ms / cnt, "launches": cnt, "algo_bytes_per_launch": ab * n,
+                       "achieved_gbs": ab * n / (ms / cnt * 1e-3) / 1e9}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_launch"])
+    # decode_plc: decoder state traffic + PCM + packet + the estimator's state (5 x 160 floats read and written) and carried hop
+    total_algo = (74368 + 640 + P + 1 + 2 * 5 * 160 * 4 + 2 * 640) if plc else (79744 + 640 + P) + (74368 + 640 + P)
+    whole = total_algo * n * hops / (res["elapsed_ms"] / 1e3) / 1e9 if world == 1 else None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["achieved_gbs"] / peak, "traffic": ncu_traffic(dom, n), "peak_source": peak_src,
+                "kernel_share_of_step": kern[dom]["ms_per_launch"] / sum(v["ms_per_launch"] for v in kern.values()),
+                "whole_step": {"algo_bytes_per_frame": total_algo, "achieved_gbs": whole, "frac": whole / peak if whole else None},
+                "kernels": kern}
+    if world == 1:
+        # the CUDA-core roofline that binds the bit-exact layers (DESIGN.md section 5): ordered FFMA chains.  In the tensor decoder mode
+        # only the encoder's fp32 layers and the decoder's bottleneck_2 stay on the FP32 pipe; the rest of the decoder's fp32 GEMMs run
+        # on the tensor cores (kernel C: mma.sync TF32, kernel D: tcgen05 UMMA)
+        enc_macs, dec_macs, dec_cuda_macs = 1475840, 1236736, 24576          # SURVEY.md section 8d, fp32 MACs per stream-frame
+        fp32_macs = (0 if plc else enc_macs) + (dec_macs if decoder_mode == "exact" else dec_cuda_macs)
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        pipe_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        roofline["fp32_pipe"] = {"achieved": res["value"] * 2 * fp32_macs / 1e12, "peak": pipe_peak, "unit": "TFLOP/s",
+                                 "frac": res["value"] * 2 * fp32_macs / 1e12 / pipe_peak, "fp32_macs_per_frame_on_cuda_cores": fp32_macs,
+                                 "peak_source": "148 SMs x 128 FP32 lanes x 2 x SM clock sampled during the run"}
+    return roofline
+
+
+def main():
+    protect_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20, help="timed steps; one step = %d hops (1 s of audio) of every stream" % HOPS_PER_STEP)
+    ap.add_argument("--warmup", type=int, default=3, help="untimed warm-up steps")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
+    ap.add_argument("--bits", type=int, default=None,
+                    help="quantized bits per frame: 64 / 120 / 184 (3.2 / 6.0 / 9.2 kbps); default 64, and 120 at --gpus 8 (BASELINE configs[4])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configs (other_configs)")
+    ap.add_argument("--workload", default="codec", choices=["codec", "decode_plc"],
+                    help="codec: encode+decode (the headline metric). decode_plc: BASELINE configs[3], decoder only with a received mask "
+                         "through the reference's concealment / comfort-noise / fade state machine (lyra_b200_decode_plc)")
+    ap.add_argument("--loss", type=float, default=0.1, help="decode_plc: packet loss probability (Bernoulli, seed 1234); 1.0 = all lost")
+    ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
+    ap.add_argument("--e2e-split", type=int, default=2, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
+    ap.add_argument("--groups", type=int, default=2,
+                    help="worker groups: the streams are divided among this many encoder/decoder context pairs, each pair with its own "
+                         "CUDA streams and, in the host-buffer pass, its own two host threads (a server's worker threads); calls on "
+                         "one context stay serialised")
+    ap.add_argument("--input", default="noise", choices=["noise", "speech"],
+                    help="synthetic input: uniform noise at 0.25 full scale (default) or the tiled reference speech clips")
+    ap.add_argument("--host-wait", default="auto", choices=["auto", "spin", "sleep"],
+                    help="how the worker threads of the host-buffer pass wait for the GPU (auto: sleep only when threads outnumber cores)")
+    ap.add_argument("--decoder-mode", default="tensor", choices=["exact", "tensor"],
+                    help="tensor (default): the decoder's fp32 GEMMs on the tensor cores (kernel D: tcgen05 UMMA), decoded PCM within "
+                         "4 int16 LSB of the oracle, packets bit-exact; exact: decoded PCM bit-identical to the oracle")
+    args = ap.parse_args()
+    if args.bits is None:
+        args.bits = 120 if args.gpus >= 8 else 64
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not land in front of the JSON line
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, bits = args.streams, args.bits
+    plc = args.workload == "decode_plc"
+    hops = args.steps * HOPS_PER_STEP
+    res = measure(args, n, bits, plc, args.loss, hops, max(3, args.warmup) * HOPS_PER_STEP, min(hops, 40), hops, world, rank, local_rank,
+                  args.decoder_mode, want_clocks=True)
+    value, e2e_value, clocks, P, G = res["value"], res["e2e_value"], res["clocks"], res["P"], res["G"]
+
+    other = None
+    if world == 1 and not args.no_other_configs and not plc:
+        # short runs of the other BASELINE configs in the same process (value, e2e and the dominant kernel's roofline each)
+        other = {}
+        plan = [("configs[1]: 1024 streams, 3.2 kbps", 1024, 64, False, 0.0),
+                ("configs[2]: 4096 streams, 6.0 kbps", 4096, 120, False, 0.0),
+                ("configs[2]: 4096 streams, 9.2 kbps", 4096, 184, False, 0.0),
+                ("configs[3]: 4096 streams, decoder only, concealment / comfort noise, loss 0.1", 4096, 64, True, 0.1),
+                ("configs[3]: 4096 streams, decoder only, all packets lost (comfort noise)", 4096, 64, True, 1.0)]
+        for name, on, obits, oplc, oloss in plan:
+            if (on, obits, oplc) == (n, bits, plc):
+                continue
+            r = measure(args, on, obits, oplc, oloss, 150, 20, 10, 150, world, rank, local_rank, args.decoder_mode, want_clocks=False)
+            rf = roofline_of(r, on, obits, oplc, world, 150, args.decoder_mode, clocks)
+            other[name] = {"value": r["value"], "unit": UNIT, "hops_timed": 150, "ms_per_hop": r["elapsed_ms"] / 150,
+                           "e2e": {"value": r["e2e_value"], "unit": UNIT},
+                           "real_time_factor": r["value"] / (50.0 * on),
+                           "roofline": {k: rf[k] for k in ("kernel", "achieved", "peak", "frac", "kernel_share_of_step")},
+                           "kernel_ms": {k: v["ms_per_launch"] for k, v in rf["kernels"].items()}}
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        kern = {}
-        for k, (ms, cnt) in prof.items():
-            if cnt:
-                ab = ALGO_BYTES.get(k, 0) + (P if k.startswith("Rvq") else 0)
-                kern[k] = {"ms_per_launch": ms / cnt, "launches": cnt, "algo_bytes_per_launch": ab * n,
-                           "achieved_gbs": ab * n / (ms / cnt * 1e-3) / 1e9}
-        dom = max(kern, key=lambda k: kern[k]["ms_per_launch"])
-        # decode_plc: decoder state traffic + PCM + packet + the estimator's state (5 x 160 floats read and written) and carried hop
-        total_algo = (74368 + 640 + P + 1 + 2 * 5 * 160 * 4 + 2 * 640) if plc else (79744 + 640 + P) + (74368 + 640 + P)
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": ncu_traffic(dom, n), "peak_source": peak_src,
-                    "kernel_share_of_step": kern[dom]["ms_per_launch"] / sum(v["ms_per_launch"] for v in kern.values()),
-                    "whole_step": {"algo_bytes_per_frame": total_algo,
-                                   "achieved_gbs": total_algo * n * args.steps / (elapsed_ms / 1e3) / 1e9 if world == 1 else None,
-                                   "frac": (total_algo * n * args.steps / (elapsed_ms / 1e3) / 1e9) / peak if world == 1 else None},
-                    "kernels": kern}
-        if world == 1 and args.decoder_mode == "exact":
-            # the roofline that actually binds the bit-exact mode: ordered FFMA chains on the CUDA cores
-            fp32_macs = 1236736 if plc else 1475840 + 1236736          # SURVEY.md section 8d, fp32 MACs per stream-frame
-            pipe_peak = 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12
-            roofline["fp32_pipe"] = {"achieved": value * 2 * fp32_macs / 1e12, "peak": pipe_peak, "unit": "TFLOP/s",
-                                     "frac": value * 2 * fp32_macs / 1e12 / pipe_peak,
-                                     "peak_source": "148 SMs x 128 FP32 lanes x 2 x SM clock sampled during the run"}
+        roofline = roofline_of(res, n, bits, plc, world, hops, args.decoder_mode, clocks)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = host_cores()
@@ -554,40 +614,46 @@ def main():
                 r["frames_per_s"] = threads * 1e6 / (r["stage_us"][2] + r["stage_us"][3])
             cpu = {"value": r["frames_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "%d streams x %d hops, one stream per thread, uniform noise 0.25 FS, %d bits" % (s, f, bits),
+                   "note": "the oracle's op-by-op C interpreter of the reference graphs, not TFLite + XNNPACK (which cannot be built offline "
+                           "and would be several times faster per core): a reported baseline, not a target",
                    "stage_us_per_frame": dict(zip(["feature_extractor", "quantizer_quantize", "quantizer_decode", "model_decode"], r["stage_us"]))}
+        state_mb = n * EncDecStateBytes() / 1e6
         line = {
             "metric": METRIC_PLC if plc else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+i8", "data": "synthetic" if args.input == "noise" else "synthetic (reference speech clips tiled over the streams)",
-            "config": {"workload": ("%d concurrent 16kHz streams per GPU, %.1f kbps, decoder only with packet-loss concealment "
-                                    "(BASELINE configs[3]): received mask Bernoulli(%.2f, seed 1234), log-mel + noise estimator on the decoded hop"
-                                    % (n, bits * 50 / 1000.0, 1.0 - args.loss)) if plc else
-                                   "%d concurrent 16kHz streams per GPU, %.1f kbps encode+decode "
-                                   "(BASELINE configs[2] at %.1f kbps; the north_star target size)" % (n, bits * 50 / 1000.0, bits * 50 / 1000.0),
-                       "streams_per_gpu": n, "bits_per_frame": bits, "tile_streams": dec.tile_streams,
-                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G, "host_threads_wait": "sleep (blocking-sync event)" if oversubscribed else "spin",
+            "ms_per_step": res["elapsed_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i8 (decoder fp32 GEMMs: split tf32 on tensor cores)" if args.decoder_mode == "tensor" else "f32+i8",
+            "data": "synthetic" if args.input == "noise" else "synthetic (reference speech clips tiled over the streams)",
+            "config": {"workload": ("%d concurrent 16kHz streams per GPU, %.1f kbps, decoder only through the reference's packet-loss state machine "
+                                    "(BASELINE configs[3]): received mask Bernoulli(%.2f, seed 1234), concealment -> fade -> comfort noise, "
+                                    "log-mel + noise estimator on hops decoded from received packets; one step = %d hops (1 s of audio per stream)"
+                                    % (n, bits * 50 / 1000.0, 1.0 - args.loss, HOPS_PER_STEP)) if plc else
+                                   codec_workload(n, bits, world),
+                       "streams_per_gpu": n, "bits_per_frame": bits, "hops_per_step": HOPS_PER_STEP, "tile_streams": res["tile_streams"],
+                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G,
+                       "host_threads_wait": "sleep (blocking-sync event)" if res["oversubscribed"] else "spin",
                        "real_time_factor": value / (50.0 * n * world),
-                       "l2": ("no flush needed: per-step state working set %d x %.0f KB = %.0f MB exceeds the 126 MB L2; PCM inputs rotate over %d buffers"
-                              if n * EncDecStateBytes() > 126e6 else
+                       "l2": ("no flush needed: per-hop state working set %d x %.0f KB = %.0f MB exceeds the 126 MB L2; PCM inputs rotate over 8 buffers"
+                              if state_mb > 126 else
                               "NOT flushed: the state working set %d x %.0f KB = %.0f MB fits in the 126 MB L2 at this stream count (as it would "
-                              "in steady-state serving); PCM inputs rotate over %d buffers; the headline configuration (4096 streams) exceeds L2")
-                             % (n, (EncDecStateBytes()) / 1024.0, n * EncDecStateBytes() / 1e6, NBUF),
+                              "in steady-state serving); PCM inputs rotate over 8 buffers; the headline configuration (4096 streams) exceeds L2")
+                             % (n, EncDecStateBytes() / 1024.0, state_mb),
                        "parallelism": "streams sharded by rank, no data-path collective",
                        "execution": ("decoder context only" if plc else
                                      "full duplex: encoder-only and decoder-only context on their own CUDA streams (host-buffer pass: "
-                                     "their own host threads); the encode of step i+1 overlaps the decode of step i, and every "
-                                     "step's decode consumes that step's packets"),
-                       "output_checksum": checksum},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (P + 1) if plc else n * (640 + P),
-                    "d2h_bytes_per_step": n * (640 + 1) if plc else n * (P + 640)},
-            "gpu_launches": int(gpu_launches),
+                                     "their own host threads); the encode of hop i+1 overlaps the decode of hop i, and every "
+                                     "hop's decode consumes that hop's packets"),
+                       "output_checksum": res["checksum"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "seconds_timed": res["e2e_s"],
+                    "h2d_bytes_per_step": HOPS_PER_STEP * (n * (P + 1) if plc else n * (640 + P)),
+                    "d2h_bytes_per_step": HOPS_PER_STEP * (n * (640 + 1) if plc else n * (P + 640))},
+            "gpu_launches": res["gpu_launches"],
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if other is not None:
+            line["other_configs"] = other
         emit(line)
-    for c in ctxs + (group_ctxs if G > 1 else []):
-        c.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
