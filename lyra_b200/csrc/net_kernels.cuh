@@ -70,7 +70,8 @@ struct TileIo {
 };
 
 // Per-tile metadata in shared memory: slot[S], active[S], n18[S] and n18[S] = the frame counter shared by all
-// active streams of the tile (or -1 if they differ, which selects the general ring path).
+// active streams of the tile (-1 if they differ, which selects the general ring path; -2 if the tile has no active stream at
+// all in this call - every stream skipped - in which case the kernels return at once: kTileIdle).
 template <int S>
 __device__ __forceinline__ void LoadTileMeta(const TileIo& io, const int* n18_global, int* slot, int* active, int* n18, int& tile) {
   tile = io.tile_list[blockIdx.x];
@@ -86,10 +87,11 @@ __device__ __forceinline__ void LoadTileMeta(const TileIo& io, const int* n18_gl
     int u = -2;
     for (int s = 0; s < S; ++s)
       if (active[s]) u = (u == -2 || u == n18[s]) ? n18[s] : -1;
-    n18[S] = u < 0 ? -1 : u;
+    n18[S] = u;
   }
   __syncthreads();
 }
+constexpr int kTileIdle = -2;
 
 // One fp32 residual unit:  d = dw(lrelu(u)); h = lrelu(pw1(d)); u' = pw2(h) + u.
 // u lives at row offset row0u of a [C][ldu] buffer; d is a [C][LDD] scratch.  When `last`, lrelu(u') is stored.
@@ -236,6 +238,7 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   int tile;
   InitWeightPipe<NT>();
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
+  if (n18[S] == kTileIdle) return;
   float* st = state + (size_t)tile * EncStateA::kUnits * S;
   const int tid = (int)threadIdx.x;
   IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.first.w), 16, 64, 64));
@@ -362,6 +365,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   int tile;
   InitWeightPipe<NT>();
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
+  if (n18[S] == kTileIdle) return;
   uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * EncStateB::kUnits * S;
   float* st = reinterpret_cast<float*>(stw);
   const int tid = (int)threadIdx.x;
@@ -566,6 +570,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   int tile;
   InitWeightPipe<NT>();
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
+  if (n18[S] == kTileIdle) return;
   uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * DecStateC::kUnits * S;
   float* st = reinterpret_cast<float*>(stw);
   const int tid = (int)threadIdx.x;
@@ -793,6 +798,7 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   int tile;
   InitWeightPipe<NT>();
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);
+  if (n18[S] == kTileIdle) return;
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const int tid = (int)threadIdx.x;
   constexpr int LDX = L::LDX;

@@ -56,7 +56,7 @@ struct DecDU {
   static constexpr int kDw = kSlOut + 48 * S * 4;             // depthwise parameters of the three units: w [3][64] | bias [64] each
   static constexpr int kW = kDw + 3 * 256 * 4;                // weight ring
   static constexpr int kI = kW + kStagesW * kDuChunkBytes;    // slot[S], active[S], n18[S]
-  static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
+  static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;     // + n18[S]
   static_assert(kMid + 128 * 4 * S * 4 <= kRingEnd, "X and the staged tile must fit under the ring blocks");
   static_assert(S * 320 * 2 <= kRingEnd - kRing, "PCM staging must fit in the ring region");
   static_assert(kXc % 128 == 0 && kOv % 128 == 0 && kW % 128 == 0 && kDw % 16 == 0, "bulk-copy / descriptor alignment");
@@ -103,7 +103,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   float* slo = smf + L::kSlOut / 4;
   int* slot = reinterpret_cast<int*>(smem + L::kI);
   int* active = slot + S;
-  int* n18 = active + S;
+  int* n18 = active + S;                                      // n18[S]: tile summary (LoadTileMeta)
   LYRA_STATIC_SMEM(DecDUShared, sh, 1);
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -123,9 +123,11 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const uint8_t* chunks = blob + P.du_chunks;
   int ph = 0;
+  const bool idle = n18[S] == kTileIdle;                      // every stream of the tile sits this call out: nothing to do
 
   // ================================================= TMA producer =================================================
-  if (warp == L::kTmaWarp) {
+  if (idle) {
+  } else if (warp == L::kTmaWarp) {
     if (lane == 0) {
       lyra_bulk_multi_begin(&sh->in_full, 128u * 4 * S * 4 + 64u * 5 * S * 4 + 48u * S * 4 + 3u * 1024);
       lyra_bulk_multi_copy(smem + L::kMid, mid + (size_t)tile * 128 * 4 * S, 128u * 4 * S * 4, &sh->in_full);

@@ -123,6 +123,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
 }
 
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }

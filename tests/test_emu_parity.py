@@ -1,6 +1,7 @@
 """CPU tier: the product kernels' source, compiled for the test-only CUDA block simulator (tests/cuda_emu),
 checked against the oracle.  Small sizes (the simulator runs every CUDA thread as a fiber)."""
 import numpy as np
+import pytest
 
 import parity_cases as pc
 from lyra_b200 import _capi
@@ -163,17 +164,19 @@ def test_emu_cpp_duplex_server_example(emu_api, oracle, tmp_path):
         assert int(out.stdout.strip().rsplit("checksum", 1)[1]) == want, out.stdout
 
 
-def test_emu_umma_probe(tmp_path):
-    """tests/cpp/umma_probe.cu on the emulator's tcgen05 / TMEM model (device_compat.h): the UMMA groundwork for the decoder's
-    tensor-core mode — descriptors, split-precision MMAs, overlapping 128-row blocks, in-place operand rewrite."""
+@pytest.mark.parametrize("probe,cases", [("umma_probe", 2), ("umma_probe2", 7)])
+def test_emu_umma_probes(tmp_path, probe, cases):
+    """tests/cpp/umma_probe{,2}.cu on the emulator's tcgen05 / TMEM model (device_compat.h): descriptors, split-precision MMAs,
+    overlapping 128-row blocks, in-place operand rewrite; A operands in tensor memory, tcgen05.st, kind::i8, bulk stores.  The same
+    sources run on the GPU tier, which is what ties the emulator's model to the hardware."""
     import os
     import subprocess
     from conftest import EMU_DIR, ROOT
-    exe = str(tmp_path / "umma_probe")
+    exe = str(tmp_path / probe)
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-DLYRA_EMU", "-x", "c++", "-I" + EMU_DIR, "-I" + os.path.join(ROOT, "lyra_b200", "csrc"),
-                           "-Wno-unknown-pragmas", os.path.join(ROOT, "tests", "cpp", "umma_probe.cu"), os.path.join(EMU_DIR, "cuda_emu.cc"), "-o", exe])
+                           "-Wno-unknown-pragmas", os.path.join(ROOT, "tests", "cpp", probe + ".cu"), os.path.join(EMU_DIR, "cuda_emu.cc"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and out.stdout.count("MATCH") == 2 and "MISMATCH" not in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and out.stdout.count("MATCH") == cases and "MISMATCH" not in out.stdout, out.stdout + out.stderr
 
 
 def test_emu_comfort_noise_generator(emu_api, oracle):

@@ -226,12 +226,15 @@ def test_decoder_only_concealment_4096(gpu_api, oracle):
     rng = np.random.default_rng(1234)
     check = [0, 77, 2048, 4095]
     refs = {k: oracle.Codec(_capi.MODEL_DIR) for k in check}
+    mels = {k: oracle.LogMel(16000, 320, 640, 160) for k in check}
     pk = rng.integers(0, 256, size=(n, 8), dtype=np.uint8)
     for f in range(5):
         rec = np.zeros(n, np.uint8) if f < 2 else (rng.random(n) < 0.9).astype(np.uint8)
         out = ctx.decode(pk, bits, received=rec)
         mel = ctx.logmel(out, num_mel_bins=160)                 # NoiseEstimator's extractor runs on every decoded hop
-        assert np.isfinite(mel).all()
+        assert np.isfinite(mel).all() and mel.shape == (n, 160)
+        for k in check:
+            assert np.array_equal(mel[k], mels[k].extract(out[k])), "log-mel mismatch frame %d stream %d" % (f, k)
         for k in check:
             opcm, _, _ = refs[k].decode(bytes(pk[k]) if rec[k] else None, bits)
             assert np.array_equal(out[k], opcm)
@@ -284,23 +287,22 @@ def test_cpp_duplex_server_example(gpu_api, oracle, tmp_path):
     print(big.stdout.strip())
 
 
-def test_umma_probe_on_hardware(tmp_path):
-    """tests/cpp/umma_probe.cu built with nvcc: the tcgen05 / TMEM instruction sequences of device_compat.h on the GPU.
-    Case 1 reproduces what tools/tcgen05_probe.cu verified; case 2 (residual unit, split precision, overlapping row blocks)
-    is the next step of the UMMA plan — reported, and required to match, here."""
+@pytest.mark.parametrize("probe,cases", [("umma_probe", 2), ("umma_probe2", 7)])
+def test_umma_probes_on_hardware(tmp_path, probe, cases):
+    """tests/cpp/umma_probe{,2}.cu built with nvcc: the tcgen05 / TMEM instruction sequences of device_compat.h that the product's
+    UMMA kernel (DecoderKernelDU) is made of - shared-memory descriptors, split-precision TF32 MMAs, A operands in tensor memory,
+    tcgen05.st / wide tcgen05.ld, kind::i8, N = 160 / 16 shapes, bulk stores.  The product depends on them: a mismatch is a failure."""
     import shutil
     import subprocess
     from conftest import ROOT
     if shutil.which("nvcc") is None:
         pytest.skip("nvcc not available on this box")
-    exe = str(tmp_path / "umma_probe")
+    exe = str(tmp_path / probe)
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I" + os.path.join(ROOT, "lyra_b200", "csrc"),
-                           "-o", exe, os.path.join(ROOT, "tests", "cpp", "umma_probe.cu")])
+                           "-o", exe, os.path.join(ROOT, "tests", "cpp", probe + ".cu")])
     out = subprocess.run(["timeout", "60", exe], capture_output=True, text=True, timeout=120)
     print(out.stdout.strip())
-    # groundwork, not product code: a mismatch (or a time-out of the probe) is reported as an expected failure, never as a red tier
-    if out.returncode != 0 or out.stdout.count("MATCH") != 2 or "MISMATCH" in out.stdout:
-        pytest.xfail("UMMA probe not matching on this hardware yet: %r" % (out.stdout.strip() or out.stderr.strip())[-300:])
+    assert out.returncode == 0 and out.stdout.count("MATCH") == cases and "MISMATCH" not in out.stdout, out.stdout + out.stderr
 
 
 # ---- packet-loss concealment, comfort noise, DTX (SURVEY.md section 8 rows f2, f4) ----
