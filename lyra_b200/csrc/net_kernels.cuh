@@ -208,10 +208,16 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
 // ================================================================================================
 //                                        ENCODER  A
 // ================================================================================================
+#ifndef LYRA_A_TN
+#define LYRA_A_TN 4
+#endif
+#ifndef LYRA_A_NT
+#define LYRA_A_NT 320
+#endif
 template <int S>
 struct EncA {
-  static constexpr int NT = 320;
-  static constexpr int TN = S >= 16 ? 8 : 4;
+  static constexpr int NT = LYRA_A_NT;
+  static constexpr int TN = S >= 16 ? 8 : LYRA_A_TN;
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;       // S = 8 tiles fit two blocks per SM
   static constexpr int LDU = 25 * S, LDD = 20 * S;
   static constexpr int kSmemU = 0;

@@ -147,6 +147,26 @@ lo_encoder* lo_encoder_create(const char* model_dir, int enable_dtx);
 void lo_encoder_free(lo_encoder* e);
 int lo_encoder_encode(lo_encoder* e, const int16_t* pcm, int n, int num_bits, uint8_t* packet);   /* packet bytes (0 = DTX), < 0 error */
 
+/* ---- Resampler / BufferedResampler (lyra/resampler.{h,cc}, lyra/buffered_resampler.{h,cc}); resampler.c ---- */
+typedef struct lo_resampler lo_resampler;
+lo_resampler* lo_resampler_create(int input_rate_hz, int output_rate_hz);                 /* rates in {8, 16, 32, 48} kHz */
+void lo_resampler_free(lo_resampler* r);
+void lo_resampler_reset(lo_resampler* r);
+int lo_resampler_input_rate(const lo_resampler* r);
+int lo_resampler_output_rate(const lo_resampler* r);
+int lo_resampler_samples_until_steady_state(const lo_resampler* r);
+int lo_resampler_resample(lo_resampler* r, const int16_t* in, int n, int16_t* out, int capacity);   /* number of outputs, -1 overflow */
+int lo_resampler_design(int input_rate, int output_rate, int* num, int* den, float* coeffs, int capacity);   /* taps per phase */
+void lo_resampler_coeffs(const lo_resampler* r, float* out);
+double lo_bessel_i0(double x);
+typedef struct lo_buffered_resampler lo_buffered_resampler;
+lo_buffered_resampler* lo_buffered_resampler_create(int internal_rate_hz, int external_rate_hz);
+void lo_buffered_resampler_free(lo_buffered_resampler* b);
+int lo_buffered_resampler_leftover(const lo_buffered_resampler* b);
+int lo_buffered_resampler_internal_samples(const lo_buffered_resampler* b, int num_external_requested);
+int lo_buffered_resampler_filter_and_buffer(lo_buffered_resampler* b, int (*generator)(void*, int, int16_t*), void* user,
+                                            int num_external_requested, int16_t* out);
+
 /* ---- whole codec, one stream (LyraEncoder::Encode / LyraDecoder::{SetEncodedPacket,DecodeSamples}
  *      restricted to 16 kHz, no DTX, packets always received or concealed with zero features) ---- */
 typedef struct lo_codec lo_codec;

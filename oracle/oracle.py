@@ -65,6 +65,12 @@ def lib():
             "lo_decoder_counters": (None, [vp, vp]), "lo_decoder_noise": (vp, [vp]), "lo_decoder_cng": (vp, [vp]),
             "lo_encoder_create": (vp, [C.c_char_p, ci]), "lo_encoder_free": (None, [vp]),
             "lo_encoder_encode": (ci, [vp, vp, ci, ci, vp]),
+            "lo_resampler_create": (vp, [ci, ci]), "lo_resampler_free": (None, [vp]), "lo_resampler_reset": (None, [vp]),
+            "lo_resampler_samples_until_steady_state": (ci, [vp]), "lo_resampler_resample": (ci, [vp, vp, ci, vp, ci]),
+            "lo_resampler_design": (ci, [ci, ci, vp, vp, vp, ci]),
+            "lo_buffered_resampler_create": (vp, [ci, ci]), "lo_buffered_resampler_free": (None, [vp]),
+            "lo_buffered_resampler_leftover": (ci, [vp]), "lo_buffered_resampler_internal_samples": (ci, [vp, ci]),
+            "lo_buffered_resampler_filter_and_buffer": (ci, [vp, vp, vp, ci, vp]),
             "lo_codec_create": (vp, [C.c_char_p]), "lo_codec_free": (None, [vp]), "lo_codec_reset": (ci, [vp]),
             "lo_codec_encode": (ci, [vp, vp, ci, vp, vp, vp]), "lo_codec_decode": (ci, [vp, vp, ci, vp, vp, vp]),
             "lo_codec_encoder_net": (vp, [vp]), "lo_codec_decoder_net": (vp, [vp]),
@@ -388,6 +394,79 @@ class Encoder:
         out = np.zeros(32, dtype=np.uint8)
         r = lib().lo_encoder_encode(self.h, _p(a), int(a.size), num_bits, _p(out))
         return None if r < 0 else bytes(out[:r])
+
+
+class Resampler:
+    """Resampler (lyra/resampler.{h,cc}): polyphase Kaiser-windowed-sinc FIR, started fully primed (17 input samples of delay)."""
+
+    def __init__(self, input_rate_hz, output_rate_hz):
+        self.h = lib().lo_resampler_create(input_rate_hz, output_rate_hz)
+        if not self.h:
+            raise ValueError("unsupported sample rates")
+        self.input_rate_hz, self.output_rate_hz = input_rate_hz, output_rate_hz
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lo_resampler_free(self.h)
+            self.h = None
+
+    def reset(self):
+        lib().lo_resampler_reset(self.h)
+
+    def resample(self, audio):
+        a = np.ascontiguousarray(audio, dtype=np.int16)
+        cap = a.size * 3 + 8
+        out = np.zeros(cap, dtype=np.int16)
+        r = lib().lo_resampler_resample(self.h, _p(a), int(a.size), _p(out), cap)
+        assert r >= 0
+        return out[:r].copy()
+
+    def samples_until_steady_state(self):
+        return lib().lo_resampler_samples_until_steady_state(self.h)
+
+
+def resampler_design(input_rate_hz, output_rate_hz):
+    """-> (num, den, coeffs[den][taps] float32): the polyphase filter bank (rate ratio input / output = num / den)."""
+    num, den = C.c_int(), C.c_int()
+    buf = np.zeros(3 * 35, dtype=np.float32)
+    taps = lib().lo_resampler_design(input_rate_hz, output_rate_hz, C.byref(num), C.byref(den), _p(buf), buf.size)
+    return num.value, den.value, buf[:den.value * taps].reshape(den.value, taps).copy()
+
+
+_GEN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
+
+
+class BufferedResampler:
+    """BufferedResampler (lyra/buffered_resampler.{h,cc}): internal 16 kHz -> external rate with leftover bookkeeping."""
+
+    def __init__(self, internal_rate_hz, external_rate_hz):
+        self.h = lib().lo_buffered_resampler_create(internal_rate_hz, external_rate_hz)
+        if not self.h:
+            raise ValueError("unsupported sample rates")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lo_buffered_resampler_free(self.h)
+            self.h = None
+
+    @property
+    def leftover(self):
+        return lib().lo_buffered_resampler_leftover(self.h)
+
+    def internal_samples(self, num_external):
+        return lib().lo_buffered_resampler_internal_samples(self.h, num_external)
+
+    def filter_and_buffer(self, generator, num_external):
+        """generator(n) -> int16[n] (or None to fail, like the reference's std::nullopt)."""
+        def thunk(_user, n, dst):
+            got = generator(n)
+            if got is None or len(got) != n:
+                return -1
+            C.memmove(dst, np.ascontiguousarray(got, dtype=np.int16).ctypes.data, 2 * n)
+            return 0
+        out = np.zeros(num_external + 1, dtype=np.int16)
+        r = lib().lo_buffered_resampler_filter_and_buffer(self.h, _GEN(thunk), None, num_external, _p(out))
+        return None if r < 0 else out[:num_external].copy()
 
 
 class Codec:
