@@ -155,6 +155,15 @@ int lyra_b200_set_cng_seed(lyra_b200_ctx* ctx, uint64_t seed);   /* default 0 */
 int lyra_b200_encode_dtx(lyra_b200_ctx* ctx, const int32_t* stream_ids, int n, const int16_t* pcm, int num_bits, uint8_t* packets,
                          int32_t* packet_bytes);
 
+/* Resampler::Resample (lyra/resampler.cc:31-66, audio_dsp::QResampler with a kernel radius of 17 input samples, started fully
+ * primed) for n streams: to_internal != 0 converts `external_rate_hz` (8000 / 32000 / 48000) to the codec's 16 kHz (LyraEncoder's
+ * input side, lyra_encoder.cc:58-66,118-122), to_internal == 0 converts 16 kHz to the external rate (LyraDecoder's output side,
+ * lyra_decoder.cc:108-114).  in[n][in_samples] -> out[n][out_stride]; out_counts[n] (may be NULL) = samples produced per stream
+ * (in_samples * out / in, +-1 when down-sampling from an odd phase); at most 960 input and 960 output samples per stream and call.  Each stream owns a delay line and phase per direction,
+ * cleared by lyra_b200_reset; a call at a different rate restarts that stream's filter. */
+int lyra_b200_resample(lyra_b200_ctx* ctx, int to_internal, const int32_t* stream_ids, int n, int external_rate_hz, const int16_t* in,
+                       int in_samples, int16_t* out, int out_stride, int32_t* out_counts);
+
 /* ---- device-resident variants (pointers are CUDA device pointers; asynchronous on the context's
  *      stream; streams 0..n-1).  Used by bench.py for the HBM-resident `value` measurement and by
  *      callers that keep audio on the GPU. ---------------------------------------------------------- */

@@ -10,9 +10,10 @@
 //   NoiseEstimator              noise_estimator.{h,cc}           lyra_b200::NoiseEstimatorB200 (: NoiseEstimatorInterface)
 //   Packet<184>                 packet.h                         lyra_b200::Packet184
 //   ComfortNoiseGenerator       comfort_noise_generator.{h,cc}   lyra_b200::ComfortNoiseGeneratorB200 (: GenerativeModel)
+//   Resampler / BufferedResampler  resampler.{h,cc} / buffered_resampler.{h,cc}   lyra_b200::ResamplerB200 / BufferedResamplerB200
 //   LyraEncoder / LyraDecoder   lyra_encoder.{h,cc} / lyra_decoder.{h,cc}       lyra_b200::LyraEncoderB200 / LyraDecoderB200
-//                                                                (16 kHz; DTX; packet-loss concealment, comfort noise and
-//                                                                 the cross-fades between them, arbitrary request sizes)
+//                                                                (8 / 16 / 32 / 48 kHz; DTX; packet-loss concealment, comfort
+//                                                                 noise and the cross-fades between them, arbitrary request sizes)
 //
 // The reference's interface headers need abseil, which is not available in this build environment, so the
 // three interfaces are restated below with std:: types (absl::Span<const T> -> pointer + size overloads on
@@ -24,8 +25,10 @@
 // API-compatible but latency-bound; throughput users call the batched C ABI directly (include/lyra_b200.h).
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <cstdlib>
 #include <memory>
 #include <mutex>
@@ -366,6 +369,100 @@ class ComfortNoiseGeneratorB200 : public GenerativeModel {
   int16_t hop_[LYRA_B200_HOP] = {0};
 };
 
+// ---- Resampler (lyra/resampler_interface.h, lyra/resampler.{h,cc}) -------------------------------------------------------
+inline bool IsSampleRateSupported(int hz) { return hz == 8000 || hz == 16000 || hz == 32000 || hz == 48000; }   // lyra_config.h:56,92-97
+class ResamplerInterface {
+ public:
+  virtual ~ResamplerInterface() {}
+  virtual std::vector<int16_t> Resample(const std::vector<int16_t>& audio) = 0;
+  virtual void Reset() = 0;
+  virtual int input_sample_rate_hz() const = 0;
+  virtual int target_sample_rate_hz() const = 0;
+  virtual int samples_until_steady_state() const = 0;
+};
+
+class ResamplerB200 : public ResamplerInterface {
+ public:
+  // one of the two rates must be the codec's 16 kHz (the only way the reference uses the class: lyra_encoder.cc:58-66,
+  // lyra_decoder.cc:108-114); equal rates pass the samples through
+  static std::unique_ptr<ResamplerB200> Create(const std::string& model_path, int input_sample_rate_hz, int target_sample_rate_hz) {
+    if (!IsSampleRateSupported(input_sample_rate_hz) || !IsSampleRateSupported(target_sample_rate_hz)) return nullptr;
+    if (input_sample_rate_hz != 16000 && target_sample_rate_hz != 16000) return nullptr;
+    const bool to_internal = target_sample_rate_hz == 16000;
+    auto s = Session::Get(model_path, to_internal ? LYRA_B200_ROLE_ENCODER : LYRA_B200_ROLE_DECODER);
+    if (!s) return nullptr;
+    const int id = s->Acquire();
+    if (id < 0) return nullptr;
+    return std::unique_ptr<ResamplerB200>(new ResamplerB200(std::move(s), id, input_sample_rate_hz, target_sample_rate_hz));
+  }
+  ~ResamplerB200() override { session_->Release(id_); }
+  std::vector<int16_t> Resample(const std::vector<int16_t>& audio) override {
+    if (in_ == out_ || audio.empty()) return audio;
+    std::vector<int16_t> result;
+    const bool to_internal = out_ == 16000;
+    const int external = to_internal ? in_ : out_;
+    std::lock_guard<std::mutex> lock(session_->mutex());
+    const size_t chunk = out_ > in_ ? (size_t)(960 / (out_ / in_)) : 960;       // the device call takes / returns up to 960 samples per stream
+    for (size_t pos = 0; pos < audio.size(); pos += chunk) {
+      const int n = (int)std::min(chunk, audio.size() - pos);
+      const int stride = (int)(((int64_t)n * out_ + in_ - 1) / in_) + 1;
+      std::vector<int16_t> chunk((size_t)stride);
+      int32_t count = 0;
+      if (lyra_b200_resample(session_->ctx(), to_internal ? 1 : 0, &id_, 1, external, audio.data() + pos, n, chunk.data(), stride, &count) != LYRA_B200_OK)
+        return std::vector<int16_t>();
+      result.insert(result.end(), chunk.begin(), chunk.begin() + count);
+    }
+    return result;
+  }
+  void Reset() override { std::lock_guard<std::mutex> lock(session_->mutex()); lyra_b200_reset(session_->ctx(), &id_, 1); }
+  int input_sample_rate_hz() const override { return in_; }
+  int target_sample_rate_hz() const override { return out_; }
+  int samples_until_steady_state() const override { return (int)(2.f * 17.f * ((float)out_ / (float)in_)); }   // resampler.cc:74-83
+
+ private:
+  ResamplerB200(std::shared_ptr<Session> s, int id, int in, int out) : session_(std::move(s)), id_(id), in_(in), out_(out) {}
+  std::shared_ptr<Session> session_;
+  int id_, in_, out_;
+};
+
+// ---- BufferedResampler (lyra/buffered_filter_interface.h, lyra/buffered_resampler.{h,cc}) --------------------------------
+class BufferedResamplerB200 {
+ public:
+  static std::unique_ptr<BufferedResamplerB200> Create(const std::string& model_path, int internal_sample_rate, int external_sample_rate) {
+    auto r = ResamplerB200::Create(model_path, internal_sample_rate, external_sample_rate);
+    if (!r) return nullptr;
+    return std::unique_ptr<BufferedResamplerB200>(new BufferedResamplerB200(std::move(r)));
+  }
+  explicit BufferedResamplerB200(std::unique_ptr<ResamplerInterface> resampler) : resampler_(std::move(resampler)) {}
+  std::optional<std::vector<int16_t>> FilterAndBuffer(const std::function<std::optional<std::vector<int16_t>>(int)>& sample_generator,
+                                                      int num_external_samples_requested) {                  // buffered_resampler.cc:63-91
+    const int n_int = GetInternalNumSamplesToGenerate(num_external_samples_requested);
+    std::vector<int16_t> samples((size_t)num_external_samples_requested);
+    const int used = std::min((int)leftover_samples_.size(), num_external_samples_requested);                // :108-119
+    std::copy(leftover_samples_.begin(), leftover_samples_.begin() + used, samples.begin());
+    leftover_samples_.erase(leftover_samples_.begin(), leftover_samples_.begin() + used);
+    auto internal = sample_generator(n_int);
+    if (!internal.has_value() || (int)internal->size() != n_int) return std::nullopt;
+    const std::vector<int16_t> external = resampler_->target_sample_rate_hz() == resampler_->input_sample_rate_hz()
+                                              ? internal.value() : resampler_->Resample(internal.value());  // :121-129
+    const int to_copy = num_external_samples_requested - used;                                               // :131-147
+    if ((int)external.size() < to_copy) return std::nullopt;
+    std::copy(external.begin(), external.begin() + to_copy, samples.begin() + used);
+    leftover_samples_.insert(leftover_samples_.end(), external.begin() + to_copy, external.end());
+    return samples;
+  }
+  int GetInternalNumSamplesToGenerate(int num_external_samples_requested) const {                            // :93-106
+    if (num_external_samples_requested <= (int)leftover_samples_.size()) return 0;
+    const int needed = num_external_samples_requested - (int)leftover_samples_.size();
+    const float ratio = (float)resampler_->target_sample_rate_hz() / (float)resampler_->input_sample_rate_hz();
+    return (int)std::ceil((float)needed / ratio);
+  }
+
+ private:
+  std::vector<int16_t> leftover_samples_;
+  std::unique_ptr<ResamplerInterface> resampler_;
+};
+
 // ---- factories with the reference's names (lyra/lyra_components.cc:42-60) ------------------------------------------
 inline std::unique_ptr<VectorQuantizerInterface> CreateQuantizer(const std::string& model_path, int role = LYRA_B200_ROLE_ENCODER) {
   return ResidualVectorQuantizerB200::Create(model_path, role);
@@ -384,9 +481,14 @@ inline int PacketSizeToNumQuantizedBits(int packet_size) { return packet_size ==
 class LyraEncoderB200 {
  public:
   static std::unique_ptr<LyraEncoderB200> Create(int sample_rate_hz, int num_channels, int bitrate, bool enable_dtx, const std::string& model_path) {
-    if (sample_rate_hz != 16000 || num_channels != 1) return nullptr;   // other rates need the resampler (lyra_encoder.cc:58-66): not on this path
+    if (!IsSampleRateSupported(sample_rate_hz) || num_channels != 1) return nullptr;   // AreParamsSupported, lyra_config.h:119-168
     const int bits = BitrateToNumQuantizedBits(bitrate);
     if (bits < 0) return nullptr;
+    std::unique_ptr<ResamplerInterface> rs;
+    if (sample_rate_hz != 16000) {                                       // lyra_encoder.cc:58-66
+      rs = ResamplerB200::Create(model_path, sample_rate_hz, 16000);
+      if (!rs) return nullptr;
+    }
     auto fe = CreateFeatureExtractor(model_path);
     auto vq = CreateQuantizer(model_path);
     if (!fe || !vq) return nullptr;
@@ -395,9 +497,11 @@ class LyraEncoderB200 {
       ne = NoiseEstimatorB200::Create(model_path, 16000, LYRA_B200_HOP, 640, 160);
       if (!ne) return nullptr;
     }
-    return std::unique_ptr<LyraEncoderB200>(new LyraEncoderB200(std::move(fe), std::move(vq), std::move(ne), bits));
+    return std::unique_ptr<LyraEncoderB200>(new LyraEncoderB200(std::move(rs), std::move(fe), std::move(vq), std::move(ne), sample_rate_hz, bits));
   }
-  std::optional<std::vector<uint8_t>> Encode(const std::vector<int16_t>& audio) {
+  std::optional<std::vector<uint8_t>> Encode(const std::vector<int16_t>& audio_in) {
+    if ((int)audio_in.size() != sample_rate_hz_ / 50) return std::nullopt;            // exactly one hop at the external rate
+    const std::vector<int16_t> audio = resampler_ ? resampler_->Resample(audio_in) : audio_in;   // lyra_encoder.cc:118-122
     if ((int)audio.size() != LYRA_B200_HOP) return std::nullopt;                      // lyra_encoder.cc:124-129
     if (noise_estimator_) {                                                           // :131-141
       if (!noise_estimator_->ReceiveSamples(audio)) return std::nullopt;
@@ -415,18 +519,21 @@ class LyraEncoderB200 {
     num_quantized_bits_ = bits;
     return true;
   }
-  int sample_rate_hz() const { return 16000; }
+  int sample_rate_hz() const { return sample_rate_hz_; }
   int num_channels() const { return 1; }
   int bitrate() const { return GetPacketSize(num_quantized_bits_) * 8 * 50; }
   int frame_rate() const { return 50; }
 
  private:
-  LyraEncoderB200(std::unique_ptr<FeatureExtractorInterface> fe, std::unique_ptr<VectorQuantizerInterface> vq,
-                  std::unique_ptr<NoiseEstimatorInterface> ne, int bits)
-      : feature_extractor_(std::move(fe)), vector_quantizer_(std::move(vq)), noise_estimator_(std::move(ne)), num_quantized_bits_(bits) {}
+  LyraEncoderB200(std::unique_ptr<ResamplerInterface> rs, std::unique_ptr<FeatureExtractorInterface> fe, std::unique_ptr<VectorQuantizerInterface> vq,
+                  std::unique_ptr<NoiseEstimatorInterface> ne, int sample_rate_hz, int bits)
+      : resampler_(std::move(rs)), feature_extractor_(std::move(fe)), vector_quantizer_(std::move(vq)), noise_estimator_(std::move(ne)),
+        sample_rate_hz_(sample_rate_hz), num_quantized_bits_(bits) {}
+  std::unique_ptr<ResamplerInterface> resampler_;
   std::unique_ptr<FeatureExtractorInterface> feature_extractor_;
   std::unique_ptr<VectorQuantizerInterface> vector_quantizer_;
   std::unique_ptr<NoiseEstimatorInterface> noise_estimator_;
+  int sample_rate_hz_;
   int num_quantized_bits_;
 };
 
@@ -438,18 +545,22 @@ class LyraDecoderB200 {
   enum FadeDirection { kFadeFromCNG = -1, kFadeToCNG = 1 };                          // lyra_decoder.h:105-108
 
   static std::unique_ptr<LyraDecoderB200> Create(int sample_rate_hz, int num_channels, const std::string& model_path) {
-    if (sample_rate_hz != 16000 || num_channels != 1) return nullptr;   // other rates need the buffered resampler (lyra_decoder.cc:108-114)
+    if (!IsSampleRateSupported(sample_rate_hz) || num_channels != 1) return nullptr;
+    auto rs = BufferedResamplerB200::Create(model_path, 16000, sample_rate_hz);        // lyra_decoder.cc:108-114
+    if (!rs) return nullptr;
     auto gm = CreateGenerativeModel(LYRA_B200_NUM_FEATURES, model_path);
     auto cng = ComfortNoiseGeneratorB200::Create(model_path, 16000, LYRA_B200_HOP, 640, 160);
     auto ne = NoiseEstimatorB200::Create(model_path, 16000, LYRA_B200_HOP, 640, 160);
     auto vq = CreateQuantizer(model_path, LYRA_B200_ROLE_DECODER);
     if (!gm || !cng || !ne || !vq) return nullptr;
-    return std::unique_ptr<LyraDecoderB200>(new LyraDecoderB200(std::move(gm), std::move(cng), std::move(vq), std::move(ne)));
+    return std::unique_ptr<LyraDecoderB200>(new LyraDecoderB200(std::move(gm), std::move(cng), std::move(vq), std::move(ne), std::move(rs), sample_rate_hz));
   }
   LyraDecoderB200(std::unique_ptr<GenerativeModelInterface> generative_model, std::unique_ptr<GenerativeModelInterface> comfort_noise_generator,
-                  std::unique_ptr<VectorQuantizerInterface> vector_quantizer, std::unique_ptr<NoiseEstimatorInterface> noise_estimator)
+                  std::unique_ptr<VectorQuantizerInterface> vector_quantizer, std::unique_ptr<NoiseEstimatorInterface> noise_estimator,
+                  std::unique_ptr<BufferedResamplerB200> resampler = nullptr, int external_sample_rate_hz = 16000)
       : generative_model_(std::move(generative_model)), comfort_noise_generator_(std::move(comfort_noise_generator)),
-        vector_quantizer_(std::move(vector_quantizer)), noise_estimator_(std::move(noise_estimator)) {}
+        vector_quantizer_(std::move(vector_quantizer)), noise_estimator_(std::move(noise_estimator)), resampler_(std::move(resampler)),
+        external_sample_rate_hz_(external_sample_rate_hz) {}
 
   bool SetEncodedPacket(const std::vector<uint8_t>& encoded) {                       // lyra_decoder.cc:172-209
     const int bits = PacketSizeToNumQuantizedBits((int)encoded.size());
@@ -463,7 +574,13 @@ class LyraDecoderB200 {
     return generative_model_->AddFeatures(features.value());                        // ZeroFeatureEstimator::Update is a no-op
   }
 
-  std::optional<std::vector<int16_t>> DecodeSamples(int num_samples) {               // lyra_decoder.cc:211-315 at the internal rate
+  std::optional<std::vector<int16_t>> DecodeSamples(int num_samples) {               // lyra_decoder.cc:211-226
+    if (num_samples < 0) return std::nullopt;
+    if (!resampler_) return DecodeSamplesInternal(num_samples);
+    return resampler_->FilterAndBuffer([this](int n) { return DecodeSamplesInternal(n); }, num_samples);
+  }
+
+  std::optional<std::vector<int16_t>> DecodeSamplesInternal(int num_samples) {       // lyra_decoder.cc:228-315 (internal rate)
     if (num_samples < 0) return std::nullopt;
     std::vector<int16_t> result;
     result.reserve((size_t)num_samples);
@@ -501,7 +618,7 @@ class LyraDecoderB200 {
     }
     return result;
   }
-  int sample_rate_hz() const { return 16000; }
+  int sample_rate_hz() const { return external_sample_rate_hz_; }
   int num_channels() const { return 1; }
   int frame_rate() const { return 50; }
   bool is_comfort_noise() const { return fade_progress_ == kFadeSamples; }           // lyra_decoder.cc:381-383
@@ -524,6 +641,8 @@ class LyraDecoderB200 {
   std::unique_ptr<GenerativeModelInterface> generative_model_, comfort_noise_generator_;
   std::unique_ptr<VectorQuantizerInterface> vector_quantizer_;
   std::unique_ptr<NoiseEstimatorInterface> noise_estimator_;
+  std::unique_ptr<BufferedResamplerB200> resampler_;
+  int external_sample_rate_hz_ = 16000;
   int concealment_progress_ = 0, fade_progress_ = 0;
   FadeDirection fade_direction_ = kFadeFromCNG;
 };

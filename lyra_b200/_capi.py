@@ -72,6 +72,7 @@ class CApi:
             "lyra_b200_set_cng_seed": (ci, [vp, C.c_uint64]),
             "lyra_b200_encode_dtx": (ci, [vp, vp, ci, vp, ci, vp, vp]),
             "lyra_b200_encode_dtx_device": (ci, [vp, ci, vp, ci, vp, vp]),
+            "lyra_b200_resample": (ci, [vp, ci, vp, ci, ci, vp, ci, vp, ci, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)   # AttributeError here = the library does not export the declared ABI
@@ -88,7 +89,7 @@ class CApi:
                "lyra_b200_decode_track_noise_device", "lyra_b200_set_split", "lyra_b200_set_blocking_sync", "lyra_b200_set_decoder_mode", "lyra_b200_decoder_mode", "lyra_b200_launch_count", "lyra_b200_profile_enable",
                "lyra_b200_profile_read", "lyra_b200_noise_estimate", "lyra_b200_decode_plc", "lyra_b200_decode_plc_device",
                "lyra_b200_plc_get_state", "lyra_b200_plc_set_state", "lyra_b200_cng_generate", "lyra_b200_set_cng_seed",
-               "lyra_b200_encode_dtx", "lyra_b200_encode_dtx_device"]
+               "lyra_b200_encode_dtx", "lyra_b200_encode_dtx_device", "lyra_b200_resample"]
 
 
 _product = None
@@ -315,6 +316,20 @@ class Context:
 
     def encode_dtx_device(self, n, d_pcm, num_bits, d_packets, d_is_noise):
         self._check(self.api.lib.lyra_b200_encode_dtx_device(self.h, n, C.c_void_p(d_pcm), num_bits, C.c_void_p(d_packets), C.c_void_p(d_is_noise)))
+
+    def resample(self, audio, external_rate_hz, to_internal, stream_ids=None):
+        """Resampler::Resample for n streams -> list of int16 arrays (one per stream; lengths may differ by one when down-sampling)."""
+        a = np.ascontiguousarray(audio, dtype=np.int16)
+        a = a.reshape(1, -1) if a.ndim == 1 else a
+        n, n_in = a.shape
+        ids = _ids(stream_ids, n)
+        ratio = (16000 / external_rate_hz) if to_internal else (external_rate_hz / 16000)
+        stride = int(np.ceil(n_in * ratio)) + 1
+        out = np.zeros((n, stride), dtype=np.int16)
+        counts = np.zeros(n, dtype=np.int32)
+        self._check(self.api.lib.lyra_b200_resample(self.h, 1 if to_internal else 0, _ptr(ids), n, int(external_rate_hz), _ptr(a), n_in,
+                                                    _ptr(out), stride, _ptr(counts)))
+        return [out[k, :counts[k]].copy() for k in range(n)]
 
     def noise_update_device(self, n, d_pcm, d_mask, d_is_noise, d_estimate):
         self._check(self.api.lib.lyra_b200_noise_update_device(self.h, n, C.c_void_p(d_pcm), C.c_void_p(d_mask or 0),

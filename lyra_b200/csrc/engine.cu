@@ -77,6 +77,12 @@ struct lyra_b200_ctx {
   int16_t* d_cng_pcm = nullptr;
   float* d_cng_feat = nullptr;
   const uint8_t* cur_skip = nullptr;         // skip mask of the call in flight (TileIo::skip)
+  // sample-rate converters: [direction 0 = to 16 kHz (encoder side), 1 = from 16 kHz (decoder side)][max_streams] state
+  int16_t* d_rs_delay[2] = {nullptr, nullptr};   // [max_streams][34]
+  int* d_rs_pos[2] = {nullptr, nullptr};         // [max_streams][2] {position, rate}
+  int16_t* d_rs_in = nullptr;                    // staging [max_streams][960]
+  int16_t* d_rs_out = nullptr;
+  int* d_rs_counts = nullptr;
   // device staging for the host-buffer API
   int16_t* d_pcm = nullptr;
   uint8_t* d_packets = nullptr;
@@ -558,6 +564,7 @@ int ResetImpl(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
     CU(cudaMemsetAsync(ctx->d_cng_hops + id, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_noise_enc + id * nu, 0, sizeof(float) * nu, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_logmel_prev_enc + id * 320, 0, sizeof(int16_t) * 320, ctx->stream));
+    for (int d = 0; d < 2; ++d) CU(cudaMemsetAsync(ctx->d_rs_pos[d] + id * 2, 0, sizeof(int) * 2, ctx->stream));   // rate 0: the next call starts fully primed
   }
   if (!ids) {
     std::vector<int> img((size_t)n * 4);
@@ -567,6 +574,7 @@ int ResetImpl(lyra_b200_ctx* ctx, const int32_t* ids, int n) {
     CU(cudaMemsetAsync(ctx->d_cng_hops, 0, sizeof(unsigned long long) * (size_t)n, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_noise_enc, 0, sizeof(float) * nu * (size_t)n, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_logmel_prev_enc, 0, sizeof(int16_t) * 320 * (size_t)n, ctx->stream));
+    for (int d = 0; d < 2; ++d) CU(cudaMemsetAsync(ctx->d_rs_pos[d], 0, sizeof(int) * 2 * (size_t)n, ctx->stream));
   }
   CU(SyncStream(ctx));
   return LYRA_B200_OK;
@@ -686,6 +694,13 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
   ok = ok && DevAlloc(&ctx->d_model_pcm, P * 320) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_cng_pcm, P * 320) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_cng_feat, P * 160) == cudaSuccess;
+  for (int d = 0; d < 2; ++d) {
+    ok = ok && DevAlloc(&ctx->d_rs_delay[d], P * (size_t)(kResamplerTaps - 1)) == cudaSuccess;
+    ok = ok && DevAlloc(&ctx->d_rs_pos[d], P * 2) == cudaSuccess;
+  }
+  ok = ok && DevAlloc(&ctx->d_rs_in, P * 960) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_rs_out, P * 968) == cudaSuccess;
+  ok = ok && DevAlloc(&ctx->d_rs_counts, P) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_is_noise, P) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_pcm, P * 320) == cudaSuccess;
   ok = ok && DevAlloc(&ctx->d_packets, P * 24) == cudaSuccess;
@@ -729,6 +744,8 @@ void lyra_b200_destroy(lyra_b200_ctx* ctx) {
   cudaFree(ctx->d_noise_enc); cudaFree(ctx->d_logmel_prev_enc); cudaFree(ctx->d_plc); cudaFree(ctx->d_cng_work); cudaFree(ctx->d_cng_hops);
   cudaFree(ctx->d_plan); cudaFree(ctx->d_skip); cudaFree(ctx->d_feed); cudaFree(ctx->d_is_cn); cudaFree(ctx->d_fade0); cudaFree(ctx->d_dir);
   cudaFree(ctx->d_model_pcm); cudaFree(ctx->d_cng_pcm); cudaFree(ctx->d_cng_feat);
+  for (int d = 0; d < 2; ++d) { cudaFree(ctx->d_rs_delay[d]); cudaFree(ctx->d_rs_pos[d]); }
+  cudaFree(ctx->d_rs_in); cudaFree(ctx->d_rs_out); cudaFree(ctx->d_rs_counts);
   cudaFree(ctx->d_pcm); cudaFree(ctx->d_packets); cudaFree(ctx->d_received); cudaFree(ctx->d_features);
   cudaFree(ctx->d_melout); cudaFree(ctx->d_indices); cudaFree(ctx->d_ids); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_slot_of);
   for (int b = 0; b < 2; ++b) {
@@ -1116,6 +1133,37 @@ int lyra_b200_cng_generate(lyra_b200_ctx* ctx, const int32_t* ids, int n, const 
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(pcm, ctx->d_cng_pcm, sizeof(int16_t) * 320 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(SyncStream(ctx));
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_resample(lyra_b200_ctx* ctx, int to_internal, const int32_t* ids, int n, int external_rate_hz, const int16_t* in,
+                       int in_samples, int16_t* out, int out_stride, int32_t* out_counts) {
+  if (!ctx || !in || !out) return LYRA_B200_EINVAL;
+  ENTER(0);
+  const int pair = external_rate_hz == 8000 ? 0 : external_rate_hz == 32000 ? 1 : external_rate_hz == 48000 ? 2 : -1;
+  if (pair < 0) { ctx->err = "the resampler converts between 16 kHz and 8 / 32 / 48 kHz"; return LYRA_B200_EINVAL; }
+  const int pr = to_internal ? pair : pair + 3;
+  const int num = ctx->spec.resampler.num[pr], den = ctx->spec.resampler.den[pr];
+  const int max_out = (in_samples * den + num - 1) / num;
+  if (in_samples <= 0 || in_samples > 960 || max_out > 960 || out_stride < max_out || out_stride > 968) {
+    ctx->err = "resample: at most 960 input and 960 output samples per stream and call, and room for ceil(n * out / in) outputs";
+    return LYRA_B200_EINVAL;
+  }
+  const int* d_ids = nullptr;
+  int rc = UploadIds(ctx, ids, n, &d_ids);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->d_rs_in, in, sizeof(int16_t) * (size_t)in_samples * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  const int dir = to_internal ? 0 : 1;
+  LYRA_LAUNCH(ResampleKernel, dim3((unsigned)n), dim3(128), sizeof(float) * (size_t)(kResamplerTaps - 1 + in_samples), ctx->stream,
+              ctx->d_blob, ctx->spec.resampler, pr, external_rate_hz, d_ids, n, ctx->d_rs_in, in_samples, ctx->d_rs_out, out_stride,
+              ctx->d_rs_counts, ctx->d_rs_delay[dir], ctx->d_rs_pos[dir]);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, ctx->d_rs_out, sizeof(int16_t) * (size_t)out_stride * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<int> counts((size_t)n);
+  CU(cudaMemcpyAsync(counts.data(), ctx->d_rs_counts, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(SyncStream(ctx));
+  if (out_counts) for (int k = 0; k < n; ++k) out_counts[k] = counts[(size_t)k];
   return LYRA_B200_OK;
 }
 

@@ -687,6 +687,59 @@ CngParams BuildCngParams(std::vector<uint8_t>* blob, const LogMelParams& lm, int
   return p;
 }
 
+// Filter banks of the sample-rate converters; the expressions (and their order) are those of oracle/resampler.c
+// lo_resampler_design, so both sides hold the same float coefficients.
+namespace {
+double BesselI0(double x) {
+  double sum = 1.0, term = 1.0;
+  const double q = x * x / 4.0;
+  for (int k = 1; k < 64; ++k) {
+    term *= q / ((double)k * (double)k);
+    sum += term;
+    if (term < 1e-17 * sum) break;
+  }
+  return sum;
+}
+}  // namespace
+
+ResamplerParams BuildResamplerParams(std::vector<uint8_t>* blob) {
+  ResamplerParams p;
+  std::memset(&p, 0, sizeof(p));
+  const int in_rate[6] = {8000, 32000, 48000, 16000, 16000, 16000}, out_rate[6] = {16000, 16000, 16000, 8000, 32000, 48000};
+  for (int pair = 0; pair < 6; ++pair) {
+    int a = in_rate[pair], b = out_rate[pair];
+    while (b) { const int t = a % b; a = b; b = t; }
+    const int num = in_rate[pair] / a, den = out_rate[pair] / a;
+    const double factor = (double)num / (double)den;
+    const double radius_factor = 17.0 * (out_rate[pair] < in_rate[pair] ? (double)((float)out_rate[pair] / (float)in_rate[pair]) : 1.0);
+    const double radius = radius_factor * (factor > 1.0 ? factor : 1.0);
+    const double cutoff = 0.9 * 0.5 / (factor > 1.0 ? factor : 1.0);
+    const double beta = 5.658;
+    const int rc = (int)std::ceil(radius - 1e-4);
+    SPEC_CHECK(2 * rc + 1 == kResamplerTaps && den <= 3, "resampler: unexpected filter size");
+    const double i0b = BesselI0(beta);
+    std::vector<float> coeffs((size_t)den * kResamplerTaps);
+    for (int ph = 0; ph < den; ++ph) {
+      const double offset = (double)ph / (double)den;
+      for (int j = 0; j < kResamplerTaps; ++j) {
+        const double x = (double)(rc - j) + offset;
+        double h = 0.0;
+        if (std::fabs(x) <= radius) {
+          const double z = 2.0 * cutoff * x;
+          const double sinc = std::fabs(z) < 1e-12 ? 1.0 : std::sin(M_PI * z) / (M_PI * z);
+          const double r = x / radius;
+          h = 2.0 * cutoff * sinc * BesselI0(beta * std::sqrt(1.0 - r * r > 0.0 ? 1.0 - r * r : 0.0)) / i0b;
+        }
+        coeffs[(size_t)ph * kResamplerTaps + j] = (float)h;
+      }
+    }
+    p.coeffs[pair] = Append(blob, coeffs);
+    p.num[pair] = num;
+    p.den[pair] = den;
+  }
+  return p;
+}
+
 ModelSpec BuildModelSpec(const std::string& model_dir) {
   ModelSpec s;
   {
@@ -706,6 +759,7 @@ ModelSpec BuildModelSpec(const std::string& model_dir) {
   s.logmel160 = BuildLogMelParams(&s.blob, 16000, 320, 640, 160);
   s.logmel64 = BuildLogMelParams(&s.blob, 16000, 320, 640, 64);
   s.cng = BuildCngParams(&s.blob, s.logmel160, 640);
+  s.resampler = BuildResamplerParams(&s.blob);
   while (s.blob.size() % 256) s.blob.push_back(0);
   return s;
 }

@@ -19,6 +19,7 @@ struct ModelSpec {
   RvqParams rvq;
   LogMelParams logmel160;         // 16 kHz, hop 320, window 640, 160 mel bins (NoiseEstimator's extractor)
   LogMelParams logmel64;          // 64 mel bins (lyra_integration_test's extractor)
+  ResamplerParams resampler;      // 8 / 32 / 48 kHz <-> 16 kHz filter banks
   CngParams cng;                  // comfort-noise generator + cross-fade tables (decoder PLC path)
   int num_features = 64;
   int bits_per_stage = 4;

@@ -123,4 +123,12 @@ struct CngParams {
   int32_t start_index, end_index, num_mel, fft, hop;
 };
 
+// Sample-rate converters (lyra/resampler.cc:31-66): polyphase Kaiser-windowed-sinc filter banks for the six (external <-> 16 kHz)
+// pairs.  Pair index: 0: 8k->16k, 1: 32k->16k, 2: 48k->16k, 3: 16k->8k, 4: 16k->32k, 5: 16k->48k.  coeffs[pair] = f32 [den][35].
+struct ResamplerParams {
+  uint32_t coeffs[6];
+  int32_t num[6], den[6];
+};
+constexpr int kResamplerTaps = 35;
+
 }  // namespace lyra_b200

@@ -26,6 +26,12 @@ def read_wav(name):
         return np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).copy()
 
 
+def read_wav_any(name, rate):
+    with wave.open(os.path.join(DATA_DIR, name)) as w:
+        assert w.getframerate() == rate and w.getnchannels() == 1 and w.getsampwidth() == 2
+        return np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).copy()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as O

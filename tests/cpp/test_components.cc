@@ -214,6 +214,46 @@ int main(int argc, char** argv) {
     auto pkt = e ? e->Encode(loud) : std::nullopt;
     CHECK(pkt.has_value() && pkt->size() == 8);
   }
+  // Resampler / BufferedResampler / the other sample rates of LyraEncoder and LyraDecoder (resampler_test.cc, buffered_resampler_test.cc,
+  // lyra_encoder_test.cc / lyra_decoder_test.cc size checks)
+  {
+    CHECK(ResamplerB200::Create(model, 16000, 44100) == nullptr && ResamplerB200::Create(model, 8000, 48000) == nullptr);
+    for (int rate : {8000, 32000, 48000}) {
+      for (int dir = 0; dir < 2; ++dir) {
+        const int a = dir ? 16000 : rate, b = dir ? rate : 16000;
+        auto rs = ResamplerB200::Create(model, a, b);
+        lo_resampler* r = lo_resampler_create(a, b);
+        CHECK(rs != nullptr && r != nullptr);
+        if (!rs || !r) continue;
+        CHECK(rs->samples_until_steady_state() == lo_resampler_samples_until_steady_state(r));
+        for (int n : {a / 50, 33, 1, a / 50 + 5}) {
+          std::vector<int16_t> x((size_t)n);
+          for (auto& v : x) v = (int16_t)(d(rng) * 3);
+          const std::vector<int16_t> got = rs->Resample(x);
+          std::vector<int16_t> want((size_t)n * 3 + 8);
+          const int m = lo_resampler_resample(r, x.data(), n, want.data(), (int)want.size());
+          CHECK((int)got.size() == m && std::memcmp(got.data(), want.data(), sizeof(int16_t) * (size_t)m) == 0);
+        }
+        lo_resampler_free(r);
+      }
+      auto e = LyraEncoderB200::Create(rate, 1, 3200, false, model);
+      auto dcd = LyraDecoderB200::Create(rate, 1, model);
+      CHECK(e && dcd && e->sample_rate_hz() == rate && dcd->sample_rate_hz() == rate);
+      if (!e || !dcd) continue;
+      const int hop = rate / 50;
+      CHECK(!e->Encode(std::vector<int16_t>(320 + (rate == 16000))).has_value() || rate == 16000);   // a 16 kHz hop is the wrong size here
+      for (int f = 0; f < 4; ++f) {
+        std::vector<int16_t> pcm((size_t)hop);
+        for (auto& v : pcm) v = (int16_t)d(rng);
+        auto pkt = e->Encode(pcm);
+        CHECK(pkt.has_value() && pkt->size() == 8);
+        CHECK(dcd->SetEncodedPacket(*pkt));
+        auto a1 = dcd->DecodeSamples(hop - 7);                     // odd request sizes exercise the leftover buffer
+        auto a2 = dcd->DecodeSamples(7);
+        CHECK(a1.has_value() && a2.has_value() && (int)a1->size() == hop - 7 && a2->size() == 7);
+      }
+    }
+  }
   std::printf(g_fail ? "FAILED (%d)\n" : "ALL OK\n", g_fail);
   return g_fail ? 1 : 0;
 }

@@ -345,3 +345,58 @@ def run_dtx_parity(Context, api, O, *, wav, frames=24, bits=64, stream_ids=(0, 3
             sizes_seen.add(int(sizes[k]))
     assert sizes_seen == {0, (bits + 7) // 8}
     ctx.close()
+
+
+def run_resampler_parity(Context, api, O, *, seed=12):
+    """lyra_b200_resample vs the oracle's Resampler: every supported pair, both directions, ragged chunk sizes (phase and delay line
+    carry over between calls), several streams with different histories, a rate switch; int16 output bit for bit."""
+    ctx = Context(8, capi=api)
+    rng = np.random.default_rng(seed)
+    ids = np.array([0, 3, 5], dtype=np.int32)
+    for rate in (8000, 32000, 48000):
+        for to_internal in (True, False):
+            a, b = (rate, 16000) if to_internal else (16000, rate)
+            refs = [O.Resampler(a, b) for _ in ids]
+            ctx.reset()
+            for chunk in (a // 50, 1, 7, a // 50 - 3, 2, a // 50):
+                x = rng.integers(-30000, 30000, size=(len(ids), chunk)).astype(np.int16)
+                got = ctx.resample(x, rate, to_internal, stream_ids=ids)
+                for k in range(len(ids)):
+                    want = refs[k].resample(x[k])
+                    assert np.array_equal(got[k], want), (rate, to_internal, chunk, k, len(got[k]), len(want))
+    # a stream that switches rate restarts from the fully primed state
+    x = rng.integers(-30000, 30000, size=(1, 160)).astype(np.int16)
+    ctx.resample(x, 8000, True, stream_ids=[2])
+    y = rng.integers(-30000, 30000, size=(1, 960)).astype(np.int16)
+    got = ctx.resample(y, 48000, True, stream_ids=[2])
+    assert np.array_equal(got[0], O.Resampler(48000, 16000).resample(y[0]))
+    ctx.close()
+
+
+def run_integration_other_rates(Context, api, O, *, rate, wav, bits=64, hops=60):
+    """lyra_integration_test.cc:60-149 at an external rate of 8 / 32 / 48 kHz through the batched C ABI: resample to 16 kHz, encode,
+    decode, resample back; the log-mel spectra (64 bins at the external rate, the oracle's extractor) of input and output stay
+    within LSD 2.0 on every hop once the filters are primed."""
+    hop = rate // 50
+    ctx = Context(2, capi=api)
+    ie, oe = O.LogMel(rate, hop, 2 * hop, 64), O.LogMel(rate, hop, 2 * hop, 64)
+    worst = 0.0
+    outs = []
+    for f in range(hops):
+        x = wav[f * hop:(f + 1) * hop]
+        internal = ctx.resample(x, rate, True, stream_ids=[1])[0]
+        assert len(internal) == 320
+        pk = ctx.encode(internal, bits, stream_ids=[1])
+        dec = ctx.decode(pk, bits, stream_ids=[1])[0]
+        y = ctx.resample(dec, rate, False, stream_ids=[1])[0]
+        assert len(y) == hop
+        outs.append(y)
+    # the codec (one hop) and the two resamplers (17 + 17 * 16000 / rate ... samples) delay the output: compare hop f of the input
+    # with hop f of the output like the reference does (its criterion tolerates the misalignment), skipping the priming hops
+    for f in range(hops):
+        fi = ie.extract(wav[f * hop:(f + 1) * hop])
+        fo = oe.extract(outs[f])
+        if f >= 3:
+            worst = max(worst, O.log_spectral_distance(fi, fo))
+    ctx.close()
+    return worst

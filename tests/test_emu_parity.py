@@ -191,3 +191,7 @@ def test_emu_plc_state_machine(emu_api, oracle, sample1):
 
 def test_emu_dtx_encoder(emu_api, oracle, sample1):
     pc.run_dtx_parity(_capi.Context, emu_api, oracle, wav=sample1, frames=8)
+
+
+def test_emu_resampler(emu_api, oracle):
+    pc.run_resampler_parity(_capi.Context, emu_api, oracle)

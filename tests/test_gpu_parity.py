@@ -368,3 +368,16 @@ def test_plc_full_size_bernoulli_loss(gpu_api, oracle):
 
 def test_dtx_encoder_parity(gpu_api, oracle, sample1):
     pc.run_dtx_parity(_capi.Context, gpu_api, oracle, wav=sample1, frames=40)
+
+
+def test_resampler_parity(gpu_api, oracle):
+    pc.run_resampler_parity(_capi.Context, gpu_api, oracle)
+
+
+@pytest.mark.parametrize("rate", [8000, 32000, 48000])
+def test_integration_criterion_other_sample_rates(gpu_api, oracle, rate):
+    from conftest import read_wav_any
+    wav = read_wav_any("sample1_%dkHz.wav" % (rate // 1000), rate)
+    worst = pc.run_integration_other_rates(_capi.Context, gpu_api, oracle, rate=rate, wav=wav)
+    print("integration LSD at %d Hz: worst hop %.3f" % (rate, worst))
+    assert worst < 2.0
