@@ -537,6 +537,8 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--bits", type=int, default=None,
                     help="quantized bits per frame: 64 / 120 / 184 (3.2 / 6.0 / 9.2 kbps); default 64, and 120 at --gpus 8 (BASELINE configs[4])")
+    ap.add_argument("--hops-per-step", type=int, default=HOPS_PER_STEP,
+                    help="hops per bench step (default %d = 1 s of audio); profiling runs under ncu use 1" % HOPS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configs (other_configs)")
     ap.add_argument("--workload", default="codec", choices=["codec", "decode_plc"],
@@ -559,6 +561,8 @@ def main():
     args = ap.parse_args()
     if args.bits is None:
         args.bits = 120 if args.gpus >= 8 else 64
+    global HOPS_PER_STEP
+    HOPS_PER_STEP = max(1, args.hops_per_step)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
