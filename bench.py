@@ -528,6 +528,7 @@ def roofline_of(res, n, bits, plc, world, hops, decoder_mode, clocks):
 
 
 def main():
+    global HOPS_PER_STEP
     protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -561,7 +562,6 @@ def main():
     args = ap.parse_args()
     if args.bits is None:
         args.bits = 120 if args.gpus >= 8 else 64
-    global HOPS_PER_STEP
     HOPS_PER_STEP = max(1, args.hops_per_step)
 
     rank = int(os.environ.get("RANK", "0"))
