@@ -424,3 +424,33 @@ __device__ __forceinline__ void lyra_bulk_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void lyra_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void lyra_named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory"); }
 #endif
+
+// ---- thread-block clusters: a pair of CTAs shares one weight stream (each CTA's producer loads half of every chunk and TMA
+//      multicasts it into both CTAs' shared memory; a stage is recycled when BOTH CTAs' MMAs have released it).  The emulator
+//      runs one block at a time: clusters do not exist there and kernels take their single-CTA path.
+#if defined(LYRA_EMU)
+static inline unsigned lyra_cluster_ctarank() { return 0; }
+static inline unsigned lyra_cluster_nctarank() { return 1; }
+static inline void lyra_cluster_sync() {}
+static inline void lyra_bulk_g2s_mc(void* smem_dst, const void* gmem_src, unsigned bytes, LyraMbar*, unsigned) { std::memcpy(smem_dst, gmem_src, bytes); }
+static inline void lyra_umma_commit_mc(LyraMbar* b, unsigned) { lyra_mbar_arrive(b); }
+#elif defined(__CUDACC__)
+__device__ __forceinline__ unsigned lyra_cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned lyra_cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ void lyra_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// bulk copy global -> the same shared-memory offset of every CTA in `cta_mask`; completes `bytes` of transaction count on the
+// mbarrier at the same offset in each of them (the barriers are armed by their own CTAs, see lyra_bulk_multi_begin)
+__device__ __forceinline__ void lyra_bulk_g2s_mc(void* smem_dst, const void* gmem_src, unsigned bytes, LyraMbar* b, unsigned cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n"
+               ::"r"(lyra_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(lyra_smem_u32(b)), "h"((unsigned short)cta_mask) : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void lyra_umma_commit_mc(LyraMbar* b, unsigned cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+               ::"r"(lyra_smem_u32(b)), "h"((unsigned short)cta_mask) : "memory");
+}
+#endif
+

@@ -77,6 +77,9 @@ struct lyra_b200_ctx {
   int16_t* d_cng_pcm = nullptr;
   float* d_cng_feat = nullptr;
   const uint8_t* cur_skip = nullptr;         // skip mask of the call in flight (TileIo::skip)
+  bool du_cluster = false;                   // DecoderKernelDU in clusters of two CTAs sharing the weight stream by TMA multicast
+                                             // (LYRA_B200_DU_CLUSTER=1).  Measured on B200: no gain (0.203 vs 0.197 ms) - the stream is bound by
+                                             // the delivery into the SMs, not by L2 reads - so it is off by default; kept for parts where it pays
   // sample-rate converters: [direction 0 = to 16 kHz (encoder side), 1 = from 16 kHz (decoder side)][max_streams] state
   int16_t* d_rs_delay[2] = {nullptr, nullptr};   // [max_streams][34]
   int* d_rs_pos[2] = {nullptr, nullptr};         // [max_streams][2] {position, rate}
@@ -296,8 +299,27 @@ int LaunchDecoderNetsUmma(lyra_b200_ctx* ctx, const Part& p, const float* d_feat
   LYRA_LAUNCH((DecoderKernelC<8, true>), dim3((unsigned)p.ntiles), dim3(LC::NT), (size_t)LC::kSmemBytes, p.st,
               ctx->d_blob, ctx->spec.dec, io, d_features, reinterpret_cast<float*>(ctx->d_state[2]), ctx->d_n18[2], ctx->d_mid_dec); }
   { ProfScope ps(ctx, 5, p.st);
+#ifdef LYRA_EMU
   LYRA_LAUNCH(DecoderKernelDU, dim3((unsigned)p.ntiles), dim3(DecDU::NT), (size_t)DecDU::kSmemBytes, p.st,
-              ctx->d_blob, ctx->spec.dec, io, ctx->d_mid_dec, reinterpret_cast<float*>(ctx->d_state[3]), ctx->d_n18[3], d_pcm); }
+              ctx->d_blob, ctx->spec.dec, io, ctx->d_mid_dec, reinterpret_cast<float*>(ctx->d_state[3]), ctx->d_n18[3], d_pcm, p.ntiles);
+#else
+  // clusters of two CTAs share the weight stream by TMA multicast (net_kernels_umma.cuh); an odd tile count gets one padding block
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((p.ntiles + 1) / 2 * 2));
+  cfg.blockDim = dim3(DecDU::NT);
+  cfg.dynamicSmemBytes = (size_t)DecDU::kSmemBytes;
+  cfg.stream = p.st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctx->du_cluster ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, DecoderKernelDU, (const uint8_t*)ctx->d_blob, ctx->spec.dec, io, (const float*)ctx->d_mid_dec,
+                        reinterpret_cast<float*>(ctx->d_state[3]), ctx->d_n18[3], d_pcm, p.ntiles));
+#endif
+  }
   ctx->launches += 2;
   CU(cudaGetLastError());
   return LYRA_B200_OK;
@@ -652,6 +674,7 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
   if (const char* e = std::getenv("LYRA_B200_BLOCKING_SYNC")) ctx->blocking_sync = std::atoi(e) != 0;
   if (const char* e = std::getenv("LYRA_B200_SPLIT")) ctx->nsplit = std::atoi(e);
+  if (const char* e = std::getenv("LYRA_B200_DU_CLUSTER")) ctx->du_cluster = std::atoi(e) != 0;
   if (const char* e = std::getenv("LYRA_B200_DECODER_MODE")) ctx->decoder_mode = std::strcmp(e, "tensor") == 0 ? LYRA_B200_DECODER_TENSOR : LYRA_B200_DECODER_EXACT;
   ctx->stream = ctx->own_stream;
   ok = ok && DevAlloc(&ctx->d_blob, ctx->spec.blob.size()) == cudaSuccess;

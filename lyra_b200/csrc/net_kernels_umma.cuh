@@ -91,7 +91,7 @@ __device__ __forceinline__ void DuArriveA(DecDUShared* sh) {
 
 __global__ void __launch_bounds__(DecDU::NT, 1)
 DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, const float* __restrict__ mid,
-                float* __restrict__ state, int* __restrict__ n18g, int16_t* __restrict__ pcm) {
+                float* __restrict__ state, int* __restrict__ n18g, int16_t* __restrict__ pcm, int ntiles) {
   using L = DecDU;
   constexpr int S = L::S, LDU = L::LDU;
   unsigned char* smem = LYRA_DYN_SMEM();
@@ -106,9 +106,28 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   int* n18 = active + S;                                      // n18[S]: tile summary (LoadTileMeta)
   LYRA_STATIC_SMEM(DecDUShared, sh, 1);
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Launched as clusters of two CTAs (engine.cu): when both tiles of the pair have work, the CTAs share the weight stream - each
+  // producer loads one half of every chunk and multicasts it into both CTAs' rings, halving the L2 traffic of the kernel's
+  // dominant stream (883 KB of weights per tile).  A CTA whose partner is a padding block or an idle tile runs on its own.
+  if ((int)blockIdx.x >= ntiles) return;                    // padding block of an odd grid (its partner sees that and runs solo)
+  bool pair = false;
+  if (lyra_cluster_nctarank() == 2) {
+    auto live = [&](int block) {
+      if (block >= ntiles) return false;
+      const int tl = io.tile_list[block];
+      bool any = false;
+      for (int ss = 0; ss < S; ++ss) {
+        const int sl = io.slot_of_stream[tl * S + ss];
+        any |= sl >= 0 && !(io.skip != nullptr && io.skip[sl]);
+      }
+      return any;
+    };
+    pair = live((int)blockIdx.x) && live((int)blockIdx.x ^ 1);      // the same value in both CTAs of the pair
+  }
+  const unsigned rank = lyra_cluster_ctarank();
 
   if (tid == 0) {
-    for (int i = 0; i < L::kStagesW; ++i) { lyra_mbar_init(&sh->w_full[i], 1); lyra_mbar_init(&sh->w_empty[i], 1); }
+    for (int i = 0; i < L::kStagesW; ++i) { lyra_mbar_init(&sh->w_full[i], 1); lyra_mbar_init(&sh->w_empty[i], pair ? 2u : 1u); }
     lyra_mbar_init(&sh->in_full, 1);
     lyra_mbar_init(&sh->a_ready, L::kRowWarps);
     lyra_mbar_init(&sh->d_ready, 1);
@@ -119,11 +138,12 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   int tile;
   LoadTileMeta<S>(io, n18g, slot, active, n18, tile);       // two block barriers inside: barrier inits and the TMEM address are visible after it
   lyra_tc_fence_after_sync();
+  if (pair) lyra_cluster_sync();                              // both CTAs' barriers exist before any remote copy or arrival
   const uint32_t tmem = sh->tmem_base;
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const uint8_t* chunks = blob + P.du_chunks;
   int ph = 0;
-  const bool idle = n18[S] == kTileIdle;                      // every stream of the tile sits this call out: nothing to do
+  const bool idle = n18[S] == kTileIdle;                      // every stream of the tile sits this call out: nothing to do (pair is false then)
 
   // ================================================= TMA producer =================================================
   if (idle) {
@@ -141,7 +161,15 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       for (int c = 0; c < kDuNumChunks; ++c) {
         const int stg = c % L::kStagesW;
         if (c >= L::kStagesW) lyra_mbar_wait(&sh->w_empty[stg], (unsigned)((c / L::kStagesW - 1) & 1));
-        lyra_bulk_g2s(wring + (size_t)stg * kDuChunkBytes, chunks + (size_t)c * kDuChunkBytes, (unsigned)kDuChunkBytes, &sh->w_full[stg]);
+        if (pair) {
+          // arm this CTA's barrier for the whole chunk; this producer fetches its half and multicasts it to both CTAs
+          constexpr unsigned kHalf = (unsigned)kDuChunkBytes / 2;
+          lyra_bulk_multi_begin(&sh->w_full[stg], (unsigned)kDuChunkBytes);
+          lyra_bulk_g2s_mc(wring + (size_t)stg * kDuChunkBytes + rank * kHalf, chunks + (size_t)c * kDuChunkBytes + rank * kHalf, kHalf,
+                           &sh->w_full[stg], 3u);
+        } else {
+          lyra_bulk_g2s(wring + (size_t)stg * kDuChunkBytes, chunks + (size_t)c * kDuChunkBytes, (unsigned)kDuChunkBytes, &sh->w_full[stg]);
+        }
         if (c == kDuUp2Chunks + L::kStagesW - 1) {
           // the wait above covered the last decoder_2/simple chunk's MMAs, the last readers of X: the ring blocks may land on it
           lyra_bulk_g2s(smem + L::kRing0, st + (size_t)DecStateD::kRing0 * S, 64u * 2 * S * 4, &sh->ring_full[0]);
@@ -158,13 +186,20 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       unsigned a_par = 0;
       int c = 0;                                             // weight chunk counter
       auto wait_a = [&]() { lyra_mbar_wait(&sh->a_ready, a_par); a_par ^= 1; lyra_tc_fence_after_sync(); };
-      auto wait_chunk = [&]() -> const unsigned char* {
-        lyra_mbar_wait(&sh->w_full[c % L::kStagesW], (unsigned)((c / L::kStagesW) & 1));
+      auto wait_chunk_at = [&](int ci) -> const unsigned char* {
+        lyra_mbar_wait(&sh->w_full[ci % L::kStagesW], (unsigned)((ci / L::kStagesW) & 1));
         lyra_tc_fence_after_sync();
-        return wring + (size_t)(c % L::kStagesW) * kDuChunkBytes;
+        return wring + (size_t)(ci % L::kStagesW) * kDuChunkBytes;
       };
-      auto release_chunk = [&]() { lyra_umma_commit(&sh->w_empty[c % L::kStagesW]); ++c; };
-      // ---- decoder_2/simple, transposed: D_mb[128 x 32] = Wt_mb[128 x 128] * X[32 x 128]^T for the five row blocks of Wt
+      auto wait_chunk = [&]() -> const unsigned char* { return wait_chunk_at(c); };
+      auto release_chunk = [&]() {                           // the stage is free once the MMAs of BOTH CTAs of a pair have read it
+        if (pair) lyra_umma_commit_mc(&sh->w_empty[c % L::kStagesW], 3u);
+        else lyra_umma_commit(&sh->w_empty[c % L::kStagesW]);
+        ++c;
+      };
+      // ---- decoder_2/simple, transposed: D_mb[128 x 32] = Wt_mb[128 x 128] * X[32 x 128]^T for the five row blocks of Wt.
+      //      This phase is bound by the delivery of its 640 KB of weights (about 30 bytes per cycle and SM with every SM streaming,
+      //      measured; neither a deeper ring nor multicast changes it), not by the 240 small MMAs.
       wait_a();
       {
         const uint32_t idesc = lyra_umma_idesc_tf32(128, 32);
@@ -197,16 +232,21 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
           wait_a();
           for (int kc = 0; kc < 2; ++kc) {
             const unsigned char* wst = wait_chunk();
-            for (int rb = 0; rb < 2; ++rb)
-              for (int k4 = 0; k4 < 4; ++k4) {
-                const int ks = kc * 4 + k4;
-                const uint64_t bh = lyra_umma_desc(wst + (size_t)k4 * 2 * lboW, lboW, 128);
-                const uint64_t bl = lyra_umma_desc(wst + kDuChunkBytes / 2 + (size_t)k4 * 2 * lboW, lboW, 128);
-                const uint32_t base = tmem + (uint32_t)(rb * L::kRbStride);
-                lyra_umma_tf32_ts(base + L::kColD, base + L::kColAlo + (uint32_t)(8 * ks), bh, idesc, ks > 0);
-                lyra_umma_tf32_ts(base + L::kColD, base + L::kColAhi + (uint32_t)(8 * ks), bl, idesc, true);
-                lyra_umma_tf32_ts(base + L::kColD, base + L::kColAhi + (uint32_t)(8 * ks), bh, idesc, true);
-              }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const int ks = kc * 4 + k4;
+              const uint64_t bh = lyra_umma_desc(wst + (size_t)k4 * 2 * lboW, lboW, 128);
+              const uint64_t bl = lyra_umma_desc(wst + kDuChunkBytes / 2 + (size_t)k4 * 2 * lboW, lboW, 128);
+#pragma unroll
+              for (int term = 0; term < 3; ++term)
+#pragma unroll
+                for (int rb = 0; rb < 2; ++rb) {             // alternate the two row blocks' accumulators: MMAs into one TMEM tile run as
+                                                             // a dependent chain (measured 56 cycles each here), interleaved ones overlap (24)
+                  const uint32_t base = tmem + (uint32_t)(rb * L::kRbStride);
+                  lyra_umma_tf32_ts(base + L::kColD, base + (term == 0 ? L::kColAlo : L::kColAhi) + (uint32_t)(8 * ks), term == 1 ? bl : bh, idesc,
+                                    ks > 0 || term > 0);
+                }
+            }
             release_chunk();
           }
           lyra_umma_commit(&sh->d_ready);
@@ -455,6 +495,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
 
   lyra_tc_fence_before_sync();
   __syncthreads();
+  if (pair) lyra_cluster_sync();                              // no CTA leaves while its partner may still signal its barriers
   if (warp == L::kMmaWarp) lyra_tmem_dealloc(tmem, L::kTmemCols);
 }
 
