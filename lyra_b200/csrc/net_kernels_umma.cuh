@@ -38,7 +38,7 @@ struct DecDU {
   static constexpr int kRowWarps = 8, kRowThreads = kRowWarps * 32;
   static constexpr int kMmaWarp = 8, kTmaWarp = 9;
   static constexpr int NT = 320;
-  static constexpr int kStagesW = 4;
+  static constexpr int kStagesW = 2;
   static constexpr int LDU = 161;                             // u: f32 [64][LDU], element (c, row = t * 8 + s); odd stride: lanes that
                                                               // differ in c (decoder_2/simple epilogue) hit different banks
   // shared memory (bytes)
