@@ -18,7 +18,7 @@
 //   last_layer  ONE 64 x 64 GEMM P[row][tap * 16 + n] = sum_ci lrelu(u')[row][ci] * W[(tap, ci)][n] on the A operand the last
 //               residual unit's epilogue leaves in tensor memory; the four taps are summed across time rows afterwards.
 //   weights     pre-split on the host into hi / lo core-matrix chunks (net_params.h kDuChunkBytes), streamed by one producer
-//               thread with TMA bulk copies through a 4-stage shared-memory ring; a stage is released by tcgen05.commit when
+//               thread with TMA bulk copies through a 2-stage shared-memory ring; a stage is released by tcgen05.commit when
 //               the MMAs that read it have completed.
 //   state       contiguous blocks (kernel C's tile, overlap tails, ring blocks, depthwise parameters) move by TMA bulk copies,
 //               in both directions; blocks are written back whole, with the lanes of inactive streams left as loaded.
