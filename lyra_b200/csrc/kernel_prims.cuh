@@ -32,16 +32,17 @@ __device__ __forceinline__ int QuantizeF32(float v, float scale, int zp) {
 }
 __device__ __forceinline__ float DequantizeI8(int q, float scale, int zp) { return __fmul_rn(scale, (float)(q - zp)); }
 
-// gemmlowp MultiplyByQuantizedMultiplier (SaturatingRoundingDoublingHighMul + RoundingDivideByPOT)
+// gemmlowp MultiplyByQuantizedMultiplier (SaturatingRoundingDoublingHighMul + RoundingDivideByPOT), branch-free:
+//   SRDHM   trunc((ab + (ab >= 0 ? 2^30 : 1 - 2^30)) / 2^31) == floor((ab + 2^30) / 2^31) for either sign of ab
+//           (ab < 0: trunc(t / 2^31) = floor((t + 2^31 - 1) / 2^31) with t = ab + 1 - 2^30);
+//   RDBPOT  (x >> e) + ((x & mask) > (mask >> 1) + (x < 0)) == (x + 2^(e-1) - (x < 0)) >> e for e >= 1, x for e = 0.
+// Same integers as the oracle's literal restatement (oracle/net_interp.c) for every int32 accumulator and positive multiplier.
 __device__ __forceinline__ int Mbqm(int x, int qm, int shift) {
   const int left = shift > 0 ? shift : 0, right = shift > 0 ? 0 : -shift;
-  const long long ab = (long long)(x * (1 << left)) * (long long)qm;
-  const long long t = ab + (ab >= 0 ? (1ll << 30) : (1ll - (1ll << 30)));
-  const int hi = (int)(t >= 0 ? (t >> 31) : -((-t) >> 31));     // truncating division by 2^31
-  const int mask = (int)((1ll << right) - 1);
-  const int rem = hi & mask;
-  const int thr = (mask >> 1) + (hi < 0 ? 1 : 0);
-  return (hi >> right) + (rem > thr ? 1 : 0);
+  const long long ab = (long long)(int)((unsigned)x << left) * (long long)qm;
+  const int hi = (int)((ab + (1ll << 30)) >> 31);
+  const int half = (int)((1u << right) >> 1);
+  return right ? (hi + half + (hi >> 31)) >> right : hi;
 }
 __device__ __forceinline__ int ClampI8(int v) { return v < -128 ? -128 : (v > 127 ? 127 : v); }
 __device__ __forceinline__ int RequantI8(int acc, int bias, int mult, int shift, int out_zp) {

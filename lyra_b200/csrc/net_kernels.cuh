@@ -11,6 +11,8 @@
 // [tile][unit][S]; dilated depthwise convs keep a ring of their last 2*dilation input rows.
 #pragma once
 
+#include <type_traits>
+
 #include "kernel_prims.cuh"
 
 // resident blocks per SM the small-M kernels (B, C) are compiled for at S = 8 (their 59-72 KB of shared memory allow 3)
@@ -102,13 +104,21 @@ template <int S, int NT, int TM, int TN1, int TN2, int WM, int KC, int C, int T,
           int WTM = 1, int WTN = 1>
 __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p, float* u, int ldu, int row0u, float* d,
                                            int groups2, float* ring, const int* n18,
-                                           const int* active, float* wbuf, bool last, const WNext& after, int pk, int& ph) {
+                                           const int* active, float* wbuf, bool last, const WNext& after, int pk, int& ph,
+                                           int dil_rt = DIL) {
   constexpr int ldd = LDD;
   // pw1's weight stream is started by whoever ran before this unit (previous GEMM or the kernel prologue)
-  if (n18[S] >= 0)
-    DwF32RingFast<S, NT, C, T, DIL>(u, ldu, row0u, d, ldd, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18[S], active);
-  else
-    DwF32Ring<S, NT>(u, ldu, row0u, d, ldd, C, T, DIL, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18, active);
+  if (n18[S] >= 0) {
+    auto dw = [&](auto dil) {
+      DwF32RingFast<S, NT, C, T, decltype(dil)::value>(u, ldu, row0u, d, ldd, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18[S], active);
+    };
+    if constexpr (DIL != 0) dw(std::integral_constant<int, DIL>());
+    else if (dil_rt == 1) dw(std::integral_constant<int, 1>());
+    else if (dil_rt == 3) dw(std::integral_constant<int, 3>());
+    else dw(std::integral_constant<int, 9>());
+  } else {
+    DwF32Ring<S, NT>(u, ldu, row0u, d, ldd, C, T, dil_rt, BlobPtr<float>(blob, p.dw.w), BlobPtr<float>(blob, p.dw.bias), ring, n18, active);
+  }
   LYRA_PHASE(pk, ph);
   {
     const float* b1 = BlobPtr<float>(blob, p.pw1.bias);
@@ -152,17 +162,40 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
   LYRA_PHASE(pk, ph);
 }
 
+// The three residual units of one stage (dilation 1, 3, 9; ring blocks of 2, 6, 18 rows back to back) as ONE copy of the code in
+// a loop that is not unrolled: the units differ only in their parameters and in the depthwise pass, and three inlined copies
+// of the two GEMMs made kernels B / C overflow the instruction cache (15-20 % of their stall samples were instruction fetches).
+template <int S, int NT, int TM, int TN1, int TN2, int WM, int KC, int C, int T, bool TC = false, int LDD = T * S, int WTM = 1, int WTN = 1>
+__device__ __forceinline__ void ResUnitsF32x3(const uint8_t* blob, const ResF32* p3, float* u, int ldu, int row0u, float* d, int groups2,
+                                              float* ring0, const int* n18, const int* active, float* wbuf, const WNext& after,
+                                              int pk, int& ph) {
+#pragma unroll 1
+  for (int i = 0; i < 3; ++i) {
+    const ResF32& p = p3[i];
+    const int dil = i == 0 ? 1 : (i == 1 ? 3 : 9);
+    float* ring = ring0 + (size_t)(i == 0 ? 0 : (i == 1 ? 2 : 8)) * C * S;       // [C][2] | [C][6] | [C][18]
+    const WNext nx = i < 2 ? NextF32(BlobPtr<float>(blob, p3[i + 1].pw1.w), KC, C, C) : after;
+    ResUnitF32<S, NT, TM, TN1, TN2, WM, KC, C, T, 0, TC, LDD, WTM, WTN>(blob, p, u, ldu, row0u, d, groups2, ring, n18, active, wbuf, i == 2, nx,
+                                                                       pk, ph, dil);
+  }
+}
+
 // One int8 residual unit on packed activations (quant_encoder_2/resnet_{1,2}, quant_decoder_0/resnet_{1,2}); the two
 // 1x1 convolutions run on the tensor cores.
 //   aq: LeakyReLU'd input (row offset row0a of [64][lda]); resq: the pre-activation residual; both updated in place.
 template <int S, int NT, int DIL>
 __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, uint32_t* aq, int lda, int row0a,
                                           uint32_t* resq, uint32_t* dq8, uint32_t* hq, uint32_t* ring,
-                                          const int* n18, const int* active, int pk, int& ph) {
+                                          const int* n18, const int* active, int pk, int& ph, int dil_rt = DIL) {
   constexpr int T = 2, C = 256, LD = PadLd(T * S);
   constexpr int NTW = S >= 16 ? 8 : 4;
-  if (n18[S] >= 0) DwI8RingFast<S, NT, C, T, DIL>(aq, lda, row0a, dq8, LD, blob, p.dw, ring, n18[S], active);
-  else DwI8Ring<S, NT>(aq, lda, row0a, dq8, LD, C, T, DIL, blob, p.dw, ring, n18, active);
+  if (n18[S] >= 0) {
+    if constexpr (DIL != 0) DwI8RingFast<S, NT, C, T, DIL>(aq, lda, row0a, dq8, LD, blob, p.dw, ring, n18[S], active);
+    else if (dil_rt == 3) DwI8RingFast<S, NT, C, T, 3>(aq, lda, row0a, dq8, LD, blob, p.dw, ring, n18[S], active);
+    else DwI8RingFast<S, NT, C, T, 9>(aq, lda, row0a, dq8, LD, blob, p.dw, ring, n18[S], active);
+  } else {
+    DwI8Ring<S, NT>(aq, lda, row0a, dq8, LD, C, T, dil_rt, blob, p.dw, ring, n18, active);
+  }
   LYRA_PHASE(pk, ph);
   {
     const int* bias = BlobPtr<int>(blob, p.pw1.bias);
@@ -203,6 +236,16 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
       });
   }
   LYRA_PHASE(pk, ph);
+}
+
+// quant_{en,de}coder resnet_1 and resnet_2 (dilation 3, 9; ring blocks of 6 and 18 rows back to back) as one copy of the code
+template <int S, int NT>
+__device__ __forceinline__ void ResUnitsI8x2(const uint8_t* blob, const ResI8* p2, uint32_t* aq, int lda, int row0a,
+                                             uint32_t* resq, uint32_t* dq8, uint32_t* hq, uint32_t* ring0,
+                                             const int* n18, const int* active, int pk, int& ph) {
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i)
+    ResUnitI8<S, NT, 0>(blob, p2[i], aq, lda, row0a, resq, dq8, hq, ring0 + (size_t)(i ? 64 * 6 : 0) * S, n18, active, pk, ph, i ? 9 : 3);
 }
 
 // ================================================================================================
@@ -283,11 +326,8 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   }
   // ---- encoder_0: three residual units, dilation 1/3/9
   LYRA_PHASE(0, ph);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1>(blob, P.r0[0], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing0 * S, n18, active, wbuf, false,
-                                                       NextF32(BlobPtr<float>(blob, P.r0[1].pw1.w), 16, 64, 64), 0, ph);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3>(blob, P.r0[1], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing1 * S, n18, active, wbuf, false,
-                                                       NextF32(BlobPtr<float>(blob, P.r0[2].pw1.w), 16, 64, 64), 0, ph);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9>(blob, P.r0[2], u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing2 * S, n18, active, wbuf, true,
+  static_assert(EncStateA::kRing1 == EncStateA::kRing0 + 64 * 2 && EncStateA::kRing2 == EncStateA::kRing1 + 64 * 6, "ring blocks back to back");
+  ResUnitsF32x3<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20>(blob, P.r0, u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing0 * S, n18, active, wbuf,
                                                        NextF32(BlobPtr<float>(blob, P.down0.w), 16, 128, 640, d), 0, ph);
   // carried rows for the next frame: the last 5 activated rows
   for (int i = tid; i < 64 * 5 * S; i += NT) {
@@ -390,12 +430,9 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   __syncthreads();
   // ---- encoder_1: three residual units @128 (second 1x1 has 2 groups)
   LYRA_PHASE(1, ph);
-  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 1>(blob, P.r1[0], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf, false,
-                                                NextF32(BlobPtr<float>(blob, P.r1[1].pw1.w), 16, 128, 128), 1, ph);
-  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 3>(blob, P.r1[1], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing1 * S, n18, active, wbuf, false,
-                                                NextF32(BlobPtr<float>(blob, P.r1[2].pw1.w), 16, 128, 128), 1, ph);
-  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 9>(blob, P.r1[2], u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing2 * S, n18, active, wbuf, true,
-                                                NextF32(BlobPtr<float>(blob, P.down1.w), 8, 256, 256), 1, ph);
+  static_assert(EncStateB::kRing1 == EncStateB::kRing0 + 128 * 2 && EncStateB::kRing2 == EncStateB::kRing1 + 128 * 6, "ring blocks back to back");
+  ResUnitsF32x3<S, NT, TM, 4, 4, L::WM4, 16, 128, 4>(blob, P.r1, u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf,
+                                                     NextF32(BlobPtr<float>(blob, P.down1.w), 8, 256, 256), 1, ph);
   for (int i = tid; i < 128 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
     if (active[r % S]) st[EncStateB::kDown1 * S + i] = u1[(size_t)c * L::LD1 + 4 * S + r];
@@ -464,8 +501,8 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   }
   // ---- quant_encoder_2/resnet_{1,2}
   LYRA_PHASE(1, ph);
-  ResUnitI8<S, NT, 3>(blob, P.q[0], aq, LQA, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, 1, ph);
-  ResUnitI8<S, NT, 9>(blob, P.q[1], aq, LQA, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ1 * S, n18, active, 1, ph);
+  static_assert(EncStateB::kRingQ1 == EncStateB::kRingQ0 + 64 * 6, "ring blocks back to back");
+  ResUnitsI8x2<S, NT>(blob, P.q, aq, LQA, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, 1, ph);
   // ---- quant_encoder_2/simpleconv: K = 4, stride 2, 256 -> 512, 4 groups, then int8 LeakyReLU
   LYRA_PHASE(1, ph);
   BatchedLoop<NT, 4, uint32_t>(64 * 2 * S, [&](int i) { return stw[EncStateB::kDown2 * S + i]; },
@@ -699,8 +736,8 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
       });
   }
   LYRA_PHASE(2, ph);
-  ResUnitI8<S, NT, 3>(blob, P.q[0], aq, LQA, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, 2, ph);
-  ResUnitI8<S, NT, 9>(blob, P.q[1], aq, LQA, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ1 * S, n18, active, 2, ph);
+  static_assert(DecStateC::kRingQ1 == DecStateC::kRingQ0 + 64 * 6, "ring blocks back to back");
+  ResUnitsI8x2<S, NT>(blob, P.q, aq, LQA, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, 2, ph);
   // ---- quant_decoder_1 upsample: 2 x TRANSPOSE_CONV (K = 4, stride 2, 128 -> 64), T 2 -> 4 (+2 tail rows)
   LYRA_PHASE(2, ph);
   {
@@ -738,14 +775,9 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   }
   // ---- decoder_1: three fp32 residual units @128
   LYRA_PHASE(2, ph);
-  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 1, TC, L::LD1, L::RWM, L::RWN>(
-      blob, P.r1[0], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, false,
-      NextF32(BlobPtr<float>(blob, P.r1[1].pw1.w), 16, 128, 128), 2, ph);
-  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 3, TC, L::LD1, L::RWM, L::RWN>(
-      blob, P.r1[1], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing1 * S, n18, active, wbuf, false,
-      NextF32(BlobPtr<float>(blob, P.r1[2].pw1.w), 16, 128, 128), 2, ph);
-  ResUnitF32<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, 9, TC, L::LD1, L::RWM, L::RWN>(
-      blob, P.r1[2], u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing2 * S, n18, active, wbuf, true, NoNext(), 2, ph);
+  static_assert(DecStateC::kRing1 == DecStateC::kRing0 + 128 * 2 && DecStateC::kRing2 == DecStateC::kRing1 + 128 * 6, "ring blocks back to back");
+  ResUnitsF32x3<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, TC, L::LD1, L::RWM, L::RWN>(
+      blob, P.r1, u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, NoNext(), 2, ph);
   {
     float* out = mid + (size_t)tile * 128 * 4 * S;
     for (int i = tid; i < 128 * 4 * S; i += NT) out[i] = u1[i];
@@ -860,11 +892,8 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   }
   // ---- decoder_2: three residual units @64, T = 20
   LYRA_PHASE(3, ph);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 1, TC, L::LDD, L::RWM, L::RWN>(blob, P.r2[0], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing0 * S, n18, active, wbuf, false,
-                                                       NextF32(BlobPtr<float>(blob, P.r2[1].pw1.w), 16, 64, 64), 3, ph);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 3, TC, L::LDD, L::RWM, L::RWN>(blob, P.r2[1], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing1 * S, n18, active, wbuf, false,
-                                                       NextF32(BlobPtr<float>(blob, P.r2[2].pw1.w), 16, 64, 64), 3, ph);
-  ResUnitF32<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, 9, TC, L::LDD, L::RWM, L::RWN>(blob, P.r2[2], u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing2 * S, n18, active, wbuf, true,
+  static_assert(DecStateD::kRing1 == DecStateD::kRing0 + 64 * 2 && DecStateD::kRing2 == DecStateD::kRing1 + 64 * 6, "ring blocks back to back");
+  ResUnitsF32x3<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20, TC, L::LDD, L::RWM, L::RWN>(blob, P.r2, u, L::LDU, 3, d, 1, st + (size_t)DecStateD::kRing0 * S, n18, active, wbuf,
                                                        NextF32(BlobPtr<float>(blob, P.last.w), 16, 16, 256), 3, ph);
   // ---- last_layer: TRANSPOSE_CONV K = 64, stride 16, 64 -> 1 ; T 20 -> 320 (+48 tail) ; float -> int16
   LYRA_PHASE(3, ph);
