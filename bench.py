@@ -170,6 +170,23 @@ def host_cores():
     return n
 
 
+def pin_rank_cores(local_rank, local_world):
+    """Under torchrun every rank keeps its host threads (the synchronous calls' waiters) on its own slice of the allowed cores, so
+    that the ranks of one box do not migrate onto each other's cores in the host-buffer pass.  Returns the slice size or None."""
+    if local_world <= 1:
+        return None
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // local_world
+        if per < 2:
+            return None
+        os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
+        os.environ["LYRA_BENCH_PINNED"] = "1"      # host_cores() now reports this rank's slice
+        return per
+    except (AttributeError, OSError):
+        return None
+
+
 def synth_pcm_np(n, nbuf, seed, kind="noise"):
     """Seeded synthetic input, `nbuf` distinct hops rotated through the steps:
     noise  — uniform noise at 0.25 full scale (the reference benchmark feeds uniform random audio, lyra/lyra_benchmark_lib.cc:233-239);
@@ -312,7 +329,8 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
             groups.append((e_, d_, gx, gy))
     group_ctxs = [c for grp in groups for c in grp[:2] if c is not None]
     # the host-buffer pass runs 2 G waiting threads per rank: they sleep instead of spin when the box has fewer cores than that
-    oversubscribed = args.host_wait == "sleep" or (args.host_wait == "auto" and world * (2 * G + 1) > host_cores() * 3 // 4)
+    oversubscribed = args.host_wait == "sleep" or (args.host_wait == "auto" and
+                                                   (1 if os.environ.get("LYRA_BENCH_PINNED") else world) * (2 * G + 1) > host_cores() * 3 // 4)
     for c in group_ctxs:
         c.set_blocking_sync(oversubscribed)
 
@@ -577,6 +595,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    pinned = pin_rank_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not land in front of the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -635,6 +654,7 @@ def main():
                        "streams_per_gpu": n, "bits_per_frame": bits, "hops_per_step": HOPS_PER_STEP, "tile_streams": res["tile_streams"],
                        "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G,
                        "host_threads_wait": "sleep (blocking-sync event)" if res["oversubscribed"] else "spin",
+                       "host_cores_per_rank": pinned if pinned else host_cores(),
                        "real_time_factor": value / (50.0 * n * world),
                        "l2": ("no flush needed: per-hop state working set %d x %.0f KB = %.0f MB exceeds the 126 MB L2; PCM inputs rotate over 8 buffers"
                               if state_mb > 126 else

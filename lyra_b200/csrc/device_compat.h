@@ -57,6 +57,13 @@ static inline void lyra_mbar_arrive(LyraMbar* b) {
   LyraMbarEmu* e = lyra_mbar_emu(b);
   if (++e->arrived == e->expected) { e->arrived = 0; e->phase ^= 1; }
 }
+// one thread arriving for `n` participants at once (mbarrier.arrive with a count operand); the count must not overshoot the phase
+static inline void lyra_mbar_arrive_n(LyraMbar* b, unsigned n) {
+  LyraMbarEmu* e = lyra_mbar_emu(b);
+  e->arrived = (uint16_t)(e->arrived + n);
+  if (e->arrived > e->expected) { std::fprintf(stderr, "cuda_emu: mbarrier arrival count overshoots the phase\n"); std::abort(); }
+  if (e->arrived == e->expected) { e->arrived = 0; e->phase ^= 1; }
+}
 // the emulated bulk copy is synchronous and fibers are cooperative, so arming + copying is one atomic step:
 // the arrival is counted after the data has been written
 static inline void lyra_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, LyraMbar* b) {
@@ -88,6 +95,9 @@ __device__ __forceinline__ void lyra_mbar_fence_init() {
 __device__ __forceinline__ void lyra_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void lyra_mbar_arrive(LyraMbar* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(lyra_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void lyra_mbar_arrive_n(LyraMbar* b, unsigned n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" ::"r"(lyra_smem_u32(b)), "r"(n) : "memory");
 }
 // arm the barrier with the byte count and issue the bulk copy that completes it
 __device__ __forceinline__ void lyra_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, LyraMbar* b) {

@@ -48,6 +48,13 @@ __device__ __forceinline__ int ClampI8(int v) { return v < -128 ? -128 : (v > 12
 __device__ __forceinline__ int RequantI8(int acc, int bias, int mult, int shift, int out_zp) {
   return ClampI8(Mbqm(acc + bias, mult, shift) + out_zp);
 }
+// requantisation parameters of four consecutive output channels (n0 % 4 == 0; the blob's arrays are 16-byte aligned): three
+// 16-byte loads instead of twelve scalar ones in every int8 epilogue
+struct RequantP4 { int b[4], m[4], s[4]; };
+__device__ __forceinline__ RequantP4 LoadRequant4(const int* __restrict__ bias, const int* __restrict__ mult, const int* __restrict__ shift, int n0) {
+  const int4 b = *reinterpret_cast<const int4*>(bias + n0), m = *reinterpret_cast<const int4*>(mult + n0), s = *reinterpret_cast<const int4*>(shift + n0);
+  return RequantP4{{b.x, b.y, b.z, b.w}, {m.x, m.y, m.z, m.w}, {s.x, s.y, s.z, s.w}};
+}
 __device__ __forceinline__ uint32_t PackI8x4(int a, int b, int c, int d) {
   return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
 }
@@ -191,6 +198,11 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
   for (int wt0 = 0; wt0 < map.nwt; wt0 += NT / 32) {
     int mg, ng;
     const bool active = map.Locate(wt0 + warp, MG, NG, mg, ng);
+    // Warps without a tile in this pass (small-M layers fill only part of the block) stay out of the K loop altogether: they
+    // would only spin on the `full` barriers, taking issue slots from the warps that compute.  Warp 0 (always busy) releases
+    // every stage on their behalf, so the `empty` barriers still see NT / 32 arrivals per phase.
+    const int nbusy = min(NT / 32, map.nwt - wt0);
+    const bool busy = warp < nbusy;
     const int t_out = active ? mg / MGS : 0, s0 = active ? (mg % MGS) * TM : 0, n0 = active ? ng * TN : 0;
     const int g = n0 / CoutG;
     const float* Abase = A + (size_t)(g * CinG) * ldA + (rowA0 + t_out * row_stride) * S + s0;
@@ -203,7 +215,8 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc2[i][j] = make_float2(0.0f, 0.0f);
 
-    for (int c = 0; c < nchunks; ++c, ++cg) {
+    if (!busy) cg += nchunks;
+    for (int c = 0; busy && c < nchunks; ++c, ++cg) {
       if (threadIdx.x == 0) {
         // producer: chunk cg + kStages - 1 goes into the stage that chunk cg - 1 occupied, once every warp has released it
         const int ci = cg + kStages - 1;
@@ -260,7 +273,10 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
         }
       }
       __syncwarp();
-      if (lane == 0) lyra_mbar_arrive(&pipe->empty[set][st]);                    // this warp is done with the stage
+      if (lane == 0) {                                                           // this warp is done with the stage
+        if (warp == 0 && nbusy < NT / 32) lyra_mbar_arrive_n(&pipe->empty[set][st], (unsigned)(1 + NT / 32 - nbusy));
+        else lyra_mbar_arrive(&pipe->empty[set][st]);
+      }
     }
     float acc[TM][TN];
 #pragma unroll

@@ -19,6 +19,10 @@
 #ifndef LYRA_BC_MIN_BLOCKS
 #define LYRA_BC_MIN_BLOCKS 3
 #endif
+// output channels per fp32 thread tile in the small-M layers of kernels B / C (8 streams x LYRA_BC_TN channels)
+#ifndef LYRA_BC_TN
+#define LYRA_BC_TN 4
+#endif
 
 namespace lyra_b200 {
 
@@ -205,9 +209,10 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
     const int out_zp = p.pw1.out_zp;
     GemmI8Mma<S, NT, NTW>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint2>(blob, p.pw1.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
+        const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         int q[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
+        for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[0][j], rq.b[j], rq.m[j], rq.s[j], out_zp) + 128];
         hq[(size_t)(n0 / 4) * LD + t * S + s] = PackI8x4(q[0], q[1], q[2], q[3]);
       });
   }
@@ -222,12 +227,13 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
     const int out_zp = p.pw2.out_zp, m3 = p.add.m3, s3 = p.add.s3, add_zp = p.add.out_zp;
     GemmI8Mma<S, NT, NTW>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint2>(blob, p.pw2.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
+        const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         const size_t ro = (size_t)(n0 / 4) * LD + t * S + s;
         const uint32_t rw = resq[ro];
         int r[4], a[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int q = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
+          const int q = RequantI8(acc[0][j], rq.b[j], rq.m[j], rq.s[j], out_zp);
           r[j] = ClampI8(Mbqm(l1[q + 128] + l2[UnpackI8(rw, j) + 128], m3, s3) + add_zp);
           a[j] = lut[r[j] + 128];
         }
@@ -256,6 +262,12 @@ __device__ __forceinline__ void ResUnitsI8x2(const uint8_t* blob, const ResI8* p
 #endif
 #ifndef LYRA_A_NT
 #define LYRA_A_NT 320
+#endif
+#ifndef LYRA_A_DOWN_TM
+#define LYRA_A_DOWN_TM 8
+#endif
+#ifndef LYRA_A_DOWN_TN
+#define LYRA_A_DOWN_TN 4
 #endif
 template <int S>
 struct EncA {
@@ -342,13 +354,16 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     // the d buffer is free from here on: it hosts this GEMM's weight ring (3 x 16 x 128 floats), twice the chunk the
     // regular ring could hold, which halves the number of block barriers of this K = 640 layer
     static_assert(kStages * 16 * 128 * 4 <= 64 * L::LDD * 4, "simpleconv weight ring must fit in d");
-    GemmF32Tap<S, NT, 8, 4, 16, 4, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), d, true, NoNext(),
-      [&](int t, int s0, int n0, float (&acc)[8][4]) {
+    // 4 output rows x S streams = 32 GEMM rows only: LYRA_A_DOWN_TM x LYRA_A_DOWN_TN thread tiles decide how many of the block's
+    // ten warps get a tile (8 x 4: four warps; 4 x 4 or 8 x 2: eight)
+    constexpr int DTM = S >= 16 ? 8 : LYRA_A_DOWN_TM, DTN = S >= 16 ? 4 : LYRA_A_DOWN_TN;
+    GemmF32Tap<S, NT, DTM, DTN, 16, 4, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), d, true, NoNext(),
+      [&](int t, int s0, int n0, float (&acc)[DTM][DTN]) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < DTN; ++j) {
           float* o = out + ((size_t)(n0 + j) * 4 + t) * S + s0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = __fadd_rn(acc[i][j], b[n0 + j]);
+          for (int i = 0; i < DTM; ++i) o[i] = __fadd_rn(acc[i][j], b[n0 + j]);
         }
       });
   }
@@ -431,7 +446,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   // ---- encoder_1: three residual units @128 (second 1x1 has 2 groups)
   LYRA_PHASE(1, ph);
   static_assert(EncStateB::kRing1 == EncStateB::kRing0 + 128 * 2 && EncStateB::kRing2 == EncStateB::kRing1 + 128 * 6, "ring blocks back to back");
-  ResUnitsF32x3<S, NT, TM, 4, 4, L::WM4, 16, 128, 4>(blob, P.r1, u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf,
+  ResUnitsF32x3<S, NT, TM, LYRA_BC_TN, LYRA_BC_TN, L::WM4, 16, 128, 4>(blob, P.r1, u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf,
                                                      NextF32(BlobPtr<float>(blob, P.down1.w), 8, 256, 256), 1, ph);
   for (int i = tid; i < 128 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
@@ -441,11 +456,11 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   LYRA_PHASE(1, ph);
   {
     const float* b = BlobPtr<float>(blob, P.down1.bias);
-    GemmF32Tap<S, NT, TM, 4, 8, L::WM2, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, true,
+    GemmF32Tap<S, NT, TM, LYRA_BC_TN, 8, L::WM2, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, true,
       NextF32(BlobPtr<float>(blob, P.m_pw1.w), 8, 256, 256),
-      [&](int t, int s0, int n0, float (&acc)[TM][4]) {
+      [&](int t, int s0, int n0, float (&acc)[TM][LYRA_BC_TN]) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < LYRA_BC_TN; ++j) {
           float* o = u2 + (size_t)(n0 + j) * 2 * S + t * S + s0;
 #pragma unroll
           for (int i = 0; i < TM; ++i) o[i] = __fadd_rn(acc[i][j], b[n0 + j]);
@@ -466,15 +481,17 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const float* b = BlobPtr<float>(blob, P.m_pw1.bias);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const QuantP q1 = P.m_q1;
-    GemmF32Tap<S, NT, TM, 4, 8, L::WM2, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, true,
+    GemmF32Tap<S, NT, TM, LYRA_BC_TN, 8, L::WM2, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, true,
       NoNext(),
-      [&](int t, int s0, int n0, float (&acc)[TM][4]) {
+      [&](int t, int s0, int n0, float (&acc)[TM][LYRA_BC_TN]) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
-          int q[4];
+          int q[LYRA_BC_TN];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) q[j] = lut[QuantizeF32(__fadd_rn(acc[i][j], b[n0 + j]), q1.scale, q1.zp) + 128];
-          hq[(size_t)(n0 / 4) * LQ2 + t * S + s0 + i] = PackI8x4(q[0], q[1], q[2], q[3]);
+          for (int j = 0; j < LYRA_BC_TN; ++j) q[j] = lut[QuantizeF32(__fadd_rn(acc[i][j], b[n0 + j]), q1.scale, q1.zp) + 128];
+          uint32_t* word = hq + (size_t)(n0 / 4) * LQ2 + t * S + s0 + i;       // channels 4k .. 4k+3 of one (row, stream), byte j = channel 4k + j
+          if constexpr (LYRA_BC_TN == 4) *word = PackI8x4(q[0], q[1], q[2], q[3]);
+          else reinterpret_cast<uint16_t*>(word)[(n0 % 4) / 2] = (uint16_t)((q[0] & 0xff) | ((q[1] & 0xff) << 8));
         }
       });
   }
@@ -487,10 +504,11 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int out_zp = P.m_pw2.out_zp;
     GemmI8Mma<S, NT, (S >= 16 ? 8 : 4)>(hq, LQ2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint2>(blob, P.m_pw2.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
+        const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         int r[4], a[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int q = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
+          const int q = RequantI8(acc[0][j], rq.b[j], rq.m[j], rq.s[j], out_zp);
           const float v = __fadd_rn(DequantizeI8(q, dq.scale, dq.zp), u2[(size_t)(n0 + j) * LD2 + t * S + s]);
           r[j] = QuantizeF32(v, q2.scale, q2.zp);
           a[j] = lut[r[j] + 128];
@@ -522,10 +540,11 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int out_zp = P.down2.out_zp;
     GemmI8Mma<S, NT, 8>(aq, LQA, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint2>(blob, P.down2.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
+        const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         (void)t;
         int q[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
+        for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[0][j], rq.b[j], rq.m[j], rq.s[j], out_zp) + 128];
         bq[(size_t)(n0 / 4) * LQB + 2 * S + s] = PackI8x4(q[0], q[1], q[2], q[3]);
       });
   }
@@ -544,12 +563,13 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int out_zp = P.bott.out_zp;
     GemmI8Mma<S, NT, 1>(bq, LQB, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint2>(blob, P.bott.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
+        const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         (void)t;
         if (!active[s]) return;
         float* o = features + (size_t)slot[s] * 64 + n0;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          o[j] = DequantizeI8(RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp), dq.scale, dq.zp);
+          o[j] = DequantizeI8(RequantI8(acc[0][j], rq.b[j], rq.m[j], rq.s[j], out_zp), dq.scale, dq.zp);
       });
   }
   if (tid < S && active[tid]) n18g[tile * S + tid] = (n18[tid] + 1) % 18;
@@ -667,12 +687,13 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     float* tail = st + (size_t)DecStateC::kUp0 * S;
     GemmI8Mma<S, NT, 8>(xq, LQB, 0, 1, 2, 128, 4, 2, 512, BlobPtr<uint2>(blob, up0.g.w),
       [&](int q, int s, int n0, int (&acc)[1][4]) {
+        const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         const int g = n0 / 128, r = (n0 % 128) / 64;
         const float* bf = BlobPtr<float>(blob, up0.bias_f32[g]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int co = (n0 + j) % 64, ch = g * 64 + co;
-          const int qv = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up0.out_zp[g]);
+          const int qv = RequantI8(acc[0][j], rq.b[j], rq.m[j], rq.s[j], up0.out_zp[g]);
           const float f = DequantizeI8(qv, up0.dq[g].scale, up0.dq[g].zp);
           if (q == 0) {
             float* o = u + (size_t)ch * LD2 + r * S + s;
@@ -708,9 +729,10 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int out_zp = P.m_pw1.out_zp;
     GemmI8Mma<S, NT, (S >= 16 ? 8 : 4)>(dq8, LQ2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint2>(blob, P.m_pw1.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
+        const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         int q[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp) + 128];
+        for (int j = 0; j < 4; ++j) q[j] = lut[RequantI8(acc[0][j], rq.b[j], rq.m[j], rq.s[j], out_zp) + 128];
         hq[(size_t)(n0 / 4) * LQ2 + t * S + s] = PackI8x4(q[0], q[1], q[2], q[3]);
       });
   }
@@ -723,10 +745,11 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int out_zp = P.m_pw2.out_zp;
     GemmI8Mma<S, NT, (S >= 16 ? 8 : 4)>(hq, LQ2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint2>(blob, P.m_pw2.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
+        const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         int r[4], a[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int q = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], out_zp);
+          const int q = RequantI8(acc[0][j], rq.b[j], rq.m[j], rq.s[j], out_zp);
           const float v = __fadd_rn(DequantizeI8(q, dq.scale, dq.zp), u[(size_t)(n0 + j) * LD2 + t * S + s]);
           r[j] = QuantizeF32(v, q2.scale, q2.zp);
           a[j] = lut[r[j] + 128];
@@ -757,12 +780,13 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     if (!TC) IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128));
     GemmI8Mma<S, NT, 8>(aq, LQA, 0, 1, 2, 128, 2, 3, 256, BlobPtr<uint2>(blob, up1.g.w),
       [&](int q, int s, int n0, int (&acc)[1][4]) {
+        const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         const int g = n0 / 128, r = (n0 % 128) / 64;
         const float* bf = BlobPtr<float>(blob, up1.bias_f32[g]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int co = (n0 + j) % 64, ch = g * 64 + co;
-          const int qv = RequantI8(acc[0][j], bias[n0 + j], mult[n0 + j], shift[n0 + j], up1.out_zp[g]);
+          const int qv = RequantI8(acc[0][j], rq.b[j], rq.m[j], rq.s[j], up1.out_zp[g]);
           const float f = DequantizeI8(qv, up1.dq[g].scale, up1.dq[g].zp);
           if (q < 2) {
             float* o = u1 + (size_t)ch * 4 * S + (2 * q + r) * S + s;
@@ -776,7 +800,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   // ---- decoder_1: three fp32 residual units @128
   LYRA_PHASE(2, ph);
   static_assert(DecStateC::kRing1 == DecStateC::kRing0 + 128 * 2 && DecStateC::kRing2 == DecStateC::kRing1 + 128 * 6, "ring blocks back to back");
-  ResUnitsF32x3<S, NT, TM, 4, 4, L::WM4, 16, 128, 4, TC, L::LD1, L::RWM, L::RWN>(
+  ResUnitsF32x3<S, NT, TM, LYRA_BC_TN, LYRA_BC_TN, L::WM4, 16, 128, 4, TC, L::LD1, L::RWM, L::RWN>(
       blob, P.r1, u1, 4 * S, 0, d1, 2, st + (size_t)DecStateC::kRing0 * S, n18, active, wbuf, NoNext(), 2, ph);
   {
     float* out = mid + (size_t)tile * 128 * 4 * S;

@@ -24,10 +24,12 @@ NAMES = {
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-    api = _capi.CApi(os.path.join(ROOT, "devtools_build", "liblyra_b200_phase.so"))
+    api = _capi.CApi(os.environ.get("LYRA_PHASE_LIB", os.path.join(ROOT, "devtools_build", "liblyra_b200_phase.so")))
     api.lib.lyra_b200_debug_phases.restype = C.c_int
     api.lib.lyra_b200_debug_phases.argtypes = [C.c_void_p, C.c_void_p]
     ctx = _capi.Context(n, capi=api)
+    if len(sys.argv) > 2:
+        ctx.set_split(int(sys.argv[2]))          # 1 = one launch per kernel for the whole batch (no concurrent sub-batches)
     buf = np.zeros((4, 1024, 48), dtype=np.int64)
     api.lib.lyra_b200_debug_phases(ctx.h, buf.ctypes.data_as(C.c_void_p))      # arms the buffer
     rng = np.random.default_rng(0)
