@@ -82,11 +82,12 @@ __device__ __forceinline__ void BatchedLoop(int n, LoadFn ld, StoreFn st) {
 // chunks apart instead of meeting at every chunk.
 // Two barrier sets alternate between consecutive GEMMs so that the first chunks of the NEXT GEMM can be issued
 // (into the other set) before the current GEMM's epilogue; each GEMM re-initialises the set its successor will use.
-constexpr int kStages = 3;
+constexpr int kStages = 3;       // default ring depth; a GEMM may ask for more (template parameter STG, at most kMaxStages)
+constexpr int kMaxStages = 6;
 
 struct WeightPipe {
-  LyraMbar full[2][kStages];
-  LyraMbar empty[2][kStages];
+  LyraMbar full[2][kMaxStages];
+  LyraMbar empty[2][kMaxStages];
   int cur;          // barrier set of the next GEMM to run (or of the prologue issued for it)
 };
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ WeightPipe* GetWeightPipe() {
 
 __device__ __forceinline__ void InitPipeSet(WeightPipe* pipe, int set, int nwarps) {
 #pragma unroll
-  for (int s = 0; s < kStages; ++s) { lyra_mbar_init(&pipe->full[set][s], 1); lyra_mbar_init(&pipe->empty[set][s], (unsigned)nwarps); }
+  for (int s = 0; s < kMaxStages; ++s) { lyra_mbar_init(&pipe->full[set][s], 1); lyra_mbar_init(&pipe->empty[set][s], (unsigned)nwarps); }
   lyra_mbar_fence_init();
 }
 
@@ -120,15 +121,19 @@ struct WNext {
   int chunk_words;    // 4-byte words per chunk (KC * N)
   int nchunks;
   void* ring;         // shared-memory ring of the next GEMM when it is not the caller's (nullptr: same ring)
+  int stages;         // ring depth of the next GEMM (its STG)
 };
-__device__ __forceinline__ WNext NoNext() { return WNext{nullptr, 0, 0, nullptr}; }
-__device__ __forceinline__ WNext NextF32(const float* w, int KC, int N, int Ktot, void* ring = nullptr) { return WNext{w, KC * N, Ktot / KC, ring}; }
+__device__ __forceinline__ WNext NoNext() { return WNext{nullptr, 0, 0, nullptr, kStages}; }
+__device__ __forceinline__ WNext NextF32(const float* w, int KC, int N, int Ktot, void* ring = nullptr, int stages = kStages) {
+  return WNext{w, KC * N, Ktot / KC, ring, stages};
+}
 
-// Thread 0: chunks 0 .. kStages-2 of a GEMM into barrier set `set` (whose buffers and barriers are idle).
-__device__ __forceinline__ void IssuePrologueSet(WeightPipe* pipe, int set, void* wbuf, const void* w, int chunk_words, int nchunks) {
+// Thread 0: chunks 0 .. stages-2 of a GEMM into barrier set `set` (whose buffers and barriers are idle).
+__device__ __forceinline__ void IssuePrologueSet(WeightPipe* pipe, int set, void* wbuf, const void* w, int chunk_words, int nchunks,
+                                                 int stages = kStages) {
 #pragma unroll
-  for (int p = 0; p < kStages - 1; ++p)
-    if (p < nchunks)
+  for (int p = 0; p < kMaxStages - 1; ++p)
+    if (p < stages - 1 && p < nchunks)
       lyra_bulk_g2s(reinterpret_cast<uint32_t*>(wbuf) + (size_t)p * chunk_words,
                     reinterpret_cast<const uint32_t*>(w) + (size_t)p * chunk_words, (unsigned)chunk_words * 4u, &pipe->full[set][p]);
 }
@@ -143,7 +148,7 @@ __device__ __forceinline__ void IssuePrologue(void* wbuf_default, const WNext& n
   __syncthreads();
   if (threadIdx.x == 0) {
     WeightPipe* pipe = GetWeightPipe();
-    IssuePrologueSet(pipe, pipe->cur, nx.ring ? nx.ring : wbuf_default, nx.w, nx.chunk_words, nx.nchunks);
+    IssuePrologueSet(pipe, pipe->cur, nx.ring ? nx.ring : wbuf_default, nx.w, nx.chunk_words, nx.nchunks, nx.stages);
   }
 }
 
@@ -173,7 +178,7 @@ struct TileMap {
 //   Thread tile TM (streams) x TN (channels).
 //   epi(t, s0, n0, acc) is called once per tile after the K loop and a block barrier, so epilogues may
 //   overwrite the A operand in place.
-template <int S, int NT, int TM, int TN, int KC, int WM, bool CIN1, typename Epi>
+template <int S, int NT, int TM, int TN, int KC, int WM, bool CIN1, int STG = kStages, typename Epi>
 __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
                                            int groups, int T_out, int N, const float* __restrict__ Wg, float* wbuf,
                                            bool pre, const WNext& nxt, Epi epi) {
@@ -189,10 +194,11 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
   const int npass = (map.nwt + NT / 32 - 1) / (NT / 32);
   const int total = npass * nchunks;                         // chunk sequence of the whole call: every pass re-streams W
   const unsigned chunk_bytes = (unsigned)(KC * N) * 4u;
-  if (nchunks < kStages - 1) LYRA_TRAP();
+  static_assert(STG >= 2 && STG <= kMaxStages, "ring depth");
+  if (nchunks < STG - 1) LYRA_TRAP();
   if (threadIdx.x == 0) {
     InitPipeSet(pipe, set ^ 1, NT / 32);                     // the set of the GEMM after this one (idle since the previous GEMM ended)
-    if (!pre) IssuePrologueSet(pipe, set, wbuf, Wg, KC * N, nchunks);
+    if (!pre) IssuePrologueSet(pipe, set, wbuf, Wg, KC * N, nchunks, STG);
   }
   int cg = 0;                                                // chunk index within the call
   for (int wt0 = 0; wt0 < map.nwt; wt0 += NT / 32) {
@@ -218,16 +224,16 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
     if (!busy) cg += nchunks;
     for (int c = 0; busy && c < nchunks; ++c, ++cg) {
       if (threadIdx.x == 0) {
-        // producer: chunk cg + kStages - 1 goes into the stage that chunk cg - 1 occupied, once every warp has released it
-        const int ci = cg + kStages - 1;
+        // producer: chunk cg + STG - 1 goes into the stage that chunk cg - 1 occupied, once every warp has released it
+        const int ci = cg + STG - 1;
         if (ci < total) {
-          const int si = ci % kStages;
-          if (ci >= kStages) lyra_mbar_wait(&pipe->empty[set][si], (unsigned)((ci / kStages - 1) & 1));
+          const int si = ci % STG;
+          if (ci >= STG) lyra_mbar_wait(&pipe->empty[set][si], (unsigned)((ci / STG - 1) & 1));
           lyra_bulk_g2s(wbuf + (size_t)si * (KC * N), Wg + (size_t)(ci % nchunks) * KC * N, chunk_bytes, &pipe->full[set][si]);
         }
       }
-      const int st = cg % kStages;
-      lyra_mbar_wait(&pipe->full[set][st], (unsigned)((cg / kStages) & 1));      // chunk cg has landed
+      const int st = cg % STG;
+      lyra_mbar_wait(&pipe->full[set][st], (unsigned)((cg / STG) & 1));      // chunk cg has landed
       if (active) {
         const float* wcur = wbuf + (size_t)st * (KC * N);
         const int kk0 = c * KC;
@@ -287,7 +293,7 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
     __syncthreads();   // every thread is past the K loop: A may be overwritten, the weight ring reused
     if (wt0 + NT / 32 >= map.nwt && threadIdx.x == 0) {
       // last pass: start the next GEMM's weight stream (other barrier set) and hand the pipe over to it
-      if (nxt.w != nullptr) IssuePrologueSet(pipe, set ^ 1, nxt.ring ? nxt.ring : wbuf, nxt.w, nxt.chunk_words, nxt.nchunks);
+      if (nxt.w != nullptr) IssuePrologueSet(pipe, set ^ 1, nxt.ring ? nxt.ring : wbuf, nxt.w, nxt.chunk_words, nxt.nchunks, nxt.stages);
       pipe->cur = set ^ 1;
     }
     if (active) epi(t_out, s0, n0, acc);

@@ -100,7 +100,7 @@ std::vector<float> PackMmaBTf32(const std::vector<float>& b, int K, int N) {
 // One chunk of the UMMA decoder's weight stream (net_params.h kDuChunkBytes): elem(row, k) for row < rows, k < kc as
 // [hi part][lo part], each [kc/4][rows/8][8][4] floats.
 template <typename Elem>
-void AppendDuChunk(std::vector<uint8_t>* out, int rows, int kc, Elem elem) {
+void AppendDuChunk(std::vector<uint8_t>* out, int rows, int kc, Elem elem, bool raw = false) {
   SPEC_CHECK(kc % 8 == 0 && rows % 8 == 0 && (size_t)2 * kc * rows * 4 <= (size_t)kDuChunkBytes, "UMMA weight chunk shape");
   std::vector<float> part((size_t)2 * kc * rows, 0.0f);
   for (int k = 0; k < kc; ++k)
@@ -113,10 +113,16 @@ void AppendDuChunk(std::vector<uint8_t>* out, int rows, int kc, Elem elem) {
       std::memcpy(&hi, &bits, 4);
       const float lo = x - hi;                                   // exact in fp32
       const size_t idx = ((size_t)(k / 4) * (rows / 8) + n / 8) * 32 + (size_t)(n % 8) * 4 + k % 4;
-      part[idx] = hi;
+      part[idx] = raw ? x : hi;
       part[(size_t)kc * rows + idx] = lo;
     }
   const size_t off = out->size();
+  if (raw) {                                                     // the unsplit values in the layout of the hi part: the kernel splits them
+    SPEC_CHECK((size_t)kc * rows * 4 == (size_t)kDuRawChunkBytes, "raw UMMA weight chunk shape");
+    out->resize(off + kDuRawChunkBytes, 0);
+    std::memcpy(out->data() + off, part.data(), (size_t)kDuRawChunkBytes);
+    return;
+  }
   out->resize(off + kDuChunkBytes, 0);
   std::memcpy(out->data() + off, part.data(), part.size() * 4);
 }
@@ -517,7 +523,7 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
         AppendDuChunk(&chunks, 128, 16, [&](int row, int k) {
           const int m = mb * 128 + row, j = m / 320, rc = m % 320, ci = kc * 16 + k;
           return j < 2 ? wu[(size_t)(j * 128 + ci) * 320 + rc] : 0.0f;
-        });
+        }, true);
     for (int g = 1; g <= 6; ++g) {
       SPEC_CHECK(n.kept[(size_t)g].size() == (size_t)64 * 64, "UMMA decoder: residual-unit GEMM shape");
       const std::vector<float>& w = n.kept[(size_t)g];         // [k = cin][n = cout]
@@ -526,7 +532,7 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
     const std::vector<float>& wl = n.kept[7];                 // last_layer: [(tap, ci)][n], 256 x 16
     for (int kc = 0; kc < 2; ++kc)
       AppendDuChunk(&chunks, 64, 32, [&](int row, int k) { return wl[(size_t)((row / 16) * 64 + kc * 32 + k) * 16 + row % 16]; });
-    SPEC_CHECK(chunks.size() == (size_t)kDuNumChunks * kDuChunkBytes, "UMMA decoder: chunk count");
+    SPEC_CHECK(chunks.size() == (size_t)kDuUp2Chunks * kDuRawChunkBytes + (size_t)(kDuNumChunks - kDuUp2Chunks) * kDuChunkBytes, "UMMA decoder: chunk count");
     while (blob->size() % 128) blob->push_back(0);
     p.du_chunks = Append(blob, chunks);
   }

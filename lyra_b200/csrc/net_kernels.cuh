@@ -20,6 +20,9 @@
 #define LYRA_BC_MIN_BLOCKS 3
 #endif
 // output channels per fp32 thread tile in the small-M layers of kernels B / C (8 streams x LYRA_BC_TN channels)
+#ifndef LYRA_BC_STAGES
+#define LYRA_BC_STAGES 3
+#endif
 #ifndef LYRA_BC_TN
 #define LYRA_BC_TN 4
 #endif
@@ -105,7 +108,7 @@ constexpr int kTileIdle = -2;
 // WTM x WTN fragments (sized so that every warp owns at most one tile: pw1 rewrites its operand in place); the weight
 // ring and its prefetch chain are not used in that mode.
 template <int S, int NT, int TM, int TN1, int TN2, int WM, int KC, int C, int T, int DIL, bool TC = false, int LDD = T * S,
-          int WTM = 1, int WTN = 1>
+          int WTM = 1, int WTN = 1, int STG = kStages>
 __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p, float* u, int ldu, int row0u, float* d,
                                            int groups2, float* ring, const int* n18,
                                            const int* active, float* wbuf, bool last, const WNext& after, int pk, int& ph,
@@ -139,8 +142,8 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
     if constexpr (TC)
       GemmTf32Mma<S, NT, WTM, WTN, true>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float2>(blob, p.pw1.wf), epi1);
     else
-      GemmF32Tap<S, NT, TM, TN1, KC, WM, false>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float>(blob, p.pw1.w), wbuf, true,
-                                                NextF32(BlobPtr<float>(blob, p.pw2.w), KC, C, C / groups2), epi1);
+      GemmF32Tap<S, NT, TM, TN1, KC, WM, false, STG>(d, ldd, 0, 1, 1, C, 1, T, C, BlobPtr<float>(blob, p.pw1.w), wbuf, true,
+                                                     NextF32(BlobPtr<float>(blob, p.pw2.w), KC, C, C / groups2, nullptr, STG), epi1);
   }
   LYRA_PHASE(pk, ph);
   {
@@ -161,7 +164,7 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
     if constexpr (TC)
       GemmTf32Mma<S, NT, WTM, WTN, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float2>(blob, p.pw2.wf), epi2);
     else
-      GemmF32Tap<S, NT, TM, TN2, KC, WM, false>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float>(blob, p.pw2.w), wbuf, true, after, epi2);
+      GemmF32Tap<S, NT, TM, TN2, KC, WM, false, STG>(d, ldd, 0, 1, 1, C / groups2, groups2, T, C, BlobPtr<float>(blob, p.pw2.w), wbuf, true, after, epi2);
   }
   LYRA_PHASE(pk, ph);
 }
@@ -169,7 +172,8 @@ __device__ __forceinline__ void ResUnitF32(const uint8_t* blob, const ResF32& p,
 // The three residual units of one stage (dilation 1, 3, 9; ring blocks of 2, 6, 18 rows back to back) as ONE copy of the code in
 // a loop that is not unrolled: the units differ only in their parameters and in the depthwise pass, and three inlined copies
 // of the two GEMMs made kernels B / C overflow the instruction cache (15-20 % of their stall samples were instruction fetches).
-template <int S, int NT, int TM, int TN1, int TN2, int WM, int KC, int C, int T, bool TC = false, int LDD = T * S, int WTM = 1, int WTN = 1>
+template <int S, int NT, int TM, int TN1, int TN2, int WM, int KC, int C, int T, bool TC = false, int LDD = T * S, int WTM = 1, int WTN = 1,
+          int STG = kStages>
 __device__ __forceinline__ void ResUnitsF32x3(const uint8_t* blob, const ResF32* p3, float* u, int ldu, int row0u, float* d, int groups2,
                                               float* ring0, const int* n18, const int* active, float* wbuf, const WNext& after,
                                               int pk, int& ph) {
@@ -178,8 +182,8 @@ __device__ __forceinline__ void ResUnitsF32x3(const uint8_t* blob, const ResF32*
     const ResF32& p = p3[i];
     const int dil = i == 0 ? 1 : (i == 1 ? 3 : 9);
     float* ring = ring0 + (size_t)(i == 0 ? 0 : (i == 1 ? 2 : 8)) * C * S;       // [C][2] | [C][6] | [C][18]
-    const WNext nx = i < 2 ? NextF32(BlobPtr<float>(blob, p3[i + 1].pw1.w), KC, C, C) : after;
-    ResUnitF32<S, NT, TM, TN1, TN2, WM, KC, C, T, 0, TC, LDD, WTM, WTN>(blob, p, u, ldu, row0u, d, groups2, ring, n18, active, wbuf, i == 2, nx,
+    const WNext nx = i < 2 ? NextF32(BlobPtr<float>(blob, p3[i + 1].pw1.w), KC, C, C, nullptr, STG) : after;
+    ResUnitF32<S, NT, TM, TN1, TN2, WM, KC, C, T, 0, TC, LDD, WTM, WTN, STG>(blob, p, u, ldu, row0u, d, groups2, ring, n18, active, wbuf, i == 2, nx,
                                                                        pk, ph, dil);
   }
 }
@@ -263,6 +267,9 @@ __device__ __forceinline__ void ResUnitsI8x2(const uint8_t* blob, const ResI8* p
 #ifndef LYRA_A_NT
 #define LYRA_A_NT 320
 #endif
+#ifndef LYRA_A_DOWN_STAGES
+#define LYRA_A_DOWN_STAGES 5
+#endif
 #ifndef LYRA_A_DOWN_TM
 #define LYRA_A_DOWN_TM 8
 #endif
@@ -275,6 +282,7 @@ struct EncA {
   static constexpr int TN = S >= 16 ? 8 : LYRA_A_TN;
   static constexpr int kMinBlocks = S <= 8 ? 2 : 1;       // S = 8 tiles fit two blocks per SM
   static constexpr int LDU = 25 * S, LDD = 20 * S;
+  static constexpr int kStgDown = S <= 8 ? LYRA_A_DOWN_STAGES : kStages;   // ring depth of encoder_0/simpleconv (ring = the d buffer)
   static constexpr int kSmemU = 0;
   static constexpr int kSmemD = kSmemU + 64 * LDU * 4;
   static constexpr int kSmemW = kSmemD + 64 * LDD * 4;
@@ -340,7 +348,7 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   LYRA_PHASE(0, ph);
   static_assert(EncStateA::kRing1 == EncStateA::kRing0 + 64 * 2 && EncStateA::kRing2 == EncStateA::kRing1 + 64 * 6, "ring blocks back to back");
   ResUnitsF32x3<S, NT, 8, L::TN, L::TN, 4, 16, 64, 20>(blob, P.r0, u, L::LDU, 5, d, 1, st + (size_t)EncStateA::kRing0 * S, n18, active, wbuf,
-                                                       NextF32(BlobPtr<float>(blob, P.down0.w), 16, 128, 640, d), 0, ph);
+                                                       NextF32(BlobPtr<float>(blob, P.down0.w), 16, 128, 640, d, L::kStgDown), 0, ph);
   // carried rows for the next frame: the last 5 activated rows
   for (int i = tid; i < 64 * 5 * S; i += NT) {
     const int c = i / (5 * S), r = i % (5 * S);
@@ -351,13 +359,13 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   {
     const float* b = BlobPtr<float>(blob, P.down0.bias);
     float* out = mid + (size_t)tile * 128 * 4 * S;
-    // the d buffer is free from here on: it hosts this GEMM's weight ring (3 x 16 x 128 floats), twice the chunk the
-    // regular ring could hold, which halves the number of block barriers of this K = 640 layer
-    static_assert(kStages * 16 * 128 * 4 <= 64 * L::LDD * 4, "simpleconv weight ring must fit in d");
+    // the d buffer is free from here on: it hosts this GEMM's weight ring (kStgDown x 16 x 128 floats).  With 32 GEMM rows a chunk is
+    // consumed in a fraction of the L2 round trip, so the ring is as deep as d allows.
+    static_assert(L::kStgDown * 16 * 128 * 4 <= 64 * L::LDD * 4, "simpleconv weight ring must fit in d");
     // 4 output rows x S streams = 32 GEMM rows only: LYRA_A_DOWN_TM x LYRA_A_DOWN_TN thread tiles decide how many of the block's
     // ten warps get a tile (8 x 4: four warps; 4 x 4 or 8 x 2: eight)
     constexpr int DTM = S >= 16 ? 8 : LYRA_A_DOWN_TM, DTN = S >= 16 ? 4 : LYRA_A_DOWN_TN;
-    GemmF32Tap<S, NT, DTM, DTN, 16, 4, false>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), d, true, NoNext(),
+    GemmF32Tap<S, NT, DTM, DTN, 16, 4, false, L::kStgDown>(u, L::LDU, 0, 5, 10, 64, 1, 4, 128, BlobPtr<float>(blob, P.down0.w), d, true, NoNext(),
       [&](int t, int s0, int n0, float (&acc)[DTM][DTN]) {
 #pragma unroll
         for (int j = 0; j < DTN; ++j) {
@@ -396,7 +404,8 @@ struct EncB {
   static constexpr int kRBBytes = kMax(128 * 4 * S * 4, 256 * 2 * S * 4);
   static constexpr int kRC = kRB + kRBBytes;
   static constexpr int kW = kRC + 64 * LQ2 * 4;
-  static constexpr int kWBytes = kMax(kStages * 8 * 256 * 4, 2 * 64 * LQ2 * 4);
+  static constexpr int kStg = S <= 8 ? LYRA_BC_STAGES : kStages;      // ring depth of the kernel's fp32 GEMMs
+  static constexpr int kWBytes = kMax(kStg * 8 * 256 * 4, 2 * 64 * LQ2 * 4);
   static constexpr int kI = kW + kWBytes;
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
 };
@@ -430,7 +439,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * EncStateB::kUnits * S;
   float* st = reinterpret_cast<float*>(stw);
   const int tid = (int)threadIdx.x;
-  IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128));
+  IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128, nullptr, L::kStg));
   int ph = 0;
   LYRA_PHASE(1, ph);
 
@@ -446,8 +455,9 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   // ---- encoder_1: three residual units @128 (second 1x1 has 2 groups)
   LYRA_PHASE(1, ph);
   static_assert(EncStateB::kRing1 == EncStateB::kRing0 + 128 * 2 && EncStateB::kRing2 == EncStateB::kRing1 + 128 * 6, "ring blocks back to back");
-  ResUnitsF32x3<S, NT, TM, LYRA_BC_TN, LYRA_BC_TN, L::WM4, 16, 128, 4>(blob, P.r1, u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf,
-                                                     NextF32(BlobPtr<float>(blob, P.down1.w), 8, 256, 256), 1, ph);
+  ResUnitsF32x3<S, NT, TM, LYRA_BC_TN, LYRA_BC_TN, L::WM4, 16, 128, 4, false, 4 * S, 1, 1, L::kStg>(
+      blob, P.r1, u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf,
+      NextF32(BlobPtr<float>(blob, P.down1.w), 8, 256, 256, nullptr, L::kStg), 1, ph);
   for (int i = tid; i < 128 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
     if (active[r % S]) st[EncStateB::kDown1 * S + i] = u1[(size_t)c * L::LD1 + 4 * S + r];
@@ -456,8 +466,8 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   LYRA_PHASE(1, ph);
   {
     const float* b = BlobPtr<float>(blob, P.down1.bias);
-    GemmF32Tap<S, NT, TM, LYRA_BC_TN, 8, L::WM2, false>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, true,
-      NextF32(BlobPtr<float>(blob, P.m_pw1.w), 8, 256, 256),
+    GemmF32Tap<S, NT, TM, LYRA_BC_TN, 8, L::WM2, false, L::kStg>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, true,
+      NextF32(BlobPtr<float>(blob, P.m_pw1.w), 8, 256, 256, nullptr, L::kStg),
       [&](int t, int s0, int n0, float (&acc)[TM][LYRA_BC_TN]) {
 #pragma unroll
         for (int j = 0; j < LYRA_BC_TN; ++j) {
@@ -481,7 +491,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const float* b = BlobPtr<float>(blob, P.m_pw1.bias);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const QuantP q1 = P.m_q1;
-    GemmF32Tap<S, NT, TM, LYRA_BC_TN, 8, L::WM2, false>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, true,
+    GemmF32Tap<S, NT, TM, LYRA_BC_TN, 8, L::WM2, false, L::kStg>(d2, LD2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<float>(blob, P.m_pw1.w), wbuf, true,
       NoNext(),
       [&](int t, int s0, int n0, float (&acc)[TM][LYRA_BC_TN]) {
 #pragma unroll

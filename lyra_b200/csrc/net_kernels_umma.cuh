@@ -19,7 +19,8 @@
 //               residual unit's epilogue leaves in tensor memory; the four taps are summed across time rows afterwards.
 //   weights     pre-split on the host into hi / lo core-matrix chunks (net_params.h kDuChunkBytes), streamed by one producer
 //               thread with TMA bulk copies through a 2-stage shared-memory ring; a stage is released by tcgen05.commit when
-//               the MMAs that read it have completed.
+//               the MMAs that read it have completed.  decoder_2/simple's chunks (three quarters of the stream, and the phase
+//               that is bound by its delivery) travel unsplit - half the bytes - and are split in place by the row warps.
 //   state       contiguous blocks (kernel C's tile, overlap tails, ring blocks, depthwise parameters) move by TMA bulk copies,
 //               in both directions; blocks are written back whole, with the lanes of inactive streams left as loaded.
 //   roles       warps 0..7: rows / epilogues / state;  warp 8 lane 0: MMA issue;  warp 9 lane 0: TMA producer.
@@ -67,6 +68,8 @@ struct DecDU {
 
 struct DecDUShared {
   LyraMbar w_full[DecDU::kStagesW], w_empty[DecDU::kStagesW];
+  LyraMbar raw_full[DecDU::kStagesW];   // producer -> row warps: an unsplit decoder_2/simple chunk has landed in the stage's hi half
+  LyraMbar s_full[DecDU::kStagesW];     // row warps -> MMA issuer: the chunk is split (hi | lo) in place
   LyraMbar in_full;        // producer -> row warps: tile, overlap tail, last_layer tail and depthwise parameters have landed
   LyraMbar a_ready;        // row warps -> MMA issuer: the operand of the next GEMM is in place
   LyraMbar d_ready;        // MMA issuer -> row warps: the accumulators of the GEMM are complete
@@ -127,7 +130,12 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   const unsigned rank = lyra_cluster_ctarank();
 
   if (tid == 0) {
-    for (int i = 0; i < L::kStagesW; ++i) { lyra_mbar_init(&sh->w_full[i], 1); lyra_mbar_init(&sh->w_empty[i], pair ? 2u : 1u); }
+    for (int i = 0; i < L::kStagesW; ++i) {
+      lyra_mbar_init(&sh->w_full[i], 1);
+      lyra_mbar_init(&sh->w_empty[i], pair ? 2u : 1u);
+      lyra_mbar_init(&sh->raw_full[i], 1);
+      lyra_mbar_init(&sh->s_full[i], L::kRowWarps);
+    }
     lyra_mbar_init(&sh->in_full, 1);
     lyra_mbar_init(&sh->a_ready, L::kRowWarps);
     lyra_mbar_init(&sh->d_ready, 1);
@@ -161,14 +169,19 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       for (int c = 0; c < kDuNumChunks; ++c) {
         const int stg = c % L::kStagesW;
         if (c >= L::kStagesW) lyra_mbar_wait(&sh->w_empty[stg], (unsigned)((c / L::kStagesW - 1) & 1));
+        // decoder_2/simple chunks arrive unsplit (half the bytes; the row warps split them in place), the others pre-split
+        const bool raw = c < kDuUp2Chunks;
+        const unsigned bytes = raw ? (unsigned)kDuRawChunkBytes : (unsigned)kDuChunkBytes;
+        const uint8_t* src = raw ? chunks + (size_t)c * kDuRawChunkBytes
+                                 : chunks + (size_t)kDuUp2Chunks * kDuRawChunkBytes + (size_t)(c - kDuUp2Chunks) * kDuChunkBytes;
+        LyraMbar* full = raw ? &sh->raw_full[stg] : &sh->w_full[stg];
         if (pair) {
           // arm this CTA's barrier for the whole chunk; this producer fetches its half and multicasts it to both CTAs
-          constexpr unsigned kHalf = (unsigned)kDuChunkBytes / 2;
-          lyra_bulk_multi_begin(&sh->w_full[stg], (unsigned)kDuChunkBytes);
-          lyra_bulk_g2s_mc(wring + (size_t)stg * kDuChunkBytes + rank * kHalf, chunks + (size_t)c * kDuChunkBytes + rank * kHalf, kHalf,
-                           &sh->w_full[stg], 3u);
+          const unsigned half = bytes / 2;
+          lyra_bulk_multi_begin(full, bytes);
+          lyra_bulk_g2s_mc(wring + (size_t)stg * kDuChunkBytes + rank * half, src + rank * half, half, full, 3u);
         } else {
-          lyra_bulk_g2s(wring + (size_t)stg * kDuChunkBytes, chunks + (size_t)c * kDuChunkBytes, (unsigned)kDuChunkBytes, &sh->w_full[stg]);
+          lyra_bulk_g2s(wring + (size_t)stg * kDuChunkBytes, src, bytes, full);
         }
         if (c == kDuUp2Chunks + L::kStagesW - 1) {
           // the wait above covered the last decoder_2/simple chunk's MMAs, the last readers of X: the ring blocks may land on it
@@ -186,8 +199,10 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       unsigned a_par = 0;
       int c = 0;                                             // weight chunk counter
       auto wait_a = [&]() { lyra_mbar_wait(&sh->a_ready, a_par); a_par ^= 1; lyra_tc_fence_after_sync(); };
+      static_assert(kDuUp2Chunks % L::kStagesW == 0, "the split and the pre-split chunks use separate barrier phase sequences");
       auto wait_chunk_at = [&](int ci) -> const unsigned char* {
-        lyra_mbar_wait(&sh->w_full[ci % L::kStagesW], (unsigned)((ci / L::kStagesW) & 1));
+        if (ci < kDuUp2Chunks) lyra_mbar_wait(&sh->s_full[ci % L::kStagesW], (unsigned)((ci / L::kStagesW) & 1));
+        else lyra_mbar_wait(&sh->w_full[ci % L::kStagesW], (unsigned)(((ci - kDuUp2Chunks) / L::kStagesW) & 1));
         lyra_tc_fence_after_sync();
         return wring + (size_t)(ci % L::kStagesW) * kDuChunkBytes;
       };
@@ -285,6 +300,28 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       }
     }
     DuArriveA(sh);
+    LYRA_PHASE(3, ph);
+
+    // ---- decoder_2/simple weights: every chunk lands as plain fp32 in the hi half of its stage; split it in place (hi stays,
+    //      lo goes to the other half) while the tensor core works on the previous one.  All eight row warps: they have nothing
+    //      else to do until the layer's accumulators are complete.
+    for (int c = 0; c < kDuUp2Chunks; ++c) {
+      const int stg = c % L::kStagesW;
+      lyra_mbar_wait(&sh->raw_full[stg], (unsigned)((c / L::kStagesW) & 1));
+      float4* wh = reinterpret_cast<float4*>(wring + (size_t)stg * kDuChunkBytes);
+      float4* wl = wh + kDuRawChunkBytes / 16;
+#pragma unroll
+      for (int i = tid; i < kDuRawChunkBytes / 16; i += L::kRowThreads) {
+        const float4 v = wh[i];
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        DuSplit(v.x, h0, l0); DuSplit(v.y, h1, l1); DuSplit(v.z, h2, l2); DuSplit(v.w, h3, l3);
+        wh[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+        wl[i] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+      }
+      lyra_fence_proxy_async();                              // the tensor core reads the stage through the asynchronous proxy
+      __syncwarp();
+      if (lane == 0) lyra_mbar_arrive(&sh->s_full[stg]);
+    }
     LYRA_PHASE(3, ph);
 
     // ---- decoder_2/simple epilogue.  TMEM lane = weight row m = (tap j, phase r, cout), column = (x-row, stream).

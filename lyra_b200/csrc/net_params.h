@@ -72,6 +72,9 @@ struct UpI8 {
 //   chunks 52..53  last_layer as ONE 64 x 64 GEMM: B row = tap * 16 + n (n = output sample within the stride), k = cin;
 //                  the four taps are summed across time rows in the epilogue
 constexpr int kDuChunkBytes = 16384;
+// decoder_2/simple's chunks (the delivery-bound part of the stream) travel as plain fp32 - the hi half of a stage - and are split
+// into hi | lo in shared memory by the kernel's row warps; the other chunks are stored pre-split
+constexpr int kDuRawChunkBytes = kDuChunkBytes / 2;
 constexpr int kDuNumChunks = 54;
 constexpr int kDuUp2Chunks = 40, kDuUnitChunk0 = 40, kDuLastChunk0 = 52;
 

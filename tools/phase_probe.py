@@ -41,7 +41,7 @@ def main():
     nblk = min(1024, n // ctx.tile_streams)
     du = os.environ.get("LYRA_B200_DECODER_MODE") == "tensor"
     if du:
-        NAMES[3] = ["loads+X", "up2 mma", "up2 epi"] + sum([["u%d ring wait" % i, "u%d dw" % i, "u%d ring upd" % i, "u%d pw1 mma" % i, "u%d epi1" % i,
+        NAMES[3] = ["loads+X", "up2 split (weight stream)", "up2 mma tail", "up2 epi"] + sum([["u%d ring wait" % i, "u%d dw" % i, "u%d ring upd" % i, "u%d pw1 mma" % i, "u%d epi1" % i,
                                                           "u%d pw2 mma" % i, "u%d epi2" % i] for i in range(3)], []) + ["last (4 taps)", "last epi+store"]
     for k in range(4):
         t = buf[k, :nblk]
