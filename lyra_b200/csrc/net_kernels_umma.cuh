@@ -92,6 +92,20 @@ __device__ __forceinline__ void DuArriveA(DecDUShared* sh) {
   if ((threadIdx.x & 31) == 0) lyra_mbar_arrive(&sh->a_ready);
 }
 
+// The thread's 64 accumulator columns in four groups of 16, with the tcgen05.ld of group g + 1 in flight while f(g, v) runs
+// (tcgen05.wait::ld covers every earlier load, so the next one is issued right after the wait).  Warp-collective.
+template <typename F>
+__device__ __forceinline__ void DuForEachAccGroup(uint32_t taddr, F f) {
+  uint32_t v[2][16];
+  lyra_tmem_ld<16>(taddr, v[0]);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    lyra_tmem_wait_ld();
+    if (g < 3) lyra_tmem_ld<16>(taddr + (uint32_t)(16 * (g + 1)), v[(g + 1) & 1]);
+    f(g * 16, v[g & 1]);
+  }
+}
+
 __global__ void __launch_bounds__(DecDU::NT, 1)
 DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, const float* __restrict__ mid,
                 float* __restrict__ state, int* __restrict__ n18g, int16_t* __restrict__ pcm, int ntiles) {
@@ -341,15 +355,16 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
           const float bias = b[co];
           float* uc = u + co * LDU + r * S;
           float* oc = ov + (co * 5 + r) * S;
+          uint32_t v2[2][16];                                // both halves of the row in flight before the first is consumed
+          lyra_tmem_ld<16>(tq + (uint32_t)(mb * 32), v2[0]);
+          lyra_tmem_ld<16>(tq + (uint32_t)(mb * 32 + 16), v2[1]);
+          lyra_tmem_wait_ld();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            uint32_t v[16];
-            lyra_tmem_ld<16>(tq + (uint32_t)(mb * 32 + half * 16), v);
-            lyra_tmem_wait_ld();
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               const int x = half * 2 + k / 8, ss = k % 8;
-              const float p = __uint_as_float(v[k]);
+              const float p = __uint_as_float(v2[half][k]);
               if (pass == 0) {
                 const float y = __fadd_rn(p, bias);
                 uc[(5 * x) * S + ss] = __fadd_rn(y, x == 0 ? oc[ss] : 0.0f);
@@ -429,15 +444,13 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       LYRA_PHASE(3, ph);
       if (has_row) {
         const float* b1 = BlobPtr<float>(blob, p.pw1.bias);
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          uint32_t v[16], hi[16], lo[16];
-          lyra_tmem_ld<16>(trow + L::kColD + (uint32_t)c0, v);
-          lyra_tmem_wait_ld();
+        DuForEachAccGroup(trow + L::kColD, [&](int c0, const uint32_t (&v)[16]) {
+          uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) DuSplit(LeakyRelu(__fadd_rn(__uint_as_float(v[j]), b1[c0 + j])), hi[j], lo[j]);
           lyra_tmem_st<16>(trow + L::kColAhi + (uint32_t)c0, hi);
           lyra_tmem_st<16>(trow + L::kColAlo + (uint32_t)c0, lo);
-        }
+        });
       }
       DuArriveA(sh);
       ring_update(32);
@@ -452,22 +465,22 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       if (has_row) {
         const float* b2 = BlobPtr<float>(blob, p.pw2.bias);
         float* uc = u + row;
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          uint32_t v[16], hi[16], lo[16];
-          lyra_tmem_ld<16>(trow + L::kColD + (uint32_t)c0, v);
-          lyra_tmem_wait_ld();
+        DuForEachAccGroup(trow + L::kColD, [&](int c0, const uint32_t (&v)[16]) {
+          uint32_t hi[16], lo[16];
+          float res[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) res[j] = uc[(c0 + j) * LDU];                 // the residual: loads first, one exposed latency
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float* o = uc + (c0 + j) * LDU;
-            const float val = __fadd_rn(__fadd_rn(__uint_as_float(v[j]), b2[c0 + j]), *o);
+            const float val = __fadd_rn(__fadd_rn(__uint_as_float(v[j]), b2[c0 + j]), res[j]);
             if (unit == 2) DuSplit(LeakyRelu(val), hi[j], lo[j]);
-            else *o = val;
+            else uc[(c0 + j) * LDU] = val;
           }
           if (unit == 2) {
             lyra_tmem_st<16>(trow + L::kColAhi + (uint32_t)c0, hi);
             lyra_tmem_st<16>(trow + L::kColAlo + (uint32_t)c0, lo);
           }
-        }
+        });
       }
       if (unit == 2) DuArriveA(sh);
       else row_sync();                                       // u' complete before anybody reads a neighbour's rows
@@ -483,13 +496,10 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
     LYRA_PHASE(3, ph);
     if (has_row) {
       float* uc = u + row;
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        uint32_t v[16];
-        lyra_tmem_ld<16>(trow + L::kColD + (uint32_t)c0, v);
-        lyra_tmem_wait_ld();
+      DuForEachAccGroup(trow + L::kColD, [&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) uc[(c0 + j) * LDU] = __uint_as_float(v[j]);
-      }
+      });
     }
     if (tid == 0) lyra_bulk_wait_read();                     // the ring blocks' bulk stores have read them: PCM staging may alias
     row_sync();
