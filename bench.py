@@ -431,6 +431,7 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
         c.profile_enable(False)
     for c in group_ctxs:
         c.set_split(args.e2e_split)
+        c.set_graphs(args.graphs == "on")       # the dense host-buffer calls replay captured CUDA graphs (one per rotating buffer pair)
     barrier()
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -505,11 +506,12 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
     e2e_value = world * n * e2e_hops / float(t.item())
     checksum = int(pin_out.to(torch.int64).sum().item())
     tile_streams = dec.tile_streams
+    graph_replays = sum(c.graph_replays() for c in group_ctxs)
     for c in ctxs + (group_ctxs if G > 1 else []):
         c.close()
     return {"value": value, "elapsed_ms": elapsed_ms, "e2e_value": e2e_value, "e2e_s": float(t.item()), "prof": prof, "clocks": clocks,
             "gpu_launches": int(gpu_launches), "checksum": checksum, "G": G, "oversubscribed": oversubscribed, "tile_streams": tile_streams,
-            "P": P}
+            "P": P, "graph_replays": graph_replays}
 
 
 def roofline_of(res, n, bits, plc, world, hops, decoder_mode, clocks):
@@ -565,6 +567,7 @@ def main():
                          "through the reference's concealment / comfort-noise / fade state machine (lyra_b200_decode_plc)")
     ap.add_argument("--loss", type=float, default=0.1, help="decode_plc: packet loss probability (Bernoulli, seed 1234); 1.0 = all lost")
     ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
+    ap.add_argument("--graphs", default="on", choices=["on", "off"], help="CUDA graphs for the host-buffer encode / decode calls of the e2e pass")
     ap.add_argument("--e2e-split", type=int, default=2, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
     ap.add_argument("--groups", type=int, default=2,
                     help="worker groups: the streams are divided among this many encoder/decoder context pairs, each pair with its own "
@@ -653,6 +656,7 @@ def main():
                                    codec_workload(n, bits, world),
                        "streams_per_gpu": n, "bits_per_frame": bits, "hops_per_step": HOPS_PER_STEP, "tile_streams": res["tile_streams"],
                        "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G,
+                       "host_pass_cuda_graphs": {"enabled": args.graphs == "on", "replayed_calls": res.get("graph_replays", 0)},
                        "host_threads_wait": "sleep (blocking-sync event)" if res["oversubscribed"] else "spin",
                        "host_cores_per_rank": pinned if pinned else host_cores(),
                        "real_time_factor": value / (50.0 * n * world),

@@ -200,6 +200,13 @@ int lyra_b200_decoder_mode(const lyra_b200_ctx* ctx);
 /* How the synchronous host-buffer calls wait for the GPU: 0 (default) spins (lowest latency), 1 sleeps on a blocking-sync
  * CUDA event — for servers that run more waiting worker threads than they have cores. */
 int lyra_b200_set_blocking_sync(lyra_b200_ctx* ctx, int enable);
+/* CUDA graphs for the synchronous host-buffer calls lyra_b200_encode / lyra_b200_decode (no reference counterpart): with
+ * enable = 1 a dense call (stream_ids == NULL) whose host buffers are page-locked is captured once - copies in, every
+ * sub-batch's kernels, copies out - and later calls with the same n, num_bits and buffers replay the graph (one launch instead
+ * of ~20 stream operations; matters for small batches).  Results are identical; anything that cannot be captured runs directly.
+ * Default 0.  lyra_b200_graph_replays counts the calls served by a replay. */
+int lyra_b200_set_graphs(lyra_b200_ctx* ctx, int enable);
+uint64_t lyra_b200_graph_replays(const lyra_b200_ctx* ctx);
 /* number of CUDA kernels this context has launched so far */
 uint64_t lyra_b200_launch_count(const lyra_b200_ctx* ctx);
 

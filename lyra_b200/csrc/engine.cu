@@ -118,6 +118,19 @@ struct lyra_b200_ctx {
   cudaEvent_t ev_sync = nullptr;
   int decoder_mode = LYRA_B200_DECODER_EXACT;   // lyra_b200_set_decoder_mode
   uint64_t launches = 0;
+  // lyra_b200_set_graphs: the dense host-buffer encode / decode calls replay a captured CUDA graph (copies in, kernels of every
+  // sub-batch, copies out) instead of re-issuing ~20 stream operations per call; one graph per (call shape, host buffers)
+  struct GraphKey {
+    int kind, n, num_bits, mode, nsplit;
+    const void *a, *b, *c;
+    bool operator==(const GraphKey& o) const {
+      return kind == o.kind && n == o.n && num_bits == o.num_bits && mode == o.mode && nsplit == o.nsplit && a == o.a && b == o.b && c == o.c;
+    }
+  };
+  struct GraphEntry { GraphKey key; void* exec; uint64_t launches; };
+  bool use_graphs = false;
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_replays = 0;
   std::string err;
   // diagnostics: CUDA-event timing of every kernel launch
   bool profiling = false;
@@ -609,6 +622,66 @@ cudaError_t DevAlloc(T** p, size_t count) {
   return e;
 }
 
+#ifndef LYRA_EMU
+bool PinnedHost(const void* p) {
+  if (p == nullptr) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+void DropGraphs(lyra_b200_ctx* ctx) {
+  for (auto& e : ctx->graphs) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(e.exec));
+  ctx->graphs.clear();
+}
+#endif
+
+// Runs `enqueue` (which only issues asynchronous work on the context's streams) either directly or, for a dense call on pinned
+// host buffers with graphs enabled, as a captured graph that later calls of the same shape replay.  Any capture problem turns
+// graphs off for the context and the call proceeds directly: correctness never depends on the graph path.
+template <typename Fn>
+int RunMaybeGraphed(lyra_b200_ctx* ctx, const lyra_b200_ctx::GraphKey& key, bool eligible, Fn enqueue) {
+#ifdef LYRA_EMU
+  (void)key; (void)eligible;
+  return enqueue();
+#else
+  if (!ctx->use_graphs || !eligible || ctx->profiling || !PinnedHost(key.a) || !PinnedHost(key.b) || !PinnedHost(key.c)) return enqueue();
+  for (auto& e : ctx->graphs)
+    if (e.key == key) {
+      CU(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(e.exec), ctx->stream));
+      ctx->launches += e.launches;
+      ++ctx->graph_replays;
+      return LYRA_B200_OK;
+    }
+  const uint64_t l0 = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->use_graphs = false;
+    return enqueue();
+  }
+  const int rc = enqueue();
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+  cudaGraphExec_t exec = nullptr;
+  if (rc == LYRA_B200_OK && ce == cudaSuccess && g != nullptr && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess) {
+    cudaGraphDestroy(g);
+    if (ctx->graphs.size() >= 32) {
+      cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(ctx->graphs.front().exec));
+      ctx->graphs.erase(ctx->graphs.begin());
+    }
+    ctx->graphs.push_back(lyra_b200_ctx::GraphEntry{key, exec, ctx->launches - l0});
+    CU(cudaGraphLaunch(exec, ctx->stream));
+    return LYRA_B200_OK;
+  }
+  // nothing was executed (the work was only recorded): give up on graphs and issue the call directly
+  if (g) cudaGraphDestroy(g);
+  cudaGetLastError();
+  ctx->use_graphs = false;
+  ctx->launches = l0;
+  return enqueue();
+#endif
+}
+
+
 }  // namespace
 
 #if defined(LYRA_PHASE_PROF) && !defined(LYRA_EMU)
@@ -778,6 +851,9 @@ void lyra_b200_destroy(lyra_b200_ctx* ctx) {
   }
   for (int k = 0; k < LYRA_B200_NUM_KERNELS; ++k)
     for (auto& ev : ctx->prof_events[k]) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+#ifndef LYRA_EMU
+  DropGraphs(ctx);
+#endif
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
   for (int i = 0; i < lyra_b200_ctx::kMaxSplit - 1; ++i) {
@@ -876,6 +952,18 @@ int lyra_b200_decode_device(lyra_b200_ctx* ctx, int n, const uint8_t* d_packets,
   return RunDecode(ctx, n, d_packets, d_received, num_bits, d_pcm);
 }
 
+int lyra_b200_set_graphs(lyra_b200_ctx* ctx, int enable) {
+  if (!ctx) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
+#ifndef LYRA_EMU
+  CU(SyncStream(ctx));
+  if (!enable) DropGraphs(ctx);
+#endif
+  ctx->use_graphs = enable != 0;
+  return LYRA_B200_OK;
+}
+uint64_t lyra_b200_graph_replays(const lyra_b200_ctx* ctx) { return ctx ? ctx->graph_replays : 0; }
+
 int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_t* pcm, int num_bits, uint8_t* packets) {
   if (!ctx || !pcm || !packets) return LYRA_B200_EINVAL;
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
@@ -883,7 +971,10 @@ int lyra_b200_encode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const int16_
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
-  if ((rc = RunEncode(ctx, n, ctx->d_pcm, num_bits, ctx->d_packets, pcm, packets))) return rc;
+  const lyra_b200_ctx::GraphKey key{0, n, num_bits, 0, ctx->nsplit, pcm, packets, nullptr};
+  if ((rc = RunMaybeGraphed(ctx, key, ids == nullptr && ctx->map_dense_n == n,
+                            [&]() { return RunEncode(ctx, n, ctx->d_pcm, num_bits, ctx->d_packets, pcm, packets); })))
+    return rc;
   CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }
@@ -896,7 +987,11 @@ int lyra_b200_decode(lyra_b200_ctx* ctx, const int32_t* ids, int n, const uint8_
   if (!BitsOk(ctx, num_bits)) return LYRA_B200_EINVAL;
   int rc = PrepareMap(ctx, ids, n);
   if (rc) return rc;
-  if ((rc = RunDecode(ctx, n, ctx->d_packets, received ? ctx->d_received : nullptr, num_bits, ctx->d_pcm, packets, received, pcm))) return rc;
+  const lyra_b200_ctx::GraphKey key{1, n, num_bits, ctx->decoder_mode, ctx->nsplit, packets, received, pcm};
+  if ((rc = RunMaybeGraphed(ctx, key, ids == nullptr && ctx->map_dense_n == n, [&]() {
+         return RunDecode(ctx, n, ctx->d_packets, received ? ctx->d_received : nullptr, num_bits, ctx->d_pcm, packets, received, pcm);
+       })))
+    return rc;
   CU(SyncStream(ctx));
   return LYRA_B200_OK;
 }

@@ -153,6 +153,50 @@ def test_schedule_independence_full_size(gpu_api, mode):
         c.close()
 
 
+@pytest.mark.parametrize("n", [64, 1024])
+def test_cuda_graphs_replay_matches_direct_calls(gpu_api, n):
+    # lyra_b200_set_graphs: dense host-buffer calls on page-locked buffers replay a captured graph; the streaming state must
+    # advance exactly as with directly issued calls (30 hops, two rotating buffer pairs, loss masks, a change of bit rate)
+    import ctypes as C
+
+    import torch
+    rng = np.random.default_rng(5)
+    ref = _capi.Context(n, capi=gpu_api)
+    gr = _capi.Context(n, capi=gpu_api)
+    gr.set_graphs(True)
+    lib = gpu_api.lib
+    pin_pcm = [torch.zeros((n, 320), dtype=torch.int16).pin_memory() for _ in range(2)]
+    pin_pk = [torch.zeros((n, 23), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    pin_rec = [torch.zeros(n, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    pin_out = torch.zeros((n, 320), dtype=torch.int16).pin_memory()
+
+    def p(t):
+        return C.c_void_p(t.data_ptr())
+    for f in range(30):
+        b = f % 2
+        bits = 64 if f < 20 else 120
+        pb = _capi.packet_bytes(bits)
+        pcm = pc.synth_pcm(rng, n, "noise" if f % 4 else "loud")
+        received = (rng.random(n) < 0.85).astype(np.uint8)
+        pk = ref.encode(pcm, bits)
+        out = ref.decode(pk, bits, received=received)
+        pin_pcm[b].numpy()[:] = pcm
+        pin_rec[b].numpy()[:] = received
+        assert lib.lyra_b200_encode(gr.h, None, n, p(pin_pcm[b]), bits, p(pin_pk[b])) == 0
+        got_pk = pin_pk[b].numpy().reshape(-1)[: n * pb].reshape(n, pb)
+        assert np.array_equal(pk, got_pk), f
+        assert lib.lyra_b200_decode(gr.h, None, n, p(pin_pk[b]), p(pin_rec[b]), bits, p(pin_out)) == 0
+        assert np.array_equal(out, pin_out.numpy()), f
+    # 30 encode + 30 decode calls over 2 buffer pairs and 2 bit rates: 4 + 4 captures, every other call is a replay
+    assert gr.graph_replays() >= 40, gr.graph_replays()
+    assert ref.graph_replays() == 0
+    gr.set_graphs(False)
+    pcm = pc.synth_pcm(rng, n, "noise")
+    assert np.array_equal(ref.encode(pcm, 64), gr.encode(pcm, 64))
+    ref.close()
+    gr.close()
+
+
 def test_golden_fixture_packets(gpu_api, sample1):
     """Committed fixtures (tests/golden/oracle_sample1.json): the GPU path reproduces them without the oracle present."""
     with open(os.path.join(GOLDEN_DIR, "oracle_sample1.json")) as f:
