@@ -118,7 +118,7 @@ void AppendDuChunk(std::vector<uint8_t>* out, int rows, int kc, Elem elem, bool 
     }
   const size_t off = out->size();
   if (raw) {                                                     // the unsplit values in the layout of the hi part: the kernel splits them
-    SPEC_CHECK((size_t)kc * rows * 4 == (size_t)kDuRawChunkBytes, "raw UMMA weight chunk shape");
+    SPEC_CHECK((size_t)kc * rows * 4 == (size_t)kDuChunkBytes / 2 && kDuRawUp2, "raw UMMA weight chunk shape");
     out->resize(off + kDuRawChunkBytes, 0);
     std::memcpy(out->data() + off, part.data(), (size_t)kDuRawChunkBytes);
     return;
@@ -523,7 +523,7 @@ DecoderParams BuildDecoder(const TflModel& m, std::vector<uint8_t>* blob) {
         AppendDuChunk(&chunks, 128, 16, [&](int row, int k) {
           const int m = mb * 128 + row, j = m / 320, rc = m % 320, ci = kc * 16 + k;
           return j < 2 ? wu[(size_t)(j * 128 + ci) * 320 + rc] : 0.0f;
-        }, true);
+        }, kDuRawUp2);
     for (int g = 1; g <= 6; ++g) {
       SPEC_CHECK(n.kept[(size_t)g].size() == (size_t)64 * 64, "UMMA decoder: residual-unit GEMM shape");
       const std::vector<float>& w = n.kept[(size_t)g];         // [k = cin][n = cout]

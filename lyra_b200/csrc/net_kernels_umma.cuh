@@ -94,6 +94,9 @@ __device__ __forceinline__ void DuArriveA(DecDUShared* sh) {
 
 // The thread's 64 accumulator columns in four groups of 16, with the tcgen05.ld of group g + 1 in flight while f(g, v) runs
 // (tcgen05.wait::ld covers every earlier load, so the next one is issued right after the wait).  Warp-collective.
+#ifndef LYRA_DU_PIPE
+#define LYRA_DU_PIPE 1
+#endif
 template <typename F>
 __device__ __forceinline__ void DuForEachAccGroup(uint32_t taddr, F f) {
   uint32_t v[2][16];
@@ -101,8 +104,9 @@ __device__ __forceinline__ void DuForEachAccGroup(uint32_t taddr, F f) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     lyra_tmem_wait_ld();
-    if (g < 3) lyra_tmem_ld<16>(taddr + (uint32_t)(16 * (g + 1)), v[(g + 1) & 1]);
+    if (LYRA_DU_PIPE && g < 3) lyra_tmem_ld<16>(taddr + (uint32_t)(16 * (g + 1)), v[(g + 1) & 1]);
     f(g * 16, v[g & 1]);
+    if (!LYRA_DU_PIPE && g < 3) lyra_tmem_ld<16>(taddr + (uint32_t)(16 * (g + 1)), v[(g + 1) & 1]);
   }
 }
 
@@ -184,10 +188,10 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
         const int stg = c % L::kStagesW;
         if (c >= L::kStagesW) lyra_mbar_wait(&sh->w_empty[stg], (unsigned)((c / L::kStagesW - 1) & 1));
         // decoder_2/simple chunks arrive unsplit (half the bytes; the row warps split them in place), the others pre-split
-        const bool raw = c < kDuUp2Chunks;
+        const bool raw = kDuRawUp2 && c < kDuUp2Chunks;
         const unsigned bytes = raw ? (unsigned)kDuRawChunkBytes : (unsigned)kDuChunkBytes;
-        const uint8_t* src = raw ? chunks + (size_t)c * kDuRawChunkBytes
-                                 : chunks + (size_t)kDuUp2Chunks * kDuRawChunkBytes + (size_t)(c - kDuUp2Chunks) * kDuChunkBytes;
+        const uint8_t* src = c < kDuUp2Chunks ? chunks + (size_t)c * kDuRawChunkBytes
+                                              : chunks + (size_t)kDuUp2Chunks * kDuRawChunkBytes + (size_t)(c - kDuUp2Chunks) * kDuChunkBytes;
         LyraMbar* full = raw ? &sh->raw_full[stg] : &sh->w_full[stg];
         if (pair) {
           // arm this CTA's barrier for the whole chunk; this producer fetches its half and multicasts it to both CTAs
@@ -215,7 +219,8 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       auto wait_a = [&]() { lyra_mbar_wait(&sh->a_ready, a_par); a_par ^= 1; lyra_tc_fence_after_sync(); };
       static_assert(kDuUp2Chunks % L::kStagesW == 0, "the split and the pre-split chunks use separate barrier phase sequences");
       auto wait_chunk_at = [&](int ci) -> const unsigned char* {
-        if (ci < kDuUp2Chunks) lyra_mbar_wait(&sh->s_full[ci % L::kStagesW], (unsigned)((ci / L::kStagesW) & 1));
+        if (!kDuRawUp2) lyra_mbar_wait(&sh->w_full[ci % L::kStagesW], (unsigned)((ci / L::kStagesW) & 1));
+        else if (ci < kDuUp2Chunks) lyra_mbar_wait(&sh->s_full[ci % L::kStagesW], (unsigned)((ci / L::kStagesW) & 1));
         else lyra_mbar_wait(&sh->w_full[ci % L::kStagesW], (unsigned)(((ci - kDuUp2Chunks) / L::kStagesW) & 1));
         lyra_tc_fence_after_sync();
         return wring + (size_t)(ci % L::kStagesW) * kDuChunkBytes;
@@ -319,7 +324,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
     // ---- decoder_2/simple weights: every chunk lands as plain fp32 in the hi half of its stage; split it in place (hi stays,
     //      lo goes to the other half) while the tensor core works on the previous one.  All eight row warps: they have nothing
     //      else to do until the layer's accumulators are complete.
-    for (int c = 0; c < kDuUp2Chunks; ++c) {
+    for (int c = 0; kDuRawUp2 && c < kDuUp2Chunks; ++c) {
       const int stg = c % L::kStagesW;
       lyra_mbar_wait(&sh->raw_full[stg], (unsigned)((c / L::kStagesW) & 1));
       float4* wh = reinterpret_cast<float4*>(wring + (size_t)stg * kDuChunkBytes);

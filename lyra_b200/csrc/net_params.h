@@ -74,7 +74,11 @@ struct UpI8 {
 constexpr int kDuChunkBytes = 16384;
 // decoder_2/simple's chunks (the delivery-bound part of the stream) travel as plain fp32 - the hi half of a stage - and are split
 // into hi | lo in shared memory by the kernel's row warps; the other chunks are stored pre-split
-constexpr int kDuRawChunkBytes = kDuChunkBytes / 2;
+#ifndef LYRA_DU_RAW
+#define LYRA_DU_RAW 1
+#endif
+constexpr bool kDuRawUp2 = LYRA_DU_RAW != 0;
+constexpr int kDuRawChunkBytes = kDuRawUp2 ? kDuChunkBytes / 2 : kDuChunkBytes;   // bytes of one decoder_2/simple chunk in the blob
 constexpr int kDuNumChunks = 54;
 constexpr int kDuUp2Chunks = 40, kDuUnitChunk0 = 40, kDuLastChunk0 = 52;
 
