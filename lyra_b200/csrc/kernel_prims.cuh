@@ -22,7 +22,9 @@ __device__ __forceinline__ const T* BlobPtr(const uint8_t* blob, uint32_t off) {
   return reinterpret_cast<const T*>(blob + off);
 }
 
-__device__ __forceinline__ float LeakyRelu(float v) { return v > 0.0f ? v : __fmul_rn(v, 0.3f); }
+// LeakyReLU(0.3): v > 0 ? v : 0.3 v.  For a slope below one that is max(v, 0.3 v) - one multiply and one FMNMX instead of a
+// compare, a multiply and a select - with the same result for every input (0.3 v < v for v > 0, > v for v < 0, -0 stays -0).
+__device__ __forceinline__ float LeakyRelu(float v) { return fmaxf(v, __fmul_rn(v, 0.3f)); }
 
 // TFLite reference AffineQuantize: round-half-away(v / scale) + zp, clamped to int8
 __device__ __forceinline__ int QuantizeF32(float v, float scale, int zp) {

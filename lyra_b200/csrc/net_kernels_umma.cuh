@@ -19,8 +19,9 @@
 //               residual unit's epilogue leaves in tensor memory; the four taps are summed across time rows afterwards.
 //   weights     pre-split on the host into hi / lo core-matrix chunks (net_params.h kDuChunkBytes), streamed by one producer
 //               thread with TMA bulk copies through a 2-stage shared-memory ring; a stage is released by tcgen05.commit when
-//               the MMAs that read it have completed.  decoder_2/simple's chunks (three quarters of the stream, and the phase
-//               that is bound by its delivery) travel unsplit - half the bytes - and are split in place by the row warps.
+//               the MMAs that read it have completed.  Build switch LYRA_DU_RAW=1: decoder_2/simple's chunks (three quarters of
+//               the stream) travel unsplit - half the bytes - and the row warps split them in place.  Measured slower (that
+//               phase 26 k -> 34 k cycles): with two stages the TMA -> split -> MMA -> release chain is longer than the bytes saved.
 //   state       contiguous blocks (kernel C's tile, overlap tails, ring blocks, depthwise parameters) move by TMA bulk copies,
 //               in both directions; blocks are written back whole, with the lanes of inactive streams left as loaded.
 //   roles       warps 0..7: rows / epilogues / state;  warp 8 lane 0: MMA issue;  warp 9 lane 0: TMA producer.
@@ -55,7 +56,8 @@ struct DecDU {
   static constexpr int kSl = kOv + 64 * 5 * S * 4;            // last_layer carried tail f32 [48][8]
   static constexpr int kSlOut = kSl + 48 * S * 4;             // ... and its successor
   static constexpr int kDw = kSlOut + 48 * S * 4;             // depthwise parameters of the three units: w [3][64] | bias [64] each
-  static constexpr int kW = kDw + 3 * 256 * 4;                // weight ring
+  static constexpr int kDw4 = kDw + 3 * 256 * 4;              // the same per channel: float4 {w0, w1, w2, bias} [3][64] (one LDS.128 per element)
+  static constexpr int kW = kDw4 + 3 * 256 * 4;               // weight ring
   static constexpr int kI = kW + kStagesW * kDuChunkBytes;    // slot[S], active[S], n18[S]
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;     // + n18[S]
   static_assert(kMid + 128 * 4 * S * 4 <= kRingEnd, "X and the staged tile must fit under the ring blocks");
@@ -304,6 +306,11 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
 
     // ---- X: kernel C's tile [128 ch][4 rows][8 streams] -> B operand (split, core-matrix layout, row = (x-row, stream), k = ch)
     lyra_mbar_wait(&sh->in_full, 0);
+    if (tid < 3 * 64) {                                       // depthwise parameters per channel (read after several barriers)
+      const int un = tid / 64, c = tid % 64;
+      const float* w = smf + L::kDw / 4 + un * 256;
+      reinterpret_cast<float4*>(smf + L::kDw4 / 4)[tid] = make_float4(w[c], w[64 + c], w[128 + c], w[192 + c]);
+    }
     {
       const float* in = smf + L::kMid / 4;
       float* xh = smf + L::kXc / 4;
@@ -402,7 +409,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       // depthwise conv (k = 3, dilation dil) over LeakyReLU(u) -> A operand (hi, lo) of pw1.  Rows before this frame come from
       // the ring (already activated): source offset, channel stride and negative slope are selected once, the loop is branch-free
       if (has_row) {
-        const float* w = smf + L::kDw / 4 + unit * 256;
+        const float4* w4 = reinterpret_cast<const float4*>(smf + L::kDw4 / 4) + unit * 64;      // per channel {w0, w1, w2, bias}
         const bool r1 = t - dil < 0, r0 = t - 2 * dil < 0;
         const int o2 = L::kU / 4 + row;
         const int o1 = r1 ? ring_off + ((base + t - dil + 2 * R) % R) * S + s : L::kU / 4 + row - dil * S;
@@ -415,13 +422,14 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
           for (int j = 0; j < 16; ++j) {
             const int c = c0 + j;
             float x2 = smf[o2 + c * LDU], x1 = smf[o1 + c * st1], x0 = smf[o0 + c * st0];
-            x2 = x2 > 0.0f ? x2 : __fmul_rn(x2, 0.3f);
-            x1 = x1 > 0.0f ? x1 : __fmul_rn(x1, n1);
-            x0 = x0 > 0.0f ? x0 : __fmul_rn(x0, n0);
-            float acc = __fmaf_rn(x0, w[c], 0.0f);
-            acc = __fmaf_rn(x1, w[64 + c], acc);
-            acc = __fmaf_rn(x2, w[128 + c], acc);
-            DuSplit(__fadd_rn(acc, w[192 + c]), hi[j], lo[j]);
+            const float4 wc = w4[c];
+            x2 = fmaxf(x2, __fmul_rn(x2, 0.3f));            // LeakyReLU; ring rows are stored activated: slope 1 leaves them as they are
+            x1 = fmaxf(x1, __fmul_rn(x1, n1));
+            x0 = fmaxf(x0, __fmul_rn(x0, n0));
+            float acc = __fmaf_rn(x0, wc.x, 0.0f);
+            acc = __fmaf_rn(x1, wc.y, acc);
+            acc = __fmaf_rn(x2, wc.z, acc);
+            DuSplit(__fadd_rn(acc, wc.w), hi[j], lo[j]);
           }
           lyra_tmem_st<16>(trow + L::kColAhi + (uint32_t)c0, hi);
           lyra_tmem_st<16>(trow + L::kColAlo + (uint32_t)c0, lo);
@@ -439,7 +447,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
 #pragma unroll 16
         for (int c = c_lo; c < c_lo + 32; ++c) {
           const float x = smf[oi + c * LDU];
-          smf[ow + c * (R * S)] = x > 0.0f ? x : __fmul_rn(x, 0.3f);
+          smf[ow + c * (R * S)] = LeakyRelu(x);
         }
       };
       ring_update(0);

@@ -72,10 +72,10 @@ struct UpI8 {
 //   chunks 52..53  last_layer as ONE 64 x 64 GEMM: B row = tap * 16 + n (n = output sample within the stride), k = cin;
 //                  the four taps are summed across time rows in the epilogue
 constexpr int kDuChunkBytes = 16384;
-// decoder_2/simple's chunks (the delivery-bound part of the stream) travel as plain fp32 - the hi half of a stage - and are split
-// into hi | lo in shared memory by the kernel's row warps; the other chunks are stored pre-split
+// LYRA_DU_RAW=1 (experiment, off): decoder_2/simple's chunks travel as plain fp32 - the hi half of a stage - and are split into
+// hi | lo in shared memory by the kernel's row warps; by default every chunk is stored pre-split
 #ifndef LYRA_DU_RAW
-#define LYRA_DU_RAW 1
+#define LYRA_DU_RAW 0
 #endif
 constexpr bool kDuRawUp2 = LYRA_DU_RAW != 0;
 constexpr int kDuRawChunkBytes = kDuRawUp2 ? kDuChunkBytes / 2 : kDuChunkBytes;   // bytes of one decoder_2/simple chunk in the blob
