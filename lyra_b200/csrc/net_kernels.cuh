@@ -20,6 +20,12 @@
 #define LYRA_BC_MIN_BLOCKS 3
 #endif
 // output channels per fp32 thread tile in the small-M layers of kernels B / C (8 streams x LYRA_BC_TN channels)
+#ifndef LYRA_B_MIN_BLOCKS
+#define LYRA_B_MIN_BLOCKS LYRA_BC_MIN_BLOCKS
+#endif
+#ifndef LYRA_C_MIN_BLOCKS
+#define LYRA_C_MIN_BLOCKS LYRA_BC_MIN_BLOCKS
+#endif
 #ifndef LYRA_BC_STAGES
 #define LYRA_BC_STAGES 3
 #endif
@@ -385,7 +391,7 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 template <int S>
 struct EncB {
   static constexpr int NT = 256;
-  static constexpr int kMinBlocks = S <= 8 ? LYRA_BC_MIN_BLOCKS : 1;
+  static constexpr int kMinBlocks = S <= 8 ? LYRA_B_MIN_BLOCKS : 1;
   static constexpr int TM = 8;                            // streams per fp32 thread tile (8 x 4 tiles: fewer smem wavefronts per FMA)
   static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
   static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;
@@ -592,7 +598,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
 template <int S, bool TC = false>
 struct DecC {
   static constexpr int NT = 256;
-  static constexpr int kMinBlocks = S <= 8 ? LYRA_BC_MIN_BLOCKS : 1;
+  static constexpr int kMinBlocks = S <= 8 ? LYRA_C_MIN_BLOCKS : 1;
   static constexpr int TM = 8;                            // streams per fp32 thread tile (8 x 4 tiles: fewer smem wavefronts per FMA)
   static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
   static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;

@@ -51,3 +51,23 @@ def test_two_rank_sharded_encode_matches_single_process(tmp_path, oracle):
     for f in range(2):
         for k in range(n):
             assert bytes(got[f, k]) == codecs[k].encode(pcm[f, k], 64)[0]
+
+
+def test_bench_rank_core_slices_are_disjoint():
+    # bench.py: under torchrun every rank keeps its host threads on its own slice of the allowed cores (host-buffer pass);
+    # run in subprocesses because the call changes the process's affinity mask
+    import json
+    import subprocess
+    code = ("import json, os, sys; sys.path.insert(0, %r); import bench; base = sorted(os.sched_getaffinity(0)); "
+            "r = bench.pin_rank_cores(int(sys.argv[1]), int(sys.argv[2])); "
+            "print(json.dumps({'ret': r, 'base': base, 'now': sorted(os.sched_getaffinity(0)), 'cores': bench.host_cores()}))" % ROOT)
+    outs = [json.loads(subprocess.check_output([sys.executable, "-c", code, str(r), "2"]).decode().strip().splitlines()[-1]) for r in range(2)]
+    base = outs[0]["base"]
+    if len(base) < 4:
+        assert outs[0]["ret"] is None and outs[0]["now"] == base      # too few cores to slice: left alone
+        return
+    a, b = set(outs[0]["now"]), set(outs[1]["now"])
+    assert a and b and not (a & b) and (a | b) <= set(base)
+    assert outs[0]["ret"] == len(a) == len(base) // 2 and outs[0]["cores"] <= len(a)
+    single = json.loads(subprocess.check_output([sys.executable, "-c", code, "0", "1"]).decode().strip().splitlines()[-1])
+    assert single["ret"] is None and single["now"] == single["base"]
