@@ -43,26 +43,29 @@ struct DecDU {
   static constexpr int kStagesW = 2;
   static constexpr int LDU = 161;                             // u: f32 [64][LDU], element (c, row = t * 8 + s); odd stride: lanes that
                                                               // differ in c (decoder_2/simple epilogue) hit different banks
-  // shared memory (bytes)
+  // shared memory (bytes): 110 KB, sized so that a kernel-A block (105 KB, 96 registers x 320 threads) fits on the SM beside this
+  // kernel's block: the FMA-bound encoder front end then fills the issue slots this latency-bound kernel leaves empty.
+  //   u        the residual stream of the three units, f32 [64][LDU]
+  //   region   decoder_2/simple's B operand X (hi | lo, 32 KB)  ->  once its MMAs are done: the carried overlap tail (10 KB), the ring
+  //            blocks of units 0 and 1 (4 + 12 KB), PCM staging.  Unit 2's ring block (36 KB, dilation 9) stays in global memory (L2):
+  //            its rows are read and replaced in place.  Kernel C's tile is read from global memory as well.
   static constexpr int kU = 0;
   static constexpr int kXc = kU + 64 * LDU * 4;               // decoder_2/simple B operand: hi | lo, each [128/4][4][8][4] f32
   static constexpr int kXPart = 32 * 4 * 32 * 4;              // 16,384
-  static constexpr int kMid = kXc + 2 * kXPart;               // kernel C's tile as it lies in HBM: f32 [128][4][8]
-  static constexpr int kRing = kXc;                           // later: the three ring blocks [64][R][8] f32, R = 2, 6, 18
-  static constexpr int kRing0 = kRing, kRing1 = kRing0 + 64 * 2 * S * 4, kRing2 = kRing1 + 64 * 6 * S * 4;
-  static constexpr int kRingEnd = kRing2 + 64 * 18 * S * 4;   // 53,248 bytes of rings over X (32,768) + tile (16,384)
-  static constexpr int kStage = kRing;                        // at the end: PCM staging int16 [8][320]
-  static constexpr int kOv = kRingEnd;                        // decoder_2/simple overlap tail f32 [64][5][8]: loaded, consumed, rewritten, stored
-  static constexpr int kSl = kOv + 64 * 5 * S * 4;            // last_layer carried tail f32 [48][8]
+  static constexpr int kRegion = kXc, kRegionBytes = 2 * kXPart;
+  static constexpr int kOv = kRegion;                         // decoder_2/simple overlap tail f32 [64][5][8]: loaded, consumed, rewritten, stored
+  static constexpr int kRing0 = kOv + 64 * 5 * S * 4, kRing1 = kRing0 + 64 * 2 * S * 4;     // ring blocks [64][R][8] f32, R = 2, 6
+  static constexpr int kStage = kRing1 + 64 * 6 * S * 4;      // at the end: PCM staging int16 [8][320]
+  static constexpr int kSl = kRegion + kRegionBytes;          // last_layer carried tail f32 [48][8]
   static constexpr int kSlOut = kSl + 48 * S * 4;             // ... and its successor
-  static constexpr int kDw = kSlOut + 48 * S * 4;             // depthwise parameters of the three units: w [3][64] | bias [64] each
-  static constexpr int kDw4 = kDw + 3 * 256 * 4;              // the same per channel: float4 {w0, w1, w2, bias} [3][64] (one LDS.128 per element)
+  static constexpr int kDw4 = kSlOut + 48 * S * 4;            // depthwise parameters per channel: float4 {w0, w1, w2, bias} [3][64]
   static constexpr int kW = kDw4 + 3 * 256 * 4;               // weight ring
   static constexpr int kI = kW + kStagesW * kDuChunkBytes;    // slot[S], active[S], n18[S]
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;     // + n18[S]
-  static_assert(kMid + 128 * 4 * S * 4 <= kRingEnd, "X and the staged tile must fit under the ring blocks");
-  static_assert(S * 320 * 2 <= kRingEnd - kRing, "PCM staging must fit in the ring region");
-  static_assert(kXc % 128 == 0 && kOv % 128 == 0 && kW % 128 == 0 && kDw % 16 == 0, "bulk-copy / descriptor alignment");
+  static_assert(kStage + S * 320 * 2 <= kRegion + kRegionBytes, "overlap tail, two ring blocks and PCM staging must fit in the X region");
+  static_assert(kXc % 128 == 0 && kOv % 128 == 0 && kRing0 % 128 == 0 && kRing1 % 128 == 0 && kW % 128 == 0 && kSl % 16 == 0 && kDw4 % 16 == 0,
+                "bulk-copy / descriptor alignment");
+  static_assert(kSmemBytes <= 113 * 1024, "must leave room for a kernel-A block on the SM");
   // tensor memory columns (512 allocated).  decoder_2/simple: block mb at columns 32 mb.  Afterwards per row block rb: A hi | A lo | D
   static constexpr int kTmemCols = 512;
   static constexpr int kColAhi = 0, kColAlo = 64, kColD = 128, kRbStride = 192;
@@ -72,10 +75,11 @@ struct DecDUShared {
   LyraMbar w_full[DecDU::kStagesW], w_empty[DecDU::kStagesW];
   LyraMbar raw_full[DecDU::kStagesW];   // producer -> row warps: an unsplit decoder_2/simple chunk has landed in the stage's hi half
   LyraMbar s_full[DecDU::kStagesW];     // row warps -> MMA issuer: the chunk is split (hi | lo) in place
-  LyraMbar in_full;        // producer -> row warps: tile, overlap tail, last_layer tail and depthwise parameters have landed
+  LyraMbar in_full;        // producer -> row warps: the last_layer tail has landed
+  LyraMbar ov_full;        // producer -> row warps: the overlap tail has landed (in the X region, after decoder_2/simple's MMAs)
   LyraMbar a_ready;        // row warps -> MMA issuer: the operand of the next GEMM is in place
   LyraMbar d_ready;        // MMA issuer -> row warps: the accumulators of the GEMM are complete
-  LyraMbar ring_full[3];   // producer -> row warps: ring block u has landed
+  LyraMbar ring_full[2];   // producer -> row warps: ring block u (units 0, 1) has landed
   uint32_t tmem_base;
 };
 
@@ -157,9 +161,10 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       lyra_mbar_init(&sh->s_full[i], L::kRowWarps);
     }
     lyra_mbar_init(&sh->in_full, 1);
+    lyra_mbar_init(&sh->ov_full, 1);
     lyra_mbar_init(&sh->a_ready, L::kRowWarps);
     lyra_mbar_init(&sh->d_ready, 1);
-    for (int i = 0; i < 3; ++i) lyra_mbar_init(&sh->ring_full[i], 1);
+    for (int i = 0; i < 2; ++i) lyra_mbar_init(&sh->ring_full[i], 1);
     lyra_mbar_fence_init();
   }
   if (warp == L::kMmaWarp) { lyra_tmem_alloc(&sh->tmem_base, L::kTmemCols); lyra_tc_fence_before_sync(); }
@@ -177,15 +182,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   if (idle) {
   } else if (warp == L::kTmaWarp) {
     if (lane == 0) {
-      lyra_bulk_multi_begin(&sh->in_full, 128u * 4 * S * 4 + 64u * 5 * S * 4 + 48u * S * 4 + 3u * 1024);
-      lyra_bulk_multi_copy(smem + L::kMid, mid + (size_t)tile * 128 * 4 * S, 128u * 4 * S * 4, &sh->in_full);
-      lyra_bulk_multi_copy(ov, st + (size_t)DecStateD::kUp2 * S, 64u * 5 * S * 4, &sh->in_full);
-      lyra_bulk_multi_copy(sl, st + (size_t)DecStateD::kLast * S, 48u * S * 4, &sh->in_full);
-      for (int un = 0; un < 3; ++un) {
-        lyra_bulk_multi_copy(smem + L::kDw + un * 1024, blob + P.r2[un].dw.w, 768u, &sh->in_full);
-        lyra_bulk_multi_copy(smem + L::kDw + un * 1024 + 768, blob + P.r2[un].dw.bias, 256u, &sh->in_full);
-      }
-      lyra_bulk_multi_end(&sh->in_full);
+      lyra_bulk_g2s(sl, st + (size_t)DecStateD::kLast * S, 48u * S * 4, &sh->in_full);
       for (int c = 0; c < kDuNumChunks; ++c) {
         const int stg = c % L::kStagesW;
         if (c >= L::kStagesW) lyra_mbar_wait(&sh->w_empty[stg], (unsigned)((c / L::kStagesW - 1) & 1));
@@ -204,10 +201,11 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
           lyra_bulk_g2s(wring + (size_t)stg * kDuChunkBytes, src, bytes, full);
         }
         if (c == kDuUp2Chunks + L::kStagesW - 1) {
-          // the wait above covered the last decoder_2/simple chunk's MMAs, the last readers of X: the ring blocks may land on it
+          // the wait above covered the last decoder_2/simple chunk's MMAs, the last readers of X: the overlap tail and the ring
+          // blocks of units 0 and 1 may land on it
+          lyra_bulk_g2s(ov, st + (size_t)DecStateD::kUp2 * S, 64u * 5 * S * 4, &sh->ov_full);
           lyra_bulk_g2s(smem + L::kRing0, st + (size_t)DecStateD::kRing0 * S, 64u * 2 * S * 4, &sh->ring_full[0]);
           lyra_bulk_g2s(smem + L::kRing1, st + (size_t)DecStateD::kRing1 * S, 64u * 6 * S * 4, &sh->ring_full[1]);
-          lyra_bulk_g2s(smem + L::kRing2, st + (size_t)DecStateD::kRing2 * S, 64u * 18 * S * 4, &sh->ring_full[2]);
         }
       }
     }
@@ -305,14 +303,13 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
     auto row_sync = [&]() { lyra_named_bar_sync(1, L::kRowThreads); };
 
     // ---- X: kernel C's tile [128 ch][4 rows][8 streams] -> B operand (split, core-matrix layout, row = (x-row, stream), k = ch)
-    lyra_mbar_wait(&sh->in_full, 0);
     if (tid < 3 * 64) {                                       // depthwise parameters per channel (read after several barriers)
       const int un = tid / 64, c = tid % 64;
-      const float* w = smf + L::kDw / 4 + un * 256;
-      reinterpret_cast<float4*>(smf + L::kDw4 / 4)[tid] = make_float4(w[c], w[64 + c], w[128 + c], w[192 + c]);
+      const float* w = BlobPtr<float>(blob, P.r2[un].dw.w);
+      reinterpret_cast<float4*>(smf + L::kDw4 / 4)[tid] = make_float4(w[c], w[64 + c], w[128 + c], BlobPtr<float>(blob, P.r2[un].dw.bias)[c]);
     }
     {
-      const float* in = smf + L::kMid / 4;
+      const float* in = mid + (size_t)tile * 128 * 4 * S;     // kernel C's tile, straight from global memory (L2): 16 floats per thread
       float* xh = smf + L::kXc / 4;
       float* xl = xh + L::kXPart / 4;
       for (int item = tid; item < 32 * 4 * 8; item += L::kRowThreads) {
@@ -354,6 +351,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
     //      out[q][r][co] = (P[j=1][x=q] + bias + carried overlap (q = 0)) + P[j=0][x=q-1]; q = 4 is the new overlap tail.
     //      Pass 0 stores the j = 1 terms (every element of u), pass 1 adds the j = 0 terms.  j is uniform per (warp, block).
     wait_d();
+    lyra_mbar_wait(&sh->ov_full, 0);                         // the carried overlap tail (it landed on X once the MMAs above were done)
     LYRA_PHASE(3, ph);
     {
       const float* b = BlobPtr<float>(blob, P.up2.bias);
@@ -400,28 +398,36 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
     auto unit_body = [&](auto unit_c) {
       constexpr int unit = decltype(unit_c)::value;
       constexpr int dil = unit == 0 ? 1 : (unit == 1 ? 3 : 9), R = 2 * dil;
-      constexpr int ring_off = (unit == 0 ? L::kRing0 : (unit == 1 ? L::kRing1 : L::kRing2)) / 4;     // [64][R][S] f32
+      // units 0, 1: ring block in shared memory (bulk-loaded, bulk-stored); unit 2 (R = 18, 36 KB): rows are read from and written
+      // to the global block directly - a thread touches 32-byte runs of 8 streams, and every read precedes the row barrier
+      // that the writes follow, exactly as for the shared-memory blocks
+      constexpr bool ring_in_smem = unit < 2;
+      constexpr int ring_off = (unit == 0 ? L::kRing0 : L::kRing1) / 4;                             // [64][R][S] f32 (units 0, 1)
       const ResF32& p = P.r2[unit];
       float* gring = st + (size_t)(unit == 0 ? DecStateD::kRing0 : (unit == 1 ? DecStateD::kRing1 : DecStateD::kRing2)) * S;
+      const float* ringp = ring_in_smem ? smf + ring_off : gring;
       const int base = (n18[s] * 20) % R;                    // ring slot of this frame's row 0 for this stream
-      lyra_mbar_wait(&sh->ring_full[unit], 0);
+      if (ring_in_smem) lyra_mbar_wait(&sh->ring_full[unit < 2 ? unit : 0], 0);
       LYRA_PHASE(3, ph);
       // depthwise conv (k = 3, dilation dil) over LeakyReLU(u) -> A operand (hi, lo) of pw1.  Rows before this frame come from
-      // the ring (already activated): source offset, channel stride and negative slope are selected once, the loop is branch-free
+      // the ring (already activated): source pointer, channel stride and negative slope are selected once, the loop is branch-free
       if (has_row) {
         const float4* w4 = reinterpret_cast<const float4*>(smf + L::kDw4 / 4) + unit * 64;      // per channel {w0, w1, w2, bias}
         const bool r1 = t - dil < 0, r0 = t - 2 * dil < 0;
-        const int o2 = L::kU / 4 + row;
-        const int o1 = r1 ? ring_off + ((base + t - dil + 2 * R) % R) * S + s : L::kU / 4 + row - dil * S;
-        const int o0 = r0 ? ring_off + ((base + t - 2 * dil + 2 * R) % R) * S + s : L::kU / 4 + row - 2 * dil * S;
+        const float* p2 = u + row;
+        const float* p1 = r1 ? ringp + ((base + t - dil + 2 * R) % R) * S + s : u + row - dil * S;
+        const float* p0 = r0 ? ringp + ((base + t - 2 * dil + 2 * R) % R) * S + s : u + row - 2 * dil * S;
         const int st1 = r1 ? R * S : LDU, st0 = r0 ? R * S : LDU;
         const float n1 = r1 ? 1.0f : 0.3f, n0 = r0 ? 1.0f : 0.3f;
         for (int c0 = 0; c0 < 64; c0 += 16) {
           uint32_t hi[16], lo[16];
+          float x1v[16], x0v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { x1v[j] = p1[(c0 + j) * st1]; x0v[j] = p0[(c0 + j) * st0]; }      // the (possibly global) loads first
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int c = c0 + j;
-            float x2 = smf[o2 + c * LDU], x1 = smf[o1 + c * st1], x0 = smf[o0 + c * st0];
+            float x2 = p2[c * LDU], x1 = x1v[j], x0 = x0v[j];
             const float4 wc = w4[c];
             x2 = fmaxf(x2, __fmul_rn(x2, 0.3f));            // LeakyReLU; ring rows are stored activated: slope 1 leaves them as they are
             x1 = fmaxf(x1, __fmul_rn(x1, n1));
@@ -443,12 +449,10 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       const bool upd = has_row && t >= 20 - R && active[s];
       auto ring_update = [&](int c_lo) {
         if (!upd) return;
-        const int ow = ring_off + ((base + t) % R) * S + s, oi = L::kU / 4 + row;
+        float* wp = (ring_in_smem ? smf + ring_off : gring) + ((base + t) % R) * S + s;
+        const float* ip = u + row;
 #pragma unroll 16
-        for (int c = c_lo; c < c_lo + 32; ++c) {
-          const float x = smf[oi + c * LDU];
-          smf[ow + c * (R * S)] = LeakyRelu(x);
-        }
+        for (int c = c_lo; c < c_lo + 32; ++c) wp[c * (R * S)] = LeakyRelu(ip[c * LDU]);
       };
       ring_update(0);
       LYRA_PHASE(3, ph);
@@ -469,7 +473,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
       ring_update(32);
       lyra_fence_proxy_async();
       row_sync();
-      if (tid == 0) { lyra_bulk_s2g(gring, smf + ring_off, (unsigned)(64 * R * S * 4)); lyra_bulk_commit(); }
+      if (ring_in_smem && tid == 0) { lyra_bulk_s2g(gring, smf + ring_off, (unsigned)(64 * R * S * 4)); lyra_bulk_commit(); }
       LYRA_PHASE(3, ph);
       // pw2 epilogue: bias + residual.  Units 0, 1: u' back to shared memory (the next depthwise conv reads neighbouring rows);
       // unit 2: LeakyReLU(u') straight into tensor memory as the A operand of last_layer
@@ -514,7 +518,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
         for (int j = 0; j < 16; ++j) uc[(c0 + j) * LDU] = __uint_as_float(v[j]);
       });
     }
-    if (tid == 0) lyra_bulk_wait_read();                     // the ring blocks' bulk stores have read them: PCM staging may alias
+    lyra_mbar_wait(&sh->in_full, 0);                         // the carried last_layer tail (loaded at kernel start)
     row_sync();
     int16_t* stage = reinterpret_cast<int16_t*>(smem + L::kStage);      // [S][320]
     if (tid < 23 * S) {
