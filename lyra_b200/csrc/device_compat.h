@@ -414,6 +414,7 @@ __device__ __forceinline__ void lyra_tmem_wait_st() { asm volatile("tcgen05.wait
 //      group may be overwritten, lyra_bulk_wait_all() once the writes themselves are complete.  One thread issues and waits.
 #if defined(LYRA_EMU)
 static inline void lyra_bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) { std::memcpy(gmem_dst, smem_src, bytes); }
+static inline void lyra_prefetch_l2(const void*, unsigned) {}
 static inline void lyra_bulk_commit() {}
 static inline void lyra_bulk_wait_read() {}
 static inline void lyra_bulk_wait_all() {}
@@ -426,6 +427,10 @@ static inline void lyra_named_bar_sync(int id, int nthreads) {
   while (st[1] == gen) cuda_emu::yield();
 }
 #elif defined(__CUDACC__)
+// asks the L2 to fetch `bytes` (multiple of 16) starting at the 16-byte aligned global address: a hint, no completion to wait for
+__device__ __forceinline__ void lyra_prefetch_l2(const void* gmem, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void lyra_bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(lyra_smem_u32(smem_src)), "r"(bytes) : "memory");
 }

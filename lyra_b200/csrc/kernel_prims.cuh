@@ -408,10 +408,13 @@ __device__ __forceinline__ void SplitTf32(float x, uint32_t& hi, uint32_t& lo) {
   lo = __float_as_uint(__fsub_rn(x, __uint_as_float(hi)));
 }
 
+#ifndef LYRA_TF32_PD
+#define LYRA_TF32_PD 4
+#endif
 template <int S, int NT, int WTM, int WTN, bool SYNC_EPI, typename Epi>
 __device__ __forceinline__ void GemmTf32Mma(const float* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
                                             int groups, int T_out, int N, const float2* __restrict__ Wf, Epi epi) {
-  constexpr int PD = 2;
+  constexpr int PD = LYRA_TF32_PD;      // k-steps of B fragments in flight from L2 (registers: 2 x WTN per step)
   constexpr int NW = NT / 32;
   const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
   const int M = T_out * S, MT = (M + 15) / 16, MTW = (MT + WTM - 1) / WTM, NTILES = N / 8, NWT = MTW * (NTILES / WTN);

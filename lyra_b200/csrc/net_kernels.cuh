@@ -108,6 +108,17 @@ __device__ __forceinline__ void LoadTileMeta(const TileIo& io, const int* n18_gl
 }
 constexpr int kTileIdle = -2;
 
+// The tile's streaming state (one contiguous block per kernel, 65-190 KB; the 262 MB working set of 4096 streams does not stay
+// in the 126 MB L2 between hops) is requested into the L2 as soon as the block knows its tile: the ring / tail loads of the
+// later phases then find it there instead of paying the HBM latency phase by phase.
+#ifndef LYRA_PREFETCH_STATE
+#define LYRA_PREFETCH_STATE 1
+#endif
+template <int ON>
+__device__ __forceinline__ void PrefetchTileState(const void* p, int bytes) {
+  if (ON && threadIdx.x == 0) lyra_prefetch_l2(p, (unsigned)bytes);
+}
+
 // One fp32 residual unit:  d = dw(lrelu(u)); h = lrelu(pw1(d)); u' = pw2(h) + u.
 // u lives at row offset row0u of a [C][ldu] buffer; d is a [C][LDD] scratch.  When `last`, lrelu(u') is stored.
 // TC (decoder tensor-core mode): the two 1x1 convolutions run as split-precision TF32 MMAs with warp tiles of
@@ -316,6 +327,7 @@ EncoderKernelA(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   if (n18[S] == kTileIdle) return;
   float* st = state + (size_t)tile * EncStateA::kUnits * S;
   const int tid = (int)threadIdx.x;
+  PrefetchTileState<LYRA_PREFETCH_STATE>(st, EncStateA::kUnits * S * 4);
   IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.first.w), 16, 64, 64));
   int ph = 0;
   LYRA_PHASE(0, ph);
@@ -445,6 +457,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * EncStateB::kUnits * S;
   float* st = reinterpret_cast<float*>(stw);
   const int tid = (int)threadIdx.x;
+  PrefetchTileState<LYRA_PREFETCH_STATE>(st, EncStateB::kUnits * S * 4);
   IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128, nullptr, L::kStg));
   int ph = 0;
   LYRA_PHASE(1, ph);
@@ -653,6 +666,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   uint32_t* stw = reinterpret_cast<uint32_t*>(state) + (size_t)tile * DecStateC::kUnits * S;
   float* st = reinterpret_cast<float*>(stw);
   const int tid = (int)threadIdx.x;
+  PrefetchTileState<LYRA_PREFETCH_STATE>(st, DecStateC::kUnits * S * 4);
   constexpr int LD2 = 2 * S;
   const UpI8& up0 = P.up0;
   const UpI8& up1 = P.up1;
@@ -879,6 +893,7 @@ DecoderKernelD(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, con
   if (n18[S] == kTileIdle) return;
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const int tid = (int)threadIdx.x;
+  PrefetchTileState<LYRA_PREFETCH_STATE>(st, DecStateD::kUnits * S * 4);
   constexpr int LDX = L::LDX;
   float* wbuf_up2 = X + 128 * LDX;       // free tail of d + the regular ring
   if (!TC) IssuePrologue<NT>(wbuf_up2, NextF32(BlobPtr<float>(blob, P.up2.w), L::KCU, 320, 256));
