@@ -15,6 +15,11 @@
 #include "device_compat.h"
 #include "net_params.h"
 
+// register prefetch depth (k-steps) of the int8 B fragments that GemmI8Mma takes straight from L2; 3 and 4 spill at 80 registers
+#ifndef LYRA_I8_PD
+#define LYRA_I8_PD 2
+#endif
+
 namespace lyra_b200 {
 
 template <typename T>
@@ -318,7 +323,7 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 template <int S, int NT, int NTW, typename Epi>
 __device__ __forceinline__ void GemmI8Mma(const uint32_t* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
                                           int groups, int T_out, int N, const uint2* __restrict__ Wf, Epi epi) {
-  constexpr int PD = 2;      // register prefetch depth of the B fragments (k-steps); deeper spills at 3 blocks/SM
+  constexpr int PD = LYRA_I8_PD;      // register prefetch depth of the B fragments (k-steps)
   const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
   const int M = T_out * S, MT = (M + 15) / 16, NTILES = N / 8, NWT = MT * (NTILES / NTW);
   const int CinG4 = CinG / 4, KS = ntaps * CinG4 / 8, CoutG = N / groups;
