@@ -176,7 +176,8 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const uint8_t* chunks = blob + P.du_chunks;
   int ph = 0;
-  const bool idle = n18[S] == kTileIdle;                      // every stream of the tile sits this call out: nothing to do (pair is false then)
+  const bool idle = n18[S] == kTileIdle;
+  if (!idle) PrefetchTileState<LYRA_PREFETCH_STATE>(st, DecStateD::kUnits * S * 4);      // unit 2 reads its ring block from global memory                      // every stream of the tile sits this call out: nothing to do (pair is false then)
 
   // ================================================= TMA producer =================================================
   if (idle) {
