@@ -90,7 +90,7 @@ __device__ __forceinline__ void BatchedLoop(int n, LoadFn ld, StoreFn st) {
 // Two barrier sets alternate between consecutive GEMMs so that the first chunks of the NEXT GEMM can be issued
 // (into the other set) before the current GEMM's epilogue; each GEMM re-initialises the set its successor will use.
 constexpr int kStages = 3;       // default ring depth; a GEMM may ask for more (template parameter STG, at most kMaxStages)
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
 
 struct WeightPipe {
   LyraMbar full[2][kMaxStages];

@@ -29,6 +29,9 @@
 #ifndef LYRA_BC_STAGES
 #define LYRA_BC_STAGES 3
 #endif
+#ifndef LYRA_B_DEEP_RINGS
+#define LYRA_B_DEEP_RINGS 0
+#endif
 #ifndef LYRA_BC_TN
 #define LYRA_BC_TN 4
 #endif
@@ -424,8 +427,19 @@ struct EncB {
   static constexpr int kW = kRC + 64 * LQ2 * 4;
   static constexpr int kStg = S <= 8 ? LYRA_BC_STAGES : kStages;      // ring depth of the kernel's fp32 GEMMs
   static constexpr int kWBytes = kMax(kStg * 8 * 256 * 4, 2 * 64 * LQ2 * 4);
+  // LYRA_B_DEEP_RINGS (experiment, off: measured slower, 0.307 vs 0.294 ms - with three blocks per SM the GEMM phases are bound by
+  // shared-memory operand delivery, not by the ring): the 8-32-row GEMMs' rings borrow the neighbouring regions that are dead
+  // while their K loops run:
+  //   encoder_1 (three units)   ring over [C | W]: hq is not written before the mixed unit      7 stages x 4 KB (8 k-rows x 128)
+  //   encoder_1/simpleconv      ring over [B | C | W]: d1 is dead, u2 is written by its epilogue  5 stages x 8 KB (8 k-rows x 256)
+  static constexpr bool kDeep = S <= 8 && LYRA_B_DEEP_RINGS != 0 && kStg == kStages;
+  static constexpr int kStgR = kDeep ? 7 : kStg, kKcR = kDeep ? 8 : 16;
+  static constexpr int kStgD = kDeep ? 5 : kStg;
   static constexpr int kI = kW + kWBytes;
   static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;
+  static constexpr int kRingR = kDeep ? kRC : kW, kRingD = kDeep ? kRB : kW;
+  static_assert(kRingR + kStgR * kKcR * 128 * 4 <= kW + kWBytes && kRingD + kStgD * 8 * 256 * 4 <= kW + kWBytes, "borrowed rings end with region W");
+  static_assert(kRingR % 16 == 0 && kRingD % 16 == 0, "bulk-copy alignment");
 };
 
 template <int S>
@@ -458,7 +472,9 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   float* st = reinterpret_cast<float*>(stw);
   const int tid = (int)threadIdx.x;
   PrefetchTileState<LYRA_PREFETCH_STATE>(st, EncStateB::kUnits * S * 4);
-  IssuePrologue<NT>(wbuf, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), 16, 128, 128, nullptr, L::kStg));
+  float* ring_r = reinterpret_cast<float*>(smem + L::kRingR);       // encoder_1's ring
+  float* ring_d = reinterpret_cast<float*>(smem + L::kRingD);       // encoder_1/simpleconv's ring
+  IssuePrologue<NT>(ring_r, NextF32(BlobPtr<float>(blob, P.r1[0].pw1.w), L::kKcR, 128, 128, nullptr, L::kStgR));
   int ph = 0;
   LYRA_PHASE(1, ph);
 
@@ -474,9 +490,9 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   // ---- encoder_1: three residual units @128 (second 1x1 has 2 groups)
   LYRA_PHASE(1, ph);
   static_assert(EncStateB::kRing1 == EncStateB::kRing0 + 128 * 2 && EncStateB::kRing2 == EncStateB::kRing1 + 128 * 6, "ring blocks back to back");
-  ResUnitsF32x3<S, NT, TM, LYRA_BC_TN, LYRA_BC_TN, L::WM4, 16, 128, 4, false, 4 * S, 1, 1, L::kStg>(
-      blob, P.r1, u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, wbuf,
-      NextF32(BlobPtr<float>(blob, P.down1.w), 8, 256, 256, nullptr, L::kStg), 1, ph);
+  ResUnitsF32x3<S, NT, TM, LYRA_BC_TN, LYRA_BC_TN, L::WM4, L::kKcR, 128, 4, false, 4 * S, 1, 1, L::kStgR>(
+      blob, P.r1, u1, L::LD1, 2, d1, 2, st + (size_t)EncStateB::kRing0 * S, n18, active, ring_r,
+      NextF32(BlobPtr<float>(blob, P.down1.w), 8, 256, 256, ring_d, L::kStgD), 1, ph);
   for (int i = tid; i < 128 * 2 * S; i += NT) {
     const int c = i / (2 * S), r = i % (2 * S);
     if (active[r % S]) st[EncStateB::kDown1 * S + i] = u1[(size_t)c * L::LD1 + 4 * S + r];
@@ -485,8 +501,8 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   LYRA_PHASE(1, ph);
   {
     const float* b = BlobPtr<float>(blob, P.down1.bias);
-    GemmF32Tap<S, NT, TM, LYRA_BC_TN, 8, L::WM2, false, L::kStg>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), wbuf, true,
-      NextF32(BlobPtr<float>(blob, P.m_pw1.w), 8, 256, 256, nullptr, L::kStg),
+    GemmF32Tap<S, NT, TM, LYRA_BC_TN, 8, L::WM2, false, L::kStgD>(u1, L::LD1, 0, 2, 4, 64, 2, 2, 256, BlobPtr<float>(blob, P.down1.w), ring_d, true,
+      NextF32(BlobPtr<float>(blob, P.m_pw1.w), 8, 256, 256, wbuf, L::kStg),
       [&](int t, int s0, int n0, float (&acc)[TM][LYRA_BC_TN]) {
 #pragma unroll
         for (int j = 0; j < LYRA_BC_TN; ++j) {
