@@ -80,6 +80,7 @@ struct DecDUShared {
   LyraMbar a_ready;        // row warps -> MMA issuer: the operand of the next GEMM is in place
   LyraMbar d_ready;        // MMA issuer -> row warps: the accumulators of the GEMM are complete
   LyraMbar ring_full[2];   // producer -> row warps: ring block u (units 0, 1) has landed
+  LyraMbar tmem_ready;     // MMA warp -> everybody: tensor memory is allocated, tmem_base is valid
   uint32_t tmem_base;
 };
 
@@ -162,22 +163,30 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
     }
     lyra_mbar_init(&sh->in_full, 1);
     lyra_mbar_init(&sh->ov_full, 1);
+    lyra_mbar_init(&sh->tmem_ready, 1);
     lyra_mbar_init(&sh->a_ready, L::kRowWarps);
     lyra_mbar_init(&sh->d_ready, 1);
     for (int i = 0; i < 2; ++i) lyra_mbar_init(&sh->ring_full[i], 1);
     lyra_mbar_fence_init();
   }
-  if (warp == L::kMmaWarp) { lyra_tmem_alloc(&sh->tmem_base, L::kTmemCols); lyra_tc_fence_before_sync(); }
   int tile;
-  LoadTileMeta<S>(io, n18g, slot, active, n18, tile);       // two block barriers inside: barrier inits and the TMEM address are visible after it
-  lyra_tc_fence_after_sync();
+  LoadTileMeta<S>(io, n18g, slot, active, n18, tile);       // two block barriers inside: the barrier inits are visible after it
   if (pair) lyra_cluster_sync();                              // both CTAs' barriers exist before any remote copy or arrival
-  const uint32_t tmem = sh->tmem_base;
   float* st = state + (size_t)tile * DecStateD::kUnits * S;
   const uint8_t* chunks = blob + P.du_chunks;
   int ph = 0;
   const bool idle = n18[S] == kTileIdle;
-  if (!idle) PrefetchTileState<LYRA_PREFETCH_STATE>(st, DecStateD::kUnits * S * 4);      // unit 2 reads its ring block from global memory                      // every stream of the tile sits this call out: nothing to do (pair is false then)
+  if (!idle) PrefetchTileState<LYRA_PREFETCH_STATE>(st, DecStateD::kUnits * S * 4);      // unit 2 reads its ring block from global memory
+  // Tensor memory is taken AFTER the block barriers above, by the MMA warp alone.  Two blocks of this kernel fit on an SM (shared
+  // memory, registers) but each needs all 512 TMEM columns, so the second one blocks in tcgen05.alloc until the first has
+  // finished - meanwhile its other warps already stage everything that does not need tensor memory (tile metadata, the X
+  // operand, the first weight chunks, depthwise parameters): the next tile's prologue runs under the current tile's tail.
+  if (!idle && warp == L::kMmaWarp) {
+    lyra_tmem_alloc(&sh->tmem_base, L::kTmemCols);
+    lyra_tc_fence_before_sync();
+    if (lane == 0) lyra_mbar_arrive(&sh->tmem_ready);
+  }
+  auto tmem_address = [&]() { lyra_mbar_wait(&sh->tmem_ready, 0); lyra_tc_fence_after_sync(); return sh->tmem_base; };                      // every stream of the tile sits this call out: nothing to do (pair is false then)
 
   // ================================================= TMA producer =================================================
   if (idle) {
@@ -215,6 +224,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   // ================================================= MMA issuer ===================================================
   else if (warp == L::kMmaWarp) {
     if (lane == 0) {
+      const uint32_t tmem = tmem_address();
       unsigned a_par = 0;
       int c = 0;                                             // weight chunk counter
       auto wait_a = [&]() { lyra_mbar_wait(&sh->a_ready, a_par); a_par ^= 1; lyra_tc_fence_after_sync(); };
@@ -296,8 +306,6 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
     const int t = row / S, s = row % S;
     const int rb = row / 128;
     const bool has_row = warp < 5;                           // whole warps: tcgen05.ld / st are warp-collective
-    const uint32_t tq = tmem + ((uint32_t)(32 * (warp % 4)) << 16);          // this warp's TMEM lane window
-    const uint32_t trow = tq + (uint32_t)(rb * L::kRbStride);                // ... at the thread's row block (residual units)
     unsigned d_par = 0;
     LYRA_PHASE(3, ph);
     auto wait_d = [&]() { lyra_mbar_wait(&sh->d_ready, d_par); d_par ^= 1; lyra_tc_fence_after_sync(); };
@@ -352,6 +360,8 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
     //      out[q][r][co] = (P[j=1][x=q] + bias + carried overlap (q = 0)) + P[j=0][x=q-1]; q = 4 is the new overlap tail.
     //      Pass 0 stores the j = 1 terms (every element of u), pass 1 adds the j = 0 terms.  j is uniform per (warp, block).
     wait_d();
+    const uint32_t tq = tmem_address() + ((uint32_t)(32 * (warp % 4)) << 16);      // this warp's TMEM lane window
+    const uint32_t trow = tq + (uint32_t)(rb * L::kRbStride);                      // ... at the thread's row block (residual units)
     lyra_mbar_wait(&sh->ov_full, 0);                         // the carried overlap tail (it landed on X once the MMAs above were done)
     LYRA_PHASE(3, ph);
     {
@@ -561,7 +571,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   lyra_tc_fence_before_sync();
   __syncthreads();
   if (pair) lyra_cluster_sync();                              // no CTA leaves while its partner may still signal its barriers
-  if (warp == L::kMmaWarp) lyra_tmem_dealloc(tmem, L::kTmemCols);
+  if (!idle && warp == L::kMmaWarp) lyra_tmem_dealloc(sh->tmem_base, L::kTmemCols);
 }
 
 }  // namespace lyra_b200
