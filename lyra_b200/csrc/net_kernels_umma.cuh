@@ -22,8 +22,9 @@
 //               the MMAs that read it have completed.  Build switch LYRA_DU_RAW=1: decoder_2/simple's chunks (three quarters of
 //               the stream) travel unsplit - half the bytes - and the row warps split them in place.  Measured slower (that
 //               phase 26 k -> 34 k cycles): with two stages the TMA -> split -> MMA -> release chain is longer than the bytes saved.
-//   state       contiguous blocks (kernel C's tile, overlap tails, ring blocks, depthwise parameters) move by TMA bulk copies,
-//               in both directions; blocks are written back whole, with the lanes of inactive streams left as loaded.
+//   state       the overlap tail, the last_layer tail and the ring blocks of units 0 and 1 move by TMA bulk copies in both directions
+//               (written back whole, with the lanes of inactive streams left as loaded); kernel C's tile and unit 2's 36 KB ring
+//               block are read from / written to global memory directly so that the block stays at 110 KB of shared memory.
 //   roles       warps 0..7: rows / epilogues / state;  warp 8 lane 0: MMA issue;  warp 9 lane 0: TMA producer.
 // Arithmetic: products carry fp32-level accuracy (error terms below 2^-21 relative) but not the oracle's fmaf-chain rounding or
 // summation order: decoded PCM is compared with a tolerance (tests/parity_cases.py TENSOR_PCM_TOL_LSB), never bit for bit.
