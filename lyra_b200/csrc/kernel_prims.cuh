@@ -414,7 +414,7 @@ __device__ __forceinline__ void SplitTf32(float x, uint32_t& hi, uint32_t& lo) {
 }
 
 #ifndef LYRA_TF32_PD
-#define LYRA_TF32_PD 4
+#define LYRA_TF32_PD 8
 #endif
 template <int S, int NT, int WTM, int WTN, bool SYNC_EPI, typename Epi>
 __device__ __forceinline__ void GemmTf32Mma(const float* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
