@@ -15,9 +15,13 @@
 #include "device_compat.h"
 #include "net_params.h"
 
-// register prefetch depth (k-steps) of the int8 B fragments that GemmI8Mma takes straight from L2; 3 and 4 spill at 80 registers
+// register prefetch depth (k-steps) of the int8 B fragments that GemmI8Mma takes straight from L2.  Deeper prefetch spills a few
+// registers at 80 per thread; measured: kernel B gains with 4 (0.294 -> 0.283 ms), kernel C loses (0.221 -> 0.254 ms)
 #ifndef LYRA_I8_PD
 #define LYRA_I8_PD 2
+#endif
+#ifndef LYRA_B_I8_PD
+#define LYRA_B_I8_PD 4
 #endif
 
 namespace lyra_b200 {
@@ -320,10 +324,10 @@ __device__ __forceinline__ void GemmF32Tap(const float* A, int ldA, int rowA0, i
 //   A warp owns one 16-row m-tile (rows m = t*S + s) and NTW consecutive 8-column n-tiles.
 //   epi(t, s, n4, acc) is called per output row and group of 4 consecutive channels n4..n4+3 (acc is [1][4]),
 //   after neighbouring lanes have exchanged their halves of the accumulator tile.
-template <int S, int NT, int NTW, typename Epi>
+template <int S, int NT, int NTW, int PDI = LYRA_I8_PD, typename Epi>
 __device__ __forceinline__ void GemmI8Mma(const uint32_t* A, int ldA, int rowA0, int row_stride, int ntaps, int CinG,
                                           int groups, int T_out, int N, const uint2* __restrict__ Wf, Epi epi) {
-  constexpr int PD = LYRA_I8_PD;      // register prefetch depth of the B fragments (k-steps)
+  constexpr int PD = PDI;             // register prefetch depth of the B fragments (k-steps)
   const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
   const int M = T_out * S, MT = (M + 15) / 16, NTILES = N / 8, NWT = MT * (NTILES / NTW);
   const int CinG4 = CinG / 4, KS = ntaps * CinG4 / 8, CoutG = N / groups;

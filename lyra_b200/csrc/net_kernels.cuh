@@ -211,7 +211,7 @@ __device__ __forceinline__ void ResUnitsF32x3(const uint8_t* blob, const ResF32*
 // One int8 residual unit on packed activations (quant_encoder_2/resnet_{1,2}, quant_decoder_0/resnet_{1,2}); the two
 // 1x1 convolutions run on the tensor cores.
 //   aq: LeakyReLU'd input (row offset row0a of [64][lda]); resq: the pre-activation residual; both updated in place.
-template <int S, int NT, int DIL>
+template <int S, int NT, int DIL, int PDI = LYRA_I8_PD>
 __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, uint32_t* aq, int lda, int row0a,
                                           uint32_t* resq, uint32_t* dq8, uint32_t* hq, uint32_t* ring,
                                           const int* n18, const int* active, int pk, int& ph, int dil_rt = DIL) {
@@ -231,7 +231,7 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
     const int* shift = BlobPtr<int>(blob, p.pw1.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, p.lr1.lut);
     const int out_zp = p.pw1.out_zp;
-    GemmI8Mma<S, NT, NTW>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint2>(blob, p.pw1.w),
+    GemmI8Mma<S, NT, NTW, PDI>(dq8, LD, 0, 1, 1, C, 1, T, C, BlobPtr<uint2>(blob, p.pw1.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
         const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         int q[4];
@@ -249,7 +249,7 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
     const int* l2 = BlobPtr<int>(blob, p.add.lut2);
     const int8_t* lut = BlobPtr<int8_t>(blob, p.lr2.lut);
     const int out_zp = p.pw2.out_zp, m3 = p.add.m3, s3 = p.add.s3, add_zp = p.add.out_zp;
-    GemmI8Mma<S, NT, NTW>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint2>(blob, p.pw2.w),
+    GemmI8Mma<S, NT, NTW, PDI>(hq, LD, 0, 1, 1, C / 4, 4, T, C, BlobPtr<uint2>(blob, p.pw2.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
         const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         const size_t ro = (size_t)(n0 / 4) * LD + t * S + s;
@@ -269,13 +269,13 @@ __device__ __forceinline__ void ResUnitI8(const uint8_t* blob, const ResI8& p, u
 }
 
 // quant_{en,de}coder resnet_1 and resnet_2 (dilation 3, 9; ring blocks of 6 and 18 rows back to back) as one copy of the code
-template <int S, int NT>
+template <int S, int NT, int PDI = LYRA_I8_PD>
 __device__ __forceinline__ void ResUnitsI8x2(const uint8_t* blob, const ResI8* p2, uint32_t* aq, int lda, int row0a,
                                              uint32_t* resq, uint32_t* dq8, uint32_t* hq, uint32_t* ring0,
                                              const int* n18, const int* active, int pk, int& ph) {
 #pragma unroll 1
   for (int i = 0; i < 2; ++i)
-    ResUnitI8<S, NT, 0>(blob, p2[i], aq, lda, row0a, resq, dq8, hq, ring0 + (size_t)(i ? 64 * 6 : 0) * S, n18, active, pk, ph, i ? 9 : 3);
+    ResUnitI8<S, NT, 0, PDI>(blob, p2[i], aq, lda, row0a, resq, dq8, hq, ring0 + (size_t)(i ? 64 * 6 : 0) * S, n18, active, pk, ph, i ? 9 : 3);
 }
 
 // ================================================================================================
@@ -427,6 +427,7 @@ struct EncB {
   static constexpr int kW = kRC + 64 * LQ2 * 4;
   static constexpr int kStg = S <= 8 ? LYRA_BC_STAGES : kStages;      // ring depth of the kernel's fp32 GEMMs
   static constexpr int kWBytes = kMax(kStg * 8 * 256 * 4, 2 * 64 * LQ2 * 4);
+  static constexpr int kI8Pd = S <= 8 ? LYRA_B_I8_PD : LYRA_I8_PD;    // k-steps of int8 weight fragments in flight from L2
   // LYRA_B_DEEP_RINGS (experiment, off: measured slower, 0.307 vs 0.294 ms - with three blocks per SM the GEMM phases are bound by
   // shared-memory operand delivery, not by the ring): the 8-32-row GEMMs' rings borrow the neighbouring regions that are dead
   // while their K loops run:
@@ -547,7 +548,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
     const QuantP dq = P.m_dq, q2 = P.m_q2;
     const int out_zp = P.m_pw2.out_zp;
-    GemmI8Mma<S, NT, (S >= 16 ? 8 : 4)>(hq, LQ2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint2>(blob, P.m_pw2.w),
+    GemmI8Mma<S, NT, (S >= 16 ? 8 : 4), L::kI8Pd>(hq, LQ2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint2>(blob, P.m_pw2.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
         const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         int r[4], a[4];
@@ -565,7 +566,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
   // ---- quant_encoder_2/resnet_{1,2}
   LYRA_PHASE(1, ph);
   static_assert(EncStateB::kRingQ1 == EncStateB::kRingQ0 + 64 * 6, "ring blocks back to back");
-  ResUnitsI8x2<S, NT>(blob, P.q, aq, LQA, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, 1, ph);
+  ResUnitsI8x2<S, NT, L::kI8Pd>(blob, P.q, aq, LQA, 2, resq, dq8, hq, stw + (size_t)EncStateB::kRingQ0 * S, n18, active, 1, ph);
   // ---- quant_encoder_2/simpleconv: K = 4, stride 2, 256 -> 512, 4 groups, then int8 LeakyReLU
   LYRA_PHASE(1, ph);
   BatchedLoop<NT, 4, uint32_t>(64 * 2 * S, [&](int i) { return stw[EncStateB::kDown2 * S + i]; },
@@ -583,7 +584,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int* shift = BlobPtr<int>(blob, P.down2.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.down2_lr.lut);
     const int out_zp = P.down2.out_zp;
-    GemmI8Mma<S, NT, 8>(aq, LQA, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint2>(blob, P.down2.w),
+    GemmI8Mma<S, NT, 8, L::kI8Pd>(aq, LQA, 0, 2, 4, 64, 4, 1, 512, BlobPtr<uint2>(blob, P.down2.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
         const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         (void)t;
@@ -606,7 +607,7 @@ EncoderKernelB(const uint8_t* __restrict__ blob, EncoderParams P, TileIo io, con
     const int* shift = BlobPtr<int>(blob, P.bott.shift);
     const QuantP dq = P.out_dq;
     const int out_zp = P.bott.out_zp;
-    GemmI8Mma<S, NT, 1>(bq, LQB, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint2>(blob, P.bott.w),
+    GemmI8Mma<S, NT, 1, L::kI8Pd>(bq, LQB, 0, 1, 3, 128, 4, 1, 64, BlobPtr<uint2>(blob, P.bott.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
         const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         (void)t;
