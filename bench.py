@@ -493,7 +493,7 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
         if errors:
             raise RuntimeError("host API failed: %s" % errors[0])
 
-    run_host(3)
+    run_host(NBUF + 1)               # warm-up: every rotating buffer pair has been through a call (graph captures included)
     barrier()
     t0 = time.perf_counter()
     run_host(e2e_hops)
