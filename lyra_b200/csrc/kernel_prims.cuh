@@ -23,6 +23,9 @@
 #ifndef LYRA_B_I8_PD
 #define LYRA_B_I8_PD 4
 #endif
+#ifndef LYRA_C_I8_PD
+#define LYRA_C_I8_PD 2
+#endif
 
 namespace lyra_b200 {
 

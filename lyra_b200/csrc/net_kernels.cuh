@@ -629,6 +629,7 @@ template <int S, bool TC = false>
 struct DecC {
   static constexpr int NT = 256;
   static constexpr int kMinBlocks = S <= 8 ? LYRA_C_MIN_BLOCKS : 1;
+  static constexpr int kI8Pd = S <= 8 ? LYRA_C_I8_PD : LYRA_I8_PD;    // prefetch depth of the four-n-tile int8 GEMMs (the eight-n-tile upsamplers keep LYRA_I8_PD)
   static constexpr int TM = 8;                            // streams per fp32 thread tile (8 x 4 tiles: fewer smem wavefronts per FMA)
   static constexpr int WM4 = 4 * S / TM >= 4 ? 4 : 4 * S / TM;   // m-groups per warp for T = 4 / 2 / 1 row layers
   static constexpr int WM2 = 2 * S / TM >= 4 ? 4 : 2 * S / TM;
@@ -774,7 +775,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int* shift = BlobPtr<int>(blob, P.m_pw1.shift);
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr1.lut);
     const int out_zp = P.m_pw1.out_zp;
-    GemmI8Mma<S, NT, (S >= 16 ? 8 : 4)>(dq8, LQ2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint2>(blob, P.m_pw1.w),
+    GemmI8Mma<S, NT, (S >= 16 ? 8 : 4), L::kI8Pd>(dq8, LQ2, 0, 1, 1, 256, 1, 2, 256, BlobPtr<uint2>(blob, P.m_pw1.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
         const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         int q[4];
@@ -790,7 +791,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
     const int8_t* lut = BlobPtr<int8_t>(blob, P.m_lr2.lut);
     const QuantP dq = P.m_dq, q2 = P.m_q2;
     const int out_zp = P.m_pw2.out_zp;
-    GemmI8Mma<S, NT, (S >= 16 ? 8 : 4)>(hq, LQ2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint2>(blob, P.m_pw2.w),
+    GemmI8Mma<S, NT, (S >= 16 ? 8 : 4), L::kI8Pd>(hq, LQ2, 0, 1, 1, 64, 4, 2, 256, BlobPtr<uint2>(blob, P.m_pw2.w),
       [&](int t, int s, int n0, int (&acc)[1][4]) {
         const RequantP4 rq = LoadRequant4(bias, mult, shift, n0);
         int r[4], a[4];
@@ -807,7 +808,7 @@ DecoderKernelC(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io,
   }
   LYRA_PHASE(2, ph);
   static_assert(DecStateC::kRingQ1 == DecStateC::kRingQ0 + 64 * 6, "ring blocks back to back");
-  ResUnitsI8x2<S, NT>(blob, P.q, aq, LQA, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, 2, ph);
+  ResUnitsI8x2<S, NT, L::kI8Pd>(blob, P.q, aq, LQA, 1, resq, dq8, hq, stw + (size_t)DecStateC::kRingQ0 * S, n18, active, 2, ph);
   // ---- quant_decoder_1 upsample: 2 x TRANSPOSE_CONV (K = 4, stride 2, 128 -> 64), T 2 -> 4 (+2 tail rows)
   LYRA_PHASE(2, ph);
   {
