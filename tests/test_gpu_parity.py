@@ -190,6 +190,12 @@ def test_cuda_graphs_replay_matches_direct_calls(gpu_api, n):
     # 30 encode + 30 decode calls over 2 buffer pairs and 2 bit rates: 4 + 4 captures, every other call is a replay
     assert gr.graph_replays() >= 40, gr.graph_replays()
     assert ref.graph_replays() == 0
+    # pageable host buffers (the ctypes wrappers allocate with numpy) cannot be captured: the call must run directly, same results
+    replays = gr.graph_replays()
+    pcm = pc.synth_pcm(rng, n, "noise")
+    pk = ref.encode(pcm, 64)
+    assert np.array_equal(pk, gr.encode(pcm, 64)) and np.array_equal(ref.decode(pk, 64), gr.decode(pk, 64))
+    assert gr.graph_replays() == replays
     gr.set_graphs(False)
     pcm = pc.synth_pcm(rng, n, "noise")
     assert np.array_equal(ref.encode(pcm, 64), gr.encode(pcm, 64))
