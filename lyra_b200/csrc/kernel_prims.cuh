@@ -15,6 +15,47 @@
 #include "device_compat.h"
 #include "net_params.h"
 
+// Weight fragments that a block reads exactly once (straight from L2 into registers).  Experiment switch LYRA_FRAG_NOALLOC: bit 0
+// (int8) / bit 1 (TF32) load them without allocating an L1 line (measured slower: co-resident blocks of the same kernel find each
+// other's fragments in the L1); + 4 loads them with the evict-last L1 policy instead.
+#ifndef LYRA_FRAG_NOALLOC
+#define LYRA_FRAG_NOALLOC 0
+#endif
+template <bool NOALLOC>
+__device__ __forceinline__ uint2 LoadFrag(const uint2* p) {
+#if defined(LYRA_EMU)
+  return *p;
+#else
+  if (NOALLOC) {
+    uint2 v;
+#if LYRA_FRAG_NOALLOC >= 4
+    asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p));
+#endif
+    return v;
+  }
+  return __ldg(p);
+#endif
+}
+template <bool NOALLOC>
+__device__ __forceinline__ float2 LoadFrag(const float2* p) {
+#if defined(LYRA_EMU)
+  return *p;
+#else
+  if (NOALLOC) {
+    float2 v;
+#if LYRA_FRAG_NOALLOC >= 4
+    asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "l"(p));
+#endif
+    return v;
+  }
+  return __ldg(p);
+#endif
+}
+
 // register prefetch depth (k-steps) of the int8 B fragments that GemmI8Mma takes straight from L2.  Deeper prefetch spills a few
 // registers at 80 per thread; measured: kernel B gains with 4 (0.294 -> 0.283 ms), kernel C loses (0.221 -> 0.254 ms)
 #ifndef LYRA_I8_PD
@@ -353,7 +394,7 @@ __device__ __forceinline__ void GemmI8Mma(const uint32_t* A, int ldA, int rowA0,
     for (int p = 0; p < PD; ++p)
       if (p < KS) {
 #pragma unroll
-        for (int j = 0; j < NTW; ++j) bf[p][j] = __ldg(wp + p * ks_stride + j * 32);
+        for (int j = 0; j < NTW; ++j) bf[p][j] = LoadFrag<(LYRA_FRAG_NOALLOC & 1) != 0>(wp + p * ks_stride + j * 32);
       }
     for (int ks0 = 0; ks0 < KS; ks0 += PD) {
 #pragma unroll
@@ -371,7 +412,7 @@ __device__ __forceinline__ void GemmI8Mma(const uint32_t* A, int ldA, int rowA0,
           }
           if (ks + PD < KS) {
 #pragma unroll
-            for (int j = 0; j < NTW; ++j) bf[p][j] = __ldg(wp + (size_t)(ks + PD) * ks_stride + j * 32);
+            for (int j = 0; j < NTW; ++j) bf[p][j] = LoadFrag<(LYRA_FRAG_NOALLOC & 1) != 0>(wp + (size_t)(ks + PD) * ks_stride + j * 32);
           }
         }
       }
@@ -462,7 +503,7 @@ __device__ __forceinline__ void GemmTf32Mma(const float* A, int ldA, int rowA0, 
     for (int p = 0; p < PD; ++p)
       if (p < KS) {
 #pragma unroll
-        for (int j = 0; j < WTN; ++j) bf[p][j] = __ldg(wp + p * ks_stride + j * 32);
+        for (int j = 0; j < WTN; ++j) bf[p][j] = LoadFrag<(LYRA_FRAG_NOALLOC & 2) != 0>(wp + p * ks_stride + j * 32);
       }
     for (int ks0 = 0; ks0 < KS; ks0 += PD) {
 #pragma unroll
@@ -493,7 +534,7 @@ __device__ __forceinline__ void GemmTf32Mma(const float* A, int ldA, int rowA0, 
           }
           if (ks + PD < KS) {
 #pragma unroll
-            for (int j = 0; j < WTN; ++j) bf[p][j] = __ldg(wp + (size_t)(ks + PD) * ks_stride + j * 32);
+            for (int j = 0; j < WTN; ++j) bf[p][j] = LoadFrag<(LYRA_FRAG_NOALLOC & 2) != 0>(wp + (size_t)(ks + PD) * ks_stride + j * 32);
           }
         }
       }
