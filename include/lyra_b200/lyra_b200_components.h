@@ -21,12 +21,17 @@
 // adapters derive from chromemedia::codec::{FeatureExtractorInterface, VectorQuantizerInterface, GenerativeModel}.
 //
 // Every object owns ONE stream id of a process-wide context (one context per device, created on first use with
-// LYRA_B200_MAX_STREAMS, default 4096, stream slots).  Per-object calls run the batched kernels with n = 1:
-// API-compatible but latency-bound; throughput users call the batched C ABI directly (include/lyra_b200.h).
+// LYRA_B200_MAX_STREAMS, default 4096, stream slots).  Per-object calls go through the session's Coalescer: calls of the
+// same kind that arrive from different threads while a launch is in flight are gathered into ONE batched C-ABI call
+// (a thread-per-stream server gets n > 1 launches without changing its code); a lone caller runs at once with n = 1.
+// Throughput users with their own batching call the batched C ABI directly (include/lyra_b200.h).
 #pragma once
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <functional>
 #include <cstdlib>
@@ -35,6 +40,7 @@
 #include <optional>
 #include <queue>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../lyra_b200.h"
@@ -101,6 +107,118 @@ class GenerativeModel : public GenerativeModelInterface {
   std::queue<std::vector<float>> features_queue_;
 };
 
+
+// ---- coalescing front for the per-object API (SURVEY.md section 7 "API impedance") ---------------------------------------
+// The reference's objects are called once per stream and hop (e.g. lyra_encoder.cc:119-151, lyra_decoder.cc:228-315); the
+// device kernels want many streams per launch.  Flat combining: a caller posts its request and, if no launch is being
+// prepared, becomes the leader - it takes every queued request with the oldest one's key (kind, argument), gathers their
+// inputs into contiguous rows, issues one batched C-ABI call and scatters the results; the other callers sleep until their
+// request is marked done.  No helper thread, no added latency for a lone caller, results identical to n = 1 calls (the
+// kernels treat streams independently; tests/cpp/test_components.cc compares threaded with serial runs bit for bit).
+// LYRA_B200_COALESCE_US (default 0) lets a leader wait that long for company before it launches.
+class Coalescer {
+ public:
+  enum Kind { kExtract, kQuantize, kDequantize, kGenerate, kCng, kLogMel, kNoiseUpdate };
+  struct Call {
+    int kind = 0, arg = 0, arg2 = 0;   // batch key: calls are merged only when all three agree
+    int id = -1;                       // stream id; -1 for the stateless quantizer calls
+    const void* in = nullptr;  size_t in_bytes = 0;     // one row in
+    void* out = nullptr;       size_t out_bytes = 0;    // one row out
+    uint8_t* flag = nullptr;                            // kNoiseUpdate: is_noise of the row
+    int rc = -1;
+    bool done = false;
+  };
+  struct Stats { uint64_t calls = 0, launches = 0, max_batch = 0; };
+
+  Coalescer(lyra_b200_ctx* ctx, std::mutex* ctx_mutex, int max_batch) : ctx_(ctx), ctx_mu_(ctx_mutex), max_batch_(max_batch) {
+    if (const char* e = std::getenv("LYRA_B200_COALESCE_US")) linger_us_ = std::atoi(e) > 0 ? std::atoi(e) : 0;
+  }
+  int Submit(Call& c) {
+    std::unique_lock<std::mutex> lk(mu_);
+    queue_.push_back(&c);
+    while (!c.done) {
+      if (leader_) { cv_.wait(lk); continue; }
+      leader_ = true;
+      if (const int us = linger_us_) { lk.unlock(); std::this_thread::sleep_for(std::chrono::microseconds(us)); lk.lock(); }
+      std::vector<Call*> batch = Take();
+      lk.unlock();
+      Run(batch);
+      lk.lock();
+      for (Call* q : batch) q->done = true;
+      ++stats_.launches;
+      stats_.calls += batch.size();
+      stats_.max_batch = std::max<uint64_t>(stats_.max_batch, batch.size());
+      leader_ = false;
+      cv_.notify_all();
+    }
+    return c.rc;
+  }
+  Stats stats() { std::lock_guard<std::mutex> lk(mu_); return stats_; }
+  void set_linger_us(int us) { std::lock_guard<std::mutex> lk(mu_); linger_us_ = us > 0 ? us : 0; }
+
+ private:
+  // the oldest request decides the key; a stream id appears at most once per batch (a second call on the same stream
+  // must see the first one's state update, so it waits for the next launch)
+  std::vector<Call*> Take() {
+    std::vector<Call*> batch, rest;
+    const Call* head = queue_.front();
+    for (Call* q : queue_) {
+      bool take = q->kind == head->kind && q->arg == head->arg && q->arg2 == head->arg2 && (int)batch.size() < max_batch_;
+      if (take && q->id >= 0) for (const Call* b : batch) if (b->id == q->id) { take = false; break; }
+      (take ? batch : rest).push_back(q);
+    }
+    queue_.swap(rest);
+    return batch;
+  }
+  void Run(const std::vector<Call*>& batch) {
+    const int n = (int)batch.size();
+    const Call& h = *batch[0];
+    int rc;
+    std::lock_guard<std::mutex> ctx_lock(*ctx_mu_);      // the context itself is single-caller (resampler, reset, getters use it too)
+    if (n == 1) {
+      rc = Issue(h, 1, &h.id, h.in, h.out, h.flag);
+    } else {
+      ids_.resize((size_t)n);
+      in_.resize((size_t)n * h.in_bytes);
+      out_.resize((size_t)n * h.out_bytes);
+      flags_.assign((size_t)n, 0);
+      for (int i = 0; i < n; ++i) {
+        ids_[(size_t)i] = batch[(size_t)i]->id;
+        std::copy_n((const uint8_t*)batch[(size_t)i]->in, h.in_bytes, in_.data() + (size_t)i * h.in_bytes);
+      }
+      rc = Issue(h, n, ids_.data(), in_.data(), out_.data(), flags_.data());
+      if (rc == LYRA_B200_OK) for (int i = 0; i < n; ++i) {
+        std::copy_n(out_.data() + (size_t)i * h.out_bytes, h.out_bytes, (uint8_t*)batch[(size_t)i]->out);
+        if (batch[(size_t)i]->flag) *batch[(size_t)i]->flag = flags_[(size_t)i];
+      }
+    }
+    for (Call* q : batch) q->rc = rc;
+  }
+  int Issue(const Call& h, int n, const int32_t* ids, const void* in, void* out, uint8_t* flags) {
+    switch (h.kind) {
+      case kExtract:     return lyra_b200_extract_features(ctx_, ids, n, (const int16_t*)in, (float*)out);
+      case kQuantize:    return lyra_b200_quantize(ctx_, n, (const float*)in, h.arg, (uint8_t*)out, nullptr);
+      case kDequantize:  return lyra_b200_dequantize(ctx_, n, (const uint8_t*)in, h.arg, (float*)out);
+      case kGenerate:    return lyra_b200_generate(ctx_, ids, n, (const float*)in, (int16_t*)out);
+      case kCng:         return lyra_b200_cng_generate(ctx_, ids, n, (const float*)in, (int16_t*)out);
+      case kLogMel:      return lyra_b200_logmel(ctx_, h.arg, ids, n, (const int16_t*)in, h.arg2, (float*)out);
+      case kNoiseUpdate: return lyra_b200_noise_update(ctx_, ids, n, (const int16_t*)in, nullptr, flags, nullptr);
+    }
+    return LYRA_B200_EINVAL;
+  }
+
+  lyra_b200_ctx* ctx_;
+  std::mutex* ctx_mu_;
+  int max_batch_, linger_us_ = 0;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::vector<Call*> queue_;
+  bool leader_ = false;
+  Stats stats_;
+  std::vector<int32_t> ids_;           // leader-only scratch (one leader at a time)
+  std::vector<uint8_t> in_, out_, flags_;
+};
+
 // ---- process-wide context + stream-id allocator ------------------------------------------------------------------
 class Session {
  public:
@@ -132,6 +250,15 @@ class Session {
   ~Session() { lyra_b200_destroy(ctx_); }
   lyra_b200_ctx* ctx() const { return ctx_; }
   std::mutex& mutex() { return mu_; }   // calls on one context are serialised
+  // one fixed-shape per-hop call of one object, merged with concurrent calls of the same kind (see Coalescer)
+  int Call(int kind, int id, const void* in, size_t in_bytes, void* out, size_t out_bytes, int arg = 0, int arg2 = 0, uint8_t* flag = nullptr) {
+    Coalescer::Call c;
+    c.kind = kind; c.arg = arg; c.arg2 = arg2; c.id = id;
+    c.in = in; c.in_bytes = in_bytes; c.out = out; c.out_bytes = out_bytes; c.flag = flag;
+    return coalescer_.Submit(c);
+  }
+  Coalescer::Stats coalescer_stats() { return coalescer_.stats(); }
+  void set_coalesce_linger_us(int us) { coalescer_.set_linger_us(us); }
   int Acquire() {
     std::lock_guard<std::mutex> lock(mu_);
     int id;
@@ -144,11 +271,12 @@ class Session {
   void Release(int id) { std::lock_guard<std::mutex> lock(mu_); free_.push_back(id); }
 
  private:
-  Session(lyra_b200_ctx* c, int n) : ctx_(c), max_streams_(n) {}
+  Session(lyra_b200_ctx* c, int n) : ctx_(c), max_streams_(n), coalescer_(c, &mu_, n) {}
   lyra_b200_ctx* ctx_;
   int max_streams_, next_ = 0;
   std::vector<int> free_;
   std::mutex mu_;
+  Coalescer coalescer_;
 };
 
 // ---- SoundStreamEncoder (lyra/soundstream_encoder.cc:36-64) --------------------------------------------------------
@@ -165,8 +293,8 @@ class SoundStreamEncoderB200 : public FeatureExtractorInterface {
   std::optional<std::vector<float>> Extract(const std::vector<int16_t>& audio) override {
     if ((int)audio.size() != LYRA_B200_HOP) return std::nullopt;
     std::vector<float> out(LYRA_B200_NUM_FEATURES);
-    std::lock_guard<std::mutex> lock(session_->mutex());
-    if (lyra_b200_extract_features(session_->ctx(), &id_, 1, audio.data(), out.data()) != LYRA_B200_OK) return std::nullopt;
+    if (session_->Call(Coalescer::kExtract, id_, audio.data(), audio.size() * sizeof(int16_t), out.data(), out.size() * sizeof(float)) != LYRA_B200_OK)
+      return std::nullopt;
     return out;
   }
 
@@ -204,12 +332,11 @@ class ResidualVectorQuantizerB200 : public VectorQuantizerInterface {
   }
   std::optional<std::string> Quantize(const std::vector<float>& features, int num_bits) const override {
     if ((int)features.size() != LYRA_B200_NUM_FEATURES) return std::nullopt;
-    std::vector<uint8_t> packet((size_t)Packet184::PacketSize(num_bits > 0 ? num_bits : 0) + 1);
-    {
-      std::lock_guard<std::mutex> lock(session_->mutex());
-      if (lyra_b200_quantize(session_->ctx(), 1, features.data(), num_bits, packet.data(), nullptr) != LYRA_B200_OK) return std::nullopt;
-    }
-    packet.resize((size_t)Packet184::PacketSize(num_bits));
+    // invalid bit counts are refused by the library (EINVAL) before anything is written; the row size is the packet size
+    if (num_bits <= 0 || num_bits > LYRA_B200_MAX_BITS) return std::nullopt;
+    std::vector<uint8_t> packet((size_t)Packet184::PacketSize(num_bits));
+    if (session_->Call(Coalescer::kQuantize, -1, features.data(), features.size() * sizeof(float), packet.data(), packet.size(), num_bits) != LYRA_B200_OK)
+      return std::nullopt;
     return Packet184::UnpackPacket(packet, num_bits);
   }
   std::optional<std::vector<float>> DecodeToLossyFeatures(const std::string& quantized_features) const override {
@@ -217,8 +344,8 @@ class ResidualVectorQuantizerB200 : public VectorQuantizerInterface {
     if (num_bits > LYRA_B200_MAX_BITS || num_bits % 4 != 0 || num_bits == 0) return std::nullopt;
     const std::vector<uint8_t> packet = Packet184::PackQuantized(quantized_features);
     std::vector<float> out(LYRA_B200_NUM_FEATURES);
-    std::lock_guard<std::mutex> lock(session_->mutex());
-    if (lyra_b200_dequantize(session_->ctx(), 1, packet.data(), num_bits, out.data()) != LYRA_B200_OK) return std::nullopt;
+    if (session_->Call(Coalescer::kDequantize, -1, packet.data(), packet.size(), out.data(), out.size() * sizeof(float), num_bits) != LYRA_B200_OK)
+      return std::nullopt;
     return out;
   }
 
@@ -242,9 +369,8 @@ class LyraGanModelB200 : public GenerativeModel {
 
  protected:
   bool RunConditioning(const std::vector<float>& features) override {
-    std::lock_guard<std::mutex> lock(session_->mutex());
     // like the reference (lyra_gan_model.cc:53-58) the hop is generated in one go; RunModel slices it
-    return lyra_b200_generate(session_->ctx(), &id_, 1, features.data(), hop_) == LYRA_B200_OK;
+    return session_->Call(Coalescer::kGenerate, id_, features.data(), features.size() * sizeof(float), hop_, sizeof(hop_)) == LYRA_B200_OK;
   }
   std::optional<std::vector<int16_t>> RunModel(int num_samples) override {
     return std::vector<int16_t>(hop_ + next_sample_in_hop(), hop_ + next_sample_in_hop() + num_samples);
@@ -275,8 +401,8 @@ class LogMelSpectrogramExtractorB200 : public FeatureExtractorInterface {
   std::optional<std::vector<float>> Extract(const std::vector<int16_t>& audio) override {
     if ((int)audio.size() != LYRA_B200_HOP) return std::nullopt;
     std::vector<float> out((size_t)num_mel_);
-    std::lock_guard<std::mutex> lock(session_->mutex());
-    if (lyra_b200_logmel(session_->ctx(), bank_, &id_, 1, audio.data(), num_mel_, out.data()) != LYRA_B200_OK) return std::nullopt;
+    if (session_->Call(Coalescer::kLogMel, id_, audio.data(), audio.size() * sizeof(int16_t), out.data(), out.size() * sizeof(float), bank_, num_mel_) != LYRA_B200_OK)
+      return std::nullopt;
     return out;
   }
 
@@ -316,8 +442,7 @@ class NoiseEstimatorB200 : public NoiseEstimatorInterface {
     hop_.insert(hop_.end(), samples.begin(), samples.end());
     if ((int)hop_.size() < LYRA_B200_HOP) return true;
     uint8_t flag = 1;
-    std::lock_guard<std::mutex> lock(session_->mutex());
-    const int rc = lyra_b200_noise_update(session_->ctx(), &id_, 1, hop_.data(), nullptr, &flag, nullptr);
+    const int rc = session_->Call(Coalescer::kNoiseUpdate, id_, hop_.data(), hop_.size() * sizeof(int16_t), nullptr, 0, 0, 0, &flag);
     hop_.clear();
     if (rc != LYRA_B200_OK) return false;
     is_noise_ = flag != 0;
@@ -355,8 +480,7 @@ class ComfortNoiseGeneratorB200 : public GenerativeModel {
 
  protected:
   bool RunConditioning(const std::vector<float>& features) override {       // FftFromFeatures + InvertFft, .cc:74-77
-    std::lock_guard<std::mutex> lock(session_->mutex());
-    return lyra_b200_cng_generate(session_->ctx(), &id_, 1, features.data(), hop_) == LYRA_B200_OK;
+    return session_->Call(Coalescer::kCng, id_, features.data(), features.size() * sizeof(float), hop_, sizeof(hop_)) == LYRA_B200_OK;
   }
   std::optional<std::vector<int16_t>> RunModel(int num_samples) override {   // .cc:79-84
     return std::vector<int16_t>(hop_ + next_sample_in_hop(), hop_ + next_sample_in_hop() + num_samples);

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "lyra_b200/lyra_b200_components.h"
@@ -253,6 +254,59 @@ int main(int argc, char** argv) {
         CHECK(a1.has_value() && a2.has_value() && (int)a1->size() == hop - 7 && a2->size() == 7);
       }
     }
+  }
+  // coalescing front: one thread per stream, each with its own SoundStreamEncoder / quantizer / LyraGanModel objects, calling
+  // concurrently; calls of a kind are merged into batched launches, results stay those of the per-stream oracle
+  {
+    const int kThreads = 6, kFrames = 3;
+    auto es = Session::Get(model, LYRA_B200_ROLE_ENCODER);
+    auto ds = Session::Get(model, LYRA_B200_ROLE_DECODER);
+    CHECK(es && ds);
+    const Coalescer::Stats e0 = es->coalescer_stats(), d0 = ds->coalescer_stats();
+    es->set_coalesce_linger_us(2000);
+    ds->set_coalesce_linger_us(2000);
+    std::vector<int> fails((size_t)kThreads, 0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < kThreads; ++t) pool.emplace_back([&, t] {
+      int& bad = fails[(size_t)t];
+      auto e = SoundStreamEncoderB200::Create(model);
+      auto q = ResidualVectorQuantizerB200::Create(model, t % 2 ? LYRA_B200_ROLE_DECODER : LYRA_B200_ROLE_ENCODER);
+      auto g = LyraGanModelB200::Create(model, 64);
+      lo_codec* r = lo_codec_create(model.c_str());
+      if (!e || !q || !g || !r) { bad = 100; return; }
+      std::mt19937 trng(100 + (unsigned)t);
+      std::uniform_int_distribution<int> td(-8192, 8191);
+      for (int f = 0; f < kFrames; ++f) {
+        std::vector<int16_t> pcm(320);
+        for (auto& v : pcm) v = (int16_t)td(trng);
+        const int bits = t % 3 == 0 ? 64 : 120;                // two batch keys for the quantizer calls
+        uint8_t rp[24];
+        int16_t rpcm[320];
+        lo_codec_encode(r, pcm.data(), bits, rp, nullptr, nullptr);
+        lo_codec_decode(r, rp, bits, rpcm, nullptr, nullptr);
+        auto feat = e->Extract(pcm);
+        if (!feat) { ++bad; continue; }
+        auto str = q->Quantize(*feat, bits);
+        if (!str) { ++bad; continue; }
+        const std::vector<uint8_t> pkt = Packet184::PackQuantized(*str);
+        bad += std::memcmp(pkt.data(), rp, pkt.size()) != 0;
+        auto lossy = q->DecodeToLossyFeatures(*str);
+        if (!lossy || !g->AddFeatures(*lossy)) { ++bad; continue; }
+        auto out = g->GenerateSamples(320);
+        bad += !out || std::memcmp(out->data(), rpcm, sizeof(rpcm)) != 0;
+      }
+      lo_codec_free(r);
+    });
+    for (auto& th : pool) th.join();
+    for (int t = 0; t < kThreads; ++t) CHECK(fails[(size_t)t] == 0);
+    es->set_coalesce_linger_us(0);
+    ds->set_coalesce_linger_us(0);
+    const Coalescer::Stats e1 = es->coalescer_stats(), d1 = ds->coalescer_stats();
+    std::printf("coalescer: encoder context %llu calls in %llu launches (largest batch %llu), decoder context %llu in %llu (largest %llu)\n",
+                (unsigned long long)(e1.calls - e0.calls), (unsigned long long)(e1.launches - e0.launches), (unsigned long long)e1.max_batch,
+                (unsigned long long)(d1.calls - d0.calls), (unsigned long long)(d1.launches - d0.launches), (unsigned long long)d1.max_batch);
+    CHECK(e1.max_batch >= 2 && d1.max_batch >= 2);             // concurrent calls did share launches
+    CHECK(e1.launches - e0.launches < e1.calls - e0.calls);
   }
   std::printf(g_fail ? "FAILED (%d)\n" : "ALL OK\n", g_fail);
   return g_fail ? 1 : 0;
