@@ -302,7 +302,10 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
     ctxs = [c for c in (enc, dec) if c is not None]
     for c in ctxs:
         c.set_split(args.split)
-    sx, sy = torch.cuda.Stream(), torch.cuda.Stream()
+    # the device pass hands the contexts its own streams: same priorities as the contexts' own ones (engine.cu: encoder-only
+    # contexts one step above the default, overridable through the same environment variables)
+    prio_x, prio_y = int(os.environ.get("LYRA_B200_ENC_PRIORITY", "-1")), int(os.environ.get("LYRA_B200_DEC_PRIORITY", "0"))
+    sx, sy = torch.cuda.Stream(priority=prio_x), torch.cuda.Stream(priority=prio_y)
     if enc:
         enc.set_stream(sx.cuda_stream)
     dec.set_stream(sy.cuda_stream)
@@ -320,7 +323,7 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
             e_ = None if plc else _capi.Context(ng, device=local_rank, roles="encoder")
             d_ = _capi.Context(ng, device=local_rank, roles="decoder")
             d_.set_decoder_mode(decoder_mode)
-            gx, gy = torch.cuda.Stream(), torch.cuda.Stream()
+            gx, gy = torch.cuda.Stream(priority=prio_x), torch.cuda.Stream(priority=prio_y)
             if e_:
                 e_.set_stream(gx.cuda_stream)
                 e_.set_split(args.split)
@@ -510,7 +513,7 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
     for c in ctxs + (group_ctxs if G > 1 else []):
         c.close()
     return {"value": value, "elapsed_ms": elapsed_ms, "e2e_value": e2e_value, "e2e_s": float(t.item()), "prof": prof, "clocks": clocks,
-            "gpu_launches": int(gpu_launches), "checksum": checksum, "G": G, "oversubscribed": oversubscribed, "tile_streams": tile_streams,
+            "gpu_launches": int(gpu_launches), "checksum": checksum, "G": G, "oversubscribed": oversubscribed, "tile_streams": tile_streams, "stream_priority": {"encoder": prio_x, "decoder": prio_y},
             "P": P, "graph_replays": graph_replays}
 
 
@@ -655,7 +658,7 @@ def main():
                                     % (n, bits * 50 / 1000.0, 1.0 - args.loss, HOPS_PER_STEP)) if plc else
                                    codec_workload(n, bits, world),
                        "streams_per_gpu": n, "bits_per_frame": bits, "hops_per_step": HOPS_PER_STEP, "tile_streams": res["tile_streams"],
-                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G,
+                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G, "stream_priority": res["stream_priority"],
                        "host_pass_cuda_graphs": {"enabled": args.graphs == "on", "replayed_calls": res.get("graph_replays", 0)},
                        "host_threads_wait": "sleep (blocking-sync event)" if res["oversubscribed"] else "spin",
                        "host_cores_per_rank": pinned if pinned else host_cores(),

@@ -738,9 +738,15 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
   ctx->tile_gen.assign((size_t)ctx->ntiles, 0u);
   const size_t P = (size_t)ctx->padded;
   bool ok = cudaSetDevice(device) == cudaSuccess;
-  ok = ok && cudaStreamCreate(&ctx->own_stream) == cudaSuccess;
+  // Stream priority of the context's own and sub-batch streams.  An encoder-only context runs one step above the default: in
+  // a full-duplex process the uplink chain (kernels A, B, RVQ) is the longer one and its FMA-bound blocks go first when both
+  // directions have blocks waiting, the decoder's latency-bound blocks fill what is left (measured on the duplex benchmark:
+  // +2.3 % over equal priorities, -3 % with the decoder first).  LYRA_B200_ENC_PRIORITY / LYRA_B200_DEC_PRIORITY override.
+  int prio = roles == LYRA_B200_ROLE_ENCODER ? -1 : 0;
+  if (const char* e = std::getenv(roles == LYRA_B200_ROLE_DECODER ? "LYRA_B200_DEC_PRIORITY" : "LYRA_B200_ENC_PRIORITY")) prio = std::atoi(e);
+  ok = ok && cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamDefault, prio) == cudaSuccess;
   for (int i = 0; i < lyra_b200_ctx::kMaxSplit - 1; ++i) {
-    ok = ok && cudaStreamCreate(&ctx->aux_stream[i]) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&ctx->aux_stream[i], cudaStreamDefault, prio) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
   }
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;

@@ -62,11 +62,16 @@ struct DecDU {
   static constexpr int kDw4 = kSlOut + 48 * S * 4;            // depthwise parameters per channel: float4 {w0, w1, w2, bias} [3][64]
   static constexpr int kW = kDw4 + 3 * 256 * 4;               // weight ring
   static constexpr int kI = kW + kStagesW * kDuChunkBytes;    // slot[S], active[S], n18[S]
-  static constexpr int kSmemBytes = kI + 3 * S * 4 + 16;     // + n18[S]
+  // LYRA_DU_SMEM_PAD: request more than the layout needs, e.g. 6144 -> 116 KB = at most one block of this kernel per SM (the second
+  // resident block waits for tensor memory most of its life while holding 110 KB that a kernel-A / B / C block could use)
+#ifndef LYRA_DU_SMEM_PAD
+#define LYRA_DU_SMEM_PAD 0
+#endif
+  static constexpr int kSmemBytes = kI + 3 * S * 4 + 16 + LYRA_DU_SMEM_PAD;     // + n18[S]
   static_assert(kStage + S * 320 * 2 <= kRegion + kRegionBytes, "overlap tail, two ring blocks and PCM staging must fit in the X region");
   static_assert(kXc % 128 == 0 && kOv % 128 == 0 && kRing0 % 128 == 0 && kRing1 % 128 == 0 && kW % 128 == 0 && kSl % 16 == 0 && kDw4 % 16 == 0,
                 "bulk-copy / descriptor alignment");
-  static_assert(kSmemBytes <= 113 * 1024, "must leave room for a kernel-A block on the SM");
+  static_assert(kSmemBytes - LYRA_DU_SMEM_PAD <= 113 * 1024, "must leave room for a kernel-A block on the SM");
   // tensor memory columns (512 allocated).  decoder_2/simple: block mb at columns 32 mb.  Afterwards per row block rb: A hi | A lo | D
   static constexpr int kTmemCols = 512;
   static constexpr int kColAhi = 0, kColAlo = 64, kColD = 128, kRbStride = 192;
@@ -82,6 +87,7 @@ struct DecDUShared {
   LyraMbar d_ready;        // MMA issuer -> row warps: the accumulators of the GEMM are complete
   LyraMbar ring_full[2];   // producer -> row warps: ring block u (units 0, 1) has landed
   LyraMbar tmem_ready;     // MMA warp -> everybody: tensor memory is allocated, tmem_base is valid
+  LyraMbar tmem_done;      // row warps -> MMA warp: the last tcgen05.ld of the tile has completed (LYRA_DU_EARLY_DEALLOC)
   uint32_t tmem_base;
 };
 
@@ -104,6 +110,9 @@ __device__ __forceinline__ void DuArriveA(DecDUShared* sh) {
 // (tcgen05.wait::ld covers every earlier load, so the next one is issued right after the wait).  Warp-collective.
 #ifndef LYRA_DU_PIPE
 #define LYRA_DU_PIPE 1
+#endif
+#ifndef LYRA_DU_EARLY_DEALLOC
+#define LYRA_DU_EARLY_DEALLOC 1
 #endif
 template <typename F>
 __device__ __forceinline__ void DuForEachAccGroup(uint32_t taddr, F f) {
@@ -165,6 +174,7 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
     lyra_mbar_init(&sh->in_full, 1);
     lyra_mbar_init(&sh->ov_full, 1);
     lyra_mbar_init(&sh->tmem_ready, 1);
+    lyra_mbar_init(&sh->tmem_done, 5);
     lyra_mbar_init(&sh->a_ready, L::kRowWarps);
     lyra_mbar_init(&sh->d_ready, 1);
     for (int i = 0; i < 2; ++i) lyra_mbar_init(&sh->ring_full[i], 1);
@@ -299,6 +309,14 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
         }
       }
     }
+#if LYRA_DU_EARLY_DEALLOC
+    // Tensor memory goes back as soon as the row warps have read the last accumulators - not at block exit, after the PCM and
+    // state stores - so that the next resident block's tcgen05.alloc returns that much earlier.
+    __syncwarp();
+    lyra_mbar_wait(&sh->tmem_done, 0);
+    lyra_tc_fence_after_sync();
+    lyra_tmem_dealloc(sh->tmem_base, L::kTmemCols);
+#endif
   }
 
   // ================================================= row warps ====================================================
@@ -529,6 +547,11 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
 #pragma unroll
         for (int j = 0; j < 16; ++j) uc[(c0 + j) * LDU] = __uint_as_float(v[j]);
       });
+#if LYRA_DU_EARLY_DEALLOC
+      lyra_tc_fence_before_sync();                           // that was the tile's last tensor-memory access: let the MMA warp free it
+      __syncwarp();
+      if (lane == 0) lyra_mbar_arrive(&sh->tmem_done);
+#endif
     }
     lyra_mbar_wait(&sh->in_full, 0);                         // the carried last_layer tail (loaded at kernel start)
     row_sync();
@@ -572,7 +595,9 @@ DecoderKernelDU(const uint8_t* __restrict__ blob, DecoderParams P, TileIo io, co
   lyra_tc_fence_before_sync();
   __syncthreads();
   if (pair) lyra_cluster_sync();                              // no CTA leaves while its partner may still signal its barriers
+#if !LYRA_DU_EARLY_DEALLOC
   if (!idle && warp == L::kMmaWarp) lyra_tmem_dealloc(sh->tmem_base, L::kTmemCols);
+#endif
 }
 
 }  // namespace lyra_b200
