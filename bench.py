@@ -302,12 +302,17 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
     ctxs = [c for c in (enc, dec) if c is not None]
     for c in ctxs:
         c.set_split(args.split)
-    # the device pass hands the contexts its own streams: same priorities as the contexts' own ones (engine.cu: encoder-only
-    # contexts one step above the default, overridable through the same environment variables)
-    prio_x, prio_y = int(os.environ.get("LYRA_B200_ENC_PRIORITY", "-1")), int(os.environ.get("LYRA_B200_DEC_PRIORITY", "0"))
+    # Stream priorities (lyra_b200_set_priority, include/lyra_b200.h).  The device-resident pass queues many hops ahead through the
+    # asynchronous *_device calls: there the encoder direction runs one step above the decoder (measured +2.8 % over equal
+    # priorities, -3 % with the decoder first).  The host-buffer pass makes synchronous calls: equal priorities (measured: the
+    # encoder-first setting costs it 2-3 %), so the encoder contexts go back to 0 before it.  Both settings are in `config`.
+    prio_x = int(os.environ.get("LYRA_BENCH_DEVICE_ENC_PRIORITY", "-1"))
+    prio_y = int(os.environ.get("LYRA_BENCH_DEVICE_DEC_PRIORITY", "0"))
     sx, sy = torch.cuda.Stream(priority=prio_x), torch.cuda.Stream(priority=prio_y)
     if enc:
+        enc.set_priority(prio_x)             # its sub-batch streams
         enc.set_stream(sx.cuda_stream)
+    dec.set_priority(prio_y)
     dec.set_stream(sy.cuda_stream)
     # worker groups: G context pairs of n / G streams each, used by the two timed passes; the full-size pair above serves the
     # per-kernel pass (one launch per kernel over all n streams)
@@ -324,18 +329,24 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
             d_ = _capi.Context(ng, device=local_rank, roles="decoder")
             d_.set_decoder_mode(decoder_mode)
             gx, gy = torch.cuda.Stream(priority=prio_x), torch.cuda.Stream(priority=prio_y)
+            d_.set_priority(prio_y)
             if e_:
+                e_.set_priority(prio_x)
                 e_.set_stream(gx.cuda_stream)
                 e_.set_split(args.split)
             d_.set_stream(gy.cuda_stream)
             d_.set_split(args.split)
             groups.append((e_, d_, gx, gy))
     group_ctxs = [c for grp in groups for c in grp[:2] if c is not None]
-    # the host-buffer pass runs 2 G waiting threads per rank: they sleep instead of spin when the box has fewer cores than that
+    # the host-buffer pass has its own number of worker groups (--e2e-groups): synchronous calls need more call chains in flight to
+    # cover their host turn-arounds and the serial RVQ stages than the asynchronous device pass does (measured at 6.0 / 9.2 kbps:
+    # 4 groups 5.8 / 5.5 M frames/s end to end, 2 groups 5.1-5.5 / 4.7 M; the device pass is best at 2)
+    Gh = max(1, args.e2e_groups)
+    while n % Gh:
+        Gh -= 1
+    # it runs 2 Gh waiting threads per rank: they sleep instead of spin when the box has fewer cores than that
     oversubscribed = args.host_wait == "sleep" or (args.host_wait == "auto" and
-                                                   (1 if os.environ.get("LYRA_BENCH_PINNED") else world) * (2 * G + 1) > host_cores() * 3 // 4)
-    for c in group_ctxs:
-        c.set_blocking_sync(oversubscribed)
+                                                   (1 if os.environ.get("LYRA_BENCH_PINNED") else world) * (2 * Gh + 1) > host_cores() * 3 // 4)
 
     def barrier():
         if world > 1:
@@ -432,7 +443,25 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
             if v[1]:
                 prof[k] = v
         c.profile_enable(False)
-    for c in group_ctxs:
+    host_prio = int(os.environ.get("LYRA_BENCH_HOST_PRIORITY", "0"))
+    if Gh == G:
+        host_groups = groups
+    else:
+        if G > 1:
+            for c in group_ctxs:
+                c.close()
+        host_groups = []
+        for _ in range(Gh):
+            e_ = None if plc else _capi.Context(n // Gh, device=local_rank, roles="encoder")
+            d_ = _capi.Context(n // Gh, device=local_rank, roles="decoder")
+            d_.set_decoder_mode(decoder_mode)
+            host_groups.append((e_, d_, None, None))
+    ng = n // Gh
+    host_ctxs = [c for grp in host_groups for c in grp[:2] if c is not None]
+    for c in host_ctxs:
+        c.set_stream(None)           # the host-buffer pass runs on the contexts' own streams ...
+        c.set_priority(host_prio)    # ... at equal priorities
+        c.set_blocking_sync(oversubscribed)
         c.set_split(args.e2e_split)
         c.set_graphs(args.graphs == "on")       # the dense host-buffer calls replay captured CUDA graphs (one per rotating buffer pair)
     barrier()
@@ -460,7 +489,7 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
 
     def run_host(count):
         threads = []
-        for g, (e_, d_, _gx, _gy) in enumerate(groups):
+        for g, (e_, d_, _gx, _gy) in enumerate(host_groups):
             if plc:
                 def downlink_only(g=g, d_=d_):
                     for i in range(count):
@@ -509,11 +538,11 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
     e2e_value = world * n * e2e_hops / float(t.item())
     checksum = int(pin_out.to(torch.int64).sum().item())
     tile_streams = dec.tile_streams
-    graph_replays = sum(c.graph_replays() for c in group_ctxs)
-    for c in ctxs + (group_ctxs if G > 1 else []):
+    graph_replays = sum(c.graph_replays() for c in host_ctxs)
+    for c in ctxs + (host_ctxs if Gh != G or G > 1 else []):
         c.close()
     return {"value": value, "elapsed_ms": elapsed_ms, "e2e_value": e2e_value, "e2e_s": float(t.item()), "prof": prof, "clocks": clocks,
-            "gpu_launches": int(gpu_launches), "checksum": checksum, "G": G, "oversubscribed": oversubscribed, "tile_streams": tile_streams, "stream_priority": {"encoder": prio_x, "decoder": prio_y},
+            "gpu_launches": int(gpu_launches), "checksum": checksum, "G": G, "Gh": Gh, "oversubscribed": oversubscribed, "tile_streams": tile_streams, "stream_priority": {"device_pass": {"encoder": prio_x, "decoder": prio_y}, "host_pass": {"encoder": host_prio, "decoder": host_prio}},
             "P": P, "graph_replays": graph_replays}
 
 
@@ -572,6 +601,7 @@ def main():
     ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
     ap.add_argument("--graphs", default="on", choices=["on", "off"], help="CUDA graphs for the host-buffer encode / decode calls of the e2e pass")
     ap.add_argument("--e2e-split", type=int, default=2, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
+    ap.add_argument("--e2e-groups", type=int, default=4, help="worker groups of the host-buffer (e2e) pass; see --groups")
     ap.add_argument("--groups", type=int, default=2,
                     help="worker groups: the streams are divided among this many encoder/decoder context pairs, each pair with its own "
                          "CUDA streams and, in the host-buffer pass, its own two host threads (a server's worker threads); calls on "
@@ -658,7 +688,7 @@ def main():
                                     % (n, bits * 50 / 1000.0, 1.0 - args.loss, HOPS_PER_STEP)) if plc else
                                    codec_workload(n, bits, world),
                        "streams_per_gpu": n, "bits_per_frame": bits, "hops_per_step": HOPS_PER_STEP, "tile_streams": res["tile_streams"],
-                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": G, "stream_priority": res["stream_priority"],
+                       "decoder_mode": args.decoder_mode, "sub_batches": {"device_pass": args.split, "host_pass": args.e2e_split}, "worker_groups": {"device_pass": G, "host_pass": res["Gh"]}, "stream_priority": res["stream_priority"],
                        "host_pass_cuda_graphs": {"enabled": args.graphs == "on", "replayed_calls": res.get("graph_replays", 0)},
                        "host_threads_wait": "sleep (blocking-sync event)" if res["oversubscribed"] else "spin",
                        "host_cores_per_rank": pinned if pinned else host_cores(),

@@ -200,6 +200,14 @@ int lyra_b200_decoder_mode(const lyra_b200_ctx* ctx);
 /* How the synchronous host-buffer calls wait for the GPU: 0 (default) spins (lowest latency), 1 sleeps on a blocking-sync
  * CUDA event — for servers that run more waiting worker threads than they have cores. */
 int lyra_b200_set_blocking_sync(lyra_b200_ctx* ctx, int enable);
+/* CUDA priority of the context's own stream and of its sub-batch streams (0 = default, negative = higher; the device clamps).
+ * A process that runs an encoder-only and a decoder-only context side by side through the asynchronous *_device calls gains
+ * about 3 % of throughput with the encoder one step above the decoder (the uplink chain is the longer one; its blocks go
+ * first, the decoder's latency-bound blocks fill what is left); with the synchronous host-buffer calls equal priorities are
+ * the better choice (measured).  Waits for the context's work, re-creates the streams, drops captured
+ * graphs.  A caller stream installed with lyra_b200_set_stream keeps its own priority.  Default 0, or the environment
+ * variables LYRA_B200_ENC_PRIORITY / LYRA_B200_DEC_PRIORITY at creation. */
+int lyra_b200_set_priority(lyra_b200_ctx* ctx, int priority);
 /* CUDA graphs for the synchronous host-buffer calls lyra_b200_encode / lyra_b200_decode (no reference counterpart): with
  * enable = 1 a dense call (stream_ids == NULL) whose host buffers are page-locked is captured once - copies in, every
  * sub-batch's kernels, copies out - and later calls with the same n, num_bits and buffers replay the graph (one launch instead

@@ -59,6 +59,7 @@ class CApi:
             "lyra_b200_set_split": (ci, [vp, ci]),
             "lyra_b200_set_blocking_sync": (ci, [vp, ci]),
             "lyra_b200_set_graphs": (ci, [vp, ci]),
+            "lyra_b200_set_priority": (ci, [vp, ci]),
             "lyra_b200_graph_replays": (C.c_uint64, [vp]),
             "lyra_b200_set_decoder_mode": (ci, [vp, ci]),
             "lyra_b200_decoder_mode": (ci, [vp]),
@@ -88,7 +89,7 @@ class CApi:
                "lyra_b200_extract_features", "lyra_b200_quantize", "lyra_b200_dequantize", "lyra_b200_generate",
                "lyra_b200_logmel", "lyra_b200_set_stream", "lyra_b200_encode_device", "lyra_b200_decode_device",
                "lyra_b200_synchronize", "lyra_b200_noise_update", "lyra_b200_noise_update_device", "lyra_b200_decode_track_noise",
-               "lyra_b200_decode_track_noise_device", "lyra_b200_set_split", "lyra_b200_set_blocking_sync", "lyra_b200_set_graphs", "lyra_b200_graph_replays", "lyra_b200_set_decoder_mode", "lyra_b200_decoder_mode", "lyra_b200_launch_count", "lyra_b200_profile_enable",
+               "lyra_b200_decode_track_noise_device", "lyra_b200_set_split", "lyra_b200_set_blocking_sync", "lyra_b200_set_graphs", "lyra_b200_set_priority", "lyra_b200_graph_replays", "lyra_b200_set_decoder_mode", "lyra_b200_decoder_mode", "lyra_b200_launch_count", "lyra_b200_profile_enable",
                "lyra_b200_profile_read", "lyra_b200_noise_estimate", "lyra_b200_decode_plc", "lyra_b200_decode_plc_device",
                "lyra_b200_plc_get_state", "lyra_b200_plc_set_state", "lyra_b200_cng_generate", "lyra_b200_set_cng_seed",
                "lyra_b200_encode_dtx", "lyra_b200_encode_dtx_device", "lyra_b200_resample"]
@@ -356,6 +357,9 @@ class Context:
 
     def set_graphs(self, enable):
         self._check(self.api.lib.lyra_b200_set_graphs(self.h, 1 if enable else 0))
+
+    def set_priority(self, priority):
+        self._check(self.api.lib.lyra_b200_set_priority(self.h, int(priority)))
 
     def graph_replays(self):
         return int(self.api.lib.lyra_b200_graph_replays(self.h))

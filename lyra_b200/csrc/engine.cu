@@ -117,6 +117,7 @@ struct lyra_b200_ctx {
   bool blocking_sync = false;        // host-buffer calls sleep on an event instead of spinning (lyra_b200_set_blocking_sync)
   cudaEvent_t ev_sync = nullptr;
   int decoder_mode = LYRA_B200_DECODER_EXACT;   // lyra_b200_set_decoder_mode
+  int priority = 0;                  // CUDA priority of own_stream / aux_stream (lyra_b200_set_priority)
   uint64_t launches = 0;
   // lyra_b200_set_graphs: the dense host-buffer encode / decode calls replay a captured CUDA graph (copies in, kernels of every
   // sub-batch, copies out) instead of re-issuing ~20 stream operations per call; one graph per (call shape, host buffers)
@@ -738,12 +739,11 @@ int lyra_b200_create_ex(const char* model_dir, int device, int max_streams, int 
   ctx->tile_gen.assign((size_t)ctx->ntiles, 0u);
   const size_t P = (size_t)ctx->padded;
   bool ok = cudaSetDevice(device) == cudaSuccess;
-  // Stream priority of the context's own and sub-batch streams.  An encoder-only context runs one step above the default: in
-  // a full-duplex process the uplink chain (kernels A, B, RVQ) is the longer one and its FMA-bound blocks go first when both
-  // directions have blocks waiting, the decoder's latency-bound blocks fill what is left (measured on the duplex benchmark:
-  // +2.3 % over equal priorities, -3 % with the decoder first).  LYRA_B200_ENC_PRIORITY / LYRA_B200_DEC_PRIORITY override.
-  int prio = roles == LYRA_B200_ROLE_ENCODER ? -1 : 0;
+  // Stream priority of the context's own and sub-batch streams: 0 unless LYRA_B200_ENC_PRIORITY / LYRA_B200_DEC_PRIORITY say
+  // otherwise (encoder-only / decoder-only contexts); lyra_b200_set_priority changes it later.
+  int prio = 0;
   if (const char* e = std::getenv(roles == LYRA_B200_ROLE_DECODER ? "LYRA_B200_DEC_PRIORITY" : "LYRA_B200_ENC_PRIORITY")) prio = std::atoi(e);
+  ctx->priority = prio;
   ok = ok && cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamDefault, prio) == cudaSuccess;
   for (int i = 0; i < lyra_b200_ctx::kMaxSplit - 1; ++i) {
     ok = ok && cudaStreamCreateWithPriority(&ctx->aux_stream[i], cudaStreamDefault, prio) == cudaSuccess;
@@ -918,6 +918,24 @@ int lyra_b200_set_blocking_sync(lyra_b200_ctx* ctx, int enable) {
   if (!ctx) return LYRA_B200_EINVAL;
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
   ctx->blocking_sync = enable != 0;
+  return LYRA_B200_OK;
+}
+
+int lyra_b200_set_priority(lyra_b200_ctx* ctx, int priority) {
+  if (!ctx) return LYRA_B200_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return LYRA_B200_ENODEV; }   // the current device is per host thread
+  CU(SyncStream(ctx));
+#ifndef LYRA_EMU
+  DropGraphs(ctx);                   // captured graphs carry the priority of the streams they were captured on
+#endif
+  const bool own = ctx->stream == ctx->own_stream;
+  cudaStream_t fresh[lyra_b200_ctx::kMaxSplit];
+  for (int i = 0; i < lyra_b200_ctx::kMaxSplit; ++i) CU(cudaStreamCreateWithPriority(&fresh[i], cudaStreamDefault, priority));
+  cudaStreamDestroy(ctx->own_stream);
+  ctx->own_stream = fresh[0];
+  for (int i = 0; i < lyra_b200_ctx::kMaxSplit - 1; ++i) { cudaStreamDestroy(ctx->aux_stream[i]); ctx->aux_stream[i] = fresh[i + 1]; }
+  if (own) ctx->stream = ctx->own_stream;
+  ctx->priority = priority;
   return LYRA_B200_OK;
 }
 

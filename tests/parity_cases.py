@@ -59,6 +59,25 @@ def run_codec_parity(Context, api, O, *, max_streams, stream_ids, frames, bits, 
     return worst
 
 
+def run_priority_switch(Context, api, O, *, n=3, frames=4, bits=64, split=2):
+    """lyra_b200_set_priority between hops (streams re-created, sub-batches in use): the streaming state is untouched, results stay
+    the oracle's."""
+    ctx = Context(max(16, n), capi=api)
+    ctx.set_split(split)
+    codecs = [O.Codec(MODEL_DIR) for _ in range(n)]
+    rng = np.random.default_rng(21)
+    for f in range(frames):
+        ctx.set_priority([-1, 0, -2, 0][f % 4])
+        pcm = synth_pcm(rng, n)
+        packets = ctx.encode(pcm, bits)
+        out = ctx.decode(packets, bits)
+        for k in range(n):
+            opkt, _, _ = codecs[k].encode(pcm[k], bits)
+            opcm, _, _ = codecs[k].decode(opkt, bits)
+            assert bytes(packets[k]) == opkt and np.array_equal(out[k], opcm), "mismatch after a priority switch (hop %d stream %d)" % (f, k)
+    ctx.close()
+
+
 def run_plugin_surface_parity(Context, api, O, *, n=5, frames=3, seed=1):
     """extract_features / quantize / dequantize / generate one by one against the oracle's pieces."""
     import os

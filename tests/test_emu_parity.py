@@ -73,6 +73,10 @@ def test_emu_cpp_components(emu_api, oracle, tmp_path):
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_emu_priority_switch(emu_api, oracle):
+    pc.run_priority_switch(_capi.Context, emu_api, oracle, n=2, frames=3)
+
+
 def test_emu_sixteen_stream_tiles(emu_api, oracle, monkeypatch):
     monkeypatch.setenv("LYRA_B200_TILE_STREAMS", "16")
     pc.run_codec_parity(_capi.Context, emu_api, oracle, max_streams=32, stream_ids=[3, 17], frames=3, bits=64)

@@ -58,6 +58,11 @@ def test_tensor_decoder_mode_full_size_matches_exact_mode(gpu_api):
     assert worst <= pc.TENSOR_PCM_TOL_LSB
 
 
+def test_priority_switch(gpu_api, oracle):
+    # lyra_b200_set_priority re-creates the context's streams between hops; state and results are unaffected
+    pc.run_priority_switch(_capi.Context, gpu_api, oracle, n=20, frames=8)
+
+
 @pytest.mark.parametrize("mode", ["exact", "tensor"])
 def test_sixteen_stream_tiles(gpu_api, oracle, sample1, monkeypatch, mode):
     # the alternative tile size (LYRA_B200_TILE_STREAMS=16, one block per SM) runs the same kernels with other tile shapes
