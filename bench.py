@@ -341,12 +341,18 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
     # the host-buffer pass has its own number of worker groups (--e2e-groups): synchronous calls need more call chains in flight to
     # cover their host turn-arounds and the serial RVQ stages than the asynchronous device pass does (measured at 6.0 / 9.2 kbps:
     # 4 groups 5.8 / 5.5 M frames/s end to end, 2 groups 5.1-5.5 / 4.7 M; the device pass is best at 2)
-    Gh = max(1, args.e2e_groups)
+    ranks_sharing = 1 if os.environ.get("LYRA_BENCH_PINNED") else world
+    if args.e2e_groups > 0:
+        Gh = args.e2e_groups
+    else:
+        # auto: 4 for the codec workloads when this rank's share of the host cores can spin-wait 2 x 4 + 1 threads, else 2; the
+        # decoder-only workloads make short calls (0.1-0.4 ms of GPU work per hop) and do better with fewer, larger ones
+        Gh = 4 if (not plc and ranks_sharing * 9 <= host_cores() * 3 // 4) else 2
     while n % Gh:
         Gh -= 1
     # it runs 2 Gh waiting threads per rank: they sleep instead of spin when the box has fewer cores than that
     oversubscribed = args.host_wait == "sleep" or (args.host_wait == "auto" and
-                                                   (1 if os.environ.get("LYRA_BENCH_PINNED") else world) * (2 * Gh + 1) > host_cores() * 3 // 4)
+                                                   ranks_sharing * (2 * Gh + 1) > host_cores() * 3 // 4)
 
     def barrier():
         if world > 1:
@@ -601,7 +607,7 @@ def main():
     ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches of a dense call, device-resident pass (1..4)")
     ap.add_argument("--graphs", default="on", choices=["on", "off"], help="CUDA graphs for the host-buffer encode / decode calls of the e2e pass")
     ap.add_argument("--e2e-split", type=int, default=2, help="sub-batches in the host-buffer pass: their copies overlap the others' kernels")
-    ap.add_argument("--e2e-groups", type=int, default=4, help="worker groups of the host-buffer (e2e) pass; see --groups")
+    ap.add_argument("--e2e-groups", type=int, default=0, help="worker groups of the host-buffer (e2e) pass (0 = auto: 4, or 2 for the decoder-only workloads and on boxes with few host cores per rank); see --groups")
     ap.add_argument("--groups", type=int, default=2,
                     help="worker groups: the streams are divided among this many encoder/decoder context pairs, each pair with its own "
                          "CUDA streams and, in the host-buffer pass, its own two host threads (a server's worker threads); calls on "
