@@ -187,6 +187,17 @@ def pin_rank_cores(local_rank, local_world):
         return None
 
 
+def host_pass_groups(requested, plc, ranks_sharing, cores, n):
+    """Worker groups of the host-buffer pass.  requested > 0 wins; auto: 4 for the codec workloads when this rank's share of the
+    host cores can spin-wait 2 x 4 + 1 threads, else 2; the decoder-only workloads make short calls (0.1-0.4 ms of GPU work per
+    hop) and do better with fewer, larger ones.  The result divides the stream count."""
+    g = requested if requested > 0 else (4 if (not plc and ranks_sharing * 9 <= cores * 3 // 4) else 2)
+    g = max(1, g)
+    while n % g:
+        g -= 1
+    return g
+
+
 def synth_pcm_np(n, nbuf, seed, kind="noise"):
     """Seeded synthetic input, `nbuf` distinct hops rotated through the steps:
     noise  — uniform noise at 0.25 full scale (the reference benchmark feeds uniform random audio, lyra/lyra_benchmark_lib.cc:233-239);
@@ -342,14 +353,7 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
     # cover their host turn-arounds and the serial RVQ stages than the asynchronous device pass does (measured at 6.0 / 9.2 kbps:
     # 4 groups 5.8 / 5.5 M frames/s end to end, 2 groups 5.1-5.5 / 4.7 M; the device pass is best at 2)
     ranks_sharing = 1 if os.environ.get("LYRA_BENCH_PINNED") else world
-    if args.e2e_groups > 0:
-        Gh = args.e2e_groups
-    else:
-        # auto: 4 for the codec workloads when this rank's share of the host cores can spin-wait 2 x 4 + 1 threads, else 2; the
-        # decoder-only workloads make short calls (0.1-0.4 ms of GPU work per hop) and do better with fewer, larger ones
-        Gh = 4 if (not plc and ranks_sharing * 9 <= host_cores() * 3 // 4) else 2
-    while n % Gh:
-        Gh -= 1
+    Gh = host_pass_groups(args.e2e_groups, plc, ranks_sharing, host_cores(), n)
     # it runs 2 Gh waiting threads per rank: they sleep instead of spin when the box has fewer cores than that
     oversubscribed = args.host_wait == "sleep" or (args.host_wait == "auto" and
                                                    ranks_sharing * (2 * Gh + 1) > host_cores() * 3 // 4)

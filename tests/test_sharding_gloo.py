@@ -71,3 +71,17 @@ def test_bench_rank_core_slices_are_disjoint():
     assert outs[0]["ret"] == len(a) == len(base) // 2 and outs[0]["cores"] <= len(a)
     single = json.loads(subprocess.check_output([sys.executable, "-c", code, "0", "1"]).decode().strip().splitlines()[-1])
     assert single["ret"] is None and single["now"] == single["base"]
+
+
+def test_bench_host_pass_groups():
+    """bench.py picks the host-buffer pass's worker groups from the workload and the host cores of the rank."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.host_pass_groups(0, False, 1, 16, 4096) == 4        # one GPU, 16 cores: 9 waiting threads fit into 12
+    assert bench.host_pass_groups(0, False, 1, 12, 4096) == 4        # a 12-core slice of an 8-GPU box
+    assert bench.host_pass_groups(0, False, 1, 8, 4096) == 2         # an 8-core slice: two groups
+    assert bench.host_pass_groups(0, False, 2, 16, 4096) == 2        # two unpinned ranks sharing 16 cores
+    assert bench.host_pass_groups(0, True, 1, 64, 4096) == 2         # decoder-only workloads: fewer, larger calls
+    assert bench.host_pass_groups(3, False, 1, 64, 4096) == 2        # an explicit request is reduced to a divisor of the stream count
+    assert bench.host_pass_groups(3, False, 1, 64, 3072) == 3
