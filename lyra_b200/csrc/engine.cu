@@ -930,7 +930,12 @@ int lyra_b200_set_priority(lyra_b200_ctx* ctx, int priority) {
 #endif
   const bool own = ctx->stream == ctx->own_stream;
   cudaStream_t fresh[lyra_b200_ctx::kMaxSplit];
-  for (int i = 0; i < lyra_b200_ctx::kMaxSplit; ++i) CU(cudaStreamCreateWithPriority(&fresh[i], cudaStreamDefault, priority));
+  for (int i = 0; i < lyra_b200_ctx::kMaxSplit; ++i)
+    if (cudaStreamCreateWithPriority(&fresh[i], cudaStreamDefault, priority) != cudaSuccess) {      // nothing has changed yet
+      while (i-- > 0) cudaStreamDestroy(fresh[i]);
+      ctx->err = "cudaStreamCreateWithPriority failed";
+      return LYRA_B200_ENODEV;
+    }
   cudaStreamDestroy(ctx->own_stream);
   ctx->own_stream = fresh[0];
   for (int i = 0; i < lyra_b200_ctx::kMaxSplit - 1; ++i) { cudaStreamDestroy(ctx->aux_stream[i]); ctx->aux_stream[i] = fresh[i + 1]; }
