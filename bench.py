@@ -188,10 +188,11 @@ def pin_rank_cores(local_rank, local_world):
 
 
 def host_pass_groups(requested, plc, ranks_sharing, cores, n):
-    """Worker groups of the host-buffer pass.  requested > 0 wins; auto: 4 for the codec workloads when this rank's share of the
-    host cores can spin-wait 2 x 4 + 1 threads, else 2; the decoder-only workloads make short calls (0.1-0.4 ms of GPU work per
-    hop) and do better with fewer, larger ones.  The result divides the stream count."""
-    g = requested if requested > 0 else (4 if (not plc and ranks_sharing * 9 <= cores * 3 // 4) else 2)
+    """Worker groups of the host-buffer pass.  requested > 0 wins; auto: 4 for the codec workloads when this rank has at least 16
+    logical host cores for its 2 x 4 spin-waiting threads (hyper-thread siblings included - the configuration measured on one
+    GPU), else 2 (the configuration measured under torchrun); the decoder-only workloads make short calls (0.1-0.4 ms of GPU
+    work per hop) and do better with fewer, larger ones.  The result divides the stream count."""
+    g = requested if requested > 0 else (4 if (not plc and ranks_sharing * 16 <= cores) else 2)
     g = max(1, g)
     while n % g:
         g -= 1

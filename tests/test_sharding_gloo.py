@@ -78,9 +78,9 @@ def test_bench_host_pass_groups():
     import sys
     sys.path.insert(0, ROOT)
     import bench
-    assert bench.host_pass_groups(0, False, 1, 16, 4096) == 4        # one GPU, 16 cores: 9 waiting threads fit into 12
-    assert bench.host_pass_groups(0, False, 1, 12, 4096) == 4        # a 12-core slice of an 8-GPU box
-    assert bench.host_pass_groups(0, False, 1, 8, 4096) == 2         # an 8-core slice: two groups
+    assert bench.host_pass_groups(0, False, 1, 16, 4096) == 4        # one GPU, 16 logical cores: the measured configuration
+    assert bench.host_pass_groups(0, False, 1, 12, 4096) == 2        # a 12-thread slice of an 8-GPU box: two groups
+    assert bench.host_pass_groups(0, False, 1, 24, 4096) == 4        # a 24-thread slice (4 ranks on that box)
     assert bench.host_pass_groups(0, False, 2, 16, 4096) == 2        # two unpinned ranks sharing 16 cores
     assert bench.host_pass_groups(0, True, 1, 64, 4096) == 2         # decoder-only workloads: fewer, larger calls
     assert bench.host_pass_groups(3, False, 1, 64, 4096) == 2        # an explicit request is reduced to a divisor of the stream count
