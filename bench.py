@@ -199,6 +199,18 @@ def host_pass_groups(requested, plc, ranks_sharing, cores, n):
     return g
 
 
+def host_pass_priorities(groups, bits, plc):
+    """(encoder, decoder) stream priorities of the host-buffer pass; LYRA_BENCH_HOST_ENC_PRIORITY / ..._DEC_PRIORITY override.
+    Equal by default (the synchronous calls of the 3.2 kbps workload lose 2-3 % with the encoder first, and four worker groups do
+    well with equal priorities at every bit rate).  With only two worker groups the longer encoder chain of the higher bit rates
+    (30 / 46 serial RVQ stages behind kernels A and B) holds the pipeline back and the encoder goes one step up: measured on one
+    B200, 2 groups, 6.0 / 9.2 kbps: 5.60 / 5.53 M frames/s end to end against 5.06 / 4.80 M with equal priorities."""
+    enc = -1 if (groups <= 2 and bits > 64 and not plc) else 0
+    enc = int(os.environ.get("LYRA_BENCH_HOST_ENC_PRIORITY", str(enc)))
+    dec = int(os.environ.get("LYRA_BENCH_HOST_DEC_PRIORITY", "0"))
+    return enc, dec
+
+
 def synth_pcm_np(n, nbuf, seed, kind="noise"):
     """Seeded synthetic input, `nbuf` distinct hops rotated through the steps:
     noise  — uniform noise at 0.25 full scale (the reference benchmark feeds uniform random audio, lyra/lyra_benchmark_lib.cc:233-239);
@@ -454,7 +466,7 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
             if v[1]:
                 prof[k] = v
         c.profile_enable(False)
-    host_prio = int(os.environ.get("LYRA_BENCH_HOST_PRIORITY", "0"))
+    host_prio_x, host_prio_y = host_pass_priorities(Gh, bits, plc)
     if Gh == G:
         host_groups = groups
     else:
@@ -469,9 +481,12 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
             host_groups.append((e_, d_, None, None))
     ng = n // Gh
     host_ctxs = [c for grp in host_groups for c in grp[:2] if c is not None]
+    for e_, d_, _gx, _gy in host_groups:     # the host-buffer pass runs on the contexts' own streams, at its own priorities
+        for c, prio in ((e_, host_prio_x), (d_, host_prio_y)):
+            if c is not None:
+                c.set_stream(None)
+                c.set_priority(prio)
     for c in host_ctxs:
-        c.set_stream(None)           # the host-buffer pass runs on the contexts' own streams ...
-        c.set_priority(host_prio)    # ... at equal priorities
         c.set_blocking_sync(oversubscribed)
         c.set_split(args.e2e_split)
         c.set_graphs(args.graphs == "on")       # the dense host-buffer calls replay captured CUDA graphs (one per rotating buffer pair)
@@ -553,7 +568,7 @@ def measure(args, n, bits, plc, loss, hops, warm_hops, kernel_hops, e2e_hops, wo
     for c in ctxs + (host_ctxs if Gh != G or G > 1 else []):
         c.close()
     return {"value": value, "elapsed_ms": elapsed_ms, "e2e_value": e2e_value, "e2e_s": float(t.item()), "prof": prof, "clocks": clocks,
-            "gpu_launches": int(gpu_launches), "checksum": checksum, "G": G, "Gh": Gh, "oversubscribed": oversubscribed, "tile_streams": tile_streams, "stream_priority": {"device_pass": {"encoder": prio_x, "decoder": prio_y}, "host_pass": {"encoder": host_prio, "decoder": host_prio}},
+            "gpu_launches": int(gpu_launches), "checksum": checksum, "G": G, "Gh": Gh, "oversubscribed": oversubscribed, "tile_streams": tile_streams, "stream_priority": {"device_pass": {"encoder": prio_x, "decoder": prio_y}, "host_pass": {"encoder": host_prio_x, "decoder": host_prio_y}},
             "P": P, "graph_replays": graph_replays}
 
 

@@ -85,3 +85,7 @@ def test_bench_host_pass_groups():
     assert bench.host_pass_groups(0, True, 1, 64, 4096) == 2         # decoder-only workloads: fewer, larger calls
     assert bench.host_pass_groups(3, False, 1, 64, 4096) == 2        # an explicit request is reduced to a divisor of the stream count
     assert bench.host_pass_groups(3, False, 1, 64, 3072) == 3
+    assert bench.host_pass_priorities(4, 120, False) == (0, 0)       # four groups: equal priorities at every bit rate
+    assert bench.host_pass_priorities(2, 64, False) == (0, 0)
+    assert bench.host_pass_priorities(2, 120, False) == (-1, 0)      # two groups, long RVQ chains: encoder first
+    assert bench.host_pass_priorities(2, 184, True) == (0, 0)        # decoder-only workload
