@@ -162,11 +162,16 @@ class Coalescer {
   std::vector<Call*> Take() {
     std::vector<Call*> batch, rest;
     const Call* head = queue_.front();
+    if (seen_.size() < (size_t)max_batch_) seen_.assign((size_t)max_batch_, 0);      // stream ids are < max_streams = max_batch_
     for (Call* q : queue_) {
       bool take = q->kind == head->kind && q->arg == head->arg && q->arg2 == head->arg2 && (int)batch.size() < max_batch_;
-      if (take && q->id >= 0) for (const Call* b : batch) if (b->id == q->id) { take = false; break; }
+      if (take && q->id >= 0 && q->id < max_batch_) {
+        take = !seen_[(size_t)q->id];
+        if (take) seen_[(size_t)q->id] = 1;
+      }
       (take ? batch : rest).push_back(q);
     }
+    for (const Call* b : batch) if (b->id >= 0 && b->id < max_batch_) seen_[(size_t)b->id] = 0;
     queue_.swap(rest);
     return batch;
   }
@@ -216,7 +221,7 @@ class Coalescer {
   bool leader_ = false;
   Stats stats_;
   std::vector<int32_t> ids_;           // leader-only scratch (one leader at a time)
-  std::vector<uint8_t> in_, out_, flags_;
+  std::vector<uint8_t> in_, out_, flags_, seen_;
 };
 
 // ---- process-wide context + stream-id allocator ------------------------------------------------------------------
